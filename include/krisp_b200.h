@@ -1,0 +1,152 @@
+/*
+ * krisp_b200.h — C ABI of libkrisp_b200.so: the B200 (sm_100a) implementation of krisp_fasta's
+ * diagnostic-region search hot path (k-mer extraction -> radix sort -> intersection over all
+ * files -> diagnostic filter).
+ *
+ * The reference (grunwaldlab/krisp 0.1.6) is pure Python and has no FFI for this path; the
+ * boundary it crosses today is its Python stage functions and the text k-mer files between them.
+ * Each entry point below names the reference interface it replaces (paths relative to
+ * src/krisp/ in the reference).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions: plain C types only; every call returns KB_OK (0) or a negative KB_E* code and
+ * leaves a message retrievable with kb_last_error(); no exceptions or aborts cross the ABI.
+ * One kb_ctx drives one GPU (one process per GPU; multi-GPU = one ctx per rank, see kb_shard_*).
+ * A ctx is not thread-safe.  The library owns all device memory and the host result buffers
+ * until the matching *_free / kb_destroy; input pointers are borrowed for the duration of the
+ * call.  Output *content* is deterministic; output *order* is not (the host canonical-sorts rows,
+ * as the reference's own row order depends on --cores).
+ */
+#ifndef KRISP_B200_H
+#define KRISP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_OK 0
+#define KB_EINVAL -1        /* bad argument / unsupported parameter combination */
+#define KB_ECUDA -2         /* CUDA runtime error (message has the CUDA error string) */
+#define KB_ENOMEM -3        /* device or host allocation failed */
+#define KB_EUNSUPPORTED -4  /* valid in the reference, not supported here (documented in DESIGN.md) */
+#define KB_EINTERNAL -5     /* invariant violated */
+
+typedef struct kb_ctx kb_ctx;
+typedef struct kb_result kb_result;
+typedef struct kb_table kb_table;
+
+/* Library / build identification: "krisp_b200 <version> sm_100a". */
+const char* kb_version(void);
+
+/* Create a context on CUDA device `device` (per-process ordinal). */
+int kb_create(int device, kb_ctx** out);
+void kb_destroy(kb_ctx* ctx);
+const char* kb_last_error(const kb_ctx* ctx);
+
+/* Launch all work on this cudaStream_t (e.g. torch's current stream).  NULL = the ctx's own stream. */
+int kb_set_stream(kb_ctx* ctx, void* cuda_stream);
+
+/*
+ * Search parameters.  Replaces the argument deduction of krisp_fasta.py:178-213 (done by the host
+ * layer) and the kstream options fixed by extractSortedKmers (krisp_fasta.py:16-43):
+ *   L, D, R      --conserved-left / --diagnostic / --conserved-right (k = L+D+R <= 252)
+ *   soft_mode    0 = map soft-masked bases to upper case (default), 1 = --omit-soft
+ *   n_files      number of input files over ALL GPUs (ingroup + outgroup), ids 0..n_files-1 (<= 256)
+ *   is_ingroup   n_files bytes; 1 iff simplename(file) is in the ingroup label set
+ *                (membership is by label: krisp_fasta.py:267, shared.py:58-73)
+ */
+int kb_configure(kb_ctx* ctx, int L, int D, int R, int soft_mode, int n_files, const uint8_t* is_ingroup);
+
+/*
+ * Tuning / diagnostics knobs:
+ *   "sort_bits"     bits of the (mixed) flank key / flank hash the radix sort orders by (default 40;
+ *                   fewer bits = fewer passes, residual collisions are resolved exactly in the group pass)
+ *   "mix"           1 (default) = store the flank key mixed by a bijection (uniform digits)
+ *   "want_records"  1 = also return every record of the surviving groups' runs (for --out_align)
+ *   "profile"       1 = time each stage with CUDA events (kb_last_profile)
+ *   "result_cap"    initial capacity of the survivor table (it grows and the group pass re-runs on overflow)
+ */
+int kb_set_option(kb_ctx* ctx, const char* name, long long value);
+
+/*
+ * Sequence ingest.  Replaces the per-record strings produced by kstream._parse_FASTA
+ * (kstream/kstream.py:556-583).  One call per input file: `bytes` = the bases of the file as ASCII,
+ * one separator byte (any byte that is not a letter, e.g. '\n') between FASTA records; headers and
+ * line breaks already removed.  `on_device` != 0 means `bytes` is a device pointer.  The copy is
+ * asynchronous on the ctx stream; a host buffer must stay valid until the next synchronising call
+ * (kb_search / kb_synchronize) and should be pinned for the copy to be truly asynchronous.
+ */
+int kb_clear_sequences(kb_ctx* ctx);
+int kb_reserve(kb_ctx* ctx, uint64_t total_bytes);
+int kb_add_sequence(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_bytes, int on_device);
+int kb_synchronize(kb_ctx* ctx);
+
+/*
+ * The whole search on one GPU.  Replaces, in one call:
+ *   extractSortedKmers  krisp_fasta.py:16  (kstream.write + GNU sort, kstream.py:250-325, :83-119)
+ *   mergeFiles          intersectAmplicons.py:232 (tree of intersectSortedStreams, shared.py:321)
+ *   filterAlignments    filterAlignments.py:31  (ingroupUniqueColumns, Amplicon.py:495)
+ * Blocking.  The result holds the surviving groups: flank words, per-column ingroup / outgroup
+ * base sets (what consensus(), Amplicon.py:550, needs), and optionally every record of the
+ * surviving groups' runs (what render_alignment, Amplicon.py:598, needs).
+ */
+int kb_search(kb_ctx* ctx, kb_result** out);
+
+/*
+ * Multi-GPU (one ctx per rank; records are sharded by a hash of the flank key).
+ *   kb_shard_extract      K1 on this rank's files, then one partition pass by destination shard.
+ *                         *records = device pointer to the partitioned records (8 bytes each),
+ *                         counts[s] = records bound for shard s (host array, n_shards entries).
+ *   kb_shard_recv_buffer  device buffer for `n_records` incoming records; the host layer fills it
+ *                         with an all-to-all (torch.distributed / NCCL) from every rank's partition.
+ *   kb_shard_search       radix sort + group pass over the received records.
+ */
+int kb_shard_extract(kb_ctx* ctx, int n_shards, void** records, uint64_t* counts);
+int kb_shard_recv_buffer(kb_ctx* ctx, uint64_t n_records, void** buffer);
+int kb_shard_search(kb_ctx* ctx, uint64_t n_records, kb_result** out);
+
+/* Result accessors (borrowed pointers, valid until kb_result_free). */
+typedef struct {
+    uint64_t n_groups;          /* surviving (left,right) groups                                  */
+    uint64_t n_records;         /* valid k-mer occurrences processed (both strands, all files)    */
+    uint64_t n_run_records;     /* records returned in `records` (0 unless want_records)          */
+    int32_t L, D, R;
+    int32_t flank_words;        /* 64-bit words per flank: bits MSB-first, left then right        */
+    int32_t mask_words;         /* 32-bit words per side: column c = nibble (7 - c%8) of word c/8 */
+    int32_t record_words;       /* 64-bit words per record: [left][right][mid][pad][file id : 8]  */
+    int32_t reserved;
+    const uint64_t* flank;      /* [n_groups][flank_words]                                        */
+    const uint32_t* in_mask;    /* [n_groups][mask_words]  bit0 A, bit1 C, bit2 G, bit3 T         */
+    const uint32_t* out_mask;   /* [n_groups][mask_words]                                         */
+    const uint32_t* group_size; /* [n_groups] records in the group                                */
+    const uint64_t* run_offset; /* [n_groups + 1] range of the group's run in `records`           */
+    const uint64_t* records;    /* [n_run_records][record_words]; a run may hold records of other
+                                   flank keys too (prefix sort): filter by the flank bits          */
+    uint64_t stats[4];          /* runs, queued runs, groups present in every file, mixed runs    */
+} kb_result_view;
+int kb_result_get(const kb_result* res, kb_result_view* view);
+void kb_result_free(kb_result* res);
+
+/* Per-stage device times of the last search in ms (needs option "profile"=1): fills up to `cap`
+ * entries of names/ms, returns the number of stages. */
+int kb_last_profile(const kb_ctx* ctx, const char** names, float* ms, int cap);
+
+/* Counters of the last search: kernels launched, algorithmic bytes the kernels read+wrote, radix passes. */
+int kb_last_counters(const kb_ctx* ctx, uint64_t* kernel_launches, uint64_t* algorithmic_bytes, int* radix_passes);
+
+/*
+ * kstream path: one file's k-mers as a packed table sorted like the reference's `*.{k}mers` file
+ * (LC_ALL=C order on left, right, then middle).  Replaces kstream.write + sortInPlace
+ * (kstream/kstream.py:250-325, :83-119); the count equals kstream.write's return value.
+ * `local_index` = order of the kb_add_sequence call.  Records are one 64-bit word each
+ * (only k-mers with 2k + 8 <= 64 bits are supported on this path).
+ */
+int kb_extract_sorted(kb_ctx* ctx, int local_index, kb_table** out);
+int kb_table_get(const kb_table* t, const uint64_t** records, uint64_t* n_records, int* record_words);
+void kb_table_free(kb_table* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

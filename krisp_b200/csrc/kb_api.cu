@@ -1,0 +1,669 @@
+// kb_api.cu — host side of libkrisp_b200.so: context, device workspaces, stage sequencing, C ABI.
+// (interface and the reference entry points each call replaces: include/krisp_b200.h)
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/krisp_b200.h"
+#include "kb_common.cuh"
+#include "kb_extract.cuh"
+#include "kb_sort.cuh"
+#include "kb_group.cuh"
+
+#define KB_VERSION_STR "krisp_b200 0.1.0 sm_100a"
+
+// ---- small RAII-free device buffer that only grows --------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct kb_result {
+    kb_result_view v;
+    std::vector<uint64_t> flank, run_offset, records;
+    std::vector<uint32_t> in_mask, out_mask, group_size;
+};
+
+struct kb_table {
+    std::vector<uint64_t> records;
+    int record_words = 1;
+};
+
+struct kb_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+
+    // configuration
+    bool configured = false;
+    KbLayout lo{};
+    int soft_mode = 0;
+    uint8_t is_ingroup[KB_MAX_FILES]{};
+    long long opt_sort_bits = 40, opt_mix = 1, opt_want_records = 0, opt_profile = 0, opt_result_cap = 1 << 16;
+
+    // sequences
+    DevBuf bases;
+    uint64_t n_bases = 0;
+    std::vector<uint64_t> file_starts;   // local files
+    std::vector<uint32_t> file_gid;
+    DevBuf d_file_starts, d_file_gid;
+
+    // workspaces
+    DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out;
+    uint64_t* h_pinned = nullptr;        // 64 x u64 scratch for small D2H reads
+    uint64_t result_cap = 0;
+
+    // last-search bookkeeping
+    uint64_t launches = 0, alg_bytes = 0;
+    int passes = 0;
+    std::vector<std::pair<std::string, float>> profile;
+    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+
+    // shard state
+    uint64_t shard_n_records = 0;
+};
+
+// layout of the `small` device buffer (u64 units)
+enum { SM_NOUT = 0, SM_NRES = 1, SM_STATS = 2 /*4*/, SM_TICKET = 8 /* u32 x 16 */, SM_HIST = 16 /* 9*256 */, SM_TOTAL = 16 + 9 * 256 };
+
+static int fail(kb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? KB_ENOMEM : KB_ECUDA,                    \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                            \
+    } while (0)
+
+static int ensure(kb_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false) {
+    if (bytes <= b.cap) return KB_OK;
+    size_t want = bytes + bytes / 16 + 256;
+    void* np = nullptr;
+    CU(cudaMalloc(&np, want));
+    if (keep && b.p && b.cap) CU(cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (b.p) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(b.p)); }
+    b.p = np; b.cap = want;
+    return KB_OK;
+}
+#define TRY(x) do { int rc__ = (x); if (rc__ != KB_OK) return rc__; } while (0)
+
+// ---- profiling helpers ---------------------------------------------------------------------------
+static void prof_begin(kb_ctx* ctx, const char* name) {
+    if (!ctx->opt_profile) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, ctx->stream);
+    ctx->prof_events.push_back({name, {a, b}});
+}
+static void prof_end(kb_ctx* ctx) {
+    if (!ctx->opt_profile || ctx->prof_events.empty()) return;
+    cudaEventRecord(ctx->prof_events.back().second.second, ctx->stream);
+}
+static void prof_collect(kb_ctx* ctx) {
+    ctx->profile.clear();
+    for (auto& e : ctx->prof_events) {
+        float ms = 0;
+        cudaEventSynchronize(e.second.second);
+        cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+        ctx->profile.push_back({e.first, ms});
+        cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second);
+    }
+    ctx->prof_events.clear();
+}
+
+extern "C" {
+
+const char* kb_version(void) { return KB_VERSION_STR; }
+
+int kb_create(int device, kb_ctx** out) {
+    if (!out) return KB_EINVAL;
+    *out = nullptr;
+    kb_ctx* ctx = new (std::nothrow) kb_ctx();
+    if (!ctx) return KB_ENOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); *out = ctx; return KB_ECUDA; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e); *out = ctx; return KB_ECUDA; }
+    ctx->n_sm = prop.multiProcessorCount;
+    if (prop.major < 10) { ctx->err = "krisp_b200 needs an sm_100a device (found sm_" + std::to_string(prop.major * 10 + prop.minor) + ")"; *out = ctx; return KB_EUNSUPPORTED; }
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); *out = ctx; return KB_ECUDA; }
+    ctx->stream = ctx->own_stream;
+    e = cudaMallocHost(&ctx->h_pinned, 64 * sizeof(uint64_t));
+    if (e != cudaSuccess) { ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(e); *out = ctx; return KB_ENOMEM; }
+    *out = ctx;
+    return KB_OK;
+}
+
+void kb_destroy(kb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->recs, &ctx->status,
+                      &ctx->small, &ctx->res_flank, &ctx->res_in, &ctx->res_out, &ctx->res_size, &ctx->res_run,
+                      &ctx->gather_off, &ctx->gather_out};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* kb_last_error(const kb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int kb_set_stream(kb_ctx* ctx, void* s) {
+    if (!ctx) return KB_EINVAL;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return KB_OK;
+}
+
+int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
+    if (!ctx || !name) return KB_EINVAL;
+    std::string n(name);
+    if (n == "sort_bits") { if (value < 1 || value > 64) return fail(ctx, KB_EINVAL, "sort_bits must be in 1..64"); ctx->opt_sort_bits = value; }
+    else if (n == "mix") ctx->opt_mix = value ? 1 : 0;
+    else if (n == "want_records") ctx->opt_want_records = value ? 1 : 0;
+    else if (n == "profile") ctx->opt_profile = value ? 1 : 0;
+    else if (n == "result_cap") { if (value < 1) return fail(ctx, KB_EINVAL, "result_cap must be >= 1"); ctx->opt_result_cap = value; }
+    else return fail(ctx, KB_EINVAL, "unknown option " + n);
+    if (ctx->configured) {   // re-derive the sort plan
+        uint8_t ing[KB_MAX_FILES];
+        memcpy(ing, ctx->is_ingroup, sizeof ing);
+        return kb_configure(ctx, ctx->lo.L, ctx->lo.D, ctx->lo.R, ctx->soft_mode, ctx->lo.n_files, ing);
+    }
+    return KB_OK;
+}
+
+int kb_configure(kb_ctx* ctx, int L, int D, int R, int soft_mode, int n_files, const uint8_t* is_ingroup) {
+    if (!ctx) return KB_EINVAL;
+    if (L < 0 || D < 0 || R < 0 || L + D + R < 1) return fail(ctx, KB_EINVAL, "need L, D, R >= 0 and k = L+D+R >= 1");
+    if (n_files < 1 || !is_ingroup) return fail(ctx, KB_EINVAL, "need n_files >= 1 and an is_ingroup array");
+    if (n_files > KB_MAX_FILES) return fail(ctx, KB_EUNSUPPORTED, "more than 256 input files (8-bit file id)");
+    const int k = L + D + R;
+    const int total_bits = 2 * k + KB_IDBITS;
+    if (total_bits > 64 * KB_MAX_W) return fail(ctx, KB_EUNSUPPORTED, "k-mer longer than 252 bases");
+    if (D > 8 * KB_MAX_MW) return fail(ctx, KB_EUNSUPPORTED, "diagnostic region longer than 128 bases");
+    KbLayout lo{};
+    lo.L = L; lo.D = D; lo.R = R; lo.k = k;
+    lo.FB = 2 * (L + R);
+    lo.FW = std::max(1, (lo.FB + 63) / 64);
+    lo.direct = total_bits <= 64;
+    if (lo.direct) lo.W = 1;
+    else { int w = (total_bits + 63) / 64; lo.W = w <= 2 ? 2 : (w <= 4 ? 4 : 8); }
+    lo.mix = lo.direct ? (int)ctx->opt_mix : 0;
+    lo.shs = (uint32_t)((lo.FB + 1) / 2);
+    const int keybits = lo.direct ? lo.FB : 32;
+    const int prefix = std::min<int>(keybits, (int)ctx->opt_sort_bits);
+    lo.P = (prefix + 7) / 8;
+    lo.cmpbits = lo.direct ? std::min(lo.FB, 8 * lo.P) : 8 * lo.P;
+    lo.n_files = n_files;
+    lo.PW = (n_files + 31) / 32;
+    lo.MW = (D + 7) / 8;
+    ctx->lo = lo;
+    ctx->soft_mode = soft_mode ? 1 : 0;
+    memset(ctx->is_ingroup, 0, sizeof ctx->is_ingroup);
+    for (int f = 0; f < n_files; f++) ctx->is_ingroup[f] = is_ingroup[f] ? 1 : 0;
+    ctx->configured = true;
+    return KB_OK;
+}
+
+int kb_clear_sequences(kb_ctx* ctx) {
+    if (!ctx) return KB_EINVAL;
+    ctx->n_bases = 0;
+    ctx->file_starts.clear();
+    ctx->file_gid.clear();
+    return KB_OK;
+}
+
+static size_t padded_len(uint64_t n_bases) {
+    return (size_t)((n_bases + KB_K1_TB - 1) / KB_K1_TB) * KB_K1_TB + KB_K1_PAD;
+}
+
+int kb_reserve(kb_ctx* ctx, uint64_t total_bytes) {
+    if (!ctx) return KB_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    return ensure(ctx, ctx->bases, padded_len(total_bytes + KB_MAX_FILES), true);
+}
+
+int kb_add_sequence(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_bytes, int on_device) {
+    if (!ctx) return KB_EINVAL;
+    if (file_id < 0 || file_id >= KB_MAX_FILES) return fail(ctx, KB_EINVAL, "file_id out of range");
+    if (n_bytes && !bytes) return fail(ctx, KB_EINVAL, "null sequence pointer");
+    CU(cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->bases, padded_len(ctx->n_bases + n_bytes + 1), true));
+    uint8_t* dst = (uint8_t*)ctx->bases.p + ctx->n_bases;
+    if (n_bytes) CU(cudaMemcpyAsync(dst, bytes, n_bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(dst + n_bytes, '\n', 1, ctx->stream));      // separator between files
+    ctx->file_starts.push_back(ctx->n_bases);
+    ctx->file_gid.push_back((uint32_t)file_id);
+    ctx->n_bases += n_bytes + 1;
+    return KB_OK;
+}
+
+int kb_synchronize(kb_ctx* ctx) {
+    if (!ctx) return KB_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+}  // extern "C"
+
+// ---- stages --------------------------------------------------------------------------------------
+static int upload_file_table(kb_ctx* ctx) {
+    const size_t nf = ctx->file_starts.size();
+    std::vector<uint64_t> fs(ctx->file_starts);
+    fs.push_back(ctx->n_bases);
+    TRY(ensure(ctx, ctx->d_file_starts, fs.size() * 8));
+    TRY(ensure(ctx, ctx->d_file_gid, std::max<size_t>(nf, 1) * 4));
+    CU(cudaMemcpyAsync(ctx->d_file_starts.p, fs.data(), fs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_file_gid.p, ctx->file_gid.data(), nf * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // fs is a stack-lifetime host buffer
+    return KB_OK;
+}
+
+static int prepare_small(kb_ctx* ctx) {
+    TRY(ensure(ctx, ctx->small, SM_TOTAL * 8));
+    CU(cudaMemsetAsync(ctx->small.p, 0, SM_TOTAL * 8, ctx->stream));
+    return KB_OK;
+}
+
+// K1 over tiles [tile0, tile0+n_tiles), windows starting in [pos_lo, pos_hi); *n_out = records written
+static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint64_t* n_out) {
+    const uint64_t n_max = 2 * (std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo) + 64;
+    TRY(ensure(ctx, ctx->entA, n_max * 8));
+    if (!lo.direct) TRY(ensure(ctx, ctx->recs, n_max * 8 * lo.W));
+    // separator padding past the data
+    const size_t plen = padded_len(ctx->n_bases);
+    TRY(ensure(ctx, ctx->bases, plen, true));
+    CU(cudaMemsetAsync((uint8_t*)ctx->bases.p + ctx->n_bases, '\n', plen - ctx->n_bases, ctx->stream));
+    TRY(upload_file_table(ctx));
+
+    KbExtractArgs a{};
+    a.bases = (const uint8_t*)ctx->bases.p;
+    a.n_bases = ctx->n_bases;
+    a.file_starts = (const uint64_t*)ctx->d_file_starts.p;
+    a.file_gid = (const uint32_t*)ctx->d_file_gid.p;
+    a.n_local_files = (int)ctx->file_gid.size();
+    a.soft_omit = ctx->soft_mode;
+    a.lo = lo;
+    a.out_entries = (uint64_t*)ctx->entA.p;
+    a.out_recs = (uint64_t*)ctx->recs.p;
+    a.n_out = (unsigned long long*)ctx->small.p + SM_NOUT;
+    a.tile0 = tile0; a.n_tiles = n_tiles;
+    a.pos_lo = pos_lo; a.pos_hi = pos_hi;
+    const size_t smem = kb_extract_smem(lo.k);
+    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->n_sm * 8);
+    prof_begin(ctx, "K1 extract");
+    if (grid) {
+        switch (lo.W) {
+            case 1: kb_extract_kernel<1><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
+            case 2: kb_extract_kernel<2><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
+            case 4: kb_extract_kernel<4><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
+            default: kb_extract_kernel<8><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
+        }
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    prof_end(ctx);
+    CU(cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NOUT, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *n_out = ctx->h_pinned[0];
+    if (*n_out > n_max) return fail(ctx, KB_EINTERNAL, "K1 wrote more records than the bound");
+    ctx->alg_bytes += (std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo) + *n_out * 8 * (lo.direct ? 1 : (1 + lo.W));
+    return KB_OK;
+}
+
+template <typename ST>
+static int launch_pass(kb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t n, uint32_t shift, uint32_t shard_n, int hist_row, int ticket_idx) {
+    const uint64_t n_tiles = (n + KB_SORT_TILE - 1) / KB_SORT_TILE;
+    CU(cudaMemsetAsync(ctx->status.p, 0, n_tiles * KB_RADIX * sizeof(ST), ctx->stream));
+    KbSortArgs<ST> a{};
+    a.in = in; a.out = out; a.n = n; a.shift = shift; a.shard_n = shard_n;
+    a.base = (const unsigned long long*)ctx->small.p + SM_HIST + (size_t)hist_row * KB_RADIX;
+    a.status = (ST*)ctx->status.p;
+    a.ticket = (uint32_t*)((uint64_t*)ctx->small.p + SM_TICKET) + ticket_idx;
+    const size_t smem = kb_onesweep_smem();
+    CU(cudaFuncSetAttribute(kb_onesweep_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kb_onesweep_kernel<ST><<<(unsigned)n_tiles, KB_SORT_THREADS, smem, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return KB_OK;
+}
+
+// sort entA[0..n) by the top 8P bits -> *sorted points to the buffer holding the result
+static int run_sort(kb_ctx* ctx, uint64_t n, int P, uint64_t** sorted) {
+    uint64_t* cur = (uint64_t*)ctx->entA.p;
+    *sorted = cur;
+    if (n == 0 || P == 0) return KB_OK;
+    if (P > 8) return fail(ctx, KB_EINTERNAL, "more than 8 radix passes");
+    TRY(ensure(ctx, ctx->entB, ctx->entA.cap));
+    uint64_t* alt = (uint64_t*)ctx->entB.p;
+    const bool wide = n >= (1ULL << 30);
+    const uint64_t n_tiles = (n + KB_SORT_TILE - 1) / KB_SORT_TILE;
+    TRY(ensure(ctx, ctx->status, n_tiles * KB_RADIX * (wide ? 8 : 4)));
+    const uint32_t shift0 = 64 - 8 * P;
+
+    prof_begin(ctx, "K2 histogram");
+    KbHistArgs h{};
+    h.in = cur; h.n = n; h.P = P; h.shift0 = shift0; h.shard_n = 0;
+    h.hist = (unsigned long long*)ctx->small.p + SM_HIST;
+    const unsigned hgrid = (unsigned)std::min<uint64_t>((n / 2 + KB_HIST_THREADS - 1) / KB_HIST_THREADS + 1, (uint64_t)ctx->n_sm * 4);
+    kb_hist_kernel<<<hgrid, KB_HIST_THREADS, 0, ctx->stream>>>(h);
+    CU(cudaGetLastError());
+    kb_scan_kernel<<<P, KB_RADIX, 0, ctx->stream>>>(h.hist);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    prof_end(ctx);
+    ctx->alg_bytes += n * 8;
+
+    for (int p = 0; p < P; p++) {
+        static const char* names[8] = {"K2 pass 0", "K2 pass 1", "K2 pass 2", "K2 pass 3", "K2 pass 4", "K2 pass 5", "K2 pass 6", "K2 pass 7"};
+        prof_begin(ctx, names[p]);
+        if (wide) TRY(launch_pass<unsigned long long>(ctx, cur, alt, n, shift0 + 8 * p, 0, p, p));
+        else TRY(launch_pass<uint32_t>(ctx, cur, alt, n, shift0 + 8 * p, 0, p, p));
+        prof_end(ctx);
+        std::swap(cur, alt);
+        ctx->alg_bytes += n * 16;
+    }
+    ctx->passes = P;
+    *sorted = cur;
+    return KB_OK;
+}
+
+static int ensure_results(kb_ctx* ctx, uint64_t cap) {
+    const KbLayout& lo = ctx->lo;
+    TRY(ensure(ctx, ctx->res_flank, cap * lo.FW * 8));
+    TRY(ensure(ctx, ctx->res_in, cap * std::max(lo.MW, 1) * 4));
+    TRY(ensure(ctx, ctx->res_out, cap * std::max(lo.MW, 1) * 4));
+    TRY(ensure(ctx, ctx->res_size, cap * 4));
+    TRY(ensure(ctx, ctx->res_run, cap * 16));
+    ctx->result_cap = cap;
+    return KB_OK;
+}
+
+static int launch_group(kb_ctx* ctx, const KbGroupArgs& a) {
+    const KbLayout& lo = a.lo;
+    const unsigned grid = (unsigned)((a.n + KB_K3_TILE - 1) / KB_K3_TILE);
+    if (lo.direct) {
+        if (lo.MW <= 1) kb_group_kernel<1, 1><<<grid, KB_K3_THREADS, 0, ctx->stream>>>(a);
+        else kb_group_kernel<1, 4><<<grid, KB_K3_THREADS, 0, ctx->stream>>>(a);
+    } else if (lo.W == 2) kb_group_kernel<2, KB_MAX_MW><<<grid, KB_K3_THREADS, 0, ctx->stream>>>(a);
+    else if (lo.W == 4) kb_group_kernel<4, KB_MAX_MW><<<grid, KB_K3_THREADS, 0, ctx->stream>>>(a);
+    else kb_group_kernel<8, KB_MAX_MW><<<grid, KB_K3_THREADS, 0, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return KB_OK;
+}
+
+// K3 over sorted[0..n) + result download
+static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result** out) {
+    const KbLayout& lo = ctx->lo;
+    kb_result* res = new (std::nothrow) kb_result();
+    if (!res) return fail(ctx, KB_ENOMEM, "host allocation failed");
+    memset(&res->v, 0, sizeof res->v);
+    res->v.L = lo.L; res->v.D = lo.D; res->v.R = lo.R;
+    res->v.flank_words = lo.FW; res->v.mask_words = lo.MW; res->v.record_words = lo.W;
+    res->v.n_records = n;
+    uint64_t n_res = 0;
+    if (n > 0) {
+        if (ctx->result_cap == 0) { int rc = ensure_results(ctx, (uint64_t)ctx->opt_result_cap); if (rc) { delete res; return rc; } }
+        for (int attempt = 0; attempt < 3; attempt++) {
+            KbGroupArgs a{};
+            a.ent = sorted; a.n = n; a.recs = (const uint64_t*)ctx->recs.p; a.lo = lo;
+            for (int f = 0; f < lo.n_files; f++) {
+                a.full[f >> 5] |= 1u << (f & 31);
+                if (ctx->is_ingroup[f]) a.ingroup[f >> 5] |= 1u << (f & 31);
+            }
+            a.n_res = (unsigned long long*)ctx->small.p + SM_NRES;
+            a.cap = ctx->result_cap;
+            a.res_flank = (uint64_t*)ctx->res_flank.p; a.res_in = (uint32_t*)ctx->res_in.p; a.res_out = (uint32_t*)ctx->res_out.p;
+            a.res_size = (uint32_t*)ctx->res_size.p; a.res_run = (uint64_t*)ctx->res_run.p;
+            a.stats = (unsigned long long*)ctx->small.p + SM_STATS;
+            cudaError_t e = cudaMemsetAsync((uint64_t*)ctx->small.p + SM_NRES, 0, 5 * 8, ctx->stream);
+            if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, cudaGetErrorString(e)); }
+            prof_begin(ctx, "K3 group");
+            int rc = launch_group(ctx, a);
+            prof_end(ctx);
+            if (rc) { delete res; return rc; }
+            e = cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NRES, 5 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("group pass: ") + cudaGetErrorString(e)); }
+            n_res = ctx->h_pinned[0];
+            for (int i = 0; i < 4; i++) res->v.stats[i] = ctx->h_pinned[1 + i];
+            ctx->alg_bytes += n * 8 * (lo.direct ? 1 : (1 + lo.W));
+            if (n_res <= ctx->result_cap) break;
+            rc = ensure_results(ctx, n_res + n_res / 8 + 16);       // table too small: grow and re-run the pass
+            if (rc) { delete res; return rc; }
+        }
+        if (n_res > ctx->result_cap) { delete res; return fail(ctx, KB_EINTERNAL, "survivor table overflow"); }
+    }
+    res->v.n_groups = n_res;
+    res->flank.resize(n_res * lo.FW);
+    res->in_mask.resize(n_res * std::max(lo.MW, 1));
+    res->out_mask.resize(n_res * std::max(lo.MW, 1));
+    res->group_size.resize(n_res);
+    res->run_offset.assign(n_res + 1, 0);
+    std::vector<uint64_t> runs(2 * n_res);
+    if (n_res) {
+        cudaError_t e = cudaMemcpyAsync(res->flank.data(), ctx->res_flank.p, n_res * lo.FW * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && lo.MW) e = cudaMemcpyAsync(res->in_mask.data(), ctx->res_in.p, n_res * lo.MW * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && lo.MW) e = cudaMemcpyAsync(res->out_mask.data(), ctx->res_out.p, n_res * lo.MW * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(res->group_size.data(), ctx->res_size.p, n_res * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(runs.data(), ctx->res_run.p, n_res * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("result download: ") + cudaGetErrorString(e)); }
+    }
+    if (ctx->opt_want_records && n_res) {
+        for (uint64_t g = 0; g < n_res; g++) res->run_offset[g + 1] = res->run_offset[g] + runs[2 * g + 1];
+        const uint64_t total = res->run_offset[n_res];
+        int rc = ensure(ctx, ctx->gather_off, n_res * 8);
+        if (!rc) rc = ensure(ctx, ctx->gather_out, total * lo.W * 8);
+        if (rc) { delete res; return rc; }
+        res->records.resize(total * lo.W);
+        cudaError_t e = cudaMemcpyAsync(ctx->gather_off.p, res->run_offset.data(), n_res * 8, cudaMemcpyHostToDevice, ctx->stream);
+        KbGatherArgs g{};
+        g.ent = sorted; g.recs = (const uint64_t*)ctx->recs.p; g.res_run = (const uint64_t*)ctx->res_run.p;
+        g.off = (const uint64_t*)ctx->gather_off.p; g.n_groups = n_res; g.out = (uint64_t*)ctx->gather_out.p; g.lo = lo;
+        const unsigned grid = (unsigned)((n_res + 7) / 8);
+        if (e == cudaSuccess) {
+            switch (lo.W) {
+                case 1: kb_gather_kernel<1><<<grid, 256, 0, ctx->stream>>>(g); break;
+                case 2: kb_gather_kernel<2><<<grid, 256, 0, ctx->stream>>>(g); break;
+                case 4: kb_gather_kernel<4><<<grid, 256, 0, ctx->stream>>>(g); break;
+                default: kb_gather_kernel<8><<<grid, 256, 0, ctx->stream>>>(g); break;
+            }
+            e = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(res->records.data(), ctx->gather_out.p, total * lo.W * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("record gather: ") + cudaGetErrorString(e)); }
+        res->v.n_run_records = total;
+    }
+    res->v.flank = res->flank.data();
+    res->v.in_mask = res->in_mask.data();
+    res->v.out_mask = res->out_mask.data();
+    res->v.group_size = res->group_size.data();
+    res->v.run_offset = res->run_offset.data();
+    res->v.records = res->records.data();
+    *out = res;
+    return KB_OK;
+}
+
+static void begin_search(kb_ctx* ctx) {
+    ctx->launches = 0; ctx->alg_bytes = 0; ctx->passes = 0;
+    for (auto& e : ctx->prof_events) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
+    ctx->prof_events.clear();
+}
+
+extern "C" {
+
+int kb_search(kb_ctx* ctx, kb_result** out) {
+    if (!ctx || !out) return KB_EINVAL;
+    *out = nullptr;
+    if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
+    CU(cudaSetDevice(ctx->device));
+    begin_search(ctx);
+    TRY(prepare_small(ctx));
+    const KbLayout& lo = ctx->lo;
+    uint64_t n = 0;
+    const uint32_t n_tiles = (uint32_t)((ctx->n_bases + KB_K1_TB - 1) / KB_K1_TB);
+    TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n));
+    if (!lo.direct && n >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
+    uint64_t* sorted = nullptr;
+    TRY(run_sort(ctx, n, lo.P, &sorted));
+    int rc = run_group(ctx, sorted, n, out);
+    prof_collect(ctx);
+    return rc;
+}
+
+int kb_shard_extract(kb_ctx* ctx, int n_shards, void** records, uint64_t* counts) {
+    if (!ctx || !records || !counts || n_shards < 1 || n_shards > KB_RADIX) return KB_EINVAL;
+    if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
+    const KbLayout& lo = ctx->lo;
+    if (!lo.direct) return fail(ctx, KB_EUNSUPPORTED, "multi-GPU sharding of multi-word records is not built yet");
+    CU(cudaSetDevice(ctx->device));
+    begin_search(ctx);
+    TRY(prepare_small(ctx));
+    uint64_t n = 0;
+    const uint32_t n_tiles = (uint32_t)((ctx->n_bases + KB_K1_TB - 1) / KB_K1_TB);
+    TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n));
+    for (int s = 0; s < n_shards; s++) counts[s] = 0;
+    *records = ctx->entA.p;
+    if (n_shards == 1 || n == 0) { counts[0] = n; ctx->shard_n_records = n; prof_collect(ctx); return KB_OK; }
+    // one partition pass by destination shard (histogram row 8 of the small buffer)
+    TRY(ensure(ctx, ctx->entB, ctx->entA.cap));
+    const bool wide = n >= (1ULL << 30);
+    const uint64_t n_tiles_s = (n + KB_SORT_TILE - 1) / KB_SORT_TILE;
+    TRY(ensure(ctx, ctx->status, n_tiles_s * KB_RADIX * (wide ? 8 : 4)));
+    const uint32_t sshift = lo.FB ? 64 - lo.FB : 0;
+    prof_begin(ctx, "K4 shard partition");
+    KbHistArgs h{};
+    h.in = (const uint64_t*)ctx->entA.p; h.n = n; h.P = 1; h.shift0 = sshift; h.shard_n = (uint32_t)n_shards;
+    h.hist = (unsigned long long*)ctx->small.p + SM_HIST + 8 * KB_RADIX;
+    const unsigned hgrid = (unsigned)std::min<uint64_t>((n / 2 + KB_HIST_THREADS - 1) / KB_HIST_THREADS + 1, (uint64_t)ctx->n_sm * 4);
+    kb_hist_kernel<<<hgrid, KB_HIST_THREADS, 0, ctx->stream>>>(h);
+    CU(cudaGetLastError());
+    // counts before the scan turns them into offsets
+    CU(cudaMemcpyAsync(ctx->h_pinned, h.hist, (size_t)std::min(n_shards, 64) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint64_t> big;
+    if (n_shards > 64) { big.resize(n_shards); CU(cudaMemcpyAsync(big.data(), h.hist, (size_t)n_shards * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
+    kb_scan_kernel<<<1, KB_RADIX, 0, ctx->stream>>>(h.hist);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    if (wide) TRY(launch_pass<unsigned long long>(ctx, (const uint64_t*)ctx->entA.p, (uint64_t*)ctx->entB.p, n, sshift, (uint32_t)n_shards, 8, 8));
+    else TRY(launch_pass<uint32_t>(ctx, (const uint64_t*)ctx->entA.p, (uint64_t*)ctx->entB.p, n, sshift, (uint32_t)n_shards, 8, 8));
+    prof_end(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < n_shards; s++) counts[s] = n_shards > 64 ? big[s] : ctx->h_pinned[s];
+    ctx->alg_bytes += n * 24;
+    *records = ctx->entB.p;
+    ctx->shard_n_records = n;
+    prof_collect(ctx);
+    return KB_OK;
+}
+
+int kb_shard_recv_buffer(kb_ctx* ctx, uint64_t n_records, void** buffer) {
+    if (!ctx || !buffer) return KB_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    // the partitioned records live in entB (or entA when n_shards == 1): receive into entA unless it is the source
+    TRY(ensure(ctx, ctx->recs, (n_records + 64) * 8));
+    *buffer = ctx->recs.p;
+    return KB_OK;
+}
+
+int kb_shard_search(kb_ctx* ctx, uint64_t n_records, kb_result** out) {
+    if (!ctx || !out) return KB_EINVAL;
+    *out = nullptr;
+    if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
+    const KbLayout& lo = ctx->lo;
+    if (!lo.direct) return fail(ctx, KB_EUNSUPPORTED, "multi-GPU sharding of multi-word records is not built yet");
+    CU(cudaSetDevice(ctx->device));
+    begin_search(ctx);
+    TRY(prepare_small(ctx));
+    // received records (in `recs`, see kb_shard_recv_buffer) become the sort input
+    TRY(ensure(ctx, ctx->entA, (n_records + 64) * 8));
+    if (n_records) CU(cudaMemcpyAsync(ctx->entA.p, ctx->recs.p, n_records * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    uint64_t* sorted = nullptr;
+    TRY(run_sort(ctx, n_records, lo.P, &sorted));
+    int rc = run_group(ctx, sorted, n_records, out);
+    prof_collect(ctx);
+    return rc;
+}
+
+int kb_result_get(const kb_result* res, kb_result_view* view) {
+    if (!res || !view) return KB_EINVAL;
+    *view = res->v;
+    return KB_OK;
+}
+void kb_result_free(kb_result* res) { delete res; }
+
+int kb_last_profile(const kb_ctx* ctx, const char** names, float* ms, int cap) {
+    if (!ctx) return KB_EINVAL;
+    int n = (int)ctx->profile.size();
+    for (int i = 0; i < n && i < cap; i++) { if (names) names[i] = ctx->profile[i].first.c_str(); if (ms) ms[i] = ctx->profile[i].second; }
+    return n;
+}
+
+int kb_last_counters(const kb_ctx* ctx, uint64_t* kernel_launches, uint64_t* algorithmic_bytes, int* radix_passes) {
+    if (!ctx) return KB_EINVAL;
+    if (kernel_launches) *kernel_launches = ctx->launches;
+    if (algorithmic_bytes) *algorithmic_bytes = ctx->alg_bytes;
+    if (radix_passes) *radix_passes = ctx->passes;
+    return KB_OK;
+}
+
+int kb_extract_sorted(kb_ctx* ctx, int local_index, kb_table** out) {
+    if (!ctx || !out) return KB_EINVAL;
+    *out = nullptr;
+    if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
+    if (local_index < 0 || local_index >= (int)ctx->file_starts.size()) return fail(ctx, KB_EINVAL, "no such sequence");
+    if (!ctx->lo.direct) return fail(ctx, KB_EUNSUPPORTED, "sorted tables of k-mers longer than 28 bases are not built yet");
+    CU(cudaSetDevice(ctx->device));
+    begin_search(ctx);
+    TRY(prepare_small(ctx));
+    KbLayout lo = ctx->lo;
+    lo.mix = 0;                                  // plain keys: the sorted order is the reference's LC_ALL=C order
+    lo.P = (2 * lo.k + 7) / 8;                   // order by every base: left, right, then middle
+    const uint64_t pos_lo = ctx->file_starts[local_index];
+    const uint64_t pos_hi = local_index + 1 < (int)ctx->file_starts.size() ? ctx->file_starts[local_index + 1] : ctx->n_bases;
+    const uint32_t tile0 = (uint32_t)(pos_lo / KB_K1_TB);
+    const uint32_t tile1 = (uint32_t)((pos_hi + KB_K1_TB - 1) / KB_K1_TB);
+    uint64_t n = 0;
+    TRY(run_extract(ctx, lo, tile0, tile1 - tile0, pos_lo, pos_hi, &n));
+    uint64_t* sorted = nullptr;
+    TRY(run_sort(ctx, n, lo.P, &sorted));
+    kb_table* t = new (std::nothrow) kb_table();
+    if (!t) return fail(ctx, KB_ENOMEM, "host allocation failed");
+    t->records.resize(n);
+    t->record_words = 1;
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(t->records.data(), sorted, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { delete t; return fail(ctx, KB_ECUDA, std::string("table download: ") + cudaGetErrorString(e)); }
+    }
+    prof_collect(ctx);
+    *out = t;
+    return KB_OK;
+}
+
+int kb_table_get(const kb_table* t, const uint64_t** records, uint64_t* n_records, int* record_words) {
+    if (!t) return KB_EINVAL;
+    if (records) *records = t->records.data();
+    if (n_records) *n_records = t->records.size();
+    if (record_words) *record_words = t->record_words;
+    return KB_OK;
+}
+void kb_table_free(kb_table* t) { delete t; }
+
+}  // extern "C"

@@ -1,0 +1,285 @@
+"""Host-side driver of the B200 search: the Python mirror of krisp_fasta's stage functions.
+
+One :class:`Searcher` owns one ``kb_ctx`` (one GPU).  ``search_files`` replaces, in one device
+pass, the reference's stage sequence in ``krisp_fasta.main`` (krisp_fasta/krisp_fasta.py:236-270):
+``sortedKmersSerial/Parallel`` -> ``mergeFiles`` -> ``filterAlignments``; what comes back is what
+``render_output`` (outputAlignments.py:101) needs: the surviving groups, their per-column base
+sets, and on request their records.
+
+No CPU fallback: everything that touches sequence data runs in libkrisp_b200.so.
+"""
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib, ingest
+from .names import simplename
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+# 4-bit base set (bit0 A, bit1 C, bit2 G, bit3 T) -> IUPAC letter; the inverse of
+# Bio.Data.IUPACData.ambiguous_dna_values as Amplicon.py:10-12 builds it (4 bases -> N)
+_IUPAC = np.frombuffer(b"?ACMGRSVTWYHKDBN", dtype=np.uint8)
+
+
+@dataclass
+class SearchResult:
+    L: int
+    D: int
+    R: int
+    n_records: int = 0
+    left: np.ndarray = None        # [n_groups, L] uint8 ASCII
+    right: np.ndarray = None       # [n_groups, R]
+    in_mask: np.ndarray = None     # [n_groups, D] 4-bit base sets over ingroup-labelled occurrences
+    out_mask: np.ndarray = None    # [n_groups, D] ... over the other occurrences
+    group_size: np.ndarray = None  # [n_groups]
+    flank_words: np.ndarray = None # [n_groups, FW] packed flank (for matching run records)
+    run_offset: np.ndarray = None  # [n_groups + 1]
+    records: np.ndarray = None     # [n_run_records, W] packed records of the survivors' runs
+    stats: dict = field(default_factory=dict)
+    profile: list = field(default_factory=list)
+    have_outgroup: bool = True
+
+    @property
+    def n_groups(self):
+        return 0 if self.left is None else int(self.left.shape[0])
+
+    def rows(self):
+        """CSV rows ``left,consensus,right`` (render_csv, Amplicon.py:663-671), canonically sorted.
+
+        Consensus column = IUPAC letter of the ingroup base set when an outgroup was given, of every
+        occurrence otherwise (krisp_fasta.py:282-283, Amplicon.py:550-558; after the diagnostic
+        filter every ingroup sequence is ingroup-only, so the per-column OR is the same set).
+        """
+        n = self.n_groups
+        if n == 0:
+            return []
+        cons = self.in_mask if self.have_outgroup else (self.in_mask | self.out_mask)
+        width = self.L + 1 + self.D + 1 + self.R
+        m = np.empty((n, width), dtype=np.uint8)
+        m[:, :self.L] = self.left
+        m[:, self.L] = ord(",")
+        m[:, self.L + 1:self.L + 1 + self.D] = _IUPAC[cons]
+        m[:, self.L + 1 + self.D] = ord(",")
+        m[:, self.L + 2 + self.D:] = self.right
+        flat = np.ascontiguousarray(m).view(f"S{width}").ravel()
+        return sorted(x.decode() for x in flat.tolist())
+
+
+def _decode_bases(words, first_bit, n_bases):
+    """[n, W] uint64 MSB-first bit strings -> [n, n_bases] ASCII letters starting at bit `first_bit`."""
+    n = words.shape[0]
+    if n == 0 or n_bases == 0:
+        return np.zeros((n, n_bases), dtype=np.uint8)
+    bits = np.unpackbits(np.ascontiguousarray(words.astype(">u8")).view(np.uint8).reshape(n, -1), axis=1)
+    sel = bits[:, first_bit:first_bit + 2 * n_bases].reshape(n, n_bases, 2)
+    return _ACGT[sel[:, :, 0] * 2 + sel[:, :, 1]]
+
+
+def _decode_masks(words, D):
+    """[n, MW] uint32 (column c = nibble 7 - c%8 of word c/8) -> [n, D] 4-bit sets."""
+    n = words.shape[0]
+    if D == 0 or n == 0:
+        return np.zeros((n, D), dtype=np.uint8)
+    shifts = (28 - 4 * np.arange(8)).astype(np.uint32)
+    nib = (words[:, :, None] >> shifts[None, None, :]) & np.uint32(0xF)
+    return nib.reshape(n, -1)[:, :D].astype(np.uint8)
+
+
+class Searcher:
+    """One GPU context.  Not thread-safe (like the library)."""
+
+    def __init__(self, device=0, stream=None):
+        self._L = _lib.load()
+        self._ctx = ctypes.c_void_p()
+        rc = self._L.kb_create(int(device), ctypes.byref(self._ctx))
+        if rc != _lib.KB_OK:
+            msg = self._L.kb_last_error(self._ctx)
+            self._L.kb_destroy(self._ctx)
+            self._ctx = None
+            raise _lib.KrispB200Error(rc, msg.decode() if msg else "kb_create failed")
+        if stream is not None:
+            self._check(self._L.kb_set_stream(self._ctx, ctypes.c_void_p(int(stream))))
+        self._keep = []          # host buffers that must outlive the async copies
+        self.lo = None
+
+    def close(self):
+        if self._ctx:
+            self._L.kb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        _lib.check(self._ctx, rc)
+
+    # ---- configuration -------------------------------------------------------------------------
+    def configure(self, L, D, R, is_ingroup, omit_soft=False):
+        arr = np.ascontiguousarray(np.asarray(is_ingroup, dtype=np.uint8))
+        self._check(self._L.kb_configure(self._ctx, int(L), int(D), int(R), int(bool(omit_soft)), int(arr.size),
+                                         arr.ctypes.data))
+        self.lo = (int(L), int(D), int(R))
+        self.n_files = int(arr.size)
+
+    def set_option(self, name, value):
+        self._check(self._L.kb_set_option(self._ctx, name.encode(), int(value)))
+
+    # ---- sequences -------------------------------------------------------------------------------
+    def clear_sequences(self):
+        self._check(self._L.kb_clear_sequences(self._ctx))
+        self._keep = []
+
+    def reserve(self, total_bytes):
+        self._check(self._L.kb_reserve(self._ctx, int(total_bytes)))
+
+    def add_sequence(self, file_id, data):
+        """`data`: numpy uint8 array (host), or a (device_pointer, n_bytes) tuple for device-resident bases."""
+        if isinstance(data, tuple):
+            ptr, n = data
+            self._check(self._L.kb_add_sequence(self._ctx, int(file_id), ctypes.c_void_p(int(ptr)), int(n), 1))
+            return
+        arr = np.ascontiguousarray(data, dtype=np.uint8)
+        self._keep.append(arr)
+        self._check(self._L.kb_add_sequence(self._ctx, int(file_id), ctypes.c_void_p(arr.ctypes.data), int(arr.size), 0))
+
+    def synchronize(self):
+        self._check(self._L.kb_synchronize(self._ctx))
+        self._keep = []
+
+    # ---- search ------------------------------------------------------------------------------------
+    def _collect(self, res_ptr, have_outgroup):
+        L, D, R = self.lo
+        view = _lib.ResultView()
+        try:
+            self._check(self._L.kb_result_get(res_ptr, ctypes.byref(view)))
+            n, FW, MW, W = int(view.n_groups), int(view.flank_words), int(view.mask_words), int(view.record_words)
+
+            def arr(ptr, count, dtype):
+                if count == 0:
+                    return np.zeros(0, dtype=dtype)
+                return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+
+            flank = arr(view.flank, n * FW, np.uint64).reshape(n, FW)
+            out = SearchResult(L=L, D=D, R=R, n_records=int(view.n_records), have_outgroup=have_outgroup)
+            out.flank_words = flank
+            out.left = _decode_bases(flank, 0, L)
+            out.right = _decode_bases(flank, 2 * L, R)
+            out.in_mask = _decode_masks(arr(view.in_mask, n * MW, np.uint32).reshape(n, MW), D)
+            out.out_mask = _decode_masks(arr(view.out_mask, n * MW, np.uint32).reshape(n, MW), D)
+            out.group_size = arr(view.group_size, n, np.uint32)
+            out.run_offset = arr(view.run_offset, n + 1, np.uint64)
+            nrr = int(view.n_run_records)
+            out.records = arr(view.records, nrr * W, np.uint64).reshape(nrr, W)
+            out.stats = dict(zip(("runs", "queued_runs", "groups_in_every_file", "mixed_runs"), [int(x) for x in view.stats]))
+        finally:
+            self._L.kb_result_free(res_ptr)
+        out.profile = self.last_profile()
+        return out
+
+    def search(self, have_outgroup=True):
+        """Run K1 -> K2 -> K3 on the sequences added so far."""
+        res = ctypes.c_void_p()
+        self._check(self._L.kb_search(self._ctx, ctypes.byref(res)))
+        self._keep = []
+        return self._collect(res, have_outgroup)
+
+    # ---- multi-GPU pieces (see krisp_b200/sharded.py) -------------------------------------------------
+    def shard_extract(self, n_shards):
+        rec = ctypes.c_void_p()
+        counts = (ctypes.c_uint64 * n_shards)()
+        self._check(self._L.kb_shard_extract(self._ctx, int(n_shards), ctypes.byref(rec), counts))
+        self._keep = []
+        return rec.value, [int(c) for c in counts]
+
+    def shard_recv_buffer(self, n_records):
+        buf = ctypes.c_void_p()
+        self._check(self._L.kb_shard_recv_buffer(self._ctx, int(n_records), ctypes.byref(buf)))
+        return buf.value
+
+    def shard_search(self, n_records, have_outgroup=True):
+        res = ctypes.c_void_p()
+        self._check(self._L.kb_shard_search(self._ctx, int(n_records), ctypes.byref(res)))
+        return self._collect(res, have_outgroup)
+
+    # ---- kstream path ------------------------------------------------------------------------------
+    def extract_sorted(self, local_index):
+        """One file's k-mer table as packed 64-bit records in the reference's sorted order."""
+        tab = ctypes.c_void_p()
+        self._check(self._L.kb_extract_sorted(self._ctx, int(local_index), ctypes.byref(tab)))
+        try:
+            ptr, n, w = ctypes.POINTER(ctypes.c_uint64)(), ctypes.c_uint64(), ctypes.c_int()
+            self._check(self._L.kb_table_get(tab, ctypes.byref(ptr), ctypes.byref(n), ctypes.byref(w)))
+            if n.value == 0:
+                return np.zeros(0, dtype=np.uint64)
+            return np.ctypeslib.as_array(ptr, shape=(n.value * w.value,)).copy()
+        finally:
+            self._L.kb_table_free(tab)
+
+    # ---- bookkeeping --------------------------------------------------------------------------------
+    def last_profile(self):
+        names = (ctypes.c_char_p * 32)()
+        ms = (ctypes.c_float * 32)()
+        n = self._L.kb_last_profile(self._ctx, names, ms, 32)
+        return [(names[i].decode(), float(ms[i])) for i in range(max(0, min(n, 32)))]
+
+    def last_counters(self):
+        a, b, p = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()
+        self._check(self._L.kb_last_counters(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(p)))
+        return {"kernel_launches": int(a.value), "algorithmic_bytes": int(b.value), "radix_passes": int(p.value)}
+
+
+def labels_for(ingroup_files, outgroup_files):
+    """(labels, is_ingroup) per input file, in the reference's file order ``files + outgroup``
+    (krisp_fasta.py:238).  Membership is by label string (krisp_fasta.py:267); a single input file is
+    never merged, so its lines carry no label and read back as ``merged_file`` (intersectAmplicons.py:310)."""
+    files = list(ingroup_files) + list(outgroup_files)
+    labels = ["merged_file"] if len(files) == 1 else [simplename(f) for f in files]
+    ingroup = {simplename(f) for f in ingroup_files}
+    return labels, [1 if lab in ingroup else 0 for lab in labels]
+
+
+class RNAInputError(ValueError):
+    pass
+
+
+def search_files(ingroup_files, outgroup_files, L, D, R, omit_soft=False, want_records=False, searcher=None,
+                 options=None):
+    """The diagnostic-region search of ``krisp_fasta <ingroup> --outgroup <outgroup>`` -> :class:`SearchResult`."""
+    files = list(ingroup_files) + list(outgroup_files)
+    labels, is_in = labels_for(ingroup_files, outgroup_files)
+    have_out = len(outgroup_files) > 0
+    if R == 0 and D > 0:
+        # kstream's split [L, -0] treats -0 as a positive split: the middle lands in the right-hand field
+        # and the diagnostic region is empty, so the filter keeps nothing (kstream.py:824-830)
+        z = np.zeros((0, 0), dtype=np.uint8)
+        return SearchResult(L=L, D=D, R=R, left=np.zeros((0, L), np.uint8), right=z, in_mask=np.zeros((0, D), np.uint8),
+                            out_mask=np.zeros((0, D), np.uint8), group_size=np.zeros(0, np.uint32), have_outgroup=have_out)
+    own = searcher is None
+    s = searcher or Searcher()
+    try:
+        s.configure(L, D, R, is_in, omit_soft)
+        s.set_option("want_records", 1 if want_records else 0)
+        for k, v in (options or {}).items():
+            s.set_option(k, v)
+        s.clear_sequences()
+        packed = []
+        for f in files:
+            arr, rna = ingest.load_file(f)
+            if rna:
+                raise RNAInputError(f"{f}: RNA input — the reference's krisp_fasta output is undefined for it "
+                                    "(U-tables never intersect DNA tables and the renderer raises KeyError)")
+            packed.append(arr)
+        s.reserve(sum(a.size + 1 for a in packed))
+        for i, arr in enumerate(packed):
+            s.add_sequence(i, arr)
+        res = s.search(have_outgroup=have_out)
+        res.labels = labels
+        res.is_ingroup = is_in
+        return res
+    finally:
+        if own:
+            s.close()
