@@ -44,7 +44,7 @@ struct kb_ctx {
     KbLayout lo{};
     int soft_mode = 0;
     uint8_t is_ingroup[KB_MAX_FILES]{};
-    long long opt_sort_bits = 40, opt_mix = 1, opt_want_records = 0, opt_profile = 0, opt_result_cap = 1 << 16;
+    long long opt_sort_bits = 40, opt_mix = 1, opt_want_records = 0, opt_profile = 0, opt_result_cap = 1 << 16, opt_sort_variant = 0;
 
     // sequences
     DevBuf bases;
@@ -173,6 +173,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "mix") ctx->opt_mix = value ? 1 : 0;
     else if (n == "want_records") ctx->opt_want_records = value ? 1 : 0;
     else if (n == "profile") ctx->opt_profile = value ? 1 : 0;
+    else if (n == "sort_variant") ctx->opt_sort_variant = value;
     else if (n == "result_cap") { if (value < 1) return fail(ctx, KB_EINVAL, "result_cap must be >= 1"); ctx->opt_result_cap = value; }
     else return fail(ctx, KB_EINVAL, "unknown option " + n);
     if (ctx->configured) {   // re-derive the sort plan
@@ -323,21 +324,34 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
     return KB_OK;
 }
 
-template <typename ST>
-static int launch_pass(kb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t n, uint32_t shift, uint32_t shard_n, int hist_row, int ticket_idx) {
-    const uint64_t n_tiles = (n + KB_SORT_TILE - 1) / KB_SORT_TILE;
+template <typename ST, int THREADS, int ITEMS, int MINB>
+static int launch_pass_v(kb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t n, uint32_t shift, uint32_t shard_n, int hist_row, int ticket_idx) {
+    constexpr uint64_t TILE = (uint64_t)THREADS * ITEMS;
+    const uint64_t n_tiles = (n + TILE - 1) / TILE;
+    TRY(ensure(ctx, ctx->status, n_tiles * KB_RADIX * sizeof(ST)));
     CU(cudaMemsetAsync(ctx->status.p, 0, n_tiles * KB_RADIX * sizeof(ST), ctx->stream));
     KbSortArgs<ST> a{};
     a.in = in; a.out = out; a.n = n; a.shift = shift; a.shard_n = shard_n;
     a.base = (const unsigned long long*)ctx->small.p + SM_HIST + (size_t)hist_row * KB_RADIX;
     a.status = (ST*)ctx->status.p;
     a.ticket = (uint32_t*)((uint64_t*)ctx->small.p + SM_TICKET) + ticket_idx;
-    const size_t smem = kb_onesweep_smem();
-    CU(cudaFuncSetAttribute(kb_onesweep_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kb_onesweep_kernel<ST><<<(unsigned)n_tiles, KB_SORT_THREADS, smem, ctx->stream>>>(a);
+    const size_t smem = kb_onesweep_smem<THREADS, ITEMS>();
+    CU(cudaFuncSetAttribute(kb_onesweep_kernel<ST, THREADS, ITEMS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kb_onesweep_kernel<ST, THREADS, ITEMS, MINB><<<(unsigned)n_tiles, THREADS, smem, ctx->stream>>>(a);
     CU(cudaGetLastError());
     ctx->launches++;
     return KB_OK;
+}
+
+template <typename ST>
+static int launch_pass(kb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t n, uint32_t shift, uint32_t shard_n, int hist_row, int ticket_idx) {
+    switch (ctx->opt_sort_variant) {
+        case 1: return launch_pass_v<ST, 256, 24, 2>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        case 2: return launch_pass_v<ST, 512, 16, 2>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        case 3: return launch_pass_v<ST, 384, 20, 2>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        case 4: return launch_pass_v<ST, 512, 24, 1>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        default: return launch_pass_v<ST, 256, 16, 3>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+    }
 }
 
 // sort entA[0..n) by the top 8P bits -> *sorted points to the buffer holding the result
@@ -349,8 +363,6 @@ static int run_sort(kb_ctx* ctx, uint64_t n, int P, uint64_t** sorted) {
     TRY(ensure(ctx, ctx->entB, ctx->entA.cap));
     uint64_t* alt = (uint64_t*)ctx->entB.p;
     const bool wide = n >= (1ULL << 30);
-    const uint64_t n_tiles = (n + KB_SORT_TILE - 1) / KB_SORT_TILE;
-    TRY(ensure(ctx, ctx->status, n_tiles * KB_RADIX * (wide ? 8 : 4)));
     const uint32_t shift0 = 64 - 8 * P;
 
     prof_begin(ctx, "K2 histogram");
@@ -544,8 +556,6 @@ int kb_shard_extract(kb_ctx* ctx, int n_shards, void** records, uint64_t* counts
     // one partition pass by destination shard (histogram row 8 of the small buffer)
     TRY(ensure(ctx, ctx->entB, ctx->entA.cap));
     const bool wide = n >= (1ULL << 30);
-    const uint64_t n_tiles_s = (n + KB_SORT_TILE - 1) / KB_SORT_TILE;
-    TRY(ensure(ctx, ctx->status, n_tiles_s * KB_RADIX * (wide ? 8 : 4)));
     const uint32_t sshift = lo.FB ? 64 - lo.FB : 0;
     prof_begin(ctx, "K4 shard partition");
     KbHistArgs h{};

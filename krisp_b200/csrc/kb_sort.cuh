@@ -80,15 +80,6 @@ __global__ void __launch_bounds__(KB_RADIX) kb_scan_kernel(unsigned long long* h
 }
 
 // ---- onesweep pass -----------------------------------------------------------------------------
-#ifndef KB_SORT_THREADS
-#define KB_SORT_THREADS 256
-#endif
-#ifndef KB_SORT_ITEMS
-#define KB_SORT_ITEMS 16
-#endif
-#define KB_SORT_TILE (KB_SORT_THREADS * KB_SORT_ITEMS)
-#define KB_SORT_WARPS (KB_SORT_THREADS / 32)
-
 // status word: value | flag in the top two bits
 template <typename T> struct KbStatus;
 template <> struct KbStatus<uint32_t> {
@@ -139,15 +130,17 @@ __device__ __forceinline__ uint32_t kb_match_digit(uint32_t d) {
 #endif
 }
 
-template <typename ST>
-__global__ void __launch_bounds__(KB_SORT_THREADS, 3) kb_onesweep_kernel(const KbSortArgs<ST> a) {
+template <typename ST, int THREADS, int ITEMS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) kb_onesweep_kernel(const KbSortArgs<ST> a) {
     using S = KbStatus<ST>;
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    static_assert(THREADS >= KB_RADIX && TILE < 65536, "one thread per digit; 16-bit ranks");
     extern __shared__ __align__(16) unsigned char kb_smem_raw[];
     uint64_t* skeys = reinterpret_cast<uint64_t*>(kb_smem_raw);                         // TILE
-    uint64_t* dbase = skeys + KB_SORT_TILE;                                             // 256: global offset - local start
+    uint64_t* dbase = skeys + TILE;                                                     // 256: global offset - local start
     uint32_t* wcnt = reinterpret_cast<uint32_t*>(dbase + KB_RADIX);                     // WARPS * 256
-    uint32_t* lstart = wcnt + KB_SORT_WARPS * KB_RADIX;                                 // 256 local digit starts
-    uint32_t* wsum = lstart + KB_RADIX;                                                 // 8 (scan scratch)
+    uint32_t* wsum = wcnt + WARPS * KB_RADIX;                                           // 8 (scan scratch)
     __shared__ uint32_t s_tile;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -156,19 +149,19 @@ __global__ void __launch_bounds__(KB_SORT_THREADS, 3) kb_onesweep_kernel(const K
     for (int j = 0; j < KB_RADIX / 32; j++) wcnt[warp * KB_RADIX + j * 32 + lane] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint64_t tile_start = (uint64_t)tile * KB_SORT_TILE;
+    const uint64_t tile_start = (uint64_t)tile * TILE;
     if (tile_start >= a.n) return;
-    const uint32_t n_tile = (uint32_t)min((uint64_t)KB_SORT_TILE, a.n - tile_start);
+    const uint32_t n_tile = (uint32_t)min((uint64_t)TILE, a.n - tile_start);
 
     // ---- load (warp-striped: stable order = warp, item, lane) ---------------------------------
-    uint64_t key[KB_SORT_ITEMS];
-    const uint32_t wbase = warp * (KB_SORT_ITEMS * 32) + lane;
-    if (n_tile == KB_SORT_TILE) {
+    uint64_t key[ITEMS];
+    const uint32_t wbase = warp * (ITEMS * 32) + lane;
+    if (n_tile == TILE) {
 #pragma unroll
-        for (int i = 0; i < KB_SORT_ITEMS; i++) key[i] = kb_ld_stream(a.in + tile_start + wbase + i * 32);
+        for (int i = 0; i < ITEMS; i++) key[i] = kb_ld_stream(a.in + tile_start + wbase + i * 32);
     } else {
 #pragma unroll
-        for (int i = 0; i < KB_SORT_ITEMS; i++) {
+        for (int i = 0; i < ITEMS; i++) {
             const uint32_t idx = wbase + i * 32;
             key[i] = idx < n_tile ? kb_ld_stream(a.in + tile_start + idx) : ~0ULL;
         }
@@ -176,9 +169,9 @@ __global__ void __launch_bounds__(KB_SORT_THREADS, 3) kb_onesweep_kernel(const K
 
     // ---- rank inside the warp -------------------------------------------------------------------
     uint32_t* mycnt = wcnt + warp * KB_RADIX;
-    uint16_t rank[KB_SORT_ITEMS];
+    uint16_t rank[ITEMS];
 #pragma unroll
-    for (int i = 0; i < KB_SORT_ITEMS; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const uint32_t d = kb_digit(key[i], a.shift, a.shard_n);
         const uint32_t peers = kb_match_digit(d);
         const uint32_t before = mycnt[d];
@@ -189,19 +182,15 @@ __global__ void __launch_bounds__(KB_SORT_THREADS, 3) kb_onesweep_kernel(const K
     }
     __syncthreads();
 
-    // ---- per-digit: tile count, warp prefixes, look-back ---------------------------------------
+    // ---- per-digit: tile count (published at once), warp prefixes, local digit starts -----------
     uint32_t cnt = 0;
+    uint32_t wc[WARPS];
     if (tid < KB_RADIX) {
 #pragma unroll
-        for (int w = 0; w < KB_SORT_WARPS; w++) {
-            const uint32_t c = wcnt[w * KB_RADIX + tid];
-            wcnt[w * KB_RADIX + tid] = cnt;
-            cnt += c;
-        }
-        ST* st = a.status + (size_t)tile * KB_RADIX + tid;
-        kb_st_relaxed(st, (ST)cnt | (tile == 0 ? S::GLOBAL : S::LOCAL));
+        for (int w = 0; w < WARPS; w++) { wc[w] = wcnt[w * KB_RADIX + tid]; cnt += wc[w]; }
+        kb_st_relaxed(a.status + (size_t)tile * KB_RADIX + tid, (ST)cnt | (tile == 0 ? S::GLOBAL : S::LOCAL));
     }
-    // exclusive scan of cnt over the 256 digits -> lstart
+    uint32_t lstart = 0;
     {
         uint32_t x = cnt;
 #pragma unroll
@@ -211,37 +200,53 @@ __global__ void __launch_bounds__(KB_SORT_THREADS, 3) kb_onesweep_kernel(const K
         if (tid < KB_RADIX) {
             uint32_t add = 0;
             for (uint32_t w = 0; w < warp; w++) add += wsum[w];
-            lstart[tid] = add + x - cnt;
+            lstart = add + x - cnt;
+            uint32_t run = lstart;                  // wcnt[w][d] := local start of (warp w, digit d)
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) { wcnt[w * KB_RADIX + tid] = run; run += wc[w]; }
         }
     }
+    __syncthreads();
+
+    // ---- stage in ranked order --------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t d = kb_digit(key[i], a.shift, a.shard_n);
+        skeys[mycnt[d] + rank[i]] = key[i];
+    }
+
+    // ---- decoupled look-back (after the staging, so predecessors had time to publish); the status
+    //      words of 4 predecessor tiles are fetched per round trip -------------------------------------
     if (tid < KB_RADIX) {
         unsigned long long excl = 0;
         if (tile > 0) {
             int t = (int)tile - 1;
-            while (true) {
-                const ST* ps = a.status + (size_t)t * KB_RADIX + tid;
-                ST v;
-                do { v = kb_ld_relaxed(ps); } while ((v & S::FLAGS) == 0);
-                excl += (unsigned long long)(v & S::VALUE);
-                if (v & S::GLOBAL) break;
-                t--;
+            bool done = false;
+            while (!done) {
+                ST v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    v[j] = (t - j >= 0) ? kb_ld_relaxed(a.status + (size_t)(t - j) * KB_RADIX + tid) : (ST)S::GLOBAL;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (!done) {
+                        while ((v[j] & S::FLAGS) == 0) v[j] = kb_ld_relaxed(a.status + (size_t)(t - j) * KB_RADIX + tid);
+                        excl += (unsigned long long)(v[j] & S::VALUE);
+                        if (v[j] & S::GLOBAL) done = true;
+                    }
+                }
+                t -= 4;
             }
             kb_st_relaxed(a.status + (size_t)tile * KB_RADIX + tid, (ST)(excl + cnt) | S::GLOBAL);
         }
-        dbase[tid] = __ldg(a.base + tid) + excl - (unsigned long long)lstart[tid];
+        dbase[tid] = __ldg(a.base + tid) + excl - (unsigned long long)lstart;
     }
     __syncthreads();
 
-    // ---- stage in ranked order, then coalesced store --------------------------------------------
+    // ---- coalesced store: each digit's run is contiguous in shared memory and in the output -----------
 #pragma unroll
-    for (int i = 0; i < KB_SORT_ITEMS; i++) {
-        const uint32_t d = kb_digit(key[i], a.shift, a.shard_n);
-        skeys[lstart[d] + mycnt[d] + rank[i]] = key[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < KB_SORT_ITEMS; i++) {
-        const uint32_t pos = i * KB_SORT_THREADS + tid;
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t pos = i * THREADS + tid;
         if (pos < n_tile) {
             const uint64_t kv = skeys[pos];
             const uint32_t d = kb_digit(kv, a.shift, a.shard_n);
@@ -250,6 +255,7 @@ __global__ void __launch_bounds__(KB_SORT_THREADS, 3) kb_onesweep_kernel(const K
     }
 }
 
+template <int THREADS, int ITEMS>
 static inline size_t kb_onesweep_smem() {
-    return (size_t)KB_SORT_TILE * 8 + KB_RADIX * 8 + (size_t)KB_SORT_WARPS * KB_RADIX * 4 + KB_RADIX * 4 + 8 * 4 + 16;
+    return (size_t)THREADS * ITEMS * 8 + KB_RADIX * 8 + (size_t)(THREADS / 32) * KB_RADIX * 4 + 8 * 4 + 16;
 }
