@@ -60,7 +60,7 @@ int kb_configure(kb_ctx* ctx, int L, int D, int R, int soft_mode, int n_files, c
 
 /*
  * Tuning / diagnostics knobs:
- *   "sort_bits"     bits of the (mixed) flank key / flank hash the radix sort orders by (default 40;
+ *   "sort_bits"     bits of the (mixed) flank key / flank hash the radix sort orders by (default 32;
  *                   fewer bits = fewer passes, residual collisions are resolved exactly in the group pass)
  *   "mix"           1 (default) = store the flank key mixed by a bijection (uniform digits)
  *   "want_records"  1 = also return every record of the surviving groups' runs (for --out_align)

@@ -44,7 +44,7 @@ struct kb_ctx {
     KbLayout lo{};
     int soft_mode = 0;
     uint8_t is_ingroup[KB_MAX_FILES]{};
-    long long opt_sort_bits = 40, opt_mix = 1, opt_want_records = 0, opt_profile = 0, opt_result_cap = 1 << 16, opt_sort_variant = 0;
+    long long opt_sort_bits = 32, opt_mix = 1, opt_want_records = 0, opt_profile = 0, opt_result_cap = 1 << 16, opt_sort_variant = 0;
 
     // sequences
     DevBuf bases;
@@ -324,7 +324,7 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
     return KB_OK;
 }
 
-template <typename ST, int THREADS, int ITEMS, int MINB>
+template <typename ST, int THREADS, int ITEMS, int MINB, bool HWMATCH>
 static int launch_pass_v(kb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t n, uint32_t shift, uint32_t shard_n, int hist_row, int ticket_idx) {
     constexpr uint64_t TILE = (uint64_t)THREADS * ITEMS;
     const uint64_t n_tiles = (n + TILE - 1) / TILE;
@@ -336,8 +336,8 @@ static int launch_pass_v(kb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_
     a.status = (ST*)ctx->status.p;
     a.ticket = (uint32_t*)((uint64_t*)ctx->small.p + SM_TICKET) + ticket_idx;
     const size_t smem = kb_onesweep_smem<THREADS, ITEMS>();
-    CU(cudaFuncSetAttribute(kb_onesweep_kernel<ST, THREADS, ITEMS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kb_onesweep_kernel<ST, THREADS, ITEMS, MINB><<<(unsigned)n_tiles, THREADS, smem, ctx->stream>>>(a);
+    CU(cudaFuncSetAttribute(kb_onesweep_kernel<ST, THREADS, ITEMS, MINB, HWMATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kb_onesweep_kernel<ST, THREADS, ITEMS, MINB, HWMATCH><<<(unsigned)n_tiles, THREADS, smem, ctx->stream>>>(a);
     CU(cudaGetLastError());
     ctx->launches++;
     return KB_OK;
@@ -346,11 +346,12 @@ static int launch_pass_v(kb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_
 template <typename ST>
 static int launch_pass(kb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t n, uint32_t shift, uint32_t shard_n, int hist_row, int ticket_idx) {
     switch (ctx->opt_sort_variant) {
-        case 1: return launch_pass_v<ST, 256, 24, 2>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
-        case 2: return launch_pass_v<ST, 512, 16, 2>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
-        case 3: return launch_pass_v<ST, 384, 20, 2>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
-        case 4: return launch_pass_v<ST, 512, 24, 1>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
-        default: return launch_pass_v<ST, 256, 16, 3>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        case 1: return launch_pass_v<ST, 256, 16, 3, false>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        case 2: return launch_pass_v<ST, 512, 16, 2, false>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        case 3: return launch_pass_v<ST, 256, 16, 3, true>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        case 4: return launch_pass_v<ST, 512, 12, 2, true>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        case 5: return launch_pass_v<ST, 256, 20, 3, true>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        default: return launch_pass_v<ST, 512, 16, 2, true>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
     }
 }
 

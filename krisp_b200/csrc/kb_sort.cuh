@@ -115,10 +115,9 @@ __device__ __forceinline__ void kb_st_relaxed(unsigned long long* p, unsigned lo
 }
 
 // lanes of the warp holding the same 8-bit digit
+template <bool HWMATCH>
 __device__ __forceinline__ uint32_t kb_match_digit(uint32_t d) {
-#ifdef KB_USE_MATCH_ANY
-    return __match_any_sync(0xFFFFFFFFu, d);
-#else
+    if constexpr (HWMATCH) return __match_any_sync(0xFFFFFFFFu, d);
     uint32_t peers = 0xFFFFFFFFu;
 #pragma unroll
     for (int b = 0; b < KB_RADIX_BITS; b++) {
@@ -127,10 +126,9 @@ __device__ __forceinline__ uint32_t kb_match_digit(uint32_t d) {
         peers &= bit ? m : ~m;
     }
     return peers;
-#endif
 }
 
-template <typename ST, int THREADS, int ITEMS, int MINB>
+template <typename ST, int THREADS, int ITEMS, int MINB, bool HWMATCH>
 __global__ void __launch_bounds__(THREADS, MINB) kb_onesweep_kernel(const KbSortArgs<ST> a) {
     using S = KbStatus<ST>;
     constexpr int TILE = THREADS * ITEMS;
@@ -173,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, MINB) kb_onesweep_kernel(const KbSort
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const uint32_t d = kb_digit(key[i], a.shift, a.shard_n);
-        const uint32_t peers = kb_match_digit(d);
+        const uint32_t peers = kb_match_digit<HWMATCH>(d);
         const uint32_t before = mycnt[d];
         __syncwarp();
         if ((peers >> lane) <= 1u) mycnt[d] = before + __popc(peers);     // highest lane of the peer set

@@ -42,7 +42,7 @@ def test_prefix_sort_is_exact(name, sort_bits, searcher):
     L, D, R = deduce_ldr(case["flags"])
     res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher,
                        options={"sort_bits": sort_bits})
-    searcher.set_option("sort_bits", 40)
+    searcher.set_option("sort_bits", 32)
     assert res.rows() == case["rows"]
     if sort_bits == 8:
         assert res.stats["mixed_runs"] > 0

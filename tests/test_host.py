@@ -1,0 +1,135 @@
+"""Host-side logic that needs no GPU: ingest, labels, flag deduction, decoding, rendering, shard maths."""
+import argparse
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+from krisp_b200 import ingest, names, render, sharded
+from krisp_b200.search import SearchResult, _decode_bases, _decode_masks, labels_for
+from oracle import model
+from tests.helpers import GOLDEN_DIR, deduce_ldr, load_golden
+
+_G = load_golden()
+_FILES = sorted(set(glob.glob(os.path.join(GOLDEN_DIR, "**", "*.fa*"), recursive=True) +
+                    glob.glob(os.path.join(GOLDEN_DIR, "**", "*.fna*"), recursive=True)))
+
+
+@pytest.mark.parametrize("path", _FILES, ids=[os.path.relpath(p, GOLDEN_DIR) for p in _FILES])
+def test_ingest_matches_reference_parser(path):
+    """pack_bytes == the reference's _parse_FASTA records (restated in oracle/model.py), joined by separators."""
+    arr, rna = ingest.load_file(path)
+    recs = [r for r in model.fasta_records(model.read_lines(path)) if r]
+    got = re.sub(rb"\n+", b"\n", arr.tobytes().strip(b"\n"))
+    assert got == "\n".join(recs).encode()
+    assert rna == model.detect_rna(recs)
+
+
+def test_ingest_edge_cases():
+    assert ingest.pack_bytes(b"").size == 0
+    assert ingest.pack_bytes(b">only header").size == 0
+    # headerless input: the first line is consumed by the FASTA probe (kstream.py:450), the rest are records
+    assert ingest.pack_bytes(b"ACGT\nGGCC\nTTAA\n").tobytes() == b"GGCC\nTTAA"
+    # CRLF and padding are stripped per line (kstream.py:574)
+    assert re.sub(rb"\n+", b"\n", ingest.pack_bytes(b">a\r\nAC GT \r\n  TT\r\n>b\r\n>c\r\nGG\r\n").tobytes().strip(b"\n")) == b"AC GTTT\nGG"
+    # '>' inside a sequence line does not start a record
+    assert re.sub(rb"\n+", b"\n", ingest.pack_bytes(b">a\nAC>GT\nTT\n").tobytes().strip(b"\n")) == b"AC>GTTT"
+    assert ingest.detect_rna(np.frombuffer(b"ACGU\nACGT", dtype=np.uint8))
+    assert not ingest.detect_rna(np.frombuffer(b"ACGUT\nACG", dtype=np.uint8))
+    assert not ingest.detect_rna(np.frombuffer(b"ACGG", dtype=np.uint8))
+
+
+@pytest.mark.parametrize("name", ["a/b/GCF_1.1_x.fna.gz", "x.fasta", "x.v2.fa.bz2", "plain", "dir/ingroup0.fasta.gz", "q.frn", "q.ffn.gz"])
+def test_names_match_reference(name):
+    assert names.basename(name) == model.basename(name)
+    assert names.simplename(name) == model.simplename(name)
+
+
+def test_labels_single_file_and_collisions():
+    labs, isin = labels_for(["only.fa"], [])
+    assert labs == ["merged_file"] and isin == [0]
+    labs, isin = labels_for(["alpha.fasta"], ["alpha.v2.fasta", "gamma.1.fa"])
+    assert labs == ["alpha", "alpha", "gamma"] and isin == [1, 1, 0]
+
+
+@pytest.mark.parametrize("case", _G["cases"], ids=[c["name"] for c in _G["cases"]])
+def test_cli_deduction_matches_reference_rule(case):
+    from krisp_b200 import krisp_fasta
+    argv = ["x.fa"]
+    for k, v in case["flags"].items():
+        argv += [f"--{k}", str(v)]
+    args = krisp_fasta.deduce(krisp_fasta.build_parser().parse_args(argv))
+    L, D, R = deduce_ldr(case["flags"])
+    assert (args.conserved_left, args.amplicon - args.conserved_left - args.conserved_right, args.conserved_right) == (L, D, R)
+
+
+def test_cli_exits_when_underspecified(capsys):
+    from krisp_b200 import krisp_fasta
+    with pytest.raises(SystemExit) as e:
+        krisp_fasta.deduce(krisp_fasta.build_parser().parse_args(["x.fa", "--conserved", "5"]))
+    assert e.value.code == 1
+
+
+def _pack(seq):
+    v = 0
+    for ch in seq:
+        v = (v << 2) | "ACGT".index(ch)
+    return v
+
+
+def test_decoders():
+    left, right = "ACGTTGCA", "GT"
+    bits = 2 * (len(left) + len(right))
+    w = np.array([[_pack(left + right) << (64 - bits)]], dtype=np.uint64)
+    assert _decode_bases(w, 0, 8).tobytes().decode() == left
+    assert _decode_bases(w, 16, 2).tobytes().decode() == right
+    # masks: column c = nibble 7 - c%8 of word c/8
+    m = np.array([[0x1248F000, 0x30000000]], dtype=np.uint32)
+    assert _decode_masks(m, 9).tolist() == [[1, 2, 4, 8, 15, 0, 0, 0, 3]]
+
+
+def test_rows_and_iupac():
+    res = SearchResult(L=2, D=3, R=1, have_outgroup=True)
+    res.left = np.frombuffer(b"ACGT", dtype=np.uint8).reshape(2, 2)
+    res.right = np.frombuffer(b"GT", dtype=np.uint8).reshape(2, 1)
+    res.in_mask = np.array([[1, 3, 15], [8, 12, 2]], dtype=np.uint8)
+    res.out_mask = np.array([[2, 4, 1], [1, 1, 1]], dtype=np.uint8)
+    assert res.rows() == ["AC,AMN,G", "GT,TKC,T"]
+    res.have_outgroup = False
+    assert res.rows() == ["AC,MVN,G", "GT,WDM,T"]
+    assert render.csv_rows(res) == ["AC,MVN,G", "GT,WDM,T"]
+
+
+def test_render_alignment_matches_reference_text():
+    """Alignment blocks of the golden cases, rebuilt from the oracle's groups, equal the reference's --out_align text."""
+    for case in _G["cases"]:
+        if "out_align" not in case:
+            continue
+        ins = [os.path.join(GOLDEN_DIR, p) for p in case["ingroup"]]
+        outs = [os.path.join(GOLDEN_DIR, p) for p in case["outgroup"]]
+        L, D, R = deduce_ldr(case["flags"])
+        groups, ingroup = model.search_groups(ins, outs, L, D, R, case["omit_soft"])
+        ing = frozenset(ingroup) if outs else None
+        blocks = []
+        for (left, right) in sorted(groups):
+            amps = {seq[1]: labs for seq, labs in groups[(left, right)].items()}
+            blocks.append(render.render_alignment(left, right, amps, ing, case["dot"]) + "\n")
+        assert "".join(blocks) == case["out_align"], case["name"]
+
+
+def test_assign_files_balances():
+    assert sharded.assign_files(5, 2) == [0, 1, 0, 1, 0]
+    owner = sharded.assign_files(4, 2, sizes=[10, 1, 1, 8])
+    loads = [sum(s for s, o in zip([10, 1, 1, 8], owner) if o == r) for r in range(2)]
+    assert sorted(loads) == [10, 10]
+
+
+def test_shard_of_key_is_a_partition():
+    keys = np.arange(0, 1 << 18, 7, dtype=np.uint64)
+    for n in (1, 2, 3, 8):
+        s = sharded.shard_of_key(keys, n)
+        assert s.min() >= 0 and s.max() < n
+        if n > 1:
+            assert len(set(s.tolist())) == n
