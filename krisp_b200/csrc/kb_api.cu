@@ -13,6 +13,7 @@
 #include "kb_extract.cuh"
 #include "kb_sort.cuh"
 #include "kb_group.cuh"
+#include "kb_group_fast.cuh"
 
 #define KB_VERSION_STR "krisp_b200 0.1.0 sm_100a"
 
@@ -44,7 +45,7 @@ struct kb_ctx {
     KbLayout lo{};
     int soft_mode = 0;
     uint8_t is_ingroup[KB_MAX_FILES]{};
-    long long opt_sort_bits = 32, opt_mix = 1, opt_want_records = 0, opt_profile = 0, opt_result_cap = 1 << 16, opt_sort_variant = 0;
+    long long opt_sort_bits = 32, opt_mix = 1, opt_want_records = 0, opt_profile = 0, opt_result_cap = 1 << 16, opt_sort_variant = 0, opt_fast_group = 1;
 
     // sequences
     DevBuf bases;
@@ -54,7 +55,7 @@ struct kb_ctx {
     DevBuf d_file_starts, d_file_gid;
 
     // workspaces
-    DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out;
+    DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out, taint;
     uint64_t* h_pinned = nullptr;        // 64 x u64 scratch for small D2H reads
     uint64_t result_cap = 0;
 
@@ -69,7 +70,7 @@ struct kb_ctx {
 };
 
 // layout of the `small` device buffer (u64 units)
-enum { SM_NOUT = 0, SM_NRES = 1, SM_STATS = 2 /*4*/, SM_TICKET = 8 /* u32 x 16 */, SM_HIST = 16 /* 9*256 */, SM_TOTAL = 16 + 9 * 256 };
+enum { SM_NOUT = 0, SM_NRES = 1, SM_STATS = 2 /*4*/, SM_NTAINT = 6, SM_TICKET = 8 /* u32 x 16 */, SM_HIST = 16 /* 9*256 */, SM_TOTAL = 16 + 9 * 256 };
 
 static int fail(kb_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -151,7 +152,7 @@ void kb_destroy(kb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->recs, &ctx->status,
                       &ctx->small, &ctx->res_flank, &ctx->res_in, &ctx->res_out, &ctx->res_size, &ctx->res_run,
-                      &ctx->gather_off, &ctx->gather_out};
+                      &ctx->gather_off, &ctx->gather_out, &ctx->taint};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -174,6 +175,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "want_records") ctx->opt_want_records = value ? 1 : 0;
     else if (n == "profile") ctx->opt_profile = value ? 1 : 0;
     else if (n == "sort_variant") ctx->opt_sort_variant = value;
+    else if (n == "fast_group") ctx->opt_fast_group = value ? 1 : 0;
     else if (n == "result_cap") { if (value < 1) return fail(ctx, KB_EINVAL, "result_cap must be >= 1"); ctx->opt_result_cap = value; }
     else return fail(ctx, KB_EINVAL, "unknown option " + n);
     if (ctx->configured) {   // re-derive the sort plan
@@ -347,11 +349,11 @@ template <typename ST>
 static int launch_pass(kb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t n, uint32_t shift, uint32_t shard_n, int hist_row, int ticket_idx) {
     switch (ctx->opt_sort_variant) {
         case 1: return launch_pass_v<ST, 256, 16, 3, false>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
-        case 2: return launch_pass_v<ST, 512, 16, 2, false>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        case 2: return launch_pass_v<ST, 512, 16, 2, true>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
         case 3: return launch_pass_v<ST, 256, 16, 3, true>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
         case 4: return launch_pass_v<ST, 512, 12, 2, true>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
         case 5: return launch_pass_v<ST, 256, 20, 3, true>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
-        default: return launch_pass_v<ST, 512, 16, 2, true>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
+        default: return launch_pass_v<ST, 512, 16, 2, false>(ctx, in, out, n, shift, shard_n, hist_row, ticket_idx);
     }
 }
 
@@ -404,8 +406,34 @@ static int ensure_results(kb_ctx* ctx, uint64_t cap) {
     return KB_OK;
 }
 
-static int launch_group(kb_ctx* ctx, const KbGroupArgs& a) {
+#define KB_TAINT_CAP (1ull << 20)
+
+static bool fast_group_ok(const kb_ctx* ctx) {
+    const KbLayout& lo = ctx->lo;
+    return ctx->opt_fast_group && lo.direct && lo.FB >= 1 && lo.MW <= 1 && lo.n_files <= 64;
+}
+
+// returns KB_OK and sets *fell_back when the taint list overflowed and the generic kernel must run instead
+static int launch_group(kb_ctx* ctx, const KbGroupArgs& a, bool allow_fast) {
     const KbLayout& lo = a.lo;
+    if (allow_fast && fast_group_ok(ctx)) {
+        TRY(ensure(ctx, ctx->taint, KB_TAINT_CAP * 8));
+        KbFastArgs x{};
+        x.g = a;
+        x.ingroup64 = (uint64_t)a.ingroup[0] | ((uint64_t)a.ingroup[1] << 32);
+        x.full64 = (uint64_t)a.full[0] | ((uint64_t)a.full[1] << 32);
+        x.taint = (unsigned long long*)ctx->taint.p;
+        x.n_taint = (unsigned long long*)ctx->small.p + SM_NTAINT;
+        x.taint_cap = KB_TAINT_CAP;
+        const unsigned grid = (unsigned)((a.n + KB_K3F_TILE - 1) / KB_K3F_TILE);
+        if (lo.D == 1) kb_group_fast_kernel<true><<<grid, KB_K3F_THREADS, 0, ctx->stream>>>(x);
+        else kb_group_fast_kernel<false><<<grid, KB_K3F_THREADS, 0, ctx->stream>>>(x);
+        CU(cudaGetLastError());
+        kb_group_taint_kernel<<<(unsigned)ctx->n_sm * 4, 256, 0, ctx->stream>>>(x);   // exits at once when the list is empty
+        CU(cudaGetLastError());
+        ctx->launches += 2;
+        return KB_OK;
+    }
     const unsigned grid = (unsigned)((a.n + KB_K3_TILE - 1) / KB_K3_TILE);
     if (lo.direct) {
         if (lo.MW <= 1) kb_group_kernel<1, 1><<<grid, KB_K3_THREADS, 0, ctx->stream>>>(a);
@@ -430,7 +458,8 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
     uint64_t n_res = 0;
     if (n > 0) {
         if (ctx->result_cap == 0) { int rc = ensure_results(ctx, (uint64_t)ctx->opt_result_cap); if (rc) { delete res; return rc; } }
-        for (int attempt = 0; attempt < 3; attempt++) {
+        bool allow_fast = true;
+        for (int attempt = 0; attempt < 4; attempt++) {
             KbGroupArgs a{};
             a.ent = sorted; a.n = n; a.recs = (const uint64_t*)ctx->recs.p; a.lo = lo;
             for (int f = 0; f < lo.n_files; f++) {
@@ -442,18 +471,19 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
             a.res_flank = (uint64_t*)ctx->res_flank.p; a.res_in = (uint32_t*)ctx->res_in.p; a.res_out = (uint32_t*)ctx->res_out.p;
             a.res_size = (uint32_t*)ctx->res_size.p; a.res_run = (uint64_t*)ctx->res_run.p;
             a.stats = (unsigned long long*)ctx->small.p + SM_STATS;
-            cudaError_t e = cudaMemsetAsync((uint64_t*)ctx->small.p + SM_NRES, 0, 5 * 8, ctx->stream);
+            cudaError_t e = cudaMemsetAsync((uint64_t*)ctx->small.p + SM_NRES, 0, 6 * 8, ctx->stream);
             if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, cudaGetErrorString(e)); }
             prof_begin(ctx, "K3 group");
-            int rc = launch_group(ctx, a);
+            int rc = launch_group(ctx, a, allow_fast);
             prof_end(ctx);
             if (rc) { delete res; return rc; }
-            e = cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NRES, 5 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            e = cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NRES, 6 * 8, cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("group pass: ") + cudaGetErrorString(e)); }
             n_res = ctx->h_pinned[0];
             for (int i = 0; i < 4; i++) res->v.stats[i] = ctx->h_pinned[1 + i];
             ctx->alg_bytes += n * 8 * (lo.direct ? 1 : (1 + lo.W));
+            if (allow_fast && fast_group_ok(ctx) && ctx->h_pinned[5] > KB_TAINT_CAP) { allow_fast = false; continue; }   // taint list overflow: generic kernel
             if (n_res <= ctx->result_cap) break;
             rc = ensure_results(ctx, n_res + n_res / 8 + 16);       // table too small: grow and re-run the pass
             if (rc) { delete res; return rc; }

@@ -178,6 +178,56 @@ __device__ __forceinline__ void kb_emit(const KbGroupArgs& a, const KbKey<WN>& k
     a.res_run[2 * slot + 1] = run_len;
 }
 
+// A run whose records carry several distinct flank keys (they share only the sort prefix): visit the
+// keys in increasing order, one sweep over the run per key.  One warp; all lanes call it.
+template <int WN, int MWN>
+__device__ __noinline__ void kb_process_mixed_run(const KbGroupArgs& a, uint64_t start, uint64_t len) {
+    const KbLayout& lo = a.lo;
+    const uint32_t lane = threadIdx.x & 31;
+    if (lane == 0) atomicAdd(a.stats + 3, 1ULL);
+    KbAcc<MWN> acc;
+    KbKey<WN> cur; bool have_cur = false;
+#pragma unroll
+    for (int j = 0; j < WN; j++) cur.w[j] = 0;
+    for (int round = 0;; round++) {
+        acc.reset();
+        KbKey<WN> best; bool have_best = false;   // smallest key > cur (round 0: smallest key)
+#pragma unroll
+        for (int j = 0; j < WN; j++) best.w[j] = 0;
+        for (uint64_t off = 0; off < len; off += 32) {
+            const bool valid = off + lane < len;
+            uint64_t rec[WN]; KbKey<WN> key;
+#pragma unroll
+            for (int j = 0; j < WN; j++) { rec[j] = 0; key.w[j] = 0; }
+            if (valid) kb_fetch<WN>(a, a.ent[start + off + lane], rec, key);
+            if (valid) {
+                if (have_cur && kb_key_eq<WN>(key, cur, lo.FW)) kb_accumulate<WN, MWN>(a, rec, acc);
+                else if ((!have_cur || kb_key_lt<WN>(cur, key, lo.FW)) && (!have_best || kb_key_lt<WN>(key, best, lo.FW))) { best = key; have_best = true; }
+            }
+        }
+        if (have_cur) {
+            kb_acc_reduce<MWN>(lo, acc);
+            bool present, diag;
+            kb_evaluate<MWN>(a, acc, present, diag);
+            if (lane == 0 && present) {
+                atomicAdd(a.stats + 2, 1ULL);
+                if (diag) kb_emit<WN, MWN>(a, cur, acc, start, len);
+            }
+        }
+        // warp minimum of `best`
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            KbKey<WN> o;
+#pragma unroll
+            for (int j = 0; j < WN; j++) o.w[j] = __shfl_xor_sync(0xFFFFFFFFu, best.w[j], d);
+            const bool oh = __shfl_xor_sync(0xFFFFFFFFu, (int)have_best, d);
+            if (oh && (!have_best || kb_key_lt<WN>(o, best, lo.FW))) { best = o; have_best = true; }
+        }
+        if (!have_best) break;
+        cur = best; have_cur = true;
+    }
+}
+
 template <int WN, int MWN>
 __global__ void __launch_bounds__(KB_K3_THREADS) kb_group_kernel(const KbGroupArgs a) {
     const KbLayout& lo = a.lo;
@@ -273,46 +323,7 @@ __global__ void __launch_bounds__(KB_K3_THREADS) kb_group_kernel(const KbGroupAr
             continue;
         }
 
-        // ---- mixed run: several distinct flank keys share the sort prefix; visit them in key order
-        if (lane == 0) atomicAdd(a.stats + 3, 1ULL);
-        KbKey<WN> cur; bool have_cur = false;
-        for (int round = 0;; round++) {
-            acc.reset();
-            KbKey<WN> best; bool have_best = false;   // smallest key > cur (round 0: smallest key)
-#pragma unroll
-            for (int j = 0; j < WN; j++) best.w[j] = 0;
-            for (uint64_t off = 0; off < len; off += 32) {
-                const bool valid = off + lane < len;
-                uint64_t rec[WN]; KbKey<WN> key;
-#pragma unroll
-                for (int j = 0; j < WN; j++) { rec[j] = 0; key.w[j] = 0; }
-                if (valid) kb_fetch<WN>(a, a.ent[start + off + lane], rec, key);
-                if (valid) {
-                    if (have_cur && kb_key_eq<WN>(key, cur, lo.FW)) kb_accumulate<WN, MWN>(a, rec, acc);
-                    else if ((!have_cur || kb_key_lt<WN>(cur, key, lo.FW)) && (!have_best || kb_key_lt<WN>(key, best, lo.FW))) { best = key; have_best = true; }
-                }
-            }
-            if (have_cur) {
-                kb_acc_reduce<MWN>(lo, acc);
-                bool present, diag;
-                kb_evaluate<MWN>(a, acc, present, diag);
-                if (lane == 0 && present) {
-                    atomicAdd(a.stats + 2, 1ULL);
-                    if (diag) kb_emit<WN, MWN>(a, cur, acc, start, len);
-                }
-            }
-            // warp minimum of `best`
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                KbKey<WN> o;
-#pragma unroll
-                for (int j = 0; j < WN; j++) o.w[j] = __shfl_xor_sync(0xFFFFFFFFu, best.w[j], d);
-                const bool oh = __shfl_xor_sync(0xFFFFFFFFu, (int)have_best, d);
-                if (oh && (!have_best || kb_key_lt<WN>(o, best, lo.FW))) { best = o; have_best = true; }
-            }
-            if (!have_best) break;
-            cur = best; have_cur = true;
-        }
+        kb_process_mixed_run<WN, MWN>(a, start, len);
     }
 }
 
