@@ -48,19 +48,30 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Launch nvidia-smi (20 ms period) and wait until it delivers samples; mark() brackets the timed region."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
+            t = time.time()
+            while not self.lines and time.time() - t < 5.0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln)
+            self.lines.append((time.time(), ln))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -72,7 +83,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = (self.t0 or 0) - 0.02
+        t1 = (self.t1 or 1e18) + 0.02
+        for ts, ln in self.lines:
+            if not (t0 <= ts <= t1):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -198,9 +213,11 @@ def run_ours(args):
 
     results = {}
 
-    def timed(load, steps, collect_rows):
+    def timed(load, steps, collect_rows, sampler=None):
         launches, prof_acc, d2h = 0, {}, 0
         barrier()
+        if sampler:
+            sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -216,6 +233,8 @@ def run_ours(args):
             results["last"] = res
         e1.record(stream)
         barrier()
+        if sampler:
+            sampler.mark_end()
         ms = e0.elapsed_time(e1) / steps
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -226,11 +245,11 @@ def run_ours(args):
     # ---- value arm: sequences resident in HBM ----------------------------------------------------
     load_resident()
     s.synchronize()
-    timed(None, args.warmup, False)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms_dev, launches, prof, _ = timed(None, args.steps, False)
+    timed(None, args.warmup, False)
+    ms_dev, launches, prof, _ = timed(None, args.steps, False, clocks if rank == 0 else None)
     clk = clocks.stop() if rank == 0 else None
     counters = s.last_counters()
     last = results["last"]
@@ -296,7 +315,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-len", type=int, default=5_000_000, help="bases per genome per GPU (default: BASELINE config 2)")

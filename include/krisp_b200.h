@@ -44,7 +44,10 @@ int kb_create(int device, kb_ctx** out);
 void kb_destroy(kb_ctx* ctx);
 const char* kb_last_error(const kb_ctx* ctx);
 
-/* Launch all work on this cudaStream_t (e.g. torch's current stream).  NULL = the ctx's own stream. */
+/* Launch all work on this cudaStream_t (e.g. torch's current stream, so that library work orders with NCCL).
+ * NULL = the (legacy) default stream, which is also torch's default; KB_STREAM_OWN = the ctx's own
+ * non-blocking stream (the initial setting). */
+#define KB_STREAM_OWN ((void*)(intptr_t)-1)
 int kb_set_stream(kb_ctx* ctx, void* cuda_stream);
 
 /*

@@ -67,6 +67,7 @@ struct kb_ctx {
 
     // shard state
     uint64_t shard_n_records = 0;
+    int shard_send_in_B = 0;             // partitioned records are in entB (else entA)
 };
 
 // layout of the `small` device buffer (u64 units)
@@ -163,7 +164,7 @@ const char* kb_last_error(const kb_ctx* ctx) { return ctx ? ctx->err.c_str() : "
 
 int kb_set_stream(kb_ctx* ctx, void* s) {
     if (!ctx) return KB_EINVAL;
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    ctx->stream = (s == KB_STREAM_OWN) ? ctx->own_stream : (cudaStream_t)s;   // NULL = the default stream
     return KB_OK;
 }
 
@@ -357,14 +358,14 @@ static int launch_pass(kb_ctx* ctx, const uint64_t* in, uint64_t* out, uint64_t 
     }
 }
 
-// sort entA[0..n) by the top 8P bits -> *sorted points to the buffer holding the result
-static int run_sort(kb_ctx* ctx, uint64_t n, int P, uint64_t** sorted) {
-    uint64_t* cur = (uint64_t*)ctx->entA.p;
+// sort in[0..n) by the top 8P bits, ping-ponging with `other` (same capacity) -> *sorted = buffer holding the result
+static int run_sort(kb_ctx* ctx, DevBuf& in, DevBuf& other, uint64_t n, int P, uint64_t** sorted) {
+    uint64_t* cur = (uint64_t*)in.p;
     *sorted = cur;
     if (n == 0 || P == 0) return KB_OK;
     if (P > 8) return fail(ctx, KB_EINTERNAL, "more than 8 radix passes");
-    TRY(ensure(ctx, ctx->entB, ctx->entA.cap));
-    uint64_t* alt = (uint64_t*)ctx->entB.p;
+    TRY(ensure(ctx, other, in.cap));
+    uint64_t* alt = (uint64_t*)other.p;
     const bool wide = n >= (1ULL << 30);
     const uint32_t shift0 = 64 - 8 * P;
 
@@ -564,7 +565,7 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
     TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n));
     if (!lo.direct && n >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
     uint64_t* sorted = nullptr;
-    TRY(run_sort(ctx, n, lo.P, &sorted));
+    TRY(run_sort(ctx, ctx->entA, ctx->entB, n, lo.P, &sorted));
     int rc = run_group(ctx, sorted, n, out);
     prof_collect(ctx);
     return rc;
@@ -583,6 +584,7 @@ int kb_shard_extract(kb_ctx* ctx, int n_shards, void** records, uint64_t* counts
     TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n));
     for (int s = 0; s < n_shards; s++) counts[s] = 0;
     *records = ctx->entA.p;
+    ctx->shard_send_in_B = 0;
     if (n_shards == 1 || n == 0) { counts[0] = n; ctx->shard_n_records = n; prof_collect(ctx); return KB_OK; }
     // one partition pass by destination shard (histogram row 8 of the small buffer)
     TRY(ensure(ctx, ctx->entB, ctx->entA.cap));
@@ -609,6 +611,7 @@ int kb_shard_extract(kb_ctx* ctx, int n_shards, void** records, uint64_t* counts
     for (int s = 0; s < n_shards; s++) counts[s] = n_shards > 64 ? big[s] : ctx->h_pinned[s];
     ctx->alg_bytes += n * 24;
     *records = ctx->entB.p;
+    ctx->shard_send_in_B = 1;
     ctx->shard_n_records = n;
     prof_collect(ctx);
     return KB_OK;
@@ -617,9 +620,11 @@ int kb_shard_extract(kb_ctx* ctx, int n_shards, void** records, uint64_t* counts
 int kb_shard_recv_buffer(kb_ctx* ctx, uint64_t n_records, void** buffer) {
     if (!ctx || !buffer) return KB_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    // the partitioned records live in entB (or entA when n_shards == 1): receive into entA unless it is the source
-    TRY(ensure(ctx, ctx->recs, (n_records + 64) * 8));
-    *buffer = ctx->recs.p;
+    // the partitioned records live in entB (entA when n_shards == 1): receive into the other ping-pong buffer,
+    // which then is the sort input — no staging copy
+    DevBuf& dst = ctx->shard_send_in_B ? ctx->entA : ctx->entB;
+    TRY(ensure(ctx, dst, (n_records + 64) * 8));
+    *buffer = dst.p;
     return KB_OK;
 }
 
@@ -632,11 +637,12 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, kb_result** out) {
     CU(cudaSetDevice(ctx->device));
     begin_search(ctx);
     TRY(prepare_small(ctx));
-    // received records (in `recs`, see kb_shard_recv_buffer) become the sort input
-    TRY(ensure(ctx, ctx->entA, (n_records + 64) * 8));
-    if (n_records) CU(cudaMemcpyAsync(ctx->entA.p, ctx->recs.p, n_records * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    // the received records (see kb_shard_recv_buffer) are the sort input; the send buffer is free again
+    DevBuf& in = ctx->shard_send_in_B ? ctx->entA : ctx->entB;
+    DevBuf& other = ctx->shard_send_in_B ? ctx->entB : ctx->entA;
+    if (in.cap < (n_records + 64) * 8) return fail(ctx, KB_EINVAL, "kb_shard_recv_buffer was not called for this many records");
     uint64_t* sorted = nullptr;
-    TRY(run_sort(ctx, n_records, lo.P, &sorted));
+    TRY(run_sort(ctx, in, other, n_records, lo.P, &sorted));
     int rc = run_group(ctx, sorted, n_records, out);
     prof_collect(ctx);
     return rc;
@@ -683,7 +689,7 @@ int kb_extract_sorted(kb_ctx* ctx, int local_index, kb_table** out) {
     uint64_t n = 0;
     TRY(run_extract(ctx, lo, tile0, tile1 - tile0, pos_lo, pos_hi, &n));
     uint64_t* sorted = nullptr;
-    TRY(run_sort(ctx, n, lo.P, &sorted));
+    TRY(run_sort(ctx, ctx->entA, ctx->entB, n, lo.P, &sorted));
     kb_table* t = new (std::nothrow) kb_table();
     if (!t) return fail(ctx, KB_ENOMEM, "host allocation failed");
     t->records.resize(n);

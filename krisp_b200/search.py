@@ -99,6 +99,7 @@ class Searcher:
             self._ctx = None
             raise _lib.KrispB200Error(rc, msg.decode() if msg else "kb_create failed")
         if stream is not None:
+            # a raw cudaStream_t handle; 0 is the default stream (torch's default), not "none"
             self._check(self._L.kb_set_stream(self._ctx, ctypes.c_void_p(int(stream))))
         self._keep = []          # host buffers that must outlive the async copies
         self.lo = None

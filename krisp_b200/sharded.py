@@ -13,7 +13,18 @@ independent:
 The reference has no counterpart (it is single-host multiprocessing, krisp_fasta.py:86-123); the file
 fan-out mirrors ``sortedKmersParallel``: files are independent extraction units.
 """
+import os
+import sys
+import time
+
 import numpy as np
+
+_DEBUG = bool(os.environ.get("KRISP_DEBUG"))
+
+
+def _dbg(msg):
+    if _DEBUG:
+        print(f"[krisp_b200 rank {os.environ.get('RANK', '?')} {time.time():.3f}] {msg}", file=sys.stderr, flush=True)
 
 
 def assign_files(n_files, world_size, sizes=None):
@@ -49,17 +60,21 @@ def exchange(searcher, send_ptr, send_counts, device, group=None):
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    _dbg(f"exchange: send_counts={send_counts}")
     sc = torch.tensor(send_counts, dtype=torch.int64, device=device)
     rc = torch.empty(world, dtype=torch.int64, device=device)
     dist.all_to_all_single(rc, sc, group=group)
     recv_counts = [int(x) for x in rc.tolist()]
     n_recv = sum(recv_counts)
+    _dbg(f"exchange: recv_counts={recv_counts}")
     recv_ptr = searcher.shard_recv_buffer(n_recv)
     send = searcher.wrap_records(send_ptr, sum(send_counts), device) if hasattr(searcher, "wrap_records") \
         else _wrap(send_ptr, sum(send_counts), device)
     recv = searcher.wrap_records(recv_ptr, n_recv, device) if hasattr(searcher, "wrap_records") \
         else _wrap(recv_ptr, n_recv, device)
+    _dbg("exchange: records all_to_all")
     dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+    _dbg("exchange: done")
     return n_recv, {"sent": int(sum(send_counts) - send_counts[dist.get_rank(group)]), "received": n_recv}
 
 
@@ -67,9 +82,27 @@ def sharded_search(searcher, device, have_outgroup=True, group=None):
     """Steps 1-3 on the sequences this rank has added to `searcher`.  Returns this rank's SearchResult."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    _dbg("shard_extract")
     send_ptr, counts = searcher.shard_extract(world)
-    n_recv, _ = exchange(searcher, send_ptr, counts, device, group)
-    return searcher.shard_search(n_recv, have_outgroup=have_outgroup)
+    prof = list(searcher.last_profile()) if hasattr(searcher, "last_profile") else []
+    ev = None
+    if device is not None and getattr(device, "type", "cpu") == "cuda":
+        import torch
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    n_recv, info = exchange(searcher, send_ptr, counts, device, group)
+    if ev:
+        ev[1].record()
+    _dbg(f"shard_search n={n_recv}")
+    res = searcher.shard_search(n_recv, have_outgroup=have_outgroup)
+    _dbg(f"shard_search done: {res.n_groups} groups")
+    if ev:
+        ev[1].synchronize()
+        prof.append(("K4 all_to_all (NCCL)", ev[0].elapsed_time(ev[1])))
+    if hasattr(res, "profile"):
+        res.profile = prof + list(res.profile)
+        res.exchange = info
+    return res
 
 
 def gather_rows(rows, group=None):

@@ -1,0 +1,50 @@
+"""torchrun worker for tests/test_gpu_sharded.py: flank-hash sharded search over NCCL on the golden cases."""
+import hashlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from krisp_b200 import ingest, sharded  # noqa: E402
+from krisp_b200.search import Searcher, labels_for  # noqa: E402
+from tests.helpers import deduce_ldr, golden_paths, load_golden  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    s = Searcher(device=local, stream=torch.cuda.current_stream().cuda_stream)
+    bad = 0
+    for case in load_golden()["cases"]:
+        L, D, R = deduce_ldr(case["flags"])
+        if 2 * (L + D + R) + 8 > 64 or (R == 0 and D > 0):
+            continue                                   # multi-word records are not sharded yet
+        ins, outs = golden_paths(case)
+        files = ins + outs
+        _, is_in = labels_for(ins, outs)
+        owner = sharded.assign_files(len(files), world, sizes=[os.path.getsize(f) for f in files])
+        s.configure(L, D, R, is_in, case["omit_soft"])
+        s.clear_sequences()
+        for i, f in enumerate(files):
+            if owner[i] == rank:
+                s.add_sequence(i, ingest.load_file(f)[0])
+        res = sharded.sharded_search(s, dev, have_outgroup=len(outs) > 0)
+        rows = sharded.gather_rows(res.rows())
+        ok = len(rows) == case["n_rows"] and hashlib.sha256("\n".join(rows).encode()).hexdigest() == case["rows_sha256"]
+        if rank == 0:
+            print(("ok   " if ok else "FAIL ") + case["name"], len(rows), flush=True)
+        bad += 0 if ok else 1
+    s.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
