@@ -95,7 +95,7 @@ def sharded_search(searcher, device, have_outgroup=True, group=None):
         ev[1].record()
     _dbg(f"shard_search n={n_recv}")
     res = searcher.shard_search(n_recv, have_outgroup=have_outgroup)
-    _dbg(f"shard_search done: {res.n_groups} groups")
+    _dbg(f"shard_search done: {getattr(res, 'n_groups', '?')} groups")
     if ev:
         ev[1].synchronize()
         prof.append(("K4 all_to_all (NCCL)", ev[0].elapsed_time(ev[1])))
