@@ -14,6 +14,8 @@
 #include "kb_sort.cuh"
 #include "kb_group.cuh"
 #include "kb_group_fast.cuh"
+#include "kb_part.cuh"
+#include "kb_hash.cuh"
 
 #define KB_VERSION_STR "krisp_b200 0.1.0 sm_100a"
 
@@ -46,6 +48,9 @@ struct kb_ctx {
     int soft_mode = 0;
     uint8_t is_ingroup[KB_MAX_FILES]{};
     long long opt_sort_bits = 32, opt_mix = 1, opt_want_records = 0, opt_profile = 0, opt_result_cap = 1 << 16, opt_sort_variant = 0, opt_fast_group = 1;
+    long long opt_group_algo = 1;        // 1 = partition + bucket hash (kb_part.cuh, kb_hash.cuh), 0 = radix sort + segmented pass
+    long long opt_bucket_bits = -1;      // -1 = from the input size
+    long long opt_hash_slots_log2 = 0;   // 0 = default
 
     // sequences
     DevBuf bases;
@@ -55,7 +60,7 @@ struct kb_ctx {
     DevBuf d_file_starts, d_file_gid;
 
     // workspaces
-    DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out, taint;
+    DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out, taint, plan;
     uint64_t* h_pinned = nullptr;        // 64 x u64 scratch for small D2H reads
     uint64_t result_cap = 0;
 
@@ -71,7 +76,8 @@ struct kb_ctx {
 };
 
 // layout of the `small` device buffer (u64 units)
-enum { SM_NOUT = 0, SM_NRES = 1, SM_STATS = 2 /*4*/, SM_NTAINT = 6, SM_TICKET = 8 /* u32 x 16 */, SM_HIST = 16 /* 9*256 */, SM_TOTAL = 16 + 9 * 256 };
+enum { SM_NOUT = 0, SM_NRES = 1, SM_STATS = 2 /*4*/, SM_NTAINT = 6, SM_ERR = 7, SM_TICKET = 8 /* u32 x 16 */, SM_HIST = 16 /* 9*256 */,
+       SM_ROOT = 16 + 9 * 256 /* u64 x 2: {0, n} */, SM_ROOTTILE = SM_ROOT + 2 /* u32 x 2: {0, tiles} */, SM_TOTAL = SM_ROOT + 4 };
 
 static int fail(kb_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -153,7 +159,7 @@ void kb_destroy(kb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->recs, &ctx->status,
                       &ctx->small, &ctx->res_flank, &ctx->res_in, &ctx->res_out, &ctx->res_size, &ctx->res_run,
-                      &ctx->gather_off, &ctx->gather_out, &ctx->taint};
+                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -177,6 +183,9 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "profile") ctx->opt_profile = value ? 1 : 0;
     else if (n == "sort_variant") ctx->opt_sort_variant = value;
     else if (n == "fast_group") ctx->opt_fast_group = value ? 1 : 0;
+    else if (n == "group_algo") ctx->opt_group_algo = value ? 1 : 0;
+    else if (n == "bucket_bits") { if (value < -1 || value > 24) return fail(ctx, KB_EINVAL, "bucket_bits must be in -1..24"); ctx->opt_bucket_bits = value; }
+    else if (n == "hash_slots_log2") { if (value != 0 && (value < 4 || value > 12)) return fail(ctx, KB_EINVAL, "hash_slots_log2 must be 0 or in 4..12"); ctx->opt_hash_slots_log2 = value; }
     else if (n == "result_cap") { if (value < 1) return fail(ctx, KB_EINVAL, "result_cap must be >= 1"); ctx->opt_result_cap = value; }
     else return fail(ctx, KB_EINVAL, "unknown option " + n);
     if (ctx->configured) {   // re-derive the sort plan
@@ -282,7 +291,8 @@ static int prepare_small(kb_ctx* ctx) {
 }
 
 // K1 over tiles [tile0, tile0+n_tiles), windows starting in [pos_lo, pos_hi); *n_out = records written
-static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint64_t* n_out) {
+static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint64_t* n_out,
+                       unsigned long long* hist = nullptr, uint32_t hist_shift = 0, uint32_t hist_bits = 0) {
     const uint64_t n_max = 2 * (std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo) + 64;
     TRY(ensure(ctx, ctx->entA, n_max * 8));
     if (!lo.direct) TRY(ensure(ctx, ctx->recs, n_max * 8 * lo.W));
@@ -305,6 +315,7 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
     a.n_out = (unsigned long long*)ctx->small.p + SM_NOUT;
     a.tile0 = tile0; a.n_tiles = n_tiles;
     a.pos_lo = pos_lo; a.pos_hi = pos_hi;
+    a.hist = hist; a.hist_shift = hist_shift; a.hist_bits = hist_bits;
     const size_t smem = kb_extract_smem(lo.k);
     const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->n_sm * 8);
     prof_begin(ctx, "K1 extract");
@@ -396,6 +407,174 @@ static int run_sort(kb_ctx* ctx, DevBuf& in, DevBuf& other, uint64_t n, int P, u
     return KB_OK;
 }
 
+
+// ---- search path: radix partition (kb_part.cuh) + bucket hash aggregation (kb_hash.cuh) ----------------
+struct PartPlan {
+    int levels = 0, bits[3] = {0, 0, 0}, bb = 0;
+    uint32_t slots_log2 = 11;
+    bool fast = false;
+    // device tables inside ctx->plan (byte offsets), per level: counts/cursors [NC], starts [NC + 1], tile prefix [NC + 1]
+    size_t off_cnt[3] = {0, 0, 0}, off_start[3] = {0, 0, 0}, off_tile0[3] = {0, 0, 0}, off_tilemap = 0, bytes = 0;
+    uint32_t nc[3] = {0, 0, 0};
+};
+
+static bool hash_fast_ok(const kb_ctx* ctx) {
+    const KbLayout& lo = ctx->lo;
+    return ctx->opt_fast_group && lo.direct && lo.FB >= 1 && lo.MW <= 1 && lo.n_files <= 64;
+}
+
+static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est) {
+    const KbLayout& lo = ctx->lo;
+    PartPlan pl;
+    pl.fast = hash_fast_ok(ctx);
+    if (ctx->opt_hash_slots_log2) pl.slots_log2 = (uint32_t)ctx->opt_hash_slots_log2;
+    else if (pl.fast) pl.slots_log2 = 11;                        // 2048 slots x 24 B = 48 KB: 4 CTAs per SM
+    else {
+        const size_t sb = kb_hash_slot_bytes(lo);
+        uint32_t l2 = 11;
+        while (l2 > 6 && ((size_t)1 << l2) * sb > 96 * 1024) l2--;
+        pl.slots_log2 = l2;
+    }
+    const int keybits = lo.direct ? lo.FB : 32;
+    int bb;
+    if (ctx->opt_bucket_bits >= 0) bb = (int)ctx->opt_bucket_bits;
+    else {
+        const uint64_t target = 3ull << pl.slots_log2;           // records per bucket
+        bb = 0;
+        while (bb < 24 && (n_est >> bb) > target) bb++;
+    }
+    bb = std::min(bb, std::min(keybits, 24));
+    pl.bb = bb;
+    pl.levels = (bb + 8) / 9;
+    for (int l = 0; l < pl.levels; l++) pl.bits[l] = bb / pl.levels + (l < bb % pl.levels ? 1 : 0);
+    const uint64_t max_tiles = n_est / KB_PT_TILE + ((uint64_t)1 << bb) + 2;
+    size_t off = 0;
+    int acc = 0;
+    for (int l = 0; l < pl.levels; l++) {
+        acc += pl.bits[l];
+        pl.nc[l] = 1u << acc;
+        pl.off_cnt[l] = off; off += (size_t)pl.nc[l] * 8;
+        pl.off_start[l] = off; off += ((size_t)pl.nc[l] + 1) * 8;
+        pl.off_tile0[l] = off; off += (((size_t)pl.nc[l] + 1) * 4 + 7) & ~(size_t)7;
+    }
+    pl.off_tilemap = off; off += (max_tiles * 4 + 7) & ~(size_t)7;
+    pl.bytes = off;
+    return pl;
+}
+
+// partition `in` (n elements; level-0 histogram already in the plan buffer) -> *parted, bucket table -> *bstart / *n_buckets
+static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& other, uint64_t n, uint64_t** parted,
+                         const unsigned long long** bstart, uint32_t* n_buckets) {
+    uint64_t* cur = (uint64_t*)in.p;
+    uint8_t* P = (uint8_t*)ctx->plan.p;
+    unsigned long long* root = (unsigned long long*)ctx->small.p + SM_ROOT;
+    uint32_t* roottile = (uint32_t*)((uint64_t*)ctx->small.p + SM_ROOTTILE);
+    // root parent {0, n}, {0, tiles}
+    ctx->h_pinned[8] = 0; ctx->h_pinned[9] = n;
+    ((uint32_t*)(ctx->h_pinned + 10))[0] = 0; ((uint32_t*)(ctx->h_pinned + 10))[1] = (uint32_t)((n + KB_PT_TILE - 1) / KB_PT_TILE);
+    CU(cudaMemcpyAsync(root, ctx->h_pinned + 8, 24, cudaMemcpyHostToDevice, ctx->stream));
+    *parted = cur; *bstart = root; *n_buckets = 1;
+    if (pl.levels == 0 || n == 0) return KB_OK;
+    TRY(ensure(ctx, other, in.cap));
+    uint64_t* alt = (uint64_t*)other.p;
+    const size_t smem = kb_part_smem();
+    CU(cudaFuncSetAttribute(kb_part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int shift = 64;
+    static const char* pnames[3] = {"K2 partition 0", "K2 partition 1", "K2 partition 2"};
+    static const char* hnames[3] = {"K2 plan 0", "K2 histogram 1", "K2 histogram 2"};
+    for (int l = 0; l < pl.levels; l++) {
+        shift -= pl.bits[l];
+        KbPartArgs a{};
+        a.in = cur; a.out = alt;
+        a.shift = (uint32_t)shift; a.bits = (uint32_t)pl.bits[l];
+        a.cursor = (unsigned long long*)(P + pl.off_cnt[l]);
+        a.hist = a.cursor;
+        uint64_t grid;
+        if (l == 0) {
+            a.pstart = root; a.ptile0 = roottile; a.tile_parent = nullptr; a.n_parents = 1;
+            grid = (n + KB_PT_TILE - 1) / KB_PT_TILE;
+        } else {
+            a.pstart = (const unsigned long long*)(P + pl.off_start[l - 1]);
+            a.ptile0 = (const uint32_t*)(P + pl.off_tile0[l - 1]);
+            a.tile_parent = (const uint32_t*)(P + pl.off_tilemap);
+            a.n_parents = pl.nc[l - 1];
+            grid = n / KB_PT_TILE + pl.nc[l - 1] + 1;
+        }
+        prof_begin(ctx, hnames[l]);
+        if (l > 0) {
+            kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((pl.nc[l - 1] + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, a.n_parents, (uint32_t*)(P + pl.off_tilemap));
+            CU(cudaGetLastError());
+            kb_part_hist_kernel<<<(unsigned)grid, KB_PT_THREADS, 0, ctx->stream>>>(a);
+            CU(cudaGetLastError());
+            ctx->launches += 2;
+            ctx->alg_bytes += n * 8;
+        }
+        KbPlanArgs pa{};
+        pa.counts = a.cursor; pa.nc = pl.nc[l]; pa.base = 0;
+        pa.start = (unsigned long long*)(P + pl.off_start[l]);
+        pa.cursor = a.cursor;
+        pa.tile0 = (uint32_t*)(P + pl.off_tile0[l]);
+        kb_plan_kernel<<<1, 1024, 0, ctx->stream>>>(pa);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        prof_end(ctx);
+        prof_begin(ctx, pnames[l]);
+        kb_part_kernel<2><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        prof_end(ctx);
+        ctx->alg_bytes += n * 16;
+        std::swap(cur, alt);
+    }
+    ctx->passes = pl.levels;
+    *parted = cur;
+    *bstart = (const unsigned long long*)(P + pl.off_start[pl.levels - 1]);
+    *n_buckets = pl.nc[pl.levels - 1];
+    return KB_OK;
+}
+
+struct HashStage {            // what run_group needs to run the bucket-hash kernels instead of the sorted-run kernels
+    const PartPlan* pl;
+    const unsigned long long* bstart;
+    uint32_t n_buckets;
+};
+
+static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
+    const KbLayout& lo = g.lo;
+    KbHashArgs x{};
+    x.g = g;
+    x.bstart = hs.bstart; x.n_buckets = hs.n_buckets; x.slots_log2 = hs.pl->slots_log2;
+    x.ingroup64 = (uint64_t)g.ingroup[0] | ((uint64_t)g.ingroup[1] << 32);
+    x.full64 = (uint64_t)g.full[0] | ((uint64_t)g.full[1] << 32);
+    x.err = (unsigned long long*)ctx->small.p + SM_ERR;
+    const unsigned grid = (unsigned)std::min<uint32_t>(hs.n_buckets, 1u << 20);
+    if (hs.pl->fast) {
+        const size_t smem = kb_hash_fast_smem(x.slots_log2);
+        if (lo.D == 1) {
+            CU(cudaFuncSetAttribute(kb_hash_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kb_hash_fast_kernel<true><<<grid, KB_KH_THREADS, smem, ctx->stream>>>(x);
+        } else {
+            CU(cudaFuncSetAttribute(kb_hash_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kb_hash_fast_kernel<false><<<grid, KB_KH_THREADS, smem, ctx->stream>>>(x);
+        }
+    } else {
+        const size_t smem = kb_hash_smem(lo, x.slots_log2);
+        switch (lo.W) {
+            case 1: CU(cudaFuncSetAttribute(kb_hash_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    kb_hash_kernel<1><<<grid, KB_KH_THREADS, smem, ctx->stream>>>(x); break;
+            case 2: CU(cudaFuncSetAttribute(kb_hash_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    kb_hash_kernel<2><<<grid, KB_KH_THREADS, smem, ctx->stream>>>(x); break;
+            case 4: CU(cudaFuncSetAttribute(kb_hash_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    kb_hash_kernel<4><<<grid, KB_KH_THREADS, smem, ctx->stream>>>(x); break;
+            default: CU(cudaFuncSetAttribute(kb_hash_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    kb_hash_kernel<8><<<grid, KB_KH_THREADS, smem, ctx->stream>>>(x); break;
+        }
+    }
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return KB_OK;
+}
+
 static int ensure_results(kb_ctx* ctx, uint64_t cap) {
     const KbLayout& lo = ctx->lo;
     TRY(ensure(ctx, ctx->res_flank, cap * lo.FW * 8));
@@ -430,7 +609,7 @@ static int launch_group(kb_ctx* ctx, const KbGroupArgs& a, bool allow_fast) {
         if (lo.D == 1) kb_group_fast_kernel<true><<<grid, KB_K3F_THREADS, 0, ctx->stream>>>(x);
         else kb_group_fast_kernel<false><<<grid, KB_K3F_THREADS, 0, ctx->stream>>>(x);
         CU(cudaGetLastError());
-        kb_group_taint_kernel<<<(unsigned)ctx->n_sm * 4, 256, 0, ctx->stream>>>(x);   // exits at once when the list is empty
+        kb_group_taint_kernel<<<(unsigned)ctx->n_sm * 16, 256, 0, ctx->stream>>>(x);   // exits at once when the list is empty
         CU(cudaGetLastError());
         ctx->launches += 2;
         return KB_OK;
@@ -448,7 +627,7 @@ static int launch_group(kb_ctx* ctx, const KbGroupArgs& a, bool allow_fast) {
 }
 
 // K3 over sorted[0..n) + result download
-static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result** out) {
+static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result** out, const HashStage* hs = nullptr) {
     const KbLayout& lo = ctx->lo;
     kb_result* res = new (std::nothrow) kb_result();
     if (!res) return fail(ctx, KB_ENOMEM, "host allocation failed");
@@ -472,19 +651,20 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
             a.res_flank = (uint64_t*)ctx->res_flank.p; a.res_in = (uint32_t*)ctx->res_in.p; a.res_out = (uint32_t*)ctx->res_out.p;
             a.res_size = (uint32_t*)ctx->res_size.p; a.res_run = (uint64_t*)ctx->res_run.p;
             a.stats = (unsigned long long*)ctx->small.p + SM_STATS;
-            cudaError_t e = cudaMemsetAsync((uint64_t*)ctx->small.p + SM_NRES, 0, 6 * 8, ctx->stream);
+            cudaError_t e = cudaMemsetAsync((uint64_t*)ctx->small.p + SM_NRES, 0, 7 * 8, ctx->stream);
             if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, cudaGetErrorString(e)); }
-            prof_begin(ctx, "K3 group");
-            int rc = launch_group(ctx, a, allow_fast);
+            prof_begin(ctx, hs ? "K3 bucket hash" : "K3 group");
+            int rc = hs ? launch_hash(ctx, a, *hs) : launch_group(ctx, a, allow_fast);
             prof_end(ctx);
             if (rc) { delete res; return rc; }
-            e = cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NRES, 6 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            e = cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NRES, 7 * 8, cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("group pass: ") + cudaGetErrorString(e)); }
             n_res = ctx->h_pinned[0];
             for (int i = 0; i < 4; i++) res->v.stats[i] = ctx->h_pinned[1 + i];
             ctx->alg_bytes += n * 8 * (lo.direct ? 1 : (1 + lo.W));
-            if (allow_fast && fast_group_ok(ctx) && ctx->h_pinned[5] > KB_TAINT_CAP) { allow_fast = false; continue; }   // taint list overflow: generic kernel
+            if (hs && ctx->h_pinned[6]) { delete res; return fail(ctx, KB_EINTERNAL, "bucket hash: a bucket could not be resolved (hash table split limit)"); }
+            if (!hs && allow_fast && fast_group_ok(ctx) && ctx->h_pinned[5] > KB_TAINT_CAP) { allow_fast = false; continue; }   // taint list overflow: generic kernel
             if (n_res <= ctx->result_cap) break;
             rc = ensure_results(ctx, n_res + n_res / 8 + 16);       // table too small: grow and re-run the pass
             if (rc) { delete res; return rc; }
@@ -508,7 +688,7 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
         if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("result download: ") + cudaGetErrorString(e)); }
     }
     if (ctx->opt_want_records && n_res) {
-        for (uint64_t g = 0; g < n_res; g++) res->run_offset[g + 1] = res->run_offset[g] + runs[2 * g + 1];
+        for (uint64_t g = 0; g < n_res; g++) res->run_offset[g + 1] = res->run_offset[g] + (hs ? (uint64_t)res->group_size[g] : runs[2 * g + 1]);
         const uint64_t total = res->run_offset[n_res];
         int rc = ensure(ctx, ctx->gather_off, n_res * 8);
         if (!rc) rc = ensure(ctx, ctx->gather_out, total * lo.W * 8);
@@ -519,7 +699,20 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
         g.ent = sorted; g.recs = (const uint64_t*)ctx->recs.p; g.res_run = (const uint64_t*)ctx->res_run.p;
         g.off = (const uint64_t*)ctx->gather_off.p; g.n_groups = n_res; g.out = (uint64_t*)ctx->gather_out.p; g.lo = lo;
         const unsigned grid = (unsigned)((n_res + 7) / 8);
-        if (e == cudaSuccess) {
+        if (e == cudaSuccess && hs) {
+            KbHGatherArgs hg{};
+            hg.ent = sorted; hg.recs = (const uint64_t*)ctx->recs.p; hg.res_run = (const uint64_t*)ctx->res_run.p;
+            hg.res_flank = (const uint64_t*)ctx->res_flank.p; hg.off = (const uint64_t*)ctx->gather_off.p;
+            hg.n_groups = n_res; hg.out = (uint64_t*)ctx->gather_out.p; hg.lo = lo;
+            switch (lo.W) {
+                case 1: kb_hgather_kernel<1><<<grid, 256, 0, ctx->stream>>>(hg); break;
+                case 2: kb_hgather_kernel<2><<<grid, 256, 0, ctx->stream>>>(hg); break;
+                case 4: kb_hgather_kernel<4><<<grid, 256, 0, ctx->stream>>>(hg); break;
+                default: kb_hgather_kernel<8><<<grid, 256, 0, ctx->stream>>>(hg); break;
+            }
+            e = cudaGetLastError();
+            ctx->launches++;
+        } else if (e == cudaSuccess) {
             switch (lo.W) {
                 case 1: kb_gather_kernel<1><<<grid, 256, 0, ctx->stream>>>(g); break;
                 case 2: kb_gather_kernel<2><<<grid, 256, 0, ctx->stream>>>(g); break;
@@ -562,6 +755,21 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
     const KbLayout& lo = ctx->lo;
     uint64_t n = 0;
     const uint32_t n_tiles = (uint32_t)((ctx->n_bases + KB_K1_TB - 1) / KB_K1_TB);
+    if (ctx->opt_group_algo) {
+        const PartPlan pl = make_plan(ctx, 2 * ctx->n_bases + 64);
+        TRY(ensure(ctx, ctx->plan, pl.bytes + 64));
+        if (pl.levels) CU(cudaMemsetAsync(ctx->plan.p, 0, pl.bytes, ctx->stream));
+        unsigned long long* h0 = pl.levels ? (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[0]) : nullptr;
+        TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0]));
+        if (!lo.direct && n >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
+        uint64_t* parted = nullptr;
+        HashStage hs{};
+        hs.pl = &pl;
+        TRY(run_partition(ctx, pl, ctx->entA, ctx->entB, n, &parted, &hs.bstart, &hs.n_buckets));
+        int rc = run_group(ctx, parted, n, out, &hs);
+        prof_collect(ctx);
+        return rc;
+    }
     TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n));
     if (!lo.direct && n >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
     uint64_t* sorted = nullptr;

@@ -42,6 +42,8 @@ struct KbExtractArgs {
     unsigned long long* n_out;   // global record counter (claimed per tile)
     uint32_t tile0, n_tiles;     // tiles [tile0, tile0 + n_tiles)
     uint64_t pos_lo, pos_hi;     // only windows starting in [pos_lo, pos_hi) are emitted (one-file tables)
+    unsigned long long* hist;    // != null: histogram of digit (element >> hist_shift) & (2^hist_bits - 1), hist_bits <= 9
+    uint32_t hist_shift, hist_bits;   // (first partition level of kb_part.cuh, fused here to save a read of the elements)
 };
 
 // 4 ASCII bytes (little-endian in x) -> 8 bits of 2-bit codes (first base in the top bits) and 4 "bad" bits
@@ -81,9 +83,13 @@ __global__ void __launch_bounds__(KB_K1_THREADS) kb_extract_kernel(const KbExtra
     uint32_t* pre = okw + NOK;                                           // NOK exclusive popcount prefix
     __shared__ unsigned long long s_base;
     __shared__ int s_flo, s_fhi;
+    __shared__ uint32_t s_hist[512];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t FB = (uint32_t)lo.FB;
+    const bool do_hist = a.hist != nullptr;
+    const uint32_t hmask = (1u << a.hist_bits) - 1u;
+    if (do_hist) for (uint32_t i = tid; i < 512; i += KB_K1_THREADS) s_hist[i] = 0;
 
     for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile0 + a.n_tiles; tile += gridDim.x) {
         const uint64_t tile_base = (uint64_t)tile * KB_K1_TB;
@@ -185,6 +191,10 @@ __global__ void __launch_bounds__(KB_K1_THREADS) kb_extract_kernel(const KbExtra
                     r[st] = v;
                 }
                 kb_st_stream128(a.out_entries + oidx, r[0], r[1]);
+                if (do_hist) {
+                    atomicAdd(&s_hist[(uint32_t)(r[0] >> a.hist_shift) & hmask], 1u);
+                    atomicAdd(&s_hist[(uint32_t)(r[1] >> a.hist_shift) & hmask], 1u);
+                }
             } else {
                 uint64_t ent[2];
 #pragma unroll
@@ -207,7 +217,18 @@ __global__ void __launch_bounds__(KB_K1_THREADS) kb_extract_kernel(const KbExtra
                     ent[st] = (h & 0xFFFFFFFF00000000ULL) | (uint64_t)(uint32_t)(oidx + st);
                 }
                 kb_st_stream128(a.out_entries + oidx, ent[0], ent[1]);
+                if (do_hist) {
+                    atomicAdd(&s_hist[(uint32_t)(ent[0] >> a.hist_shift) & hmask], 1u);
+                    atomicAdd(&s_hist[(uint32_t)(ent[1] >> a.hist_shift) & hmask], 1u);
+                }
             }
+        }
+    }
+    if (do_hist) {
+        __syncthreads();
+        for (uint32_t i = tid; i <= hmask; i += KB_K1_THREADS) {
+            const uint32_t c = s_hist[i];
+            if (c) atomicAdd(a.hist + i, (unsigned long long)c);
         }
     }
 }

@@ -1,0 +1,213 @@
+// kb_part.cuh — K2 (search path): most-significant-digit radix PARTITION of the 64-bit sort elements.
+//
+// The reference sorts every k-mer table with GNU sort (kstream/kstream.py:83-119) only so that the
+// merge can walk equal (left,right) keys together (shared.py:442-475).  The search needs grouping, not
+// order: records are partitioned by the top `bb` bits of the (mixed) flank key / flank hash into 2^bb
+// buckets of a few thousand records, and the group pass (kb_hash.cuh) resolves the complete keys of one
+// bucket in a shared-memory hash table.  bb <= 24 is split into at most three levels of <= 8 bits.
+//
+// One level = ONE read + ONE write of every element, like an LSD onesweep pass, but because no order
+// has to be kept inside a bucket the pass needs neither stable ranking nor a look-back chain:
+//   * rank inside the tile  : shared-memory atomicAdd on 256 digit counters (1 instruction per element
+//                             instead of 8 ballots + counter bookkeeping)
+//   * tile offset per digit : ONE global atomicAdd per (tile, digit) on a cursor initialised with the
+//                             exclusive prefix of the digit histogram (exact, dense output)
+//   * the elements are staged in shared memory in digit order, so every digit's run leaves the CTA as a
+//     contiguous, coalesced store.
+// Level l partitions every bucket ("parent") of level l-1 on its own: tiles never straddle parents, the
+// cursor of (parent p, digit d) is child c = p * 2^bits + d.  Child counts come from kb_part_hist_kernel
+// (level >= 2; level 1 is fused into K1) and are turned into offsets / cursors / tile maps by
+// kb_plan_kernel + kb_tilemap_kernel.
+#pragma once
+#include "kb_common.cuh"
+
+#define KB_PT_THREADS 512
+#define KB_PT_ITEMS 16
+#define KB_PT_TILE (KB_PT_THREADS * KB_PT_ITEMS)
+#define KB_PT_MAXR 512                               // digits of at most 9 bits
+
+struct KbPartArgs {
+    const uint64_t* in;
+    uint64_t* out;
+    const unsigned long long* pstart;   // [n_parents + 1] parent ranges in `in`
+    const uint32_t* ptile0;             // [n_parents + 1] first tile of each parent
+    const uint32_t* tile_parent;        // [tiles]  (ignored when n_parents == 1)
+    uint32_t n_parents;
+    uint32_t shift, bits;               // digit = (e >> shift) & (2^bits - 1)
+    unsigned long long* cursor;         // [n_parents << bits] absolute output offsets, advanced atomically
+    unsigned long long* hist;           // kb_part_hist_kernel: [n_parents << bits] child counts (zeroed)
+};
+
+__device__ __forceinline__ bool kb_part_tile(const KbPartArgs& a, uint32_t tile, uint32_t& parent, uint64_t& s, uint32_t& n_tile) {
+    if (tile >= __ldg(a.ptile0 + a.n_parents)) return false;
+    parent = a.n_parents == 1 ? 0u : __ldg(a.tile_parent + tile);
+    const uint64_t ps = a.pstart[parent], pe = a.pstart[parent + 1];
+    s = ps + (uint64_t)(tile - __ldg(a.ptile0 + parent)) * KB_PT_TILE;
+    n_tile = (uint32_t)min((uint64_t)KB_PT_TILE, pe - s);
+    return true;
+}
+
+// ---- child histogram of one level (reads the previous level's output) ----------------------------
+__global__ void __launch_bounds__(KB_PT_THREADS) kb_part_hist_kernel(const KbPartArgs a) {
+    __shared__ uint32_t cnt[KB_PT_MAXR];
+    const uint32_t tid = threadIdx.x;
+    uint32_t parent, n_tile; uint64_t s;
+    if (!kb_part_tile(a, blockIdx.x, parent, s, n_tile)) return;
+    if (tid < KB_PT_MAXR) cnt[tid] = 0;
+    __syncthreads();
+    const uint32_t dmask = (1u << a.bits) - 1u;
+#pragma unroll 4
+    for (uint32_t i = tid; i < n_tile; i += KB_PT_THREADS) {
+        const uint64_t e = kb_ld_stream(a.in + s + i);
+        atomicAdd(&cnt[(uint32_t)(e >> a.shift) & dmask], 1u);
+    }
+    __syncthreads();
+    if (tid <= dmask) {
+        const uint32_t c = cnt[tid];
+        if (c) atomicAdd(a.hist + (((size_t)parent << a.bits) | tid), (unsigned long long)c);
+    }
+}
+
+// ---- counts -> offsets, cursors, tile prefix (ONE CTA) ----------------------------------------------
+// counts[nc] (u64) -> start[nc + 1] exclusive prefix (+ base), cursor[c] = start[c],
+// tile0[nc + 1] = exclusive prefix of ceil(count / TILE).
+struct KbPlanArgs {
+    const unsigned long long* counts;
+    uint32_t nc;
+    unsigned long long base;            // offset of the first child
+    unsigned long long* start;          // [nc + 1]
+    unsigned long long* cursor;         // [nc] (may be null)
+    uint32_t* tile0;                    // [nc + 1] (may be null)
+    // optional: also fold groups of `fold` consecutive counts into parent counts (level-1 histogram from a
+    // fused finer histogram); null = off
+    unsigned long long* folded; uint32_t fold;
+};
+
+__global__ void __launch_bounds__(1024) kb_plan_kernel(const KbPlanArgs a) {
+    __shared__ unsigned long long ws[32], wt[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (a.nc + 1023u) / 1024u;
+    const uint32_t c0 = min(a.nc, tid * per), c1 = min(a.nc, c0 + per);
+    unsigned long long sum = 0, tsum = 0;
+    for (uint32_t c = c0; c < c1; c++) { const unsigned long long v = a.counts[c]; sum += v; tsum += (v + KB_PT_TILE - 1) / KB_PT_TILE; }
+    unsigned long long x = sum, y = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long ox = __shfl_up_sync(0xFFFFFFFFu, x, d), oy = __shfl_up_sync(0xFFFFFFFFu, y, d);
+        if (lane >= (uint32_t)d) { x += ox; y += oy; }
+    }
+    if (lane == 31) { ws[warp] = x; wt[warp] = y; }
+    __syncthreads();
+    unsigned long long addx = 0, addy = 0;
+    for (uint32_t w = 0; w < warp; w++) { addx += ws[w]; addy += wt[w]; }
+    unsigned long long run = a.base + addx + x - sum, trun = addy + y - tsum;
+    for (uint32_t c = c0; c < c1; c++) {
+        const unsigned long long v = a.counts[c];
+        a.start[c] = run;
+        if (a.cursor) a.cursor[c] = run;
+        if (a.tile0) a.tile0[c] = (uint32_t)trun;
+        run += v; trun += (v + KB_PT_TILE - 1) / KB_PT_TILE;
+    }
+    if (tid == 1023) {
+        a.start[a.nc] = run;
+        if (a.tile0) a.tile0[a.nc] = (uint32_t)trun;
+    }
+    if (a.folded) {
+        for (uint32_t p = tid; p < a.nc / a.fold; p += 1024) {
+            unsigned long long s = 0;
+            for (uint32_t j = 0; j < a.fold; j++) s += a.counts[(size_t)p * a.fold + j];
+            a.folded[p] = s;
+        }
+    }
+}
+
+// tile -> parent map: one warp per parent
+__global__ void __launch_bounds__(256) kb_tilemap_kernel(const uint32_t* tile0, uint32_t n_parents, uint32_t* tile_parent) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t p = blockIdx.x * 8 + (threadIdx.x >> 5); p < n_parents; p += gridDim.x * 8) {
+        const uint32_t t0 = tile0[p], t1 = tile0[p + 1];
+        for (uint32_t t = t0 + lane; t < t1; t += 32) tile_parent[t] = p;
+    }
+}
+
+// ---- one partition level -------------------------------------------------------------------------------
+template <int MINB>
+__global__ void __launch_bounds__(KB_PT_THREADS, MINB) kb_part_kernel(const KbPartArgs a) {
+    extern __shared__ __align__(16) unsigned char kb_smem_raw[];
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(kb_smem_raw);                   // TILE
+    uint64_t* dbase = skeys + KB_PT_TILE;                                         // MAXR: global offset - local start
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(dbase + KB_PT_MAXR);              // MAXR: digit counters, then local starts
+    uint32_t* wsum = cnt + KB_PT_MAXR;                                            // MAXR / 32
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t parent, n_tile; uint64_t s;
+    if (!kb_part_tile(a, blockIdx.x, parent, s, n_tile)) return;
+    if (tid < KB_PT_MAXR) cnt[tid] = 0;
+    __syncthreads();
+
+    const uint32_t dmask = (1u << a.bits) - 1u;
+    uint64_t key[KB_PT_ITEMS];
+    uint16_t rank[KB_PT_ITEMS];
+    if (n_tile == KB_PT_TILE) {
+#pragma unroll
+        for (int i = 0; i < KB_PT_ITEMS; i++) key[i] = kb_ld_stream(a.in + s + i * KB_PT_THREADS + tid);
+#pragma unroll
+        for (int i = 0; i < KB_PT_ITEMS; i++) rank[i] = (uint16_t)atomicAdd(&cnt[(uint32_t)(key[i] >> a.shift) & dmask], 1u);
+    } else {
+#pragma unroll
+        for (int i = 0; i < KB_PT_ITEMS; i++) {
+            const uint32_t idx = i * KB_PT_THREADS + tid;
+            key[i] = idx < n_tile ? kb_ld_stream(a.in + s + idx) : 0ULL;
+        }
+#pragma unroll
+        for (int i = 0; i < KB_PT_ITEMS; i++) {
+            const uint32_t idx = i * KB_PT_THREADS + tid;
+            rank[i] = idx < n_tile ? (uint16_t)atomicAdd(&cnt[(uint32_t)(key[i] >> a.shift) & dmask], 1u) : (uint16_t)0;
+        }
+    }
+    __syncthreads();
+
+    // ---- per digit: claim the output range (global cursor), local start -----------------------------
+    uint32_t c = 0, lstart = 0;
+    unsigned long long g = 0;
+    if (tid < KB_PT_MAXR) {
+        c = cnt[tid];
+        if (c) g = atomicAdd(a.cursor + (((size_t)parent << a.bits) | tid), (unsigned long long)c);
+    }
+    {
+        uint32_t x = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (uint32_t)d) x += y; }
+        if (tid < KB_PT_MAXR && lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (tid < KB_PT_MAXR) {
+            uint32_t add = 0;
+            for (uint32_t w = 0; w < warp; w++) add += wsum[w];
+            lstart = add + x - c;
+            cnt[tid] = lstart;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage in digit order ------------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < KB_PT_ITEMS; i++) {
+        const uint32_t idx = i * KB_PT_THREADS + tid;
+        if (n_tile == KB_PT_TILE || idx < n_tile) skeys[cnt[(uint32_t)(key[i] >> a.shift) & dmask] + rank[i]] = key[i];
+    }
+    if (tid < KB_PT_MAXR) dbase[tid] = g - (unsigned long long)lstart;
+    __syncthreads();
+
+    // ---- coalesced store ------------------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < KB_PT_ITEMS; i++) {
+        const uint32_t pos = i * KB_PT_THREADS + tid;
+        if (n_tile == KB_PT_TILE || pos < n_tile) {
+            const uint64_t kv = skeys[pos];
+            a.out[dbase[(uint32_t)(kv >> a.shift) & dmask] + pos] = kv;
+        }
+    }
+}
+
+static inline size_t kb_part_smem() { return (size_t)KB_PT_TILE * 8 + KB_PT_MAXR * 8 + KB_PT_MAXR * 4 + (KB_PT_MAXR / 32) * 4 + 16; }
+static_assert(KB_PT_THREADS >= KB_PT_MAXR, "one thread per digit");

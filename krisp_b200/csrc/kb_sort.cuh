@@ -118,12 +118,18 @@ __device__ __forceinline__ void kb_st_relaxed(unsigned long long* p, unsigned lo
 template <bool HWMATCH>
 __device__ __forceinline__ uint32_t kb_match_digit(uint32_t d) {
     if constexpr (HWMATCH) return __match_any_sync(0xFFFFFFFFu, d);
+    // one ballot per digit bit; a lane keeps the ballot if its own bit is set, the complement otherwise
     uint32_t peers = 0xFFFFFFFFu;
 #pragma unroll
     for (int b = 0; b < KB_RADIX_BITS; b++) {
-        const bool bit = (d >> b) & 1u;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
-        peers &= bit ? m : ~m;
+        uint32_t m;
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                     "and.b32 t, %1, %2;\n\t"
+                     "setp.ne.u32 p, t, 0;\n\t"
+                     "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+                     "@!p not.b32 %0, %0;\n\t}"
+                     : "=r"(m) : "r"(d), "r"(1u << b));
+        peers &= m;
     }
     return peers;
 }

@@ -40,29 +40,74 @@ def test_prefix_sort_is_exact(name, sort_bits, searcher):
     case = next(c for c in _G["cases"] if c["name"] == name)
     ins, outs = golden_paths(case)
     L, D, R = deduce_ldr(case["flags"])
-    res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher,
-                       options={"sort_bits": sort_bits})
-    searcher.set_option("sort_bits", 32)
+    try:
+        res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher,
+                           options={"sort_bits": sort_bits, "group_algo": 0})
+    finally:
+        searcher.set_option("sort_bits", 32)
+        searcher.set_option("group_algo", 1)
     assert res.rows() == case["rows"]
     if sort_bits == 8:
         assert res.stats["mixed_runs"] > 0
 
 
+@pytest.mark.parametrize("algo", [0, 1], ids=["sorted", "hash"])
 @pytest.mark.parametrize("name", ["c1_spacer_25_1_2", "p_spacer_4x5", "p_6_1_2", "p_0_2_6", "p_8_0_8", "c1_no_outgroup", "c1_single_file"])
-def test_generic_group_kernel_matches_too(name, searcher):
-    """The warp-per-run kernel (used for multi-word records, > 64 files, D > 8) on shapes the fast path normally takes."""
+def test_generic_group_kernel_matches_too(name, algo, searcher):
+    """The generic kernels (used for multi-word records, > 64 files, D > 8) on shapes the fast paths normally take."""
     import hashlib as _h
     from krisp_b200.search import search_files
     case = next(c for c in _G["cases"] if c["name"] == name)
     ins, outs = golden_paths(case)
     L, D, R = deduce_ldr(case["flags"])
     try:
-        res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher, options={"fast_group": 0})
+        res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher,
+                           options={"fast_group": 0, "group_algo": algo})
     finally:
         searcher.set_option("fast_group", 1)
+        searcher.set_option("group_algo", 1)
     rows = res.rows()
     assert len(rows) == case["n_rows"]
     assert _h.sha256("\n".join(rows).encode()).hexdigest() == case["rows_sha256"]
+
+
+@pytest.mark.parametrize("every", _G["cases"], ids=[c["name"] for c in _G["cases"]])
+def test_sorted_path_matches_reference_golden(every, searcher):
+    """The radix-sort + segmented-pass path (group_algo 0) on every golden case."""
+    from krisp_b200.search import search_files
+    ins, outs = golden_paths(every)
+    L, D, R = deduce_ldr(every["flags"])
+    try:
+        res = search_files(ins, outs, L, D, R, omit_soft=every["omit_soft"], searcher=searcher, options={"group_algo": 0})
+    finally:
+        searcher.set_option("group_algo", 1)
+    rows = res.rows()
+    assert len(rows) == every["n_rows"]
+    assert hashlib.sha256("\n".join(rows).encode()).hexdigest() == every["rows_sha256"]
+
+
+@pytest.mark.parametrize("fast", [1, 0], ids=["fast", "generic"])
+@pytest.mark.parametrize("bucket_bits,slots", [(0, 4), (0, 0), (3, 5), (10, 6), (17, 0), (24, 4)])
+@pytest.mark.parametrize("name", ["c1_spacer_25_1_2", "p_spacer_3x3", "p_primer_3x3", "p_5_2_3", "p_30_40_30", "p_6_1_2", "c1_single_file"])
+def test_bucket_hash_is_exact_for_any_bucket_and_table_size(name, bucket_bits, slots, fast, searcher):
+    """Partition depth (0-3 levels) and hash-table size only change the work split: tiny tables force buckets to be
+    split by further hash bits and streamed once per part; the rows must not change."""
+    from krisp_b200.search import search_files
+    case = next(c for c in _G["cases"] if c["name"] == name)
+    ins, outs = golden_paths(case)
+    L, D, R = deduce_ldr(case["flags"])
+    try:
+        res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher,
+                           options={"bucket_bits": bucket_bits, "hash_slots_log2": slots, "fast_group": fast})
+    finally:
+        searcher.set_option("bucket_bits", -1)
+        searcher.set_option("hash_slots_log2", 0)
+        searcher.set_option("fast_group", 1)
+    rows = res.rows()
+    assert len(rows) == case["n_rows"]
+    assert hashlib.sha256("\n".join(rows).encode()).hexdigest() == case["rows_sha256"]
+    if bucket_bits == 0 and slots == 4:
+        assert res.stats["mixed_runs"] > 0          # = bucket splits
 
 
 _TABLES = _G["tables"]
@@ -118,3 +163,66 @@ def test_cli_csv_and_out_align_match_reference(case, capsys, tmp_path):
     assert out[0] == "left_seq,diag_seq,right_seq"
     assert sorted(out[1:]) == case["rows"]
     assert ap.read_text() == case["out_align"]
+
+
+def _search_panel(searcher, genomes, L, D, R, omit_soft=False, options=None, want_records=False):
+    """The panel's genomes straight from memory (K1 ingest layout) through one Searcher."""
+    searcher.configure(L, D, R, [1 if g.is_ingroup else 0 for g in genomes], omit_soft)
+    searcher.set_option("want_records", 1 if want_records else 0)
+    for k, v in (options or {}).items():
+        searcher.set_option(k, v)
+    searcher.clear_sequences()
+    for i, g in enumerate(genomes):
+        searcher.add_sequence(i, np.frombuffer(g.joined(), dtype=np.uint8))
+    return searcher.search(have_outgroup=any(not g.is_ingroup for g in genomes))
+
+
+def _oracle_panel(genomes, L, D, R, omit_soft=False):
+    from oracle import oracle
+    recs = [[r.tobytes() for r in g.records] for g in genomes]
+    rows, _ = oracle.search_records(recs, [g.name for g in genomes], {g.name for g in genomes if g.is_ingroup},
+                                    any(not g.is_ingroup for g in genomes), L, D, R, omit_soft)
+    return rows
+
+
+@pytest.mark.parametrize("algo", [1, 0], ids=["hash", "sorted"])
+@pytest.mark.parametrize("shape", [(6, 6, 300_000, 25, 1, 2, False), (6, 6, 300_000, 25, 1, 2, True), (5, 4, 200_000, 32, 60, 32, False),
+                                   (3, 3, 400_000, 12, 3, 12, False), (20, 20, 100_000, 25, 1, 2, False), (40, 40, 20_000, 10, 4, 10, False)],
+                         ids=["spacer", "spacer_omit", "primer", "12_3_12", "bench_shape_small", "80_files"])
+def test_seeded_panel_matches_oracle(shape, algo, searcher):
+    """Seeded synthetic panels (bench.py's generator) at sizes the C oracle finishes in seconds:
+    multi-level partitions, Ns, soft-masking, duplicated segments, > 64 files."""
+    from krisp_b200.panel import make_panel
+    n_in, n_out, glen, L, D, R, omit = shape
+    gs = make_panel(n_in, n_out, glen)
+    try:
+        res = _search_panel(searcher, gs, L, D, R, omit, options={"group_algo": algo})
+    finally:
+        searcher.set_option("group_algo", 1)
+    want = _oracle_panel(gs, L, D, R, omit)
+    assert len(want) > 0
+    assert res.rows() == want
+
+
+def test_group_sizes_and_gather_agree_with_sorted_path(searcher):
+    """--out_align inputs: the bucket-hash path's group sizes and gathered records equal the sorted path's."""
+    from krisp_b200.panel import make_panel
+    gs = make_panel(4, 4, 150_000)
+    out = []
+    for algo in (1, 0):
+        try:
+            res = _search_panel(searcher, gs, 25, 1, 2, options={"group_algo": algo}, want_records=True)
+        finally:
+            searcher.set_option("group_algo", 1)
+            searcher.set_option("want_records", 0)
+        FB = 2 * 27
+        per_group = {}
+        for g in range(res.n_groups):
+            a, b = int(res.run_offset[g]), int(res.run_offset[g + 1])
+            recs = res.records[a:b, 0]
+            fw = res.flank_words[g, 0]
+            mine = np.sort(recs[(recs >> np.uint64(64 - FB)) == (fw >> np.uint64(64 - FB))])
+            per_group[int(fw)] = (int(res.group_size[g]), mine.tobytes())
+            assert int(res.group_size[g]) == mine.size
+        out.append(per_group)
+    assert out[0] == out[1] and len(out[0]) > 0
