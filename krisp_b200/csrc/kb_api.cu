@@ -543,7 +543,7 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
     const KbLayout& lo = g.lo;
     KbHashArgs x{};
     x.g = g;
-    x.bstart = hs.bstart; x.n_buckets = hs.n_buckets; x.slots_log2 = hs.pl->slots_log2;
+    x.bstart = hs.bstart; x.n_buckets = hs.n_buckets; x.slots_log2 = hs.pl->slots_log2; x.bb = (uint32_t)hs.pl->bb;
     x.ingroup64 = (uint64_t)g.ingroup[0] | ((uint64_t)g.ingroup[1] << 32);
     x.full64 = (uint64_t)g.full[0] | ((uint64_t)g.full[1] << 32);
     x.err = (unsigned long long*)ctx->small.p + SM_ERR;
@@ -637,7 +637,8 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
     res->v.n_records = n;
     uint64_t n_res = 0;
     if (n > 0) {
-        if (ctx->result_cap == 0) { int rc = ensure_results(ctx, (uint64_t)ctx->opt_result_cap); if (rc) { delete res; return rc; } }
+        // (re)size for the current layout: the buffers only grow, so this is a no-op unless the configuration got wider
+        { int rc = ensure_results(ctx, std::max<uint64_t>(ctx->result_cap, (uint64_t)ctx->opt_result_cap)); if (rc) { delete res; return rc; } }
         bool allow_fast = true;
         for (int attempt = 0; attempt < 4; attempt++) {
             KbGroupArgs a{};

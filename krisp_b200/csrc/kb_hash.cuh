@@ -22,38 +22,49 @@
 #define KB_KH_THREADS 256
 #define KB_KH_STACK 48
 #define KB_KH_EMPTY 0xFFFFFFFFFFFFFFFFULL     // DIRECT keys have at most 56 bits
-#define KB_KH_SUBSHIFT 12                     // split bits = hh >> 12 (slot index = low bits, slots <= 4096)
+#define KB_KH_NONE 0xFFFFFFFFu
+#define KB_KH_MAXSPLIT 20
 
 struct KbHashArgs {
     KbGroupArgs g;                       // ent = partitioned elements; results; stats
     const unsigned long long* bstart;    // [n_buckets + 1]
     uint32_t n_buckets;
+    uint32_t bb;                         // bucket bits: every element of a bucket has the same top bb bits
     uint32_t slots_log2;
     uint64_t ingroup64, full64;          // fast kernel (<= 64 files)
     unsigned long long* err;             // != 0: a bucket could not be resolved
 };
 
-__device__ __forceinline__ uint32_t kb_kh_hash_direct(uint64_t key) { return (uint32_t)((key * KB_MIX_C1) >> 32); }
-__device__ __forceinline__ uint32_t kb_kh_hash_indirect(uint64_t e) { return (uint32_t)(e >> 32) * 0x9E3779B1u; }
+// The 32 key (or flank-hash) bits right below the bucket bits, left-aligned.  Mixed keys (kb_mix) and flank
+// hashes are uniform there, so these bits index the table directly: the first `nb` bits select the part of a
+// split bucket, the next slots_log2 bits the home slot.
+__device__ __forceinline__ uint32_t kb_kh_bits(uint64_t e, uint32_t bb, uint32_t hmask) { return (uint32_t)((e << bb) >> 32) & hmask; }
+__device__ __forceinline__ uint32_t kb_kh_hmask(uint32_t keybits, uint32_t bb) {
+    const uint32_t rem = keybits - bb;
+    return rem >= 32 ? 0xFFFFFFFFu : (rem == 0 ? 0u : (0xFFFFFFFFu << (32 - rem)));
+}
+__device__ __forceinline__ uint32_t kb_kh_part(uint32_t hh, uint32_t nb) { return nb ? (hh >> (32 - nb)) : 0u; }
+__device__ __forceinline__ uint32_t kb_kh_slot(uint32_t hh, uint32_t nb, uint32_t slots_log2) { return (hh << nb) >> (32 - slots_log2); }
 
 __device__ __forceinline__ uint32_t kb_ld_shared_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 
 // work-stack bookkeeping shared by both kernels (thread 0 between barriers)
 struct KbKhCtl {
     uint32_t sp, over, nkeys, nsurv;
-    uint32_t stack[KB_KH_STACK];         // residue (24 bits) | nbits << 24
+    uint32_t stack[KB_KH_STACK];         // part (24 bits) | nbits << 24
 };
 
 // ===== fast kernel: one-word records, <= 64 files, D <= 8 ================================================
+// slot (24 bytes): key u64 | files 0-31 | files 32-63 | ingroup column sets | outgroup column sets
+struct KbKhSlot { unsigned long long key; uint32_t pres[2]; uint32_t msk[2]; };
+
 template <bool D1>
 __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_fast_kernel(const KbHashArgs x) {
     extern __shared__ __align__(16) unsigned char kb_smem_raw[];
     const KbGroupArgs& a = x.g;
     const KbLayout& lo = a.lo;
     const uint32_t S = 1u << x.slots_log2, smask = S - 1u;
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(kb_smem_raw);   // S
-    uint32_t* pres = reinterpret_cast<uint32_t*>(keys + S);                           // 2S: files 0-31, 32-63 (later: count, mark)
-    uint32_t* msk = pres + 2 * S;                                                     // 2S: ingroup, outgroup column sets
+    KbKhSlot* tab = reinterpret_cast<KbKhSlot*>(kb_smem_raw);
     __shared__ KbKhCtl ctl;
     __shared__ uint32_t s_closed, s_present, s_rounds, s_splits;
 
@@ -63,7 +74,29 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_fast_kernel(const KbHas
     const uint32_t mshift = 64 - lo.FB - D2;
     const uint32_t colmask = lo.D ? (0xFFFFFFFFu << (4 * (8 - lo.D))) : 0u;
     const uint32_t limit = S - (S >> 2);
+    const uint32_t hmask = kb_kh_hmask((uint32_t)lo.FB, x.bb);
+    const uint32_t ing_lo = (uint32_t)x.ingroup64, ing_hi = (uint32_t)(x.ingroup64 >> 32);
     if (tid == 0) { s_closed = 0; s_present = 0; s_rounds = 0; s_splits = 0; }
+
+    // rest of the probe sequence after the home slot missed: find the key or claim an empty slot
+    auto probe = [&](uint64_t key, uint32_t slot, bool insert) -> uint32_t {
+        for (uint32_t step = 0; step <= S; step++) {
+            const unsigned long long k = tab[slot].key;
+            if (k == key) return slot;
+            if (k == KB_KH_EMPTY) {
+                if (!insert) return KB_KH_NONE;
+                const unsigned long long old = atomicCAS(&tab[slot].key, KB_KH_EMPTY, (unsigned long long)key);
+                if (old == KB_KH_EMPTY) {
+                    if (atomicAdd(&ctl.nkeys, 1u) >= limit) ctl.over = 1;
+                    return slot;
+                }
+                if (old == key) return slot;
+            }
+            slot = (slot + 1) & smask;
+        }
+        ctl.over = 1;
+        return KB_KH_NONE;
+    };
 
     for (uint32_t b = blockIdx.x; b < x.n_buckets; b += gridDim.x) {
         const uint64_t bs = x.bstart[b], be = x.bstart[b + 1];
@@ -76,125 +109,107 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_fast_kernel(const KbHas
             if (sp == 0) break;
             const uint32_t item = ctl.stack[sp - 1];
             __syncthreads();
-            const uint32_t res = item & 0xFFFFFFu, nb = item >> 24, rmask = (1u << nb) - 1u;
+            const uint32_t part = item & 0xFFFFFFu, nb = item >> 24;
             if (tid == 0) { ctl.sp = sp - 1; ctl.over = 0; ctl.nkeys = 0; ctl.nsurv = 0; s_rounds++; }
-            for (uint32_t i = tid; i < S; i += KB_KH_THREADS) { keys[i] = KB_KH_EMPTY; pres[2 * i] = 0; pres[2 * i + 1] = 0; msk[2 * i] = 0; msk[2 * i + 1] = 0; }
+            for (uint32_t i = tid; i < S; i += KB_KH_THREADS) { tab[i].key = KB_KH_EMPTY; tab[i].pres[0] = 0; tab[i].pres[1] = 0; tab[i].msk[0] = 0; tab[i].msk[1] = 0; }
             __syncthreads();
 
-            // ---- stream the bucket through the table ---------------------------------------------------
-            auto find_or_insert = [&](uint64_t key, uint32_t hh, bool insert) -> uint32_t {
-                uint32_t slot = hh & smask;
-                for (uint32_t step = 0; step <= S; step++) {
-                    const unsigned long long k = keys[slot];
-                    if (k == key) return slot;
-                    if (k == KB_KH_EMPTY) {
-                        if (!insert) return 0xFFFFFFFFu;
-                        const unsigned long long old = atomicCAS(&keys[slot], KB_KH_EMPTY, (unsigned long long)key);
-                        if (old == KB_KH_EMPTY) {
-                            if (atomicAdd(&ctl.nkeys, 1u) >= limit) ctl.over = 1;
-                            return slot;
-                        }
-                        if (old == key) return slot;
-                    }
-                    slot = (slot + 1) & smask;
-                }
-                ctl.over = 1;
-                return 0xFFFFFFFFu;
-            };
+            // ---- stream the bucket through the table (4 coalesced loads in flight per thread) ---------------
             for (uint64_t i0 = bs; i0 < be; i0 += 4 * KB_KH_THREADS) {
+                const uint32_t left = (uint32_t)min((uint64_t)(4 * KB_KH_THREADS), be - i0);
                 uint64_t r[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint64_t i = i0 + u * KB_KH_THREADS + tid;
-                    r[u] = i < be ? kb_ld_stream(a.ent + i) : 0ULL;
-                }
+                for (int u = 0; u < 4; u++) r[u] = (u * KB_KH_THREADS + tid < left) ? kb_ld_stream(a.ent + i0 + u * KB_KH_THREADS + tid) : 0ULL;
                 if (kb_ld_shared_volatile(&ctl.over)) break;
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const uint64_t i = i0 + u * KB_KH_THREADS + tid;
-                    if (i >= be) continue;
                     const uint64_t e = r[u];
                     const uint64_t key = e >> kshift;
-                    const uint32_t hh = kb_kh_hash_direct(key);
-                    if (((hh >> KB_KH_SUBSHIFT) & rmask) != res) continue;
-                    const uint32_t slot = find_or_insert(key, hh, true);
-                    if (slot == 0xFFFFFFFFu) continue;
-                    const uint32_t id = (uint32_t)e & 0xFFu;
-                    atomicOr(&pres[2 * slot + (id >> 5)], 1u << (id & 31));
-                    if (D2) {
-                        uint32_t oh;
-                        if (D1) oh = 0x10000000u << ((uint32_t)(e >> mshift) & 3u);
-                        else oh = kb_onehot8(((uint32_t)(e >> mshift) & ((1u << D2) - 1u)) << (16 - D2)) & colmask;
-                        uint32_t* p = &msk[2 * slot + (((x.ingroup64 >> id) & 1ULL) ? 0 : 1)];
-                        if ((kb_ld_shared_volatile(p) & oh) != oh) atomicOr(p, oh);
+                    const uint32_t hh = kb_kh_bits(e, x.bb, hmask);
+                    const bool act = (u * KB_KH_THREADS + tid < left) && kb_kh_part(hh, nb) == part;
+                    uint32_t slot = kb_kh_slot(hh, nb, x.slots_log2);
+                    bool found = false;
+                    if (act) found = tab[slot].key == key;                   // the common case: the key sits in its home slot
+                    if (act && !found) { slot = probe(key, slot, true); found = slot != KB_KH_NONE; }
+                    __syncwarp();                                            // reconverge before the accumulation
+                    if (found) {
+                        const uint32_t id = (uint32_t)e & 0xFFu;
+                        atomicOr(&tab[slot].pres[id >> 5], 1u << (id & 31));
+                        if (D2) {
+                            uint32_t oh;
+                            if (D1) oh = 0x10000000u << ((uint32_t)(e >> mshift) & 3u);
+                            else oh = kb_onehot8(((uint32_t)(e >> mshift) & ((1u << D2) - 1u)) << (16 - D2)) & colmask;
+                            const uint32_t isin = (((id & 32u) ? ing_hi : ing_lo) >> (id & 31)) & 1u;
+                            uint32_t* p = &tab[slot].msk[isin ^ 1u];
+                            if ((kb_ld_shared_volatile(p) & oh) != oh) atomicOr(p, oh);
+                        }
                     }
                 }
             }
             __syncthreads();
-            if (ctl.over) {                                   // too many distinct keys: split this part by one more hash bit
+            if (ctl.over) {                                   // too many distinct keys: split this part by one more bit
                 __syncthreads();
                 if (tid == 0) {
                     s_splits++;
-                    if (nb >= 20 || ctl.sp + 2 > KB_KH_STACK) atomicExch(x.err, 1ULL);
-                    else { ctl.stack[ctl.sp] = res | ((nb + 1) << 24); ctl.stack[ctl.sp + 1] = (res | (1u << nb)) | ((nb + 1) << 24); ctl.sp += 2; }
+                    if (nb >= KB_KH_MAXSPLIT || ctl.sp + 2 > KB_KH_STACK) atomicExch(x.err, 1ULL);
+                    else { ctl.stack[ctl.sp] = (part << 1) | ((nb + 1) << 24); ctl.stack[ctl.sp + 1] = ((part << 1) | 1u) | ((nb + 1) << 24); ctl.sp += 2; }
                 }
                 __syncthreads();
                 continue;
             }
 
-            // ---- scan the table: S6 / S7, emit survivors -----------------------------------------------------
+            // ---- scan the table: S6 / S7, emit survivors; afterwards pres[0] = record count, pres[1] = mark ----
             uint32_t n_closed = 0, n_present = 0, any = 0;
             for (uint32_t slot = tid; slot < S; slot += KB_KH_THREADS) {
-                const unsigned long long k = keys[slot];
+                const unsigned long long k = tab[slot].key;
+                if (k == KB_KH_EMPTY) continue;
                 uint32_t mark = 0;
-                if (k != KB_KH_EMPTY) {
-                    n_closed++;
-                    const uint64_t P = (uint64_t)pres[2 * slot] | ((uint64_t)pres[2 * slot + 1] << 32);
-                    if (P == x.full64) {
-                        n_present++;
-                        const uint32_t in = msk[2 * slot], out = msk[2 * slot + 1];
-                        bool ok = true;
-                        if (lo.D) {
-                            uint32_t y = in & out;
-                            y |= y >> 1; y |= y >> 2;
-                            ok = (~y & 0x11111111u & colmask) != 0;
-                        }
-                        if (ok) {
-                            const unsigned long long gs = atomicAdd(a.n_res, 1ULL);
-                            any = 1;
-                            if (gs < a.cap) {
-                                uint64_t kk = k;
-                                if (lo.mix) kk = kb_unmix(kk, lo.FB, lo.shs);
-                                a.res_flank[gs] = kk << kshift;
-                                if (lo.MW) { a.res_in[gs] = in; a.res_out[gs] = out; }
-                                a.res_run[2 * gs] = bs;
-                                a.res_run[2 * gs + 1] = be - bs;
-                                mark = (uint32_t)gs + 1u;
-                            }
+                n_closed++;
+                const uint64_t P = (uint64_t)tab[slot].pres[0] | ((uint64_t)tab[slot].pres[1] << 32);
+                if (P == x.full64) {
+                    n_present++;
+                    const uint32_t in = tab[slot].msk[0], out = tab[slot].msk[1];
+                    bool ok = true;
+                    if (lo.D) {
+                        uint32_t y = in & out;
+                        y |= y >> 1; y |= y >> 2;
+                        ok = (~y & 0x11111111u & colmask) != 0;
+                    }
+                    if (ok) {
+                        const unsigned long long gs = atomicAdd(a.n_res, 1ULL);
+                        any = 1;
+                        if (gs < a.cap) {
+                            uint64_t kk = k;
+                            if (lo.mix) kk = kb_unmix(kk, lo.FB, lo.shs);
+                            a.res_flank[gs] = kk << kshift;
+                            if (lo.MW) { a.res_in[gs] = in; a.res_out[gs] = out; }
+                            a.res_run[2 * gs] = bs;
+                            a.res_run[2 * gs + 1] = be - bs;
+                            mark = (uint32_t)gs + 1u;
                         }
                     }
-                    pres[2 * slot] = 0; pres[2 * slot + 1] = mark;
                 }
+                tab[slot].pres[0] = 0; tab[slot].pres[1] = mark;
             }
             if (any) ctl.nsurv = 1;
             if (n_closed) atomicAdd(&s_closed, n_closed);
             if (n_present) atomicAdd(&s_present, n_present);
             __syncthreads();
 
-            // ---- survivors' group sizes: second stream of the bucket ------------------------------------------
+            // ---- survivors' group sizes: second stream of the bucket (L2) ---------------------------------------
             if (ctl.nsurv) {
                 for (uint64_t i = bs + tid; i < be; i += KB_KH_THREADS) {
                     const uint64_t e = a.ent[i];
                     const uint64_t key = e >> kshift;
-                    const uint32_t hh = kb_kh_hash_direct(key);
-                    if (((hh >> KB_KH_SUBSHIFT) & rmask) != res) continue;
-                    const uint32_t slot = find_or_insert(key, hh, false);
-                    if (slot != 0xFFFFFFFFu && pres[2 * slot + 1]) atomicAdd(&pres[2 * slot], 1u);
+                    const uint32_t hh = kb_kh_bits(e, x.bb, hmask);
+                    if (kb_kh_part(hh, nb) != part) continue;
+                    const uint32_t slot = probe(key, kb_kh_slot(hh, nb, x.slots_log2), false);
+                    if (slot != KB_KH_NONE && tab[slot].pres[1]) atomicAdd(&tab[slot].pres[0], 1u);
                 }
                 __syncthreads();
                 for (uint32_t slot = tid; slot < S; slot += KB_KH_THREADS) {
-                    const uint32_t mark = keys[slot] != KB_KH_EMPTY ? pres[2 * slot + 1] : 0u;
-                    if (mark) a.res_size[mark - 1] = pres[2 * slot];
+                    const uint32_t mark = tab[slot].key != KB_KH_EMPTY ? tab[slot].pres[1] : 0u;
+                    if (mark) a.res_size[mark - 1] = tab[slot].pres[0];
                 }
             }
             __syncthreads();
@@ -209,13 +224,13 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_fast_kernel(const KbHas
     }
 }
 
-static inline size_t kb_hash_fast_smem(uint32_t slots_log2) { return ((size_t)1 << slots_log2) * (8 + 8 + 8) + 16; }
+static inline size_t kb_hash_fast_smem(uint32_t slots_log2) { return ((size_t)1 << slots_log2) * sizeof(KbKhSlot) + 16; }
 
 // ===== generic kernel: any record width, up to 256 files, D <= 128 ====================================
-// Slot = tag (0 empty, 1 being written, else 0x80000000 | hash) + FW key words + PW presence words +
-// MW ingroup + MW outgroup mask words.  A slot is claimed by CAS on the tag; the winner writes the key
-// words and publishes the tag inside the same loop iteration, readers retry while the tag says "being
-// written" (no thread ever spins inside a critical section).
+// Slot = tag (0 empty, 1 being written, else 0x80000000 | key bits) + FW key words + PW presence words +
+// MW ingroup + MW outgroup mask words + 2 words (survivor's record count, mark).  A slot is claimed by CAS
+// on the tag; the winner writes the key words and publishes the tag inside the same loop iteration, readers
+// retry while the tag says "being written" (no thread ever waits inside a critical section).
 #define KB_KH_TAG_EMPTY 0u
 #define KB_KH_TAG_BUSY 1u
 
@@ -240,17 +255,38 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_kernel(const KbHashArgs
 
     const uint32_t tid = threadIdx.x;
     const uint32_t limit = S - (S >> 2);
+    const uint32_t hmask = kb_kh_hmask(WN == 1 ? (uint32_t)lo.FB : 32u, x.bb);
     if (tid == 0) { s_closed = 0; s_present = 0; s_rounds = 0; s_splits = 0; }
 
-    auto hash_of = [&](uint64_t e, const KbKey<WN>& key) -> uint32_t {
-        if constexpr (WN == 1) return kb_kh_hash_direct(key.w[0]);
-        else return kb_kh_hash_indirect(e);
-    };
     auto key_matches = [&](uint32_t slot, const KbKey<WN>& key) -> bool {
         bool eq = true;
 #pragma unroll
         for (int j = 0; j < WN; j++) if (j < FW) eq = eq && (keys[(size_t)slot * FW + j] == key.w[j]);
         return eq;
+    };
+    auto find_or_insert = [&](const KbKey<WN>& key, uint32_t hh, uint32_t slot, bool insert) -> uint32_t {
+        const uint32_t want = 0x80000000u | hh;
+        uint32_t step = 0;
+        while (step <= S) {
+            const uint32_t t = kb_ld_shared_volatile(&tags[slot]);
+            if (t == KB_KH_TAG_EMPTY) {
+                if (!insert) return KB_KH_NONE;
+                if (atomicCAS(&tags[slot], KB_KH_TAG_EMPTY, KB_KH_TAG_BUSY) == KB_KH_TAG_EMPTY) {
+#pragma unroll
+                    for (int j = 0; j < WN; j++) if (j < FW) keys[(size_t)slot * FW + j] = key.w[j];
+                    __threadfence_block();
+                    *reinterpret_cast<volatile uint32_t*>(&tags[slot]) = want;
+                    if (atomicAdd(&ctl.nkeys, 1u) >= limit) ctl.over = 1;
+                    return slot;
+                }
+                continue;                                  // lost the race: look at the same slot again
+            }
+            if (t == KB_KH_TAG_BUSY) continue;             // being written by another thread
+            if (t == want) { __threadfence_block(); if (key_matches(slot, key)) return slot; }
+            slot = (slot + 1) & smask; step++;
+        }
+        ctl.over = 1;
+        return KB_KH_NONE;
     };
 
     for (uint32_t b = blockIdx.x; b < x.n_buckets; b += gridDim.x) {
@@ -264,59 +300,39 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_kernel(const KbHashArgs
             if (sp == 0) break;
             const uint32_t item = ctl.stack[sp - 1];
             __syncthreads();
-            const uint32_t res = item & 0xFFFFFFu, nb = item >> 24, rmask = (1u << nb) - 1u;
+            const uint32_t part = item & 0xFFFFFFu, nb = item >> 24;
             if (tid == 0) { ctl.sp = sp - 1; ctl.over = 0; ctl.nkeys = 0; ctl.nsurv = 0; s_rounds++; }
             for (uint32_t i = tid; i < S; i += KB_KH_THREADS) tags[i] = KB_KH_TAG_EMPTY;
             for (uint32_t i = tid; i < S * (uint32_t)(2 + PW + 2 * MW); i += KB_KH_THREADS) aux[i] = 0;   // aux, pres, min_, mout are contiguous
             __syncthreads();
 
-            auto find_or_insert = [&](const KbKey<WN>& key, uint32_t hh, bool insert) -> uint32_t {
-                const uint32_t want = 0x80000000u | hh;
-                uint32_t slot = hh & smask;
-                uint32_t step = 0;
-                while (step <= S) {
-                    const uint32_t t = kb_ld_shared_volatile(&tags[slot]);
-                    if (t == KB_KH_TAG_EMPTY) {
-                        if (!insert) return 0xFFFFFFFFu;
-                        if (atomicCAS(&tags[slot], KB_KH_TAG_EMPTY, KB_KH_TAG_BUSY) == KB_KH_TAG_EMPTY) {
-#pragma unroll
-                            for (int j = 0; j < WN; j++) if (j < FW) keys[(size_t)slot * FW + j] = key.w[j];
-                            __threadfence_block();
-                            *reinterpret_cast<volatile uint32_t*>(&tags[slot]) = want;
-                            if (atomicAdd(&ctl.nkeys, 1u) >= limit) ctl.over = 1;
-                            return slot;
-                        }
-                        continue;                                  // lost the race: look at the same slot again
-                    }
-                    if (t == KB_KH_TAG_BUSY) continue;             // being written by another thread
-                    if (t == want) { __threadfence_block(); if (key_matches(slot, key)) return slot; }
-                    slot = (slot + 1) & smask; step++;
-                }
-                ctl.over = 1;
-                return 0xFFFFFFFFu;
-            };
-
             for (uint64_t i0 = bs; i0 < be; i0 += KB_KH_THREADS) {
                 if (kb_ld_shared_volatile(&ctl.over)) break;
                 const uint64_t i = i0 + tid;
-                if (i >= be) continue;
-                const uint64_t e = kb_ld_stream(a.ent + i);
-                if constexpr (WN > 1) { if (((kb_kh_hash_indirect(e) >> KB_KH_SUBSHIFT) & rmask) != res) continue; }
+                uint64_t e = 0;
+                uint32_t hh = 0;
+                bool act = i < be;
+                if (act) { e = kb_ld_stream(a.ent + i); hh = kb_kh_bits(e, x.bb, hmask); act = kb_kh_part(hh, nb) == part; }
                 uint64_t rec[WN]; KbKey<WN> key;
-                kb_fetch<WN>(a, e, rec, key);
-                const uint32_t hh = hash_of(e, key);
-                if constexpr (WN == 1) { if (((hh >> KB_KH_SUBSHIFT) & rmask) != res) continue; }
-                const uint32_t slot = find_or_insert(key, hh, true);
-                if (slot == 0xFFFFFFFFu) continue;
-                const uint32_t id = (uint32_t)rec[WN - 1] & 0xFFu;
-                atomicOr(&pres[(size_t)slot * PW + (id >> 5)], 1u << (id & 31));
-                const bool isin = (a.ingroup[id >> 5] >> (id & 31)) & 1u;
-                uint32_t* m = (isin ? min_ : mout) + (size_t)slot * MW;
-                for (int j = 0; j < MW; j++) {
-                    const int ncol = min(8, lo.D - 8 * j);
-                    const uint32_t v = (uint32_t)kb_rec_bits<WN>(rec, lo.FB + 16 * j, 2 * ncol) << (16 - 2 * ncol);
-                    const uint32_t oh = kb_onehot8(v) & (0xFFFFFFFFu << (4 * (8 - ncol)));
-                    if ((kb_ld_shared_volatile(m + j) & oh) != oh) atomicOr(m + j, oh);
+#pragma unroll
+                for (int j = 0; j < WN; j++) { rec[j] = 0; key.w[j] = 0; }
+                uint32_t slot = KB_KH_NONE;
+                if (act) {
+                    kb_fetch<WN>(a, e, rec, key);
+                    slot = find_or_insert(key, hh, kb_kh_slot(hh, nb, x.slots_log2), true);
+                }
+                __syncwarp();
+                if (slot != KB_KH_NONE) {
+                    const uint32_t id = (uint32_t)rec[WN - 1] & 0xFFu;
+                    atomicOr(&pres[(size_t)slot * PW + (id >> 5)], 1u << (id & 31));
+                    const bool isin = (a.ingroup[id >> 5] >> (id & 31)) & 1u;
+                    uint32_t* m = (isin ? min_ : mout) + (size_t)slot * MW;
+                    for (int j = 0; j < MW; j++) {
+                        const int ncol = min(8, lo.D - 8 * j);
+                        const uint32_t v = (uint32_t)kb_rec_bits<WN>(rec, lo.FB + 16 * j, 2 * ncol) << (16 - 2 * ncol);
+                        const uint32_t oh = kb_onehot8(v) & (0xFFFFFFFFu << (4 * (8 - ncol)));
+                        if ((kb_ld_shared_volatile(m + j) & oh) != oh) atomicOr(m + j, oh);
+                    }
                 }
             }
             __syncthreads();
@@ -324,8 +340,8 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_kernel(const KbHashArgs
                 __syncthreads();
                 if (tid == 0) {
                     s_splits++;
-                    if (nb >= 20 || ctl.sp + 2 > KB_KH_STACK) atomicExch(x.err, 1ULL);
-                    else { ctl.stack[ctl.sp] = res | ((nb + 1) << 24); ctl.stack[ctl.sp + 1] = (res | (1u << nb)) | ((nb + 1) << 24); ctl.sp += 2; }
+                    if (nb >= KB_KH_MAXSPLIT || ctl.sp + 2 > KB_KH_STACK) atomicExch(x.err, 1ULL);
+                    else { ctl.stack[ctl.sp] = (part << 1) | ((nb + 1) << 24); ctl.stack[ctl.sp + 1] = ((part << 1) | 1u) | ((nb + 1) << 24); ctl.sp += 2; }
                 }
                 __syncthreads();
                 continue;
@@ -377,13 +393,12 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_kernel(const KbHashArgs
             if (ctl.nsurv) {
                 for (uint64_t i = bs + tid; i < be; i += KB_KH_THREADS) {
                     const uint64_t e = a.ent[i];
-                    if constexpr (WN > 1) { if (((kb_kh_hash_indirect(e) >> KB_KH_SUBSHIFT) & rmask) != res) continue; }
+                    const uint32_t hh = kb_kh_bits(e, x.bb, hmask);
+                    if (kb_kh_part(hh, nb) != part) continue;
                     uint64_t rec[WN]; KbKey<WN> key;
                     kb_fetch<WN>(a, e, rec, key);
-                    const uint32_t hh = hash_of(e, key);
-                    if constexpr (WN == 1) { if (((hh >> KB_KH_SUBSHIFT) & rmask) != res) continue; }
-                    const uint32_t slot = find_or_insert(key, hh, false);
-                    if (slot != 0xFFFFFFFFu && aux[2 * slot + 1]) atomicAdd(&aux[2 * slot], 1u);
+                    const uint32_t slot = find_or_insert(key, hh, kb_kh_slot(hh, nb, x.slots_log2), false);
+                    if (slot != KB_KH_NONE && aux[2 * slot + 1]) atomicAdd(&aux[2 * slot], 1u);
                 }
                 __syncthreads();
                 for (uint32_t slot = tid; slot < S; slot += KB_KH_THREADS) {
