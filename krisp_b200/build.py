@@ -8,8 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkrisp_b200.so")
 SOURCES = ["kb_api.cu"]
-HEADERS = ["kb_common.cuh", "kb_extract.cuh", "kb_group.cuh", "kb_group_fast.cuh", "kb_sort.cuh",
-           os.path.join("..", "..", "include", "krisp_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "krisp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC,-O2", "-shared", "-Xptxas", "-v"]
 

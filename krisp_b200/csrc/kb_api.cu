@@ -16,6 +16,7 @@
 #include "kb_group_fast.cuh"
 #include "kb_part.cuh"
 #include "kb_hash.cuh"
+#include "kb_hash_stream.cuh"
 
 #define KB_VERSION_STR "krisp_b200 0.1.0 sm_100a"
 
@@ -51,6 +52,7 @@ struct kb_ctx {
     long long opt_group_algo = 1;        // 1 = partition + bucket hash (kb_part.cuh, kb_hash.cuh), 0 = radix sort + segmented pass
     long long opt_bucket_bits = -1;      // -1 = from the input size
     long long opt_hash_slots_log2 = 0;   // 0 = default
+    long long opt_hash_stream = 1;       // 1 = persistent TMA-fed bucket hash kernel for the fast shape
 
     // sequences
     DevBuf bases;
@@ -60,7 +62,7 @@ struct kb_ctx {
     DevBuf d_file_starts, d_file_gid;
 
     // workspaces
-    DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out, taint, plan;
+    DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out, taint, plan, deferred;
     uint64_t* h_pinned = nullptr;        // 64 x u64 scratch for small D2H reads
     uint64_t result_cap = 0;
 
@@ -159,7 +161,7 @@ void kb_destroy(kb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->recs, &ctx->status,
                       &ctx->small, &ctx->res_flank, &ctx->res_in, &ctx->res_out, &ctx->res_size, &ctx->res_run,
-                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan};
+                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -184,6 +186,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "sort_variant") ctx->opt_sort_variant = value;
     else if (n == "fast_group") ctx->opt_fast_group = value ? 1 : 0;
     else if (n == "group_algo") ctx->opt_group_algo = value ? 1 : 0;
+    else if (n == "hash_stream") ctx->opt_hash_stream = value ? 1 : 0;
     else if (n == "bucket_bits") { if (value < -1 || value > 24) return fail(ctx, KB_EINVAL, "bucket_bits must be in -1..24"); ctx->opt_bucket_bits = value; }
     else if (n == "hash_slots_log2") { if (value != 0 && (value < 4 || value > 12)) return fail(ctx, KB_EINVAL, "hash_slots_log2 must be 0 or in 4..12"); ctx->opt_hash_slots_log2 = value; }
     else if (n == "result_cap") { if (value < 1) return fail(ctx, KB_EINVAL, "result_cap must be >= 1"); ctx->opt_result_cap = value; }
@@ -294,7 +297,7 @@ static int prepare_small(kb_ctx* ctx) {
 static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint64_t* n_out,
                        unsigned long long* hist = nullptr, uint32_t hist_shift = 0, uint32_t hist_bits = 0) {
     const uint64_t n_max = 2 * (std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo) + 64;
-    TRY(ensure(ctx, ctx->entA, n_max * 8));
+    TRY(ensure(ctx, ctx->entA, (n_max + 2048) * 8));   // slack: bulk copies of the stream kernel read whole 4 KB stages
     if (!lo.direct) TRY(ensure(ctx, ctx->recs, n_max * 8 * lo.W));
     // separator padding past the data
     const size_t plen = padded_len(ctx->n_bases);
@@ -428,7 +431,7 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est) {
     PartPlan pl;
     pl.fast = hash_fast_ok(ctx);
     if (ctx->opt_hash_slots_log2) pl.slots_log2 = (uint32_t)ctx->opt_hash_slots_log2;
-    else if (pl.fast) pl.slots_log2 = 11;                        // 2048 slots x 24 B = 48 KB: 4 CTAs per SM
+    else if (pl.fast) pl.slots_log2 = ctx->opt_hash_stream ? 10 : 11;   // 24 KB (+ 24 KB ring) / 48 KB of table: 4 CTAs per SM
     else {
         const size_t sb = kb_hash_slot_bytes(lo);
         uint32_t l2 = 11;
@@ -439,7 +442,8 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est) {
     int bb;
     if (ctx->opt_bucket_bits >= 0) bb = (int)ctx->opt_bucket_bits;
     else {
-        const uint64_t target = 3ull << pl.slots_log2;           // records per bucket
+        // records per bucket: half a table of distinct keys, each expected in most of the files
+        const uint64_t target = ((uint64_t)1 << pl.slots_log2) / 2 * (uint64_t)std::min(std::max(lo.n_files, 1), 12);
         bb = 0;
         while (bb < 24 && (n_est >> bb) > target) bb++;
     }
@@ -548,6 +552,41 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
     x.full64 = (uint64_t)g.full[0] | ((uint64_t)g.full[1] << 32);
     x.err = (unsigned long long*)ctx->small.p + SM_ERR;
     const unsigned grid = (unsigned)std::min<uint32_t>(hs.n_buckets, 1u << 20);
+    if (hs.pl->fast && ctx->opt_hash_stream) {
+        TRY(ensure(ctx, ctx->deferred, (size_t)hs.n_buckets * 4 + 64));
+        KbHStreamArgs xs{};
+        xs.h = x; xs.n = g.n;
+        xs.deferred = (uint32_t*)ctx->deferred.p;
+        xs.n_deferred = (unsigned long long*)ctx->small.p + SM_NTAINT;       // zeroed with the result counters
+        const size_t smem = kb_hash_stream_smem(x.slots_log2);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (220 * 1024) / (smem + 1024)));
+        const unsigned sgrid = (unsigned)std::min<uint64_t>((uint64_t)ctx->n_sm * per_sm, std::max<uint64_t>(1, g.n / 4096));
+        // fallback for the deferred buckets: the splitting kernel with a roomier table
+        KbHashArgs fb = x;
+        fb.slots_log2 = ctx->opt_hash_slots_log2 ? x.slots_log2 : std::max<uint32_t>(x.slots_log2, 11);
+        fb.list = xs.deferred; fb.n_list = xs.n_deferred;
+        const size_t fsmem = kb_hash_fast_smem(fb.slots_log2);
+        KbHSizeArgs sz{};
+        sz.ent = g.ent; sz.n_res = g.n_res; sz.cap = g.cap; sz.res_flank = g.res_flank; sz.res_run = g.res_run; sz.res_size = g.res_size; sz.lo = lo;
+        if (lo.D == 1) {
+            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(kb_hash_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            kb_hash_stream_kernel<true><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);
+            CU(cudaGetLastError());
+            kb_hash_fast_kernel<true><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
+        } else {
+            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(kb_hash_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            kb_hash_stream_kernel<false><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);
+            CU(cudaGetLastError());
+            kb_hash_fast_kernel<false><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
+        }
+        CU(cudaGetLastError());
+        kb_hsize_kernel<<<(unsigned)ctx->n_sm * 4, 256, 0, ctx->stream>>>(sz);
+        CU(cudaGetLastError());
+        ctx->launches += 3;
+        return KB_OK;
+    }
     if (hs.pl->fast) {
         const size_t smem = kb_hash_fast_smem(x.slots_log2);
         if (lo.D == 1) {
@@ -832,7 +871,7 @@ int kb_shard_recv_buffer(kb_ctx* ctx, uint64_t n_records, void** buffer) {
     // the partitioned records live in entB (entA when n_shards == 1): receive into the other ping-pong buffer,
     // which then is the sort input — no staging copy
     DevBuf& dst = ctx->shard_send_in_B ? ctx->entA : ctx->entB;
-    TRY(ensure(ctx, dst, (n_records + 64) * 8));
+    TRY(ensure(ctx, dst, (n_records + 2048) * 8));
     *buffer = dst.p;
     return KB_OK;
 }
@@ -849,7 +888,7 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, kb_result** out) {
     // the received records (see kb_shard_recv_buffer) are the sort input; the send buffer is free again
     DevBuf& in = ctx->shard_send_in_B ? ctx->entA : ctx->entB;
     DevBuf& other = ctx->shard_send_in_B ? ctx->entB : ctx->entA;
-    if (in.cap < (n_records + 64) * 8) return fail(ctx, KB_EINVAL, "kb_shard_recv_buffer was not called for this many records");
+    if (in.cap < (n_records + 2048) * 8) return fail(ctx, KB_EINVAL, "kb_shard_recv_buffer was not called for this many records");
     uint64_t* sorted = nullptr;
     TRY(run_sort(ctx, in, other, n_records, lo.P, &sorted));
     int rc = run_group(ctx, sorted, n_records, out);

@@ -33,6 +33,8 @@ struct KbHashArgs {
     uint32_t slots_log2;
     uint64_t ingroup64, full64;          // fast kernel (<= 64 files)
     unsigned long long* err;             // != 0: a bucket could not be resolved
+    const uint32_t* list;                // != null: process only the buckets list[0 .. *n_list)
+    const unsigned long long* n_list;
 };
 
 // The 32 key (or flank-hash) bits right below the bucket bits, left-aligned.  Mixed keys (kb_mix) and flank
@@ -98,7 +100,9 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_fast_kernel(const KbHas
         return KB_KH_NONE;
     };
 
-    for (uint32_t b = blockIdx.x; b < x.n_buckets; b += gridDim.x) {
+    const uint32_t n_work = x.list ? (uint32_t)min((unsigned long long)x.n_buckets, *x.n_list) : x.n_buckets;
+    for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const uint32_t b = x.list ? x.list[wi] : wi;
         const uint64_t bs = x.bstart[b], be = x.bstart[b + 1];
         if (be == bs) continue;
         __syncthreads();

@@ -86,10 +86,10 @@ def test_sorted_path_matches_reference_golden(every, searcher):
     assert hashlib.sha256("\n".join(rows).encode()).hexdigest() == every["rows_sha256"]
 
 
-@pytest.mark.parametrize("fast", [1, 0], ids=["fast", "generic"])
+@pytest.mark.parametrize("fast,stream", [(1, 1), (1, 0), (0, 0)], ids=["stream", "fast", "generic"])
 @pytest.mark.parametrize("bucket_bits,slots", [(0, 4), (0, 0), (3, 5), (10, 6), (17, 0), (24, 4)])
 @pytest.mark.parametrize("name", ["c1_spacer_25_1_2", "p_spacer_3x3", "p_primer_3x3", "p_5_2_3", "p_30_40_30", "p_6_1_2", "c1_single_file"])
-def test_bucket_hash_is_exact_for_any_bucket_and_table_size(name, bucket_bits, slots, fast, searcher):
+def test_bucket_hash_is_exact_for_any_bucket_and_table_size(name, bucket_bits, slots, fast, stream, searcher):
     """Partition depth (0-3 levels) and hash-table size only change the work split: tiny tables force buckets to be
     split by further hash bits and streamed once per part; the rows must not change."""
     from krisp_b200.search import search_files
@@ -98,8 +98,9 @@ def test_bucket_hash_is_exact_for_any_bucket_and_table_size(name, bucket_bits, s
     L, D, R = deduce_ldr(case["flags"])
     try:
         res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher,
-                           options={"bucket_bits": bucket_bits, "hash_slots_log2": slots, "fast_group": fast})
+                           options={"bucket_bits": bucket_bits, "hash_slots_log2": slots, "fast_group": fast, "hash_stream": stream})
     finally:
+        searcher.set_option("hash_stream", 1)
         searcher.set_option("bucket_bits", -1)
         searcher.set_option("hash_slots_log2", 0)
         searcher.set_option("fast_group", 1)
