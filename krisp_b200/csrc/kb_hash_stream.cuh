@@ -20,7 +20,7 @@
 
 #define KB_HS_CONSUMERS 256
 #define KB_HS_WARPS (KB_HS_CONSUMERS / 32)
-#define KB_HS_THREADS (KB_HS_CONSUMERS + 32)
+#define KB_HS_THREADS KB_HS_CONSUMERS
 #define KB_HS_CHUNK 1024                      // records per stage (8 KB)
 #define KB_HS_PER (KB_HS_CHUNK / KB_HS_CONSUMERS)
 #define KB_HS_STAGES 3
@@ -77,6 +77,13 @@ __device__ __forceinline__ uint32_t kb_lower_bound(const unsigned long long* bst
     return lo;
 }
 
+// Slot = KbKhSlot (24 bytes: key | files 0-31 | files 32-63 | ingroup sets | outgroup sets).  With D == 1 and at most
+// 54 flank bits (the spacer shape 25/1/2) the two 4-bit base sets live in bits 56-63 of the KEY word instead
+// (ingroup 56-59, outgroup 60-63): the one LDS.64 that checks the key also tells whether the record's base is
+// already recorded, so a record costs two table accesses (key load, presence RED) instead of three.
+typedef KbKhSlot KbHsSlot;
+#define KB_HS_KEYMASK 0x00FFFFFFFFFFFFFFULL
+
 template <bool D1>
 __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbHStreamArgs xs) {
     extern __shared__ __align__(16) unsigned char kb_smem_raw[];
@@ -84,12 +91,13 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
     const KbGroupArgs& a = x.g;
     const KbLayout& lo = a.lo;
     const uint32_t S = 1u << x.slots_log2, smask = S - 1u;
+    // dynamic shared memory: ring | per-warp queues | table | control words | mbarriers
     uint64_t* ring = reinterpret_cast<uint64_t*>(kb_smem_raw);                                  // STAGES * CHUNK
     uint64_t* queue = ring + KB_HS_STAGES * KB_HS_CHUNK;                                        // WARPS * QCAP
-    KbKhSlot* tab = reinterpret_cast<KbKhSlot*>(queue + KB_HS_WARPS * KB_HS_QCAP);              // S
-    __shared__ __align__(8) uint64_t bars[2 * KB_HS_STAGES];                                    // full[STAGES], empty[STAGES]
+    KbHsSlot* tab = reinterpret_cast<KbHsSlot*>(queue + KB_HS_WARPS * KB_HS_QCAP);              // S
+    uint32_t* s_ctl = reinterpret_cast<uint32_t*>(tab + S);   // per bucket parity p: [p] over, [2 + p] distinct keys, [4 + p] survivors; [8 + s] warps done with stage s
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ctl + 16);                                   // full[STAGES]
     __shared__ uint32_t s_b0, s_b1;
-    __shared__ uint32_t s_ctl[6];        // per bucket parity p: [p] over, [2 + p] distinct keys, [4 + p] survivors
     __shared__ uint32_t s_closed, s_present, s_rounds, s_defer;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -98,9 +106,9 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
         const unsigned long long v1 = (blockIdx.x + 1 == gridDim.x) ? xs.n : (unsigned long long)(blockIdx.x + 1) * xs.n / gridDim.x;
         s_b0 = kb_lower_bound(x.bstart, x.n_buckets, v0);
         s_b1 = kb_lower_bound(x.bstart, x.n_buckets, v1);
-        for (int s = 0; s < KB_HS_STAGES; s++) { kb_mbar_init(&bars[s], 1); kb_mbar_init(&bars[KB_HS_STAGES + s], KB_HS_WARPS); }
+        for (int s = 0; s < KB_HS_STAGES; s++) kb_mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < 6; i++) s_ctl[i] = 0;
+        for (int i = 0; i < 16; i++) s_ctl[i] = 0;
         s_closed = 0; s_present = 0; s_rounds = 0; s_defer = 0;
     }
     __syncthreads();
@@ -110,22 +118,22 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
     if (r_begin >= r_end) return;
     const uint64_t idx0 = r_begin & ~1ULL;                               // 16-byte aligned stream start
     const uint32_t nchunks = (uint32_t)((r_end - idx0 + KB_HS_CHUNK - 1) / KB_HS_CHUNK);
-    const uint32_t ring_a = kb_smem_u32(ring), bars_a = kb_smem_u32(bars);
+    uint32_t smem_a = kb_smem_u32(kb_smem_raw);
+    asm volatile("" : "+r"(smem_a));                                     // opaque: keep the base in a register, never re-derive it
+    const uint32_t ring_a = smem_a;
+    const uint32_t tab_a = ring_a + (KB_HS_STAGES * KB_HS_CHUNK + KB_HS_WARPS * KB_HS_QCAP) * 8;
+    const uint32_t ctl_a = tab_a + S * (uint32_t)sizeof(KbHsSlot);
+    const uint32_t bars_a = ctl_a + 64;
+    const uint64_t* src = a.ent + idx0;
 
-    if (warp == KB_HS_WARPS) {
-        // ---- producer: one lane keeps the ring full --------------------------------------------------------
-        if (lane == 0) {
-            for (uint32_t k = 0; k < nchunks; k++) {
-                const uint32_t s = k % KB_HS_STAGES, u = k / KB_HS_STAGES;
-                if (u > 0) kb_mbar_wait_backoff(bars_a + 8 * (KB_HS_STAGES + s), (u - 1) & 1u);
-                kb_mbar_expect_tx(bars_a + 8 * s, KB_HS_CHUNK * 8);
-                kb_bulk_g2s(ring_a + s * (KB_HS_CHUNK * 8), a.ent + idx0 + (uint64_t)k * KB_HS_CHUNK, KB_HS_CHUNK * 8, bars_a + 8 * s);
-            }
+    // the ring is primed by one thread; afterwards the LAST warp to finish a stage re-arms it (no producer warp, no polling)
+    if (tid == 0) {
+        for (uint32_t k = 0; k < min(nchunks, (uint32_t)KB_HS_STAGES); k++) {
+            kb_mbar_expect_tx(bars_a + 8 * k, KB_HS_CHUNK * 8);
+            kb_bulk_g2s(ring_a + k * (KB_HS_CHUNK * 8), src + (uint64_t)k * KB_HS_CHUNK, KB_HS_CHUNK * 8, bars_a + 8 * k);
         }
-        return;
     }
 
-    // ---- consumers ------------------------------------------------------------------------------------------
     const uint32_t kshift = 64 - lo.FB;
     const uint32_t D2 = 2 * lo.D;
     const uint32_t mshift = 64 - lo.FB - D2;
@@ -134,23 +142,28 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
     const uint32_t hmask = kb_kh_hmask((uint32_t)lo.FB, x.bb);
     const uint32_t ing_lo = (uint32_t)x.ingroup64, ing_hi = (uint32_t)(x.ingroup64 >> 32);
     const uint32_t sshift = 32 - x.slots_log2;
-    const uint32_t tab_a = kb_smem_u32(tab), ctl_a = kb_smem_u32(s_ctl);
-    const uint32_t q_a = kb_smem_u32(queue) + warp * (KB_HS_QCAP * 8);
+    const uint32_t q_a = ring_a + (KB_HS_STAGES * KB_HS_CHUNK) * 8 + warp * (KB_HS_QCAP * 8);
     const uint32_t lt_mask = kb_lanemask_lt();
     uint32_t par = 0;                    // parity of the current bucket
     uint32_t qn = 0;                     // records waiting in this warp's queue (warp-uniform)
 
-    // record -> its bits in the table slot (sa = shared address of the slot)
-    auto accumulate = [&](uint32_t sa, uint64_t e) {
+    const bool packed = D1 && lo.FB <= 54;       // base sets inside the key word
+    // record -> its bits in the table slot (sa = shared address of the slot, khi = high half of the key word as last read)
+    auto accumulate = [&](uint32_t sa, uint64_t e, uint32_t khi) {
         const uint32_t id = (uint32_t)e & 0xFFu;
         kb_reds_or(sa + 8 + ((id >> 3) & 4u), 1u << (id & 31));
         if (D2) {
-            uint32_t oh;
-            if (D1) oh = 0x10000000u << ((uint32_t)(e >> mshift) & 3u);
-            else oh = kb_onehot8(((uint32_t)(e >> mshift) & ((1u << D2) - 1u)) << (16 - D2)) & colmask;
             const uint32_t isin = (((id & 32u) ? ing_hi : ing_lo) >> (id & 31)) & 1u;
-            const uint32_t ma = sa + 20 - 4 * isin;
-            if ((kb_lds32(ma) & oh) != oh) kb_reds_or(ma, oh);
+            if (packed) {
+                const uint32_t bit = (isin ? 0x01000000u : 0x10000000u) << ((uint32_t)(e >> mshift) & 3u);   // bit 24 + code (in) / 28 + code (out) of the high half
+                if (!(khi & bit)) kb_reds_or(sa + 4, bit);
+            } else {
+                uint32_t oh;
+                if (D1) oh = 0x10000000u << ((uint32_t)(e >> mshift) & 3u);
+                else oh = kb_onehot8(((uint32_t)(e >> mshift) & ((1u << D2) - 1u)) << (16 - D2)) & colmask;
+                const uint32_t ma = sa + 20 - 4 * isin;
+                if ((kb_lds32(ma) & oh) != oh) kb_reds_or(ma, oh);
+            }
         }
     };
     // full probe (dense: called with the queued records of a whole warp): find the key or claim an empty slot
@@ -158,7 +171,7 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
         const uint64_t key = e >> kshift;
         uint32_t slot = kb_kh_bits(e, x.bb, hmask) >> sshift;
         for (uint32_t step = 0; step <= S; step++) {
-            const uint32_t sa = tab_a + slot * (uint32_t)sizeof(KbKhSlot);
+            const uint32_t sa = tab_a + slot * (uint32_t)sizeof(KbHsSlot);
             uint64_t k = kb_lds64(sa);
             if (k == KB_KH_EMPTY) {
                 k = kb_atoms_cas64(sa, KB_KH_EMPTY, key);
@@ -167,7 +180,7 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
                     k = key;
                 }
             }
-            if (k == key) { accumulate(sa, e); return; }
+            if ((packed ? (k & KB_HS_KEYMASK) : k) == key) { accumulate(sa, e, (uint32_t)(k >> 32)); return; }
             slot = (slot + 1) & smask;
         }
         kb_sts32(ctl_a + 4 * par, 1u);
@@ -181,18 +194,20 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
     // the common case inline: the key sits in its home slot; everything else goes through the queue
     auto handle = [&](uint64_t e, bool act) {
         const uint64_t key = e >> kshift;
-        const uint32_t sa = tab_a + (kb_kh_bits(e, x.bb, hmask) >> sshift) * (uint32_t)sizeof(KbKhSlot);
-        const bool hit = act && kb_lds64(sa) == key;
+        const uint32_t sa = tab_a + (kb_kh_bits(e, x.bb, hmask) >> sshift) * (uint32_t)sizeof(KbHsSlot);
+        const uint64_t k = kb_lds64(sa);
+        const bool hit = act && (packed ? (k & KB_HS_KEYMASK) : k) == key;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, act && !hit);
         if (act && !hit) kb_sts64(q_a + (qn + __popc(m & lt_mask)) * 8, e);
         qn += __popc(m);
-        if (hit) accumulate(sa, e);
+        if (hit) accumulate(sa, e, (uint32_t)(k >> 32));
         __syncwarp();
         if (qn >= 32) drain();
     };
 
-    for (uint32_t i = tid; i < S; i += KB_HS_CONSUMERS) { tab[i].key = KB_KH_EMPTY; tab[i].pres[0] = 0; tab[i].pres[1] = 0; tab[i].msk[0] = 0; tab[i].msk[1] = 0; }
-    kb_consumer_sync();
+    if (tid < KB_HS_CONSUMERS) for (uint32_t i = tid; i < S; i += KB_HS_CONSUMERS) { tab[i].key = KB_KH_EMPTY; tab[i].msk[0] = 0; tab[i].msk[1] = 0; tab[i].pres[0] = 0; tab[i].pres[1] = 0; }
+    __syncthreads();
+    if (warp == KB_HS_WARPS) return;     // (spare warp of the launch shape; all work is done by the 8 consumer warps)
 
     uint32_t b = b0;
     uint64_t bs = r_begin, be = x.bstart[b + 1];
@@ -234,14 +249,17 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
                 uint32_t flags = 0, n_closed = 0, n_present = 0;
                 if (!over) {
                     for (uint32_t q = 0, slot = tid; slot < S; q++, slot += KB_HS_CONSUMERS) {
-                        if (tab[slot].key == KB_KH_EMPTY) continue;
+                        const unsigned long long kk0 = tab[slot].key;
+                        if (kk0 == KB_KH_EMPTY) continue;
                         n_closed++;
                         const uint64_t P = (uint64_t)tab[slot].pres[0] | ((uint64_t)tab[slot].pres[1] << 32);
                         if (P != x.full64) continue;
                         n_present++;
                         bool ok = true;
                         if (lo.D) {
-                            uint32_t y = tab[slot].msk[0] & tab[slot].msk[1];
+                            const uint32_t m_in = packed ? ((uint32_t)(kk0 >> 56) & 0xFu) << 28 : tab[slot].msk[0];
+                            const uint32_t m_out = packed ? ((uint32_t)(kk0 >> 60) & 0xFu) << 28 : tab[slot].msk[1];
+                            uint32_t y = m_in & m_out;
                             y |= y >> 1; y |= y >> 2;
                             ok = (~y & 0x11111111u & colmask) != 0;
                         }
@@ -257,16 +275,19 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
                     if (!defer && ((flags >> q) & 1u)) {
                         const unsigned long long gs = atomicAdd(a.n_res, 1ULL);
                         if (gs < a.cap) {
-                            uint64_t kk = kk0;
+                            uint64_t kk = packed ? (kk0 & KB_HS_KEYMASK) : kk0;
                             if (lo.mix) kk = kb_unmix(kk, lo.FB, lo.shs);
                             a.res_flank[gs] = kk << kshift;
-                            if (lo.MW) { a.res_in[gs] = tab[slot].msk[0]; a.res_out[gs] = tab[slot].msk[1]; }
+                            if (lo.MW) {
+                                a.res_in[gs] = packed ? ((uint32_t)(kk0 >> 56) & 0xFu) << 28 : tab[slot].msk[0];
+                                a.res_out[gs] = packed ? ((uint32_t)(kk0 >> 60) & 0xFu) << 28 : tab[slot].msk[1];
+                            }
                             a.res_run[2 * gs] = bs;
                             a.res_run[2 * gs + 1] = be - bs;
                             a.res_size[gs] = 0xFFFFFFFFu;                    // filled by kb_hsize_kernel
                         }
                     }
-                    tab[slot].key = KB_KH_EMPTY; tab[slot].pres[0] = 0; tab[slot].pres[1] = 0; tab[slot].msk[0] = 0; tab[slot].msk[1] = 0;
+                    tab[slot].key = KB_KH_EMPTY; tab[slot].msk[0] = 0; tab[slot].msk[1] = 0; tab[slot].pres[0] = 0; tab[slot].pres[1] = 0;
                 }
                 if (!defer) { n_closed_t += n_closed; n_present_t += n_present; }
                 if (tid == 0) {
@@ -282,8 +303,18 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
                 }
             }
         }
+        // ---- release the stage: the last of the 8 warps re-arms it with the chunk STAGES ahead ---------------------
         __syncwarp();
-        if (lane == 0) kb_mbar_arrive(bars_a + 8 * (KB_HS_STAGES + s));
+        if (lane == 0) {
+            if (kb_atoms_add(ctl_a + 4 * (8 + s), 1u) == KB_HS_WARPS - 1) {
+                kb_sts32(ctl_a + 4 * (8 + s), 0u);
+                const uint32_t kn = k + KB_HS_STAGES;
+                if (kn < nchunks) {
+                    kb_mbar_expect_tx(bars_a + 8 * s, KB_HS_CHUNK * 8);
+                    kb_bulk_g2s(stage_a, src + (uint64_t)kn * KB_HS_CHUNK, KB_HS_CHUNK * 8, bars_a + 8 * s);
+                }
+            }
+        }
     }
 
     n_closed_t = __reduce_add_sync(0xFFFFFFFFu, n_closed_t);
@@ -298,7 +329,7 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
 }
 
 static inline size_t kb_hash_stream_smem(uint32_t slots_log2) {
-    return (size_t)KB_HS_STAGES * KB_HS_CHUNK * 8 + (size_t)KB_HS_WARPS * KB_HS_QCAP * 8 + ((size_t)1 << slots_log2) * sizeof(KbKhSlot) + 128;
+    return (size_t)KB_HS_STAGES * KB_HS_CHUNK * 8 + (size_t)KB_HS_WARPS * KB_HS_QCAP * 8 + ((size_t)1 << slots_log2) * sizeof(KbHsSlot) + 64 + 8 * KB_HS_STAGES + 16;
 }
 
 // ---- group sizes of the survivors emitted by the stream kernel: one warp per survivor ----------------------
