@@ -213,19 +213,28 @@ def run_ours(args):
 
     results = {}
 
+    host_ms = {}
+
     def timed(load, steps, collect_rows, sampler=None):
         launches, prof_acc, d2h = 0, {}, 0
+        host_ms.clear()
         barrier()
         if sampler:
             sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
+            t_a = time.perf_counter()
             if load is not None:
                 load()
+            t_b = time.perf_counter()
             res = search()
+            t_c = time.perf_counter()
             if collect_rows:
                 results["rows"] = res.rows()
+            t_d = time.perf_counter()
+            for nm, dt in (("load", t_b - t_a), ("search", t_c - t_b), ("rows", t_d - t_c)):
+                host_ms[nm] = host_ms.get(nm, 0.0) + dt * 1e3 / steps
             launches += s.last_counters()["kernel_launches"]
             for name, ms in res.profile:
                 prof_acc.setdefault(name, []).append(ms)
@@ -256,7 +265,9 @@ def run_ours(args):
 
     # ---- e2e arm: pinned host buffers through the C ABI, rows decoded on the host -----------------
     timed(load_host, 1, True)
-    ms_e2e, _, _, d2h_bytes = timed(load_host, args.steps, True)
+    ms_e2e, _, prof_e2e, d2h_bytes = timed(load_host, args.steps, True)
+    e2e_host_ms = dict(host_ms)
+    e2e_stage_ms = {k: sum(v) / len(v) for k, v in prof_e2e.items()}
     rows = results["rows"]
     n_rows_total = len(rows)
     if world > 1:
@@ -314,7 +325,8 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (>= 0.2 GB of bases, 3.2 GB of records per GPU; 126 MB L2)",
                    "parallelism": f"flank-hash sharded x{world}" if world > 1 else "single GPU"},
         "e2e": {"value": total_bases / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes},
+                "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes,
+                "host_ms": e2e_host_ms, "stage_ms": e2e_stage_ms},
         "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "stage_ms": stage_ms,
     }
     if cb:

@@ -41,6 +41,10 @@ struct kb_ctx {
     int device = 0;
     int n_sm = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host -> device sequence copies run here, so that K1 can start on the first files while the rest is in flight
+    std::vector<cudaEvent_t> copy_events;   // event pool: copy_events[i] = "local file i is resident" (null entry = copied on the main stream)
+    std::vector<cudaEvent_t> file_event;
+    cudaEvent_t main_event = nullptr;
     std::string err;
 
     // configuration
@@ -57,6 +61,7 @@ struct kb_ctx {
     // sequences
     DevBuf bases;
     uint64_t n_bases = 0;
+    std::vector<uint64_t> file_table_host;
     std::vector<uint64_t> file_starts;   // local files
     std::vector<uint32_t> file_gid;
     DevBuf d_file_starts, d_file_gid;
@@ -67,7 +72,7 @@ struct kb_ctx {
     uint64_t result_cap = 0;
 
     // last-search bookkeeping
-    uint64_t launches = 0, alg_bytes = 0;
+    uint64_t launches = 0, alg_bytes = 0, alg_rec_bytes = 0;   // alg_rec_bytes: per-record bytes of stages enqueued before the record count is known
     int passes = 0;
     std::vector<std::pair<std::string, float>> profile;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
@@ -149,6 +154,9 @@ int kb_create(int device, kb_ctx** out) {
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { ctx->err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); *out = ctx; return KB_ECUDA; }
     ctx->stream = ctx->own_stream;
+    e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->main_event, cudaEventDisableTiming);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); *out = ctx; return KB_ECUDA; }
     e = cudaMallocHost(&ctx->h_pinned, 64 * sizeof(uint64_t));
     if (e != cudaSuccess) { ctx->err = std::string("cudaMallocHost: ") + cudaGetErrorString(e); *out = ctx; return KB_ENOMEM; }
     *out = ctx;
@@ -164,6 +172,9 @@ void kb_destroy(kb_ctx* ctx) {
                       &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (cudaEvent_t ev : ctx->copy_events) cudaEventDestroy(ev);
+    if (ctx->main_event) cudaEventDestroy(ctx->main_event);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -237,6 +248,7 @@ int kb_clear_sequences(kb_ctx* ctx) {
     ctx->n_bases = 0;
     ctx->file_starts.clear();
     ctx->file_gid.clear();
+    ctx->file_event.clear();
     return KB_OK;
 }
 
@@ -247,6 +259,7 @@ static size_t padded_len(uint64_t n_bases) {
 int kb_reserve(kb_ctx* ctx, uint64_t total_bytes) {
     if (!ctx) return KB_EINVAL;
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
     return ensure(ctx, ctx->bases, padded_len(total_bytes + KB_MAX_FILES), true);
 }
 
@@ -255,12 +268,35 @@ int kb_add_sequence(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_b
     if (file_id < 0 || file_id >= KB_MAX_FILES) return fail(ctx, KB_EINVAL, "file_id out of range");
     if (n_bytes && !bytes) return fail(ctx, KB_EINVAL, "null sequence pointer");
     CU(cudaSetDevice(ctx->device));
-    TRY(ensure(ctx, ctx->bases, padded_len(ctx->n_bases + n_bytes + 1), true));
+    if (ctx->bases.cap < padded_len(ctx->n_bases + n_bytes + 1)) {
+        CU(cudaStreamSynchronize(ctx->copy_stream));                 // the buffer moves: no copy may be in flight
+        TRY(ensure(ctx, ctx->bases, padded_len(ctx->n_bases + n_bytes + 1), true));
+    }
     uint8_t* dst = (uint8_t*)ctx->bases.p + ctx->n_bases;
-    if (n_bytes) CU(cudaMemcpyAsync(dst, bytes, n_bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(dst + n_bytes, '\n', 1, ctx->stream));      // separator between files
+    cudaEvent_t ev = nullptr;
+    if (on_device) {
+        if (n_bytes) CU(cudaMemcpyAsync(dst, bytes, n_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemsetAsync(dst + n_bytes, '\n', 1, ctx->stream));      // separator between files
+    } else {
+        // host buffers go over the copy stream; kb_search launches K1 on the files that have arrived
+        const size_t idx = ctx->file_starts.size();
+        if (idx == 0) {                                              // the copy stream starts after whatever the main stream still does with the buffer
+            CU(cudaEventRecord(ctx->main_event, ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->main_event, 0));
+        }
+        while (ctx->copy_events.size() <= idx) {
+            cudaEvent_t ne;
+            CU(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming));
+            ctx->copy_events.push_back(ne);
+        }
+        ev = ctx->copy_events[idx];
+        if (n_bytes) CU(cudaMemcpyAsync(dst, bytes, n_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaMemsetAsync(dst + n_bytes, '\n', 1, ctx->copy_stream));
+        CU(cudaEventRecord(ev, ctx->copy_stream));
+    }
     ctx->file_starts.push_back(ctx->n_bases);
     ctx->file_gid.push_back((uint32_t)file_id);
+    ctx->file_event.push_back(ev);
     ctx->n_bases += n_bytes + 1;
     return KB_OK;
 }
@@ -268,6 +304,7 @@ int kb_add_sequence(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_b
 int kb_synchronize(kb_ctx* ctx) {
     if (!ctx) return KB_EINVAL;
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return KB_OK;
 }
@@ -277,13 +314,13 @@ int kb_synchronize(kb_ctx* ctx) {
 // ---- stages --------------------------------------------------------------------------------------
 static int upload_file_table(kb_ctx* ctx) {
     const size_t nf = ctx->file_starts.size();
-    std::vector<uint64_t> fs(ctx->file_starts);
+    std::vector<uint64_t>& fs = ctx->file_table_host;        // lives in the ctx: the async copy needs no synchronisation
+    fs = ctx->file_starts;
     fs.push_back(ctx->n_bases);
     TRY(ensure(ctx, ctx->d_file_starts, fs.size() * 8));
     TRY(ensure(ctx, ctx->d_file_gid, std::max<size_t>(nf, 1) * 4));
     CU(cudaMemcpyAsync(ctx->d_file_starts.p, fs.data(), fs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_file_gid.p, ctx->file_gid.data(), nf * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));   // fs is a stack-lifetime host buffer
     return KB_OK;
 }
 
@@ -295,7 +332,7 @@ static int prepare_small(kb_ctx* ctx) {
 
 // K1 over tiles [tile0, tile0+n_tiles), windows starting in [pos_lo, pos_hi); *n_out = records written
 static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint64_t* n_out,
-                       unsigned long long* hist = nullptr, uint32_t hist_shift = 0, uint32_t hist_bits = 0) {
+                       unsigned long long* hist = nullptr, uint32_t hist_shift = 0, uint32_t hist_bits = 0, bool no_sync = false) {
     const uint64_t n_max = 2 * (std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo) + 64;
     TRY(ensure(ctx, ctx->entA, (n_max + 2048) * 8));   // slack: bulk copies of the stream kernel read whole 4 KB stages
     if (!lo.direct) TRY(ensure(ctx, ctx->recs, n_max * 8 * lo.W));
@@ -320,9 +357,38 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
     a.pos_lo = pos_lo; a.pos_hi = pos_hi;
     a.hist = hist; a.hist_shift = hist_shift; a.hist_bits = hist_bits;
     const size_t smem = kb_extract_smem(lo.k);
-    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->n_sm * 8);
     prof_begin(ctx, "K1 extract");
-    if (grid) {
+    // Tile batches: when the sequences are still arriving from the host (copy stream), K1 runs on the tiles whose
+    // bytes (+ halo) are resident while the later files are in flight; otherwise one launch covers everything.
+    std::vector<std::pair<uint32_t, cudaEvent_t>> batches;      // (end tile, event to wait for)
+    {
+        const size_t nf = ctx->file_starts.size();
+        const uint32_t t_end = tile0 + n_tiles;
+        const uint64_t step = std::max<uint64_t>(ctx->n_bases / 10, 8ull << 20);
+        uint64_t next = step;
+        for (size_t f = 0; f < nf; f++) {
+            if (!ctx->file_event[f]) continue;
+            const uint64_t resident = f + 1 < nf ? ctx->file_starts[f + 1] : ctx->n_bases;   // bytes [0, resident) are there once event f fired
+            if (f + 1 < nf && resident < next) continue;
+            next = resident + step;
+            uint32_t t1 = f + 1 < nf ? (uint32_t)std::min<uint64_t>(t_end, resident > KB_K1_PAD ? (resident - KB_K1_MAXHALO - 64) / KB_K1_TB : 0) : t_end;
+            if (f + 1 == nf) { batches.push_back({t_end, ctx->file_event[f]}); break; }
+            if (t1 > tile0 && (batches.empty() || t1 > batches.back().first)) batches.push_back({t1, ctx->file_event[f]});
+        }
+        if (batches.empty() || batches.back().first < t_end) {
+            // device-resident sequences (or none pending): everything at once, after every pending copy
+            cudaEvent_t last = nullptr;
+            for (size_t f = 0; f < nf; f++) if (ctx->file_event[f]) last = ctx->file_event[f];
+            batches.push_back({t_end, last});
+        }
+    }
+    uint32_t t0 = tile0;
+    for (auto& bt : batches) {
+        if (bt.second) CU(cudaStreamWaitEvent(ctx->stream, bt.second, 0));
+        const uint32_t nt = bt.first > t0 ? bt.first - t0 : 0;
+        if (!nt) continue;
+        a.tile0 = t0; a.n_tiles = nt;
+        const uint32_t grid = std::min<uint32_t>(nt, (uint32_t)ctx->n_sm * 8);
         switch (lo.W) {
             case 1: kb_extract_kernel<1><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
             case 2: kb_extract_kernel<2><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
@@ -331,8 +397,15 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
         }
         CU(cudaGetLastError());
         ctx->launches++;
+        t0 = bt.first;
     }
     prof_end(ctx);
+    if (no_sync) {                                         // the count stays on the device; the caller sizes grids with the bound
+        *n_out = n_max;
+        ctx->alg_bytes += std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo;
+        ctx->alg_rec_bytes += 8 * (lo.direct ? 1 : (1 + lo.W));
+        return KB_OK;
+    }
     CU(cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NOUT, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     *n_out = ctx->h_pinned[0];
@@ -466,17 +539,18 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est) {
     return pl;
 }
 
-// partition `in` (n elements; level-0 histogram already in the plan buffer) -> *parted, bucket table -> *bstart / *n_buckets
+// partition `in` (at most n elements — the exact count is K1's device counter; level-0 histogram already in the plan buffer)
+// -> *parted, bucket table -> *bstart / *n_buckets
 static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& other, uint64_t n, uint64_t** parted,
                          const unsigned long long** bstart, uint32_t* n_buckets) {
     uint64_t* cur = (uint64_t*)in.p;
     uint8_t* P = (uint8_t*)ctx->plan.p;
     unsigned long long* root = (unsigned long long*)ctx->small.p + SM_ROOT;
     uint32_t* roottile = (uint32_t*)((uint64_t*)ctx->small.p + SM_ROOTTILE);
-    // root parent {0, n}, {0, tiles}
-    ctx->h_pinned[8] = 0; ctx->h_pinned[9] = n;
-    ((uint32_t*)(ctx->h_pinned + 10))[0] = 0; ((uint32_t*)(ctx->h_pinned + 10))[1] = (uint32_t)((n + KB_PT_TILE - 1) / KB_PT_TILE);
-    CU(cudaMemcpyAsync(root, ctx->h_pinned + 8, 24, cudaMemcpyHostToDevice, ctx->stream));
+    // root parent {0, n}, {0, tiles} from K1's record counter (n is only an upper bound here: no host round trip)
+    kb_root_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long*)ctx->small.p + SM_NOUT, root, roottile);
+    CU(cudaGetLastError());
+    ctx->launches++;
     *parted = cur; *bstart = root; *n_buckets = 1;
     if (pl.levels == 0 || n == 0) return KB_OK;
     TRY(ensure(ctx, other, in.cap));
@@ -511,7 +585,7 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
             kb_part_hist_kernel<<<(unsigned)grid, KB_PT_THREADS, 0, ctx->stream>>>(a);
             CU(cudaGetLastError());
             ctx->launches += 2;
-            ctx->alg_bytes += n * 8;
+            ctx->alg_rec_bytes += 8;
         }
         KbPlanArgs pa{};
         pa.counts = a.cursor; pa.nc = pl.nc[l]; pa.base = 0;
@@ -527,7 +601,7 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
         CU(cudaGetLastError());
         ctx->launches++;
         prof_end(ctx);
-        ctx->alg_bytes += n * 16;
+        ctx->alg_rec_bytes += 16;
         std::swap(cur, alt);
     }
     ctx->passes = pl.levels;
@@ -555,7 +629,7 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
     if (hs.pl->fast && ctx->opt_hash_stream) {
         TRY(ensure(ctx, ctx->deferred, (size_t)hs.n_buckets * 4 + 64));
         KbHStreamArgs xs{};
-        xs.h = x; xs.n = g.n;
+        xs.h = x; xs.n_ptr = (const unsigned long long*)ctx->small.p + SM_NOUT;
         xs.deferred = (uint32_t*)ctx->deferred.p;
         xs.n_deferred = (unsigned long long*)ctx->small.p + SM_NTAINT;       // zeroed with the result counters
         const size_t smem = kb_hash_stream_smem(x.slots_log2);
@@ -667,6 +741,7 @@ static int launch_group(kb_ctx* ctx, const KbGroupArgs& a, bool allow_fast) {
 
 // K3 over sorted[0..n) + result download
 static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result** out, const HashStage* hs = nullptr) {
+    // (hs != null: n is an upper bound; the exact count arrives with the first read-back)
     const KbLayout& lo = ctx->lo;
     kb_result* res = new (std::nothrow) kb_result();
     if (!res) return fail(ctx, KB_ENOMEM, "host allocation failed");
@@ -697,14 +772,21 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
             int rc = hs ? launch_hash(ctx, a, *hs) : launch_group(ctx, a, allow_fast);
             prof_end(ctx);
             if (rc) { delete res; return rc; }
-            e = cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NRES, 7 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            // one read-back: [0] K1's record count, [1] survivors, [2..5] stats, [6] taint / deferred count, [7] error flag
+            e = cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NOUT, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("group pass: ") + cudaGetErrorString(e)); }
-            n_res = ctx->h_pinned[0];
-            for (int i = 0; i < 4; i++) res->v.stats[i] = ctx->h_pinned[1 + i];
+            n_res = ctx->h_pinned[1];
+            for (int i = 0; i < 4; i++) res->v.stats[i] = ctx->h_pinned[2 + i];
+            if (hs && attempt == 0) {                       // the search path ran without a host round trip: `n` was only a bound until now
+                n = ctx->h_pinned[0];
+                res->v.n_records = n;
+                ctx->alg_bytes += n * ctx->alg_rec_bytes;
+            }
             ctx->alg_bytes += n * 8 * (lo.direct ? 1 : (1 + lo.W));
-            if (hs && ctx->h_pinned[6]) { delete res; return fail(ctx, KB_EINTERNAL, "bucket hash: a bucket could not be resolved (hash table split limit)"); }
-            if (!hs && allow_fast && fast_group_ok(ctx) && ctx->h_pinned[5] > KB_TAINT_CAP) { allow_fast = false; continue; }   // taint list overflow: generic kernel
+            if (hs && ctx->h_pinned[7]) { delete res; return fail(ctx, KB_EINTERNAL, "bucket hash: a bucket could not be resolved (hash table split limit)"); }
+            if (hs && !lo.direct && n >= (1ULL << 32)) { delete res; return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode"); }
+            if (!hs && allow_fast && fast_group_ok(ctx) && ctx->h_pinned[6] > KB_TAINT_CAP) { allow_fast = false; continue; }   // taint list overflow: generic kernel
             if (n_res <= ctx->result_cap) break;
             rc = ensure_results(ctx, n_res + n_res / 8 + 16);       // table too small: grow and re-run the pass
             if (rc) { delete res; return rc; }
@@ -778,7 +860,7 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
 }
 
 static void begin_search(kb_ctx* ctx) {
-    ctx->launches = 0; ctx->alg_bytes = 0; ctx->passes = 0;
+    ctx->launches = 0; ctx->alg_bytes = 0; ctx->alg_rec_bytes = 0; ctx->passes = 0;
     for (auto& e : ctx->prof_events) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
     ctx->prof_events.clear();
 }
@@ -800,8 +882,8 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
         TRY(ensure(ctx, ctx->plan, pl.bytes + 64));
         if (pl.levels) CU(cudaMemsetAsync(ctx->plan.p, 0, pl.bytes, ctx->stream));
         unsigned long long* h0 = pl.levels ? (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[0]) : nullptr;
-        TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0]));
-        if (!lo.direct && n >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
+        TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0], true));
+        if (!lo.direct && n >= (1ULL << 32) + 64) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
         uint64_t* parted = nullptr;
         HashStage hs{};
         hs.pl = &pl;

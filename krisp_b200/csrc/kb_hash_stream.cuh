@@ -30,7 +30,7 @@
 
 struct KbHStreamArgs {
     KbHashArgs h;
-    unsigned long long n;                // elements in h.g.ent
+    const unsigned long long* n_ptr;     // elements in h.g.ent (device-resident: K1's record counter)
     uint32_t* deferred;                  // [n_buckets] bucket ids left to kb_hash_fast_kernel
     unsigned long long* n_deferred;
 };
@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        const unsigned long long v0 = (unsigned long long)blockIdx.x * xs.n / gridDim.x;
-        const unsigned long long v1 = (blockIdx.x + 1 == gridDim.x) ? xs.n : (unsigned long long)(blockIdx.x + 1) * xs.n / gridDim.x;
+        const unsigned long long n = *xs.n_ptr;
+        const unsigned long long v0 = (unsigned long long)blockIdx.x * n / gridDim.x;
+        const unsigned long long v1 = (blockIdx.x + 1 == gridDim.x) ? n : (unsigned long long)(blockIdx.x + 1) * n / gridDim.x;
         s_b0 = kb_lower_bound(x.bstart, x.n_buckets, v0);
         s_b1 = kb_lower_bound(x.bstart, x.n_buckets, v1);
         for (int s = 0; s < KB_HS_STAGES; s++) kb_mbar_init(&bars[s], 1);

@@ -121,6 +121,15 @@ __global__ void __launch_bounds__(1024) kb_plan_kernel(const KbPlanArgs a) {
     }
 }
 
+// root parent table of level 0 from K1's device-resident record counter: {0, n}, {0, tiles}
+__global__ void kb_root_kernel(const unsigned long long* n_ptr, unsigned long long* root, uint32_t* roottile) {
+    if (threadIdx.x == 0) {
+        const unsigned long long n = *n_ptr;
+        root[0] = 0; root[1] = n;
+        roottile[0] = 0; roottile[1] = (uint32_t)((n + KB_PT_TILE - 1) / KB_PT_TILE);
+    }
+}
+
 // tile -> parent map: one warp per parent
 __global__ void __launch_bounds__(256) kb_tilemap_kernel(const uint32_t* tile0, uint32_t n_parents, uint32_t* tile_parent) {
     const uint32_t lane = threadIdx.x & 31;

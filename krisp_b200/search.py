@@ -9,7 +9,6 @@ sets, and on request their records.
 No CPU fallback: everything that touches sequence data runs in libkrisp_b200.so.
 """
 import ctypes
-from dataclasses import dataclass, field
 
 import numpy as np
 
@@ -22,27 +21,69 @@ _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 _IUPAC = np.frombuffer(b"?ACMGRSVTWYHKDBN", dtype=np.uint8)
 
 
-@dataclass
 class SearchResult:
-    L: int
-    D: int
-    R: int
-    n_records: int = 0
-    left: np.ndarray = None        # [n_groups, L] uint8 ASCII
-    right: np.ndarray = None       # [n_groups, R]
-    in_mask: np.ndarray = None     # [n_groups, D] 4-bit base sets over ingroup-labelled occurrences
-    out_mask: np.ndarray = None    # [n_groups, D] ... over the other occurrences
-    group_size: np.ndarray = None  # [n_groups]
-    flank_words: np.ndarray = None # [n_groups, FW] packed flank (for matching run records)
-    run_offset: np.ndarray = None  # [n_groups + 1]
-    records: np.ndarray = None     # [n_run_records, W] packed records of the survivors' runs
-    stats: dict = field(default_factory=dict)
-    profile: list = field(default_factory=list)
-    have_outgroup: bool = True
+    """Survivor table of one search.
+
+    Packed, as the library returns it: ``flank_words`` [n_groups, FW] (MSB-first flank bits), ``in_words`` / ``out_words``
+    [n_groups, MW] (column sets), ``group_size`` [n_groups], and with want_records ``run_offset`` [n_groups + 1] into
+    ``records`` [n, W].  Decoded lazily on first access: ``left`` [n_groups, L] / ``right`` [n_groups, R] ASCII,
+    ``in_mask`` / ``out_mask`` [n_groups, D] 4-bit base sets over the ingroup-labelled / the other occurrences.
+    """
+
+    def __init__(self, L, D, R, n_records=0, left=None, right=None, in_mask=None, out_mask=None, group_size=None,
+                 flank_words=None, run_offset=None, records=None, stats=None, profile=None, have_outgroup=True,
+                 in_words=None, out_words=None):
+        self.L, self.D, self.R, self.n_records = L, D, R, n_records
+        self._left, self._right, self._in_mask, self._out_mask = left, right, in_mask, out_mask
+        self.in_words, self.out_words = in_words, out_words
+        self.group_size, self.flank_words, self.run_offset, self.records = group_size, flank_words, run_offset, records
+        self.stats, self.profile, self.have_outgroup = stats or {}, profile or [], have_outgroup
 
     @property
     def n_groups(self):
-        return 0 if self.left is None else int(self.left.shape[0])
+        if self.flank_words is not None:
+            return int(self.flank_words.shape[0])
+        return 0 if self._left is None else int(self._left.shape[0])
+
+    @property
+    def left(self):
+        if self._left is None:
+            self._left = _decode_bases(self.flank_words, 0, self.L)
+        return self._left
+
+    @left.setter
+    def left(self, value):
+        self._left = value
+
+    @property
+    def right(self):
+        if self._right is None:
+            self._right = _decode_bases(self.flank_words, 2 * self.L, self.R)
+        return self._right
+
+    @right.setter
+    def right(self, value):
+        self._right = value
+
+    @property
+    def in_mask(self):
+        if self._in_mask is None:
+            self._in_mask = _decode_masks(self.in_words, self.D)
+        return self._in_mask
+
+    @in_mask.setter
+    def in_mask(self, value):
+        self._in_mask = value
+
+    @property
+    def out_mask(self):
+        if self._out_mask is None:
+            self._out_mask = _decode_masks(self.out_words, self.D)
+        return self._out_mask
+
+    @out_mask.setter
+    def out_mask(self, value):
+        self._out_mask = value
 
     def rows(self):
         """CSV rows ``left,consensus,right`` (render_csv, Amplicon.py:663-671), canonically sorted.
@@ -62,8 +103,9 @@ class SearchResult:
         m[:, self.L + 1:self.L + 1 + self.D] = _IUPAC[cons]
         m[:, self.L + 1 + self.D] = ord(",")
         m[:, self.L + 2 + self.D:] = self.right
-        flat = np.ascontiguousarray(m).view(f"S{width}").ravel()
-        return sorted(x.decode() for x in flat.tolist())
+        flat = np.sort(np.ascontiguousarray(m).view(f"S{width}").ravel())      # bytewise order = str order for ASCII
+        text = flat.tobytes().decode("ascii")
+        return [text[i:i + width] for i in range(0, len(text), width)]
 
 
 def _decode_bases(words, first_bit, n_bases):
@@ -167,10 +209,8 @@ class Searcher:
             flank = arr(view.flank, n * FW, np.uint64).reshape(n, FW)
             out = SearchResult(L=L, D=D, R=R, n_records=int(view.n_records), have_outgroup=have_outgroup)
             out.flank_words = flank
-            out.left = _decode_bases(flank, 0, L)
-            out.right = _decode_bases(flank, 2 * L, R)
-            out.in_mask = _decode_masks(arr(view.in_mask, n * MW, np.uint32).reshape(n, MW), D)
-            out.out_mask = _decode_masks(arr(view.out_mask, n * MW, np.uint32).reshape(n, MW), D)
+            out.in_words = arr(view.in_mask, n * MW, np.uint32).reshape(n, MW)
+            out.out_words = arr(view.out_mask, n * MW, np.uint32).reshape(n, MW)
             out.group_size = arr(view.group_size, n, np.uint32)
             out.run_offset = arr(view.run_offset, n + 1, np.uint64)
             nrr = int(view.n_run_records)
@@ -258,7 +298,8 @@ def search_files(ingroup_files, outgroup_files, L, D, R, omit_soft=False, want_r
         # and the diagnostic region is empty, so the filter keeps nothing (kstream.py:824-830)
         z = np.zeros((0, 0), dtype=np.uint8)
         return SearchResult(L=L, D=D, R=R, left=np.zeros((0, L), np.uint8), right=z, in_mask=np.zeros((0, D), np.uint8),
-                            out_mask=np.zeros((0, D), np.uint8), group_size=np.zeros(0, np.uint32), have_outgroup=have_out)
+                            out_mask=np.zeros((0, D), np.uint8), group_size=np.zeros(0, np.uint32), have_outgroup=have_out,
+                            flank_words=np.zeros((0, 1), np.uint64))
     own = searcher is None
     s = searcher or Searcher()
     try:
