@@ -204,7 +204,7 @@ def run_ours(args):
     def search():
         if world == 1:
             return s.search(have_outgroup=True)
-        return sharded.sharded_search(s, dev, have_outgroup=True)
+        return sharded.sharded_search(s, dev, have_outgroup=True, total_bases=total_bases)
 
     def barrier():
         if world > 1:

@@ -63,8 +63,11 @@ int kb_configure(kb_ctx* ctx, int L, int D, int R, int soft_mode, int n_files, c
 
 /*
  * Tuning / diagnostics knobs:
- *   "sort_bits"     bits of the (mixed) flank key / flank hash the radix sort orders by (default 32;
- *                   fewer bits = fewer passes, residual collisions are resolved exactly in the group pass)
+ *   "group_algo"    1 (default) = radix partition + per-bucket hash aggregation; 0 = radix sort + segmented pass
+ *   "bucket_bits"   top bits of the (mixed) flank key / flank hash the partition separates (-1 = from the input size)
+ *   "hash_slots_log2" log2 of the shared-memory hash table size (0 = default); "hash_stream" 1 = TMA-fed persistent kernel
+ *   "sort_bits"     (group_algo 0) bits of the key the radix sort orders by (default 32; fewer bits = fewer passes,
+ *                   residual collisions are resolved exactly in the group pass)
  *   "mix"           1 (default) = store the flank key mixed by a bijection (uniform digits)
  *   "want_records"  1 = also return every record of the surviving groups' runs (for --out_align)
  *   "profile"       1 = time each stage with CUDA events (kb_last_profile)
@@ -97,17 +100,26 @@ int kb_synchronize(kb_ctx* ctx);
 int kb_search(kb_ctx* ctx, kb_result** out);
 
 /*
- * Multi-GPU (one ctx per rank; records are sharded by a hash of the flank key).
- *   kb_shard_extract      K1 on this rank's files, then one partition pass by destination shard.
- *                         *records = device pointer to the partitioned records (8 bytes each),
- *                         counts[s] = records bound for shard s (host array, n_shards entries).
- *   kb_shard_recv_buffer  device buffer for `n_records` incoming records; the host layer fills it
- *                         with an all-to-all (torch.distributed / NCCL) from every rank's partition.
- *   kb_shard_search       radix sort + group pass over the received records.
+ * Multi-GPU (one ctx per rank).  Every rule of the search is local to one (left,right) key, so records are sharded by
+ * the TOP bits of the mixed flank key: level 0 of the radix partition (2^bits0 "digits") is done where the records are
+ * extracted, every digit is owned by one shard (contiguous digit ranges), the exchange moves each level-0 bucket to its
+ * owner, and the remaining partition levels + the bucket hash run there.  The reference has no counterpart (single host,
+ * krisp_fasta.py:86-123); the file fan-out mirrors sortedKmersParallel: files are independent extraction units.
+ *   kb_shard_plan         all ranks call it with the same n_shards and total_bases (bases over ALL ranks) so that they
+ *                         derive the same plan; shard_index = this rank.  *n_digits = level-0 fan-out.
+ *   kb_shard_extract      K1 on this rank's files + partition level 0.  *records = device pointer to the records
+ *                         (8 bytes each) grouped by digit, hence by destination shard; shard_counts[s] = records bound
+ *                         for shard s; digit_counts[d] = records of digit d (n_digits entries; host arrays).
+ *   kb_shard_recv_buffer  device buffer for `n_records` incoming records; the host layer fills it with an all-to-all
+ *                         (torch.distributed / NCCL) in source-rank order.
+ *   kb_shard_search       remaining partition levels + bucket hash over the received records.  piece_counts[src * dps + j]
+ *                         = records received from rank `src` with digit (first digit of this shard + j), dps = digits of
+ *                         this shard = first(shard_index + 1) - first(shard_index), first(s) = s * n_digits / n_shards.
  */
-int kb_shard_extract(kb_ctx* ctx, int n_shards, void** records, uint64_t* counts);
+int kb_shard_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bases, int* n_digits);
+int kb_shard_extract(kb_ctx* ctx, void** records, uint64_t* shard_counts, uint64_t* digit_counts);
 int kb_shard_recv_buffer(kb_ctx* ctx, uint64_t n_records, void** buffer);
-int kb_shard_search(kb_ctx* ctx, uint64_t n_records, kb_result** out);
+int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_counts, kb_result** out);
 
 /* Result accessors (borrowed pointers, valid until kb_result_free). */
 typedef struct {
@@ -126,7 +138,7 @@ typedef struct {
     const uint64_t* run_offset; /* [n_groups + 1] range of the group's run in `records`           */
     const uint64_t* records;    /* [n_run_records][record_words]; a run may hold records of other
                                    flank keys too (prefix sort): filter by the flank bits          */
-    uint64_t stats[4];          /* runs, queued runs, groups present in every file, mixed runs    */
+    uint64_t stats[4];          /* groups, buckets (or queued runs), groups present in every file, bucket splits (or mixed runs) */
 } kb_result_view;
 int kb_result_get(const kb_result* res, kb_result_view* view);
 void kb_result_free(kb_result* res);

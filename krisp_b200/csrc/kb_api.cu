@@ -37,6 +37,25 @@ struct kb_table {
     int record_words = 1;
 };
 
+// partition plan of the search path (kb_part.cuh / kb_hash.cuh); see make_plan
+struct PartPlan {
+    int levels = 0, bits[3] = {0, 0, 0}, bb = 0;
+    uint32_t slots_log2 = 11;
+    bool fast = false;
+    // device tables inside ctx->plan (byte offsets), per level: counts/cursors [NC], starts [NC + 1], tile prefix [NC + 1]
+    size_t off_cnt[3] = {0, 0, 0}, off_start[3] = {0, 0, 0}, off_tile0[3] = {0, 0, 0}, off_tilemap = 0, bytes = 0;
+    uint32_t nc[3] = {0, 0, 0};          // children per level over the whole key space: 2^(bits[0] + ... + bits[l])
+    uint32_t ncl[3] = {0, 0, 0};         // children per level this GPU works on (= nc on one GPU; its shard's part on several)
+};
+
+struct CustomParents {                  // parents of the first level run, when they are not the previous level's children
+    const unsigned long long* pstart;   // [n + 1]
+    const uint32_t* ptile0;             // [n + 1]
+    const uint32_t* prow;               // [n]
+    uint32_t n;
+    uint64_t max_tiles;
+};
+
 struct kb_ctx {
     int device = 0;
     int n_sm = 148;
@@ -78,6 +97,10 @@ struct kb_ctx {
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
 
     // shard state
+    PartPlan shard_plan;
+    int shard_n = 0, shard_index = 0;
+    std::vector<uint64_t> shard_tab_host;
+    DevBuf shard_tab;
     uint64_t shard_n_records = 0;
     int shard_send_in_B = 0;             // partitioned records are in entB (else entA)
 };
@@ -169,7 +192,7 @@ void kb_destroy(kb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->recs, &ctx->status,
                       &ctx->small, &ctx->res_flank, &ctx->res_in, &ctx->res_out, &ctx->res_size, &ctx->res_run,
-                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred};
+                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -485,21 +508,14 @@ static int run_sort(kb_ctx* ctx, DevBuf& in, DevBuf& other, uint64_t n, int P, u
 
 
 // ---- search path: radix partition (kb_part.cuh) + bucket hash aggregation (kb_hash.cuh) ----------------
-struct PartPlan {
-    int levels = 0, bits[3] = {0, 0, 0}, bb = 0;
-    uint32_t slots_log2 = 11;
-    bool fast = false;
-    // device tables inside ctx->plan (byte offsets), per level: counts/cursors [NC], starts [NC + 1], tile prefix [NC + 1]
-    size_t off_cnt[3] = {0, 0, 0}, off_start[3] = {0, 0, 0}, off_tile0[3] = {0, 0, 0}, off_tilemap = 0, bytes = 0;
-    uint32_t nc[3] = {0, 0, 0};
-};
-
 static bool hash_fast_ok(const kb_ctx* ctx) {
     const KbLayout& lo = ctx->lo;
     return ctx->opt_fast_group && lo.direct && lo.FB >= 1 && lo.MW <= 1 && lo.n_files <= 64;
 }
 
-static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est) {
+// n_est: records this GPU partitions.  min_bits0 / min_levels: multi-GPU constraints (level 0 decides the owner shard and
+// level 1 runs after the exchange).
+static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int min_bits0 = 0, int min_levels = 0) {
     const KbLayout& lo = ctx->lo;
     PartPlan pl;
     pl.fast = hash_fast_ok(ctx);
@@ -521,15 +537,23 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est) {
         while (bb < 24 && (n_est >> bb) > target) bb++;
     }
     bb = std::min(bb, std::min(keybits, 24));
+    if (min_levels) bb = std::min(std::max(bb, min_bits0 + min_levels - 1), keybits);
     pl.bb = bb;
-    pl.levels = (bb + 8) / 9;
-    for (int l = 0; l < pl.levels; l++) pl.bits[l] = bb / pl.levels + (l < bb % pl.levels ? 1 : 0);
+    pl.levels = std::max((bb + 8) / 9, min_levels);
+    if (min_levels && pl.levels) {
+        pl.bits[0] = std::max((bb + pl.levels - 1) / pl.levels, min_bits0);
+        const int rb = bb - pl.bits[0], rl = pl.levels - 1;
+        for (int l = 1; l < pl.levels; l++) pl.bits[l] = rb / rl + (l - 1 < rb % rl ? 1 : 0);
+    } else {
+        for (int l = 0; l < pl.levels; l++) pl.bits[l] = bb / pl.levels + (l < bb % pl.levels ? 1 : 0);
+    }
     const uint64_t max_tiles = n_est / KB_PT_TILE + ((uint64_t)1 << bb) + 2;
     size_t off = 0;
     int acc = 0;
     for (int l = 0; l < pl.levels; l++) {
         acc += pl.bits[l];
         pl.nc[l] = 1u << acc;
+        pl.ncl[l] = pl.nc[l];
         pl.off_cnt[l] = off; off += (size_t)pl.nc[l] * 8;
         pl.off_start[l] = off; off += ((size_t)pl.nc[l] + 1) * 8;
         pl.off_tile0[l] = off; off += (((size_t)pl.nc[l] + 1) * 4 + 7) & ~(size_t)7;
@@ -539,28 +563,30 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est) {
     return pl;
 }
 
-// partition `in` (at most n elements — the exact count is K1's device counter; level-0 histogram already in the plan buffer)
-// -> *parted, bucket table -> *bstart / *n_buckets
-static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& other, uint64_t n, uint64_t** parted,
-                         const unsigned long long** bstart, uint32_t* n_buckets) {
+// Partition levels [l_begin, l_end) of `in` (at most n elements) -> *parted, child table of the last level -> *bstart / *n_buckets.
+// l_begin == 0: the exact element count is K1's device counter and the level-0 histogram is already in the plan buffer;
+// l_begin > 0 needs `cp` (the parents of that level).
+static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& other, uint64_t n, int l_begin, int l_end,
+                         const CustomParents* cp, uint64_t** parted, const unsigned long long** bstart, uint32_t* n_buckets) {
     uint64_t* cur = (uint64_t*)in.p;
     uint8_t* P = (uint8_t*)ctx->plan.p;
     unsigned long long* root = (unsigned long long*)ctx->small.p + SM_ROOT;
     uint32_t* roottile = (uint32_t*)((uint64_t*)ctx->small.p + SM_ROOTTILE);
-    // root parent {0, n}, {0, tiles} from K1's record counter (n is only an upper bound here: no host round trip)
+    // root parent {0, n}, {0, tiles} from the device-resident record counter (n is only an upper bound here: no host round trip)
     kb_root_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long*)ctx->small.p + SM_NOUT, root, roottile);
     CU(cudaGetLastError());
     ctx->launches++;
     *parted = cur; *bstart = root; *n_buckets = 1;
-    if (pl.levels == 0 || n == 0) return KB_OK;
+    if (l_end <= l_begin || n == 0) return KB_OK;
     TRY(ensure(ctx, other, in.cap));
     uint64_t* alt = (uint64_t*)other.p;
     const size_t smem = kb_part_smem();
     CU(cudaFuncSetAttribute(kb_part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int shift = 64;
+    for (int l = 0; l < l_begin; l++) shift -= pl.bits[l];
     static const char* pnames[3] = {"K2 partition 0", "K2 partition 1", "K2 partition 2"};
     static const char* hnames[3] = {"K2 plan 0", "K2 histogram 1", "K2 histogram 2"};
-    for (int l = 0; l < pl.levels; l++) {
+    for (int l = l_begin; l < l_end; l++) {
         shift -= pl.bits[l];
         KbPartArgs a{};
         a.in = cur; a.out = alt;
@@ -571,16 +597,20 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
         if (l == 0) {
             a.pstart = root; a.ptile0 = roottile; a.tile_parent = nullptr; a.n_parents = 1;
             grid = (n + KB_PT_TILE - 1) / KB_PT_TILE;
+        } else if (l == l_begin) {
+            a.pstart = cp->pstart; a.ptile0 = cp->ptile0; a.prow = cp->prow; a.n_parents = cp->n;
+            a.tile_parent = (const uint32_t*)(P + pl.off_tilemap);
+            grid = cp->max_tiles;
         } else {
             a.pstart = (const unsigned long long*)(P + pl.off_start[l - 1]);
             a.ptile0 = (const uint32_t*)(P + pl.off_tile0[l - 1]);
             a.tile_parent = (const uint32_t*)(P + pl.off_tilemap);
-            a.n_parents = pl.nc[l - 1];
-            grid = n / KB_PT_TILE + pl.nc[l - 1] + 1;
+            a.n_parents = pl.ncl[l - 1];
+            grid = n / KB_PT_TILE + pl.ncl[l - 1] + 1;
         }
         prof_begin(ctx, hnames[l]);
         if (l > 0) {
-            kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((pl.nc[l - 1] + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, a.n_parents, (uint32_t*)(P + pl.off_tilemap));
+            kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, a.n_parents, (uint32_t*)(P + pl.off_tilemap));
             CU(cudaGetLastError());
             kb_part_hist_kernel<<<(unsigned)grid, KB_PT_THREADS, 0, ctx->stream>>>(a);
             CU(cudaGetLastError());
@@ -588,7 +618,7 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
             ctx->alg_rec_bytes += 8;
         }
         KbPlanArgs pa{};
-        pa.counts = a.cursor; pa.nc = pl.nc[l]; pa.base = 0;
+        pa.counts = a.cursor; pa.nc = pl.ncl[l]; pa.base = 0;
         pa.start = (unsigned long long*)(P + pl.off_start[l]);
         pa.cursor = a.cursor;
         pa.tile0 = (uint32_t*)(P + pl.off_tile0[l]);
@@ -604,10 +634,10 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
         ctx->alg_rec_bytes += 16;
         std::swap(cur, alt);
     }
-    ctx->passes = pl.levels;
+    ctx->passes += l_end - l_begin;
     *parted = cur;
-    *bstart = (const unsigned long long*)(P + pl.off_start[pl.levels - 1]);
-    *n_buckets = pl.nc[pl.levels - 1];
+    *bstart = (const unsigned long long*)(P + pl.off_start[l_end - 1]);
+    *n_buckets = pl.ncl[l_end - 1];
     return KB_OK;
 }
 
@@ -887,7 +917,7 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
         uint64_t* parted = nullptr;
         HashStage hs{};
         hs.pl = &pl;
-        TRY(run_partition(ctx, pl, ctx->entA, ctx->entB, n, &parted, &hs.bstart, &hs.n_buckets));
+        TRY(run_partition(ctx, pl, ctx->entA, ctx->entB, n, 0, pl.levels, nullptr, &parted, &hs.bstart, &hs.n_buckets));
         int rc = run_group(ctx, parted, n, out, &hs);
         prof_collect(ctx);
         return rc;
@@ -901,48 +931,65 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
     return rc;
 }
 
-int kb_shard_extract(kb_ctx* ctx, int n_shards, void** records, uint64_t* counts) {
-    if (!ctx || !records || !counts || n_shards < 1 || n_shards > KB_RADIX) return KB_EINVAL;
+// ---- multi-GPU: level 0 of the partition decides the owner shard (contiguous digit ranges), the exchange moves every
+//      level-0 bucket to its owner, levels >= 1 and the bucket hash run there ------------------------------------------
+static uint32_t shard_first_digit(uint32_t shard, uint32_t n_shards, uint32_t n_digits) {
+    return (uint32_t)(((uint64_t)shard * n_digits) / n_shards);
+}
+
+int kb_shard_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bases, int* n_digits) {
+    if (!ctx || n_shards < 1 || n_shards > 256 || shard_index < 0 || shard_index >= n_shards) return KB_EINVAL;
     if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
     const KbLayout& lo = ctx->lo;
     if (!lo.direct) return fail(ctx, KB_EUNSUPPORTED, "multi-GPU sharding of multi-word records is not built yet");
+    int min_bits0 = 0;
+    while ((1 << min_bits0) < n_shards) min_bits0++;
+    if (lo.FB < min_bits0 + 1) return fail(ctx, KB_EUNSUPPORTED, "flank key too short to shard over this many GPUs");
+    // every rank derives the same plan from the same numbers: records per shard ~ 2 * total bases / shards
+    PartPlan pl = make_plan(ctx, 2 * total_bases / (uint64_t)n_shards + 64, min_bits0, 2);
+    if (pl.levels < 2 || pl.bits[0] < min_bits0 || pl.bb > lo.FB) return fail(ctx, KB_EINTERNAL, "shard plan");
+    ctx->shard_plan = pl;
+    ctx->shard_n = n_shards;
+    ctx->shard_index = shard_index;
+    if (n_digits) *n_digits = (int)pl.nc[0];
+    return KB_OK;
+}
+
+int kb_shard_extract(kb_ctx* ctx, void** records, uint64_t* shard_counts, uint64_t* digit_counts) {
+    if (!ctx || !records || !shard_counts || !digit_counts) return KB_EINVAL;
+    if (!ctx->configured || ctx->shard_n < 1) return fail(ctx, KB_EINVAL, "kb_configure / kb_shard_plan have not been called");
+    const KbLayout& lo = ctx->lo;
+    const PartPlan& pl = ctx->shard_plan;
     CU(cudaSetDevice(ctx->device));
     begin_search(ctx);
     TRY(prepare_small(ctx));
+    // the plan buffer also has to hold this rank's tile map: its own records may outnumber the per-shard estimate
+    const size_t tilemap_extra = (size_t)((2 * ctx->n_bases + 64) / KB_PT_TILE + 2) * 4;
+    TRY(ensure(ctx, ctx->plan, pl.bytes + tilemap_extra + 64));
+    CU(cudaMemsetAsync(ctx->plan.p, 0, pl.bytes, ctx->stream));
     uint64_t n = 0;
     const uint32_t n_tiles = (uint32_t)((ctx->n_bases + KB_K1_TB - 1) / KB_K1_TB);
-    TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n));
-    for (int s = 0; s < n_shards; s++) counts[s] = 0;
-    *records = ctx->entA.p;
-    ctx->shard_send_in_B = 0;
-    if (n_shards == 1 || n == 0) { counts[0] = n; ctx->shard_n_records = n; prof_collect(ctx); return KB_OK; }
-    // one partition pass by destination shard (histogram row 8 of the small buffer)
-    TRY(ensure(ctx, ctx->entB, ctx->entA.cap));
-    const bool wide = n >= (1ULL << 30);
-    const uint32_t sshift = lo.FB ? 64 - lo.FB : 0;
-    prof_begin(ctx, "K4 shard partition");
-    KbHistArgs h{};
-    h.in = (const uint64_t*)ctx->entA.p; h.n = n; h.P = 1; h.shift0 = sshift; h.shard_n = (uint32_t)n_shards;
-    h.hist = (unsigned long long*)ctx->small.p + SM_HIST + 8 * KB_RADIX;
-    const unsigned hgrid = (unsigned)std::min<uint64_t>((n / 2 + KB_HIST_THREADS - 1) / KB_HIST_THREADS + 1, (uint64_t)ctx->n_sm * 4);
-    kb_hist_kernel<<<hgrid, KB_HIST_THREADS, 0, ctx->stream>>>(h);
-    CU(cudaGetLastError());
-    // counts before the scan turns them into offsets
-    CU(cudaMemcpyAsync(ctx->h_pinned, h.hist, (size_t)std::min(n_shards, 64) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    std::vector<uint64_t> big;
-    if (n_shards > 64) { big.resize(n_shards); CU(cudaMemcpyAsync(big.data(), h.hist, (size_t)n_shards * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
-    kb_scan_kernel<<<1, KB_RADIX, 0, ctx->stream>>>(h.hist);
-    CU(cudaGetLastError());
-    ctx->launches += 2;
-    if (wide) TRY(launch_pass<unsigned long long>(ctx, (const uint64_t*)ctx->entA.p, (uint64_t*)ctx->entB.p, n, sshift, (uint32_t)n_shards, 8, 8));
-    else TRY(launch_pass<uint32_t>(ctx, (const uint64_t*)ctx->entA.p, (uint64_t*)ctx->entB.p, n, sshift, (uint32_t)n_shards, 8, 8));
-    prof_end(ctx);
+    unsigned long long* h0 = (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[0]);
+    TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0], true));
+    uint64_t* parted = nullptr;
+    const unsigned long long* start0 = nullptr;
+    uint32_t nd = 0;
+    TRY(run_partition(ctx, pl, ctx->entA, ctx->entB, n, 0, 1, nullptr, &parted, &start0, &nd));
+    // level-0 bucket offsets -> per-digit and per-shard counts
+    std::vector<uint64_t> st((size_t)nd + 1);
+    CU(cudaMemcpyAsync(st.data(), start0, ((size_t)nd + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    for (int s = 0; s < n_shards; s++) counts[s] = n_shards > 64 ? big[s] : ctx->h_pinned[s];
-    ctx->alg_bytes += n * 24;
-    *records = ctx->entB.p;
-    ctx->shard_send_in_B = 1;
-    ctx->shard_n_records = n;
+    for (uint32_t d = 0; d < nd; d++) digit_counts[d] = st[d + 1] - st[d];
+    for (int sh = 0; sh < ctx->shard_n; sh++) {
+        const uint32_t d0 = shard_first_digit((uint32_t)sh, (uint32_t)ctx->shard_n, nd), d1 = shard_first_digit((uint32_t)sh + 1, (uint32_t)ctx->shard_n, nd);
+        shard_counts[sh] = st[d1] - st[d0];
+    }
+    const uint64_t n_local = st[nd];
+    ctx->alg_bytes += n_local * ctx->alg_rec_bytes;
+    ctx->alg_rec_bytes = 0;
+    *records = parted;
+    ctx->shard_send_in_B = (parted == (uint64_t*)ctx->entB.p) ? 1 : 0;
+    ctx->shard_n_records = n_local;
     prof_collect(ctx);
     return KB_OK;
 }
@@ -950,30 +997,64 @@ int kb_shard_extract(kb_ctx* ctx, int n_shards, void** records, uint64_t* counts
 int kb_shard_recv_buffer(kb_ctx* ctx, uint64_t n_records, void** buffer) {
     if (!ctx || !buffer) return KB_EINVAL;
     CU(cudaSetDevice(ctx->device));
-    // the partitioned records live in entB (entA when n_shards == 1): receive into the other ping-pong buffer,
-    // which then is the sort input — no staging copy
+    // the partitioned records live in one ping-pong buffer: receive into the other one, which then is the input of the
+    // next partition level — no staging copy
     DevBuf& dst = ctx->shard_send_in_B ? ctx->entA : ctx->entB;
     TRY(ensure(ctx, dst, (n_records + 2048) * 8));
     *buffer = dst.p;
     return KB_OK;
 }
 
-int kb_shard_search(kb_ctx* ctx, uint64_t n_records, kb_result** out) {
-    if (!ctx || !out) return KB_EINVAL;
+int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_counts, kb_result** out) {
+    if (!ctx || !out || (n_records && !piece_counts)) return KB_EINVAL;
     *out = nullptr;
-    if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
-    const KbLayout& lo = ctx->lo;
-    if (!lo.direct) return fail(ctx, KB_EUNSUPPORTED, "multi-GPU sharding of multi-word records is not built yet");
+    if (!ctx->configured || ctx->shard_n < 1) return fail(ctx, KB_EINVAL, "kb_configure / kb_shard_plan have not been called");
     CU(cudaSetDevice(ctx->device));
     begin_search(ctx);
     TRY(prepare_small(ctx));
-    // the received records (see kb_shard_recv_buffer) are the sort input; the send buffer is free again
+    PartPlan pl = ctx->shard_plan;
+    // the received records (see kb_shard_recv_buffer) are this level's input; the send buffer is free again
     DevBuf& in = ctx->shard_send_in_B ? ctx->entA : ctx->entB;
     DevBuf& other = ctx->shard_send_in_B ? ctx->entB : ctx->entA;
     if (in.cap < (n_records + 2048) * 8) return fail(ctx, KB_EINVAL, "kb_shard_recv_buffer was not called for this many records");
-    uint64_t* sorted = nullptr;
-    TRY(run_sort(ctx, in, other, n_records, lo.P, &sorted));
-    int rc = run_group(ctx, sorted, n_records, out);
+    const uint32_t nd = pl.nc[0];
+    const uint32_t d_lo = shard_first_digit((uint32_t)ctx->shard_index, (uint32_t)ctx->shard_n, nd);
+    const uint32_t dps = shard_first_digit((uint32_t)ctx->shard_index + 1, (uint32_t)ctx->shard_n, nd) - d_lo;
+    // pieces = (source rank, level-0 digit) in arrival order: parents of level 1; pieces of one digit share a cursor row
+    const uint32_t np = (uint32_t)ctx->shard_n * dps;
+    std::vector<uint64_t>& hp = ctx->shard_tab_host;
+    hp.assign(((size_t)np + 1) * 2 + 2, 0);                 // pstart [np + 1] u64 | ptile0 [np + 1] u32 | prow [np] u32
+    uint64_t* h_start = hp.data();
+    uint32_t* h_tile0 = (uint32_t*)(hp.data() + np + 1);
+    uint32_t* h_row = h_tile0 + np + 1;
+    uint64_t run = 0, trun = 0;
+    for (uint32_t pi = 0; pi < np; pi++) {
+        h_start[pi] = run; h_tile0[pi] = (uint32_t)trun; h_row[pi] = pi % dps;
+        run += piece_counts[pi]; trun += (piece_counts[pi] + KB_PT_TILE - 1) / KB_PT_TILE;
+    }
+    h_start[np] = run; h_tile0[np] = (uint32_t)trun;
+    if (run != n_records) return fail(ctx, KB_EINVAL, "piece counts do not add up to the number of received records");
+    if (!ctx->lo.direct && n_records >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
+    TRY(ensure(ctx, ctx->shard_tab, hp.size() * 8));
+    CU(cudaMemcpyAsync(ctx->shard_tab.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_pinned[8] = n_records;                            // the "record counter" the stream kernel and the root table read
+    CU(cudaMemcpyAsync((uint64_t*)ctx->small.p + SM_NOUT, ctx->h_pinned + 8, 8, cudaMemcpyHostToDevice, ctx->stream));
+    // local child counts: dps rows at level 0, then the usual fan-out
+    { uint32_t c = dps; pl.ncl[0] = c; for (int l = 1; l < pl.levels; l++) { c <<= pl.bits[l]; pl.ncl[l] = c; } }
+    const size_t tilemap_extra = (size_t)(trun + np + 2) * 4;
+    TRY(ensure(ctx, ctx->plan, pl.bytes + tilemap_extra + 64));
+    CU(cudaMemsetAsync(ctx->plan.p, 0, pl.bytes, ctx->stream));
+    CustomParents cp{};
+    cp.pstart = (const unsigned long long*)ctx->shard_tab.p;
+    cp.ptile0 = (const uint32_t*)((uint64_t*)ctx->shard_tab.p + np + 1);
+    cp.prow = cp.ptile0 + np + 1;
+    cp.n = np;
+    cp.max_tiles = trun + 1;
+    uint64_t* parted = nullptr;
+    HashStage hs{};
+    hs.pl = &pl;
+    TRY(run_partition(ctx, pl, in, other, n_records, 1, pl.levels, &cp, &parted, &hs.bstart, &hs.n_buckets));
+    int rc = run_group(ctx, parted, n_records, out, &hs);
     prof_collect(ctx);
     return rc;
 }

@@ -32,18 +32,22 @@ struct KbPartArgs {
     const unsigned long long* pstart;   // [n_parents + 1] parent ranges in `in`
     const uint32_t* ptile0;             // [n_parents + 1] first tile of each parent
     const uint32_t* tile_parent;        // [tiles]  (ignored when n_parents == 1)
+    const uint32_t* prow;               // [n_parents] cursor row of each parent; null = the parent index itself.  (Multi-GPU: the
+                                        // pieces of one level-0 digit received from different ranks share a row.)
     uint32_t n_parents;
     uint32_t shift, bits;               // digit = (e >> shift) & (2^bits - 1)
     unsigned long long* cursor;         // [n_parents << bits] absolute output offsets, advanced atomically
     unsigned long long* hist;           // kb_part_hist_kernel: [n_parents << bits] child counts (zeroed)
 };
 
-__device__ __forceinline__ bool kb_part_tile(const KbPartArgs& a, uint32_t tile, uint32_t& parent, uint64_t& s, uint32_t& n_tile) {
+// tile -> its range [s, s + n_tile) and the cursor row of its parent
+__device__ __forceinline__ bool kb_part_tile(const KbPartArgs& a, uint32_t tile, uint32_t& row, uint64_t& s, uint32_t& n_tile) {
     if (tile >= __ldg(a.ptile0 + a.n_parents)) return false;
-    parent = a.n_parents == 1 ? 0u : __ldg(a.tile_parent + tile);
+    const uint32_t parent = a.n_parents == 1 ? 0u : __ldg(a.tile_parent + tile);
     const uint64_t ps = a.pstart[parent], pe = a.pstart[parent + 1];
     s = ps + (uint64_t)(tile - __ldg(a.ptile0 + parent)) * KB_PT_TILE;
     n_tile = (uint32_t)min((uint64_t)KB_PT_TILE, pe - s);
+    row = a.prow ? __ldg(a.prow + parent) : parent;
     return true;
 }
 

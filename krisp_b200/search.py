@@ -144,6 +144,7 @@ class Searcher:
             # a raw cudaStream_t handle; 0 is the default stream (torch's default), not "none"
             self._check(self._L.kb_set_stream(self._ctx, ctypes.c_void_p(int(stream))))
         self._keep = []          # host buffers that must outlive the async copies
+        self.bases_added = 0     # bytes handed to add_sequence since the last clear_sequences
         self.lo = None
 
     def close(self):
@@ -175,6 +176,7 @@ class Searcher:
     def clear_sequences(self):
         self._check(self._L.kb_clear_sequences(self._ctx))
         self._keep = []
+        self.bases_added = 0
 
     def reserve(self, total_bytes):
         self._check(self._L.kb_reserve(self._ctx, int(total_bytes)))
@@ -183,9 +185,11 @@ class Searcher:
         """`data`: numpy uint8 array (host), or a (device_pointer, n_bytes) tuple for device-resident bases."""
         if isinstance(data, tuple):
             ptr, n = data
+            self.bases_added += int(n)
             self._check(self._L.kb_add_sequence(self._ctx, int(file_id), ctypes.c_void_p(int(ptr)), int(n), 1))
             return
         arr = np.ascontiguousarray(data, dtype=np.uint8)
+        self.bases_added += int(arr.size)
         self._keep.append(arr)
         self._check(self._L.kb_add_sequence(self._ctx, int(file_id), ctypes.c_void_p(arr.ctypes.data), int(arr.size), 0))
 
@@ -229,21 +233,33 @@ class Searcher:
         return self._collect(res, have_outgroup)
 
     # ---- multi-GPU pieces (see krisp_b200/sharded.py) -------------------------------------------------
-    def shard_extract(self, n_shards):
+    def shard_plan(self, n_shards, shard_index, total_bases):
+        """Same call on every rank (same n_shards / total_bases): fixes the partition plan.  Returns the level-0 fan-out."""
+        nd = ctypes.c_int()
+        self._check(self._L.kb_shard_plan(self._ctx, int(n_shards), int(shard_index), int(total_bases), ctypes.byref(nd)))
+        self._shard = (int(n_shards), int(shard_index), int(nd.value))
+        return int(nd.value)
+
+    def shard_extract(self):
+        """K1 + partition level 0 -> (device pointer of the records grouped by digit, counts per shard, counts per digit)."""
+        n_shards, _, nd = self._shard
         rec = ctypes.c_void_p()
         counts = (ctypes.c_uint64 * n_shards)()
-        self._check(self._L.kb_shard_extract(self._ctx, int(n_shards), ctypes.byref(rec), counts))
+        digits = (ctypes.c_uint64 * nd)()
+        self._check(self._L.kb_shard_extract(self._ctx, ctypes.byref(rec), counts, digits))
         self._keep = []
-        return rec.value, [int(c) for c in counts]
+        return rec.value, [int(c) for c in counts], [int(c) for c in digits]
 
     def shard_recv_buffer(self, n_records):
         buf = ctypes.c_void_p()
         self._check(self._L.kb_shard_recv_buffer(self._ctx, int(n_records), ctypes.byref(buf)))
         return buf.value
 
-    def shard_search(self, n_records, have_outgroup=True):
+    def shard_search(self, n_records, piece_counts, have_outgroup=True):
+        """piece_counts: flat [source rank][digit of this shard] record counts, in arrival order."""
+        arr = (ctypes.c_uint64 * max(1, len(piece_counts)))(*[int(c) for c in piece_counts])
         res = ctypes.c_void_p()
-        self._check(self._L.kb_shard_search(self._ctx, int(n_records), ctypes.byref(res)))
+        self._check(self._L.kb_shard_search(self._ctx, int(n_records), arr, ctypes.byref(res)))
         return self._collect(res, have_outgroup)
 
     # ---- kstream path ------------------------------------------------------------------------------

@@ -1,13 +1,16 @@
-"""Multi-GPU search: one process per GPU, records sharded by a hash of the flank key.
+"""Multi-GPU search: one process per GPU, records sharded by the top bits of the mixed flank key.
 
 Every rule of the search is local to one (left,right) key, so after ONE exchange step the GPUs are
 independent:
 
-  1. each rank ingests its own subset of the input files and runs K1 + one partition pass
-     (``kb_shard_extract``): records grouped by destination shard, counts per shard;
-  2. counts all-to-all, then the records all-to-all (``torch.distributed.all_to_all_single`` over
-     NCCL / NVLink; ``gloo`` in the CPU tests) straight between library-owned device buffers;
-  3. each rank sorts and groups its shard (``kb_shard_search``); survivor rows are gathered on rank 0
+  0. all ranks agree on the partition plan (``kb_shard_plan``: same shard count, same total size);
+  1. each rank ingests its own subset of the input files and runs K1 + partition level 0
+     (``kb_shard_extract``): records grouped by level-0 digit, hence by owner shard (contiguous digit ranges);
+  2. counts all-to-all, per-digit counts all-gather, then the records all-to-all
+     (``torch.distributed.all_to_all_single`` over NCCL / NVLink; ``gloo`` in the CPU tests) straight between
+     library-owned device buffers;
+  3. each rank runs the remaining partition levels and the bucket hash on its shard (``kb_shard_search``); the
+     (source rank, digit) pieces it received are the parents of level 1; survivor rows are gathered on rank 0
      (set semantics: no ordering step).
 
 The reference has no counterpart (it is single-host multiprocessing, krisp_fasta.py:86-123); the file
@@ -54,47 +57,63 @@ def _wrap(ptr, n, device):
     return torch.as_tensor(_DeviceArray(ptr, n), device=device)
 
 
-def exchange(searcher, send_ptr, send_counts, device, group=None):
-    """Counts all-to-all + records all-to-all.  Returns the number of records received (they sit in the
-    searcher's receive buffer, ordered by source rank)."""
+def first_digit(shard, n_shards, n_digits):
+    """First level-0 digit owned by `shard` (the host restatement of shard_first_digit in csrc/kb_api.cu)."""
+    return (shard * n_digits) // n_shards
+
+
+def exchange(searcher, send_ptr, send_counts, digit_counts, device, group=None):
+    """Counts all-to-all + per-digit counts all-gather + records all-to-all.  Returns (records received — they sit in
+    the searcher's receive buffer, ordered by source rank and digit —, the piece counts [source][digit of my shard], info)."""
     import torch
     import torch.distributed as dist
-    world = dist.get_world_size(group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     _dbg(f"exchange: send_counts={send_counts}")
     sc = torch.tensor(send_counts, dtype=torch.int64, device=device)
     rc = torch.empty(world, dtype=torch.int64, device=device)
     dist.all_to_all_single(rc, sc, group=group)
+    dg = torch.tensor(digit_counts, dtype=torch.int64, device=device)
+    alld = torch.empty(world * len(digit_counts), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(alld, dg, group=group)
     recv_counts = [int(x) for x in rc.tolist()]
+    nd = len(digit_counts)
+    lo, hi = first_digit(rank, world, nd), first_digit(rank + 1, world, nd)
+    pieces = alld.view(world, nd)[:, lo:hi].reshape(-1).tolist()
     n_recv = sum(recv_counts)
     _dbg(f"exchange: recv_counts={recv_counts}")
     recv_ptr = searcher.shard_recv_buffer(n_recv)
-    send = searcher.wrap_records(send_ptr, sum(send_counts), device) if hasattr(searcher, "wrap_records") \
-        else _wrap(send_ptr, sum(send_counts), device)
-    recv = searcher.wrap_records(recv_ptr, n_recv, device) if hasattr(searcher, "wrap_records") \
-        else _wrap(recv_ptr, n_recv, device)
+    wrap = searcher.wrap_records if hasattr(searcher, "wrap_records") else _wrap
+    send = wrap(send_ptr, sum(send_counts), device)
+    recv = wrap(recv_ptr, n_recv, device)
     _dbg("exchange: records all_to_all")
     dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
     _dbg("exchange: done")
-    return n_recv, {"sent": int(sum(send_counts) - send_counts[dist.get_rank(group)]), "received": n_recv}
+    return n_recv, pieces, {"sent": int(sum(send_counts) - send_counts[rank]), "received": n_recv}
 
 
-def sharded_search(searcher, device, have_outgroup=True, group=None):
-    """Steps 1-3 on the sequences this rank has added to `searcher`.  Returns this rank's SearchResult."""
+def sharded_search(searcher, device, have_outgroup=True, group=None, total_bases=None):
+    """Steps 0-3 on the sequences this rank has added to `searcher`.  Returns this rank's SearchResult.
+    `total_bases` = bases over all ranks (all-reduced from ``searcher.bases_added`` when not given)."""
+    import torch
     import torch.distributed as dist
-    world = dist.get_world_size(group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if total_bases is None:
+        t = torch.tensor([int(getattr(searcher, "bases_added", 0))], dtype=torch.int64, device=device)
+        dist.all_reduce(t, group=group)
+        total_bases = int(t.item())
+    searcher.shard_plan(world, rank, total_bases)
     _dbg("shard_extract")
-    send_ptr, counts = searcher.shard_extract(world)
+    send_ptr, counts, digits = searcher.shard_extract()
     prof = list(searcher.last_profile()) if hasattr(searcher, "last_profile") else []
     ev = None
     if device is not None and getattr(device, "type", "cpu") == "cuda":
-        import torch
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    n_recv, info = exchange(searcher, send_ptr, counts, device, group)
+    n_recv, pieces, info = exchange(searcher, send_ptr, counts, digits, device, group)
     if ev:
         ev[1].record()
     _dbg(f"shard_search n={n_recv}")
-    res = searcher.shard_search(n_recv, have_outgroup=have_outgroup)
+    res = searcher.shard_search(n_recv, pieces, have_outgroup=have_outgroup)
     _dbg(f"shard_search done: {getattr(res, 'n_groups', '?')} groups")
     if ev:
         ev[1].synchronize()
@@ -117,8 +136,6 @@ def gather_rows(rows, group=None):
     return sorted(out)
 
 
-def shard_of_key(mixed_key, n_shards):
-    """Destination shard of a mixed flank key — the host restatement of kb_digit()'s shard mode
-    (csrc/kb_sort.cuh): the low 16 bits scaled to [0, n_shards)."""
-    low = np.asarray(mixed_key, dtype=np.uint64) & np.uint64(0xFFFF)
-    return ((low << np.uint64(16)) * np.uint64(n_shards)) >> np.uint64(32)
+def digit_of_key(mixed_key, flank_bits, bits0):
+    """Level-0 digit of a mixed flank key — the host restatement of the device digit (csrc/kb_part.cuh): its top bits."""
+    return np.asarray(mixed_key, dtype=np.uint64) >> np.uint64(flank_bits - bits0)

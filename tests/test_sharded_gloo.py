@@ -1,7 +1,7 @@
 """world_size-2 `gloo` test of the multi-GPU host logic (file assignment, counts + records all-to-all,
 per-shard search, row gather) on CPU.  The per-rank "searcher" here is a TEST DOUBLE built on the oracle
 model: it packs records exactly like K1 (mixed flank key | middle | file id) and partitions them with the
-host restatement of the device shard function, so the exchange carries the real record format."""
+host restatement of the device's level-0 digit, so the exchange carries the real record format."""
 import os
 import socket
 
@@ -50,17 +50,28 @@ class FakeSearcher:
             v |= m << (64 - self.FB - 2 * self.D)
         return v
 
-    def shard_extract(self, world):
+    def shard_plan(self, world, rank, total_bases):
+        # any plan every rank agrees on: 2^bits0 level-0 digits, at least one per shard
+        self.world, self.rank = world, rank
+        self.bits0 = max(3, (world - 1).bit_length())
+        assert self.FB > self.bits0 and total_bases > 0
+        return 1 << self.bits0
+
+    def shard_extract(self):
+        world = self.world
         recs = []
         for fid, path in self.files:
             for line in model.kmer_lines(model.fasta_records(model.read_lines(path)), self.L, self.D, self.R, self.omit):
                 left, mid, right = line.split(",")
                 recs.append(self._pack(left, mid, right, fid))
         arr = np.array(recs, dtype=np.uint64)
-        shard = sharded.shard_of_key(arr >> np.uint64(64 - self.FB), world) if arr.size else np.zeros(0, np.uint64)
-        order = np.argsort(shard, kind="stable")
+        nd = 1 << self.bits0
+        digit = sharded.digit_of_key(arr >> np.uint64(64 - self.FB), self.FB, self.bits0) if arr.size else np.zeros(0, np.uint64)
+        order = np.argsort(digit, kind="stable")
         self.send = arr[order].view(np.int64).copy()
-        return "send", [int((shard == s).sum()) for s in range(world)]
+        digits = [int((digit == d).sum()) for d in range(nd)]
+        firsts = [sharded.first_digit(s, world, nd) for s in range(world + 1)]
+        return "send", [sum(digits[firsts[s]:firsts[s + 1]]) for s in range(world)], digits
 
     def shard_recv_buffer(self, n):
         self.recv = np.zeros(n, dtype=np.int64)
@@ -69,8 +80,18 @@ class FakeSearcher:
     def wrap_records(self, handle, n, device):
         return torch.from_numpy(self.send if handle == "send" else self.recv)[:n]
 
-    def shard_search(self, n, have_outgroup=True):
+    def shard_search(self, n, pieces, have_outgroup=True):
         L, D, R = self.L, self.D, self.R
+        # the pieces must describe what arrived: (source, digit) runs in order, all digits inside this shard's range
+        nd = 1 << self.bits0
+        lo, hi = sharded.first_digit(self.rank, self.world, nd), sharded.first_digit(self.rank + 1, self.world, nd)
+        assert len(pieces) == self.world * (hi - lo) and sum(pieces) == n
+        got = self.recv[:n].view(np.uint64)
+        pos = 0
+        for i, c in enumerate(pieces):
+            d = lo + i % (hi - lo)
+            assert np.all((got[pos:pos + c] >> np.uint64(64 - self.bits0)) == np.uint64(d))
+            pos += c
         groups = {}
         for v in self.recv[:n].view(np.uint64).tolist():
             key = v >> (64 - self.FB)
@@ -112,7 +133,7 @@ def _worker(rank, world, port, case, out_q):
         owner = sharded.assign_files(len(files), world, sizes=[os.path.getsize(f) for f in files])
         mine = [(i, f) for i, f in enumerate(files) if owner[i] == rank]
         s = FakeSearcher(L, D, R, is_in, mine, case["omit_soft"])
-        res = sharded.sharded_search(s, torch.device("cpu"), have_outgroup=len(outs) > 0)
+        res = sharded.sharded_search(s, torch.device("cpu"), have_outgroup=len(outs) > 0, total_bases=sum(os.path.getsize(f) for f in files))
         rows = sharded.gather_rows(res.rows())
         if rank == 0:
             out_q.put(rows)
