@@ -126,10 +126,11 @@ def test_assign_files_balances():
     assert sorted(loads) == [10, 10]
 
 
-def test_shard_of_key_is_a_partition():
+def test_digit_ranges_partition_the_key_space():
+    """Every level-0 digit has exactly one owner shard, and owners are contiguous digit ranges."""
     keys = np.arange(0, 1 << 18, 7, dtype=np.uint64)
+    digits = sharded.digit_of_key(keys, 18, 5)
+    assert digits.min() == 0 and digits.max() == 31
     for n in (1, 2, 3, 8):
-        s = sharded.shard_of_key(keys, n)
-        assert s.min() >= 0 and s.max() < n
-        if n > 1:
-            assert len(set(s.tolist())) == n
+        firsts = [sharded.first_digit(s, n, 32) for s in range(n + 1)]
+        assert firsts[0] == 0 and firsts[-1] == 32 and all(a < b for a, b in zip(firsts, firsts[1:]))
