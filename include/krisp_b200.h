@@ -117,6 +117,24 @@ int kb_search(kb_ctx* ctx, kb_result** out);
  *                         this shard = first(shard_index + 1) - first(shard_index), first(s) = s * n_digits / n_shards.
  */
 int kb_shard_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bases, int* n_digits);
+
+/*
+ * Fused partition + exchange over NVLink peer memory (the GPUs of one box; one process per GPU).  Instead of partitioning
+ * locally and calling an all-to-all, partition level 0 stores every digit's run straight into the owner's receive buffer
+ * (coalesced peer stores), so the transfer overlaps the partition tile by tile:
+ *   kb_shard_ipc_export   (re)allocate this rank's receive buffer for `capacity_records` and export its CUDA IPC handle
+ *                         (64 bytes); ranks exchange the handles (torch.distributed all_gather) ...
+ *   kb_shard_ipc_import   ... and map each other's buffers (handles[r] = rank r's; the own entry is not opened).
+ *   kb_shard_count        K1 on this rank's files (level-0 histogram fused): digit_counts[d], n_digits entries.  The host
+ *                         layer all-gathers them; that tells every rank where its piece of every digit starts in the
+ *                         owner's buffer (pieces are laid out by source rank, then digit).
+ *   kb_shard_scatter      partition level 0 with piece_base[d] = element offset of this rank's piece of digit d in its
+ *                         owner's receive buffer.  After a barrier across ranks, kb_shard_search runs on the receive buffer.
+ */
+int kb_shard_ipc_export(kb_ctx* ctx, uint64_t capacity_records, uint8_t* handle64);
+int kb_shard_ipc_import(kb_ctx* ctx, int n_ranks, const uint8_t* handles);
+int kb_shard_count(kb_ctx* ctx, uint64_t* digit_counts);
+int kb_shard_scatter(kb_ctx* ctx, const uint64_t* piece_base);
 int kb_shard_extract(kb_ctx* ctx, void** records, uint64_t* shard_counts, uint64_t* digit_counts);
 int kb_shard_recv_buffer(kb_ctx* ctx, uint64_t n_records, void** buffer);
 int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_counts, kb_result** out);

@@ -101,6 +101,10 @@ struct kb_ctx {
     int shard_n = 0, shard_index = 0;
     std::vector<uint64_t> shard_tab_host;
     DevBuf shard_tab;
+    DevBuf recvbuf;                      // IPC-exported receive buffer of the fused partition + exchange
+    std::vector<void*> peer_ptr;         // peer_ptr[r] = rank r's receive buffer mapped here (own entry = recvbuf.p)
+    std::vector<uint64_t> scatter_host;  // staging of the per-digit tables of kb_shard_scatter
+    int shard_direct = 0;                // the last exchange went through kb_shard_scatter (input of kb_shard_search = recvbuf)
     uint64_t shard_n_records = 0;
     int shard_send_in_B = 0;             // partitioned records are in entB (else entA)
 };
@@ -195,6 +199,8 @@ void kb_destroy(kb_ctx* ctx) {
                       &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (size_t r = 0; r < ctx->peer_ptr.size(); r++) if (ctx->peer_ptr[r] && ctx->peer_ptr[r] != ctx->recvbuf.p) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
+    if (ctx->recvbuf.p) cudaFree(ctx->recvbuf.p);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (cudaEvent_t ev : ctx->copy_events) cudaEventDestroy(ev);
     if (ctx->main_event) cudaEventDestroy(ctx->main_event);
@@ -989,7 +995,116 @@ int kb_shard_extract(kb_ctx* ctx, void** records, uint64_t* shard_counts, uint64
     ctx->alg_rec_bytes = 0;
     *records = parted;
     ctx->shard_send_in_B = (parted == (uint64_t*)ctx->entB.p) ? 1 : 0;
+    ctx->shard_direct = 0;
     ctx->shard_n_records = n_local;
+    prof_collect(ctx);
+    return KB_OK;
+}
+
+int kb_shard_ipc_export(kb_ctx* ctx, uint64_t capacity_records, uint8_t* handle64) {
+    if (!ctx || !handle64) return KB_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    const size_t bytes = (size_t)(capacity_records + 2048) * 8;
+    if (bytes > ctx->recvbuf.cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->recvbuf.p) CU(cudaFree(ctx->recvbuf.p));
+        ctx->recvbuf.p = nullptr; ctx->recvbuf.cap = 0;
+        CU(cudaMalloc(&ctx->recvbuf.p, bytes));            // a plain cudaMalloc allocation: exportable
+        ctx->recvbuf.cap = bytes;
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->recvbuf.p));
+    memcpy(handle64, &h, 64);
+    return KB_OK;
+}
+
+int kb_shard_ipc_import(kb_ctx* ctx, int n_ranks, const uint8_t* handles) {
+    if (!ctx || !handles || n_ranks < 1 || n_ranks != ctx->shard_n) return KB_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t r = 0; r < ctx->peer_ptr.size(); r++)
+        if (ctx->peer_ptr[r] && ctx->peer_ptr[r] != ctx->recvbuf.p) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
+    ctx->peer_ptr.assign((size_t)n_ranks, nullptr);
+    for (int r = 0; r < n_ranks; r++) {
+        if (r == ctx->shard_index) { ctx->peer_ptr[r] = ctx->recvbuf.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_ptr[r] = p;
+    }
+    return KB_OK;
+}
+
+int kb_shard_count(kb_ctx* ctx, uint64_t* digit_counts) {
+    if (!ctx || !digit_counts) return KB_EINVAL;
+    if (!ctx->configured || ctx->shard_n < 1) return fail(ctx, KB_EINVAL, "kb_configure / kb_shard_plan have not been called");
+    const KbLayout& lo = ctx->lo;
+    const PartPlan& pl = ctx->shard_plan;
+    CU(cudaSetDevice(ctx->device));
+    begin_search(ctx);
+    TRY(prepare_small(ctx));
+    const size_t tilemap_extra = (size_t)((2 * ctx->n_bases + 64) / KB_PT_TILE + 2) * 4;
+    TRY(ensure(ctx, ctx->plan, pl.bytes + tilemap_extra + 64));
+    CU(cudaMemsetAsync(ctx->plan.p, 0, pl.bytes, ctx->stream));
+    uint64_t n = 0;
+    const uint32_t n_tiles = (uint32_t)((ctx->n_bases + KB_K1_TB - 1) / KB_K1_TB);
+    unsigned long long* h0 = (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[0]);
+    TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0], true));
+    std::vector<uint64_t>& st = ctx->scatter_host;
+    st.assign(pl.nc[0], 0);
+    CU(cudaMemcpyAsync(st.data(), h0, (size_t)pl.nc[0] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint64_t n_local = 0;
+    for (uint32_t d = 0; d < pl.nc[0]; d++) { digit_counts[d] = st[d]; n_local += st[d]; }
+    ctx->alg_bytes += n_local * ctx->alg_rec_bytes;
+    ctx->alg_rec_bytes = 0;
+    ctx->shard_n_records = n_local;
+    prof_collect(ctx);
+    return KB_OK;
+}
+
+int kb_shard_scatter(kb_ctx* ctx, const uint64_t* piece_base) {
+    if (!ctx || !piece_base) return KB_EINVAL;
+    if (!ctx->configured || ctx->shard_n < 1) return fail(ctx, KB_EINVAL, "kb_configure / kb_shard_plan have not been called");
+    if ((int)ctx->peer_ptr.size() != ctx->shard_n) return fail(ctx, KB_EINVAL, "kb_shard_ipc_import has not been called");
+    const PartPlan& pl = ctx->shard_plan;
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t nd = pl.nc[0];
+    const uint64_t n = ctx->shard_n_records;
+    uint8_t* P = (uint8_t*)ctx->plan.p;
+    // per digit: cursor = start of this rank's piece in the owner's buffer; destination = the owner's buffer
+    std::vector<uint64_t>& hp = ctx->scatter_host;
+    hp.assign((size_t)nd * 2, 0);
+    for (int sh = 0; sh < ctx->shard_n; sh++) {
+        const uint32_t d0 = shard_first_digit((uint32_t)sh, (uint32_t)ctx->shard_n, nd), d1 = shard_first_digit((uint32_t)sh + 1, (uint32_t)ctx->shard_n, nd);
+        for (uint32_t d = d0; d < d1; d++) { hp[d] = piece_base[d]; hp[nd + d] = (uint64_t)(reinterpret_cast<uintptr_t>(ctx->peer_ptr[sh]) >> 3); }
+    }
+    TRY(ensure(ctx, ctx->shard_tab, ((size_t)nd * 2 + 8) * 8));
+    unsigned long long* cursor = (unsigned long long*)(P + pl.off_cnt[0]);
+    CU(cudaMemcpyAsync(cursor, hp.data(), (size_t)nd * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->shard_tab.p, hp.data() + nd, (size_t)nd * 8, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long* root = (unsigned long long*)ctx->small.p + SM_ROOT;
+    uint32_t* roottile = (uint32_t*)((uint64_t*)ctx->small.p + SM_ROOTTILE);
+    kb_root_kernel<<<1, 32, 0, ctx->stream>>>((const unsigned long long*)ctx->small.p + SM_NOUT, root, roottile);
+    CU(cudaGetLastError());
+    KbPartArgs a{};
+    a.in = (const uint64_t*)ctx->entA.p; a.out = nullptr;
+    a.pstart = root; a.ptile0 = roottile; a.tile_parent = nullptr; a.n_parents = 1;
+    a.shift = (uint32_t)(64 - pl.bits[0]); a.bits = (uint32_t)pl.bits[0];
+    a.cursor = cursor; a.hist = cursor;
+    a.out_elems = (const unsigned long long*)ctx->shard_tab.p;
+    const size_t smem = kb_part_smem();
+    CU(cudaFuncSetAttribute(kb_part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(ctx, "K2 partition 0 + exchange (peer stores)");
+    if (n) kb_part_kernel<2><<<(unsigned)((n + KB_PT_TILE - 1) / KB_PT_TILE), KB_PT_THREADS, smem, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    prof_end(ctx);
+    ctx->launches += 2;
+    ctx->alg_bytes += n * 16;
+    ctx->passes += 1;
+    ctx->shard_direct = 1;
     prof_collect(ctx);
     return KB_OK;
 }
@@ -1014,9 +1129,9 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_count
     TRY(prepare_small(ctx));
     PartPlan pl = ctx->shard_plan;
     // the received records (see kb_shard_recv_buffer) are this level's input; the send buffer is free again
-    DevBuf& in = ctx->shard_send_in_B ? ctx->entA : ctx->entB;
-    DevBuf& other = ctx->shard_send_in_B ? ctx->entB : ctx->entA;
-    if (in.cap < (n_records + 2048) * 8) return fail(ctx, KB_EINVAL, "kb_shard_recv_buffer was not called for this many records");
+    DevBuf& in = ctx->shard_direct ? ctx->recvbuf : (ctx->shard_send_in_B ? ctx->entA : ctx->entB);
+    DevBuf& other = ctx->shard_direct ? ctx->entA : (ctx->shard_send_in_B ? ctx->entB : ctx->entA);
+    if (in.cap < (n_records + 2048) * 8) return fail(ctx, KB_EINVAL, "the receive buffer is smaller than the number of received records");
     const uint32_t nd = pl.nc[0];
     const uint32_t d_lo = shard_first_digit((uint32_t)ctx->shard_index, (uint32_t)ctx->shard_n, nd);
     const uint32_t dps = shard_first_digit((uint32_t)ctx->shard_index + 1, (uint32_t)ctx->shard_n, nd) - d_lo;

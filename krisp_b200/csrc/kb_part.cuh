@@ -38,6 +38,9 @@ struct KbPartArgs {
     uint32_t shift, bits;               // digit = (e >> shift) & (2^bits - 1)
     unsigned long long* cursor;         // [n_parents << bits] absolute output offsets, advanced atomically
     unsigned long long* hist;           // kb_part_hist_kernel: [n_parents << bits] child counts (zeroed)
+    const unsigned long long* out_elems; // != null: child c is written to the buffer at element address out_elems[c] (= pointer / 8)
+                                        // instead of `out` — multi-GPU: the owner's receive buffer, a peer mapping over NVLink; the
+                                        // cursor of c then counts from the first element of this rank's piece in that buffer
 };
 
 // tile -> its range [s, s + n_tile) and the cursor row of its parent
@@ -208,7 +211,12 @@ __global__ void __launch_bounds__(KB_PT_THREADS, MINB) kb_part_kernel(const KbPa
         const uint32_t idx = i * KB_PT_THREADS + tid;
         if (n_tile == KB_PT_TILE || idx < n_tile) skeys[cnt[(uint32_t)(key[i] >> a.shift) & dmask] + rank[i]] = key[i];
     }
-    if (tid < KB_PT_MAXR) dbase[tid] = g - (unsigned long long)lstart;
+    if (tid < KB_PT_MAXR) {
+        // element address (pointer / 8) of the digit's run minus its position in the staged tile
+        const unsigned long long base = a.out_elems ? (c ? a.out_elems[((size_t)parent << a.bits) | tid] : 0ULL)
+                                                    : (unsigned long long)(reinterpret_cast<uintptr_t>(a.out) >> 3);
+        dbase[tid] = base + g - (unsigned long long)lstart;
+    }
     __syncthreads();
 
     // ---- coalesced store ------------------------------------------------------------------------------
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(KB_PT_THREADS, MINB) kb_part_kernel(const KbPa
         const uint32_t pos = i * KB_PT_THREADS + tid;
         if (n_tile == KB_PT_TILE || pos < n_tile) {
             const uint64_t kv = skeys[pos];
-            a.out[dbase[(uint32_t)(kv >> a.shift) & dmask] + pos] = kv;
+            *reinterpret_cast<uint64_t*>((dbase[(uint32_t)(kv >> a.shift) & dmask] + pos) << 3) = kv;
         }
     }
 }

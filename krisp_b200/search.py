@@ -250,6 +250,27 @@ class Searcher:
         self._keep = []
         return rec.value, [int(c) for c in counts], [int(c) for c in digits]
 
+    # fused partition + exchange over peer memory (see include/krisp_b200.h)
+    def shard_ipc_export(self, capacity_records):
+        buf = ctypes.create_string_buffer(64)
+        self._check(self._L.kb_shard_ipc_export(self._ctx, int(capacity_records), buf))
+        return buf.raw
+
+    def shard_ipc_import(self, handles):
+        blob = b"".join(handles)
+        self._check(self._L.kb_shard_ipc_import(self._ctx, len(handles), blob))
+
+    def shard_count(self):
+        n_shards, _, nd = self._shard
+        digits = (ctypes.c_uint64 * nd)()
+        self._check(self._L.kb_shard_count(self._ctx, digits))
+        self._keep = []
+        return [int(c) for c in digits]
+
+    def shard_scatter(self, piece_base):
+        arr = (ctypes.c_uint64 * len(piece_base))(*[int(c) for c in piece_base])
+        self._check(self._L.kb_shard_scatter(self._ctx, arr))
+
     def shard_recv_buffer(self, n_records):
         buf = ctypes.c_void_p()
         self._check(self._L.kb_shard_recv_buffer(self._ctx, int(n_records), ctypes.byref(buf)))

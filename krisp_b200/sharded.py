@@ -91,9 +91,60 @@ def exchange(searcher, send_ptr, send_counts, digit_counts, device, group=None):
     return n_recv, pieces, {"sent": int(sum(send_counts) - send_counts[rank]), "received": n_recv}
 
 
-def sharded_search(searcher, device, have_outgroup=True, group=None, total_bases=None):
+def direct_search(searcher, device, have_outgroup=True, group=None):
+    """Steps 1-3 with the exchange FUSED into partition level 0: every rank stores each digit's run straight into the
+    owner's receive buffer over NVLink peer memory (CUDA IPC mappings of library-owned buffers), so the only collectives
+    left are two small ones (digit counts all-gather, one barrier).  GPUs of one box only."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    digits = searcher.shard_count()                                   # K1 (+ level-0 histogram)
+    prof = list(searcher.last_profile())
+    nd = len(digits)
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev[0].record()
+    dg = torch.tensor(digits, dtype=torch.int64, device=device)
+    alld = torch.empty(world * nd, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(alld, dg, group=group)
+    table = alld.view(world, nd).cpu().numpy()                        # [source][digit]
+    firsts = [first_digit(s, world, nd) for s in range(world + 1)]
+    # receive-buffer layout of shard s: pieces by source rank, then digit
+    need = [int(table[:, firsts[s]:firsts[s + 1]].sum()) for s in range(world)]
+    state = searcher.__dict__.setdefault("_ipc_state", {"cap": [0] * world, "world": world})
+    if state["world"] != world or any(n > c for n, c in zip(need, state["cap"])):
+        # some buffer is too small: every rank sees the same table, so every rank takes this branch together
+        state["cap"] = [max(c, n + n // 4 + 4096) for n, c in zip(need, state["cap"])]
+        state["world"] = world
+        mine = torch.frombuffer(bytearray(searcher.shard_ipc_export(state["cap"][rank])), dtype=torch.uint8).to(device)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        blob = allh.cpu().numpy().tobytes()
+        searcher.shard_ipc_import([blob[64 * r:64 * (r + 1)] for r in range(world)])
+    piece_base = [0] * nd
+    for s in range(world):
+        sub = table[:, firsts[s]:firsts[s + 1]]
+        flat = np.concatenate([[0], np.cumsum(sub.reshape(-1))])      # pieces in (source, digit) order
+        dps = firsts[s + 1] - firsts[s]
+        for j in range(dps):
+            piece_base[firsts[s] + j] = int(flat[rank * dps + j])
+    searcher.shard_scatter(piece_base)                                # partition level 0 -> peer stores
+    prof += [p for p in searcher.last_profile() if p[0].startswith("K2 partition 0")]
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    dist.all_reduce(flag, group=group)                                # every rank's stores have landed
+    ev[1].record()
+    pieces = table[:, firsts[rank]:firsts[rank + 1]].reshape(-1).tolist()
+    res = searcher.shard_search(need[rank], pieces, have_outgroup=have_outgroup)
+    ev[1].synchronize()
+    prof.append(("K4 count all-gather + partition/exchange + barrier", ev[0].elapsed_time(ev[1])))
+    res.profile = prof + list(res.profile)
+    res.exchange = {"sent": int(sum(digits) - sum(digits[firsts[rank]:firsts[rank + 1]])), "received": need[rank]}
+    return res
+
+
+def sharded_search(searcher, device, have_outgroup=True, group=None, total_bases=None, exchange_mode=None):
     """Steps 0-3 on the sequences this rank has added to `searcher`.  Returns this rank's SearchResult.
-    `total_bases` = bases over all ranks (all-reduced from ``searcher.bases_added`` when not given)."""
+    `total_bases` = bases over all ranks (all-reduced from ``searcher.bases_added`` when not given).
+    `exchange_mode`: "p2p" = fused partition + exchange over peer memory (default on CUDA), "nccl" = all-to-all."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -102,6 +153,11 @@ def sharded_search(searcher, device, have_outgroup=True, group=None, total_bases
         dist.all_reduce(t, group=group)
         total_bases = int(t.item())
     searcher.shard_plan(world, rank, total_bases)
+    on_cuda = device is not None and getattr(device, "type", "cpu") == "cuda"
+    if exchange_mode is None:
+        exchange_mode = os.environ.get("KRISP_EXCHANGE", "p2p" if on_cuda and hasattr(searcher, "shard_scatter") else "nccl")
+    if exchange_mode == "p2p":
+        return direct_search(searcher, device, have_outgroup, group)
     _dbg("shard_extract")
     send_ptr, counts, digits = searcher.shard_extract()
     prof = list(searcher.last_profile()) if hasattr(searcher, "last_profile") else []

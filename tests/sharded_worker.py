@@ -34,12 +34,13 @@ def main():
         for i, f in enumerate(files):
             if owner[i] == rank:
                 s.add_sequence(i, ingest.load_file(f)[0])
-        res = sharded.sharded_search(s, dev, have_outgroup=len(outs) > 0)
-        rows = sharded.gather_rows(res.rows())
-        ok = len(rows) == case["n_rows"] and hashlib.sha256("\n".join(rows).encode()).hexdigest() == case["rows_sha256"]
-        if rank == 0:
-            print(("ok   " if ok else "FAIL ") + case["name"], len(rows), flush=True)
-        bad += 0 if ok else 1
+        for mode in ("p2p", "nccl"):                   # fused partition + exchange over peer memory / NCCL all-to-all
+            res = sharded.sharded_search(s, dev, have_outgroup=len(outs) > 0, exchange_mode=mode)
+            rows = sharded.gather_rows(res.rows())
+            ok = len(rows) == case["n_rows"] and hashlib.sha256("\n".join(rows).encode()).hexdigest() == case["rows_sha256"]
+            if rank == 0:
+                print(("ok   " if ok else "FAIL ") + case["name"], mode, len(rows), flush=True)
+            bad += 0 if ok else 1
     s.close()
     dist.barrier()
     dist.destroy_process_group()
