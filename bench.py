@@ -132,7 +132,7 @@ def cpu_baseline(sample_len, steps=1, warmup=0):
         rows, _ = oracle.search_records(recs, labels, ing, True, L_, D_, R_)
     dt = (time.perf_counter() - t0) / steps
     return {"value": bases / dt / 1e9, "unit": UNIT, "cores": oracle.threads(), "kind": "port",
-            "sample": f"{N_IN}+{N_OUT} genomes x {sample_len} bp ({bases / 1e6:.1f} Mbp), 25/1/2, oracle/krisp_oracle.c (OpenMP)",
+            "sample": f"{N_IN}+{N_OUT} genomes x {sample_len} bp ({bases / 1e6:.1f} Mbp), {L_}/{D_}/{R_}, oracle/krisp_oracle.c (OpenMP)",
             "seconds_per_step": dt, "rows": len(rows)}
 
 
@@ -144,7 +144,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": max(1, args.steps), "warmup": min(args.warmup, 1), "ms_per_step": cb["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"synthetic bacterial panel 20+20 genomes, 25/1/2 spacer mode; bounded sample: {cb['sample']}"},
+            "config": {"workload": f"synthetic bacterial panel 20+20 genomes, {L_}/{D_}/{R_}; bounded sample: {cb['sample']}"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -319,7 +319,8 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 (2-bit packed bases)", "data": "synthetic",
         "config": {"workload": f"synthetic bacterial panel: {N_IN} ingroup + {N_OUT} outgroup genomes x {genome_len} bp "
-                               f"with planted group SNPs, --conserved-left 25 --diagnostic 1 --conserved-right 2 (28-mer, one 64-bit record)",
+                               f"with planted group SNPs, --conserved-left {L_} --diagnostic {D_} --conserved-right {R_} ({L_ + D_ + R_}-mer, "
+                               f"{'one 64-bit record' if 2 * (L_ + D_ + R_) + 8 <= 64 else 'multi-word records'})",
                    "total_bases": total_bases, "records": int(n_rec) if world == 1 else None,
                    "radix_passes": counters["radix_passes"], "rows": n_rows_total,
                    "l2": "inputs larger than L2 (>= 0.2 GB of bases, 3.2 GB of records per GPU; 126 MB L2)",
@@ -345,8 +346,13 @@ def main():
     ap.add_argument("--genome-len", type=int, default=5_000_000, help="bases per genome per GPU (default: BASELINE config 2)")
     ap.add_argument("--cpu-sample-len", type=int, default=1_000_000, help="genome length of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ldr", nargs=3, type=int, metavar=("L", "D", "R"), help="--conserved-left / --diagnostic / --conserved-right "
+                    "(default 25 1 2 = BASELINE config 2; 32 60 32 = config 3, primer mode)")
     ap.add_argument("--option", nargs=2, action="append", metavar=("NAME", "VALUE"), help="kb_set_option passthrough")
     args = ap.parse_args()
+    if args.ldr:
+        global L_, D_, R_
+        L_, D_, R_ = args.ldr
     if args.impl == "reference":
         run_reference(args)
     else:
