@@ -76,6 +76,7 @@ struct kb_ctx {
     long long opt_bucket_bits = -1;      // -1 = from the input size
     long long opt_hash_slots_log2 = 0;   // 0 = default
     long long opt_hash_stream = 1;       // 1 = persistent TMA-fed bucket hash kernel for the fast shape
+    long long opt_shard_bits0 = 0;       // multi-GPU: bits of partition level 0 (the exchange); 0 = log2(shards) + 2
 
     // sequences
     DevBuf bases;
@@ -227,6 +228,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "fast_group") ctx->opt_fast_group = value ? 1 : 0;
     else if (n == "group_algo") ctx->opt_group_algo = value ? 1 : 0;
     else if (n == "hash_stream") ctx->opt_hash_stream = value ? 1 : 0;
+    else if (n == "shard_bits0") { if (value < 0 || value > 9) return fail(ctx, KB_EINVAL, "shard_bits0 must be in 0..9"); ctx->opt_shard_bits0 = value; }
     else if (n == "bucket_bits") { if (value < -1 || value > 24) return fail(ctx, KB_EINVAL, "bucket_bits must be in -1..24"); ctx->opt_bucket_bits = value; }
     else if (n == "hash_slots_log2") { if (value != 0 && (value < 4 || value > 12)) return fail(ctx, KB_EINVAL, "hash_slots_log2 must be 0 or in 4..12"); ctx->opt_hash_slots_log2 = value; }
     else if (n == "result_cap") { if (value < 1) return fail(ctx, KB_EINVAL, "result_cap must be >= 1"); ctx->opt_result_cap = value; }
@@ -519,9 +521,10 @@ static bool hash_fast_ok(const kb_ctx* ctx) {
     return ctx->opt_fast_group && lo.direct && lo.FB >= 1 && lo.MW <= 1 && lo.n_files <= 64;
 }
 
-// n_est: records this GPU partitions.  min_bits0 / min_levels: multi-GPU constraints (level 0 decides the owner shard and
-// level 1 runs after the exchange).
-static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int min_bits0 = 0, int min_levels = 0) {
+// n_est: records over the whole key space (all GPUs).  bits0 > 0 (multi-GPU): level 0 — the exchange — separates exactly bits0 bits
+// (>= log2 of the shard count: it decides the owner; few digits = long runs = efficient peer stores), the levels after the exchange
+// share the remaining bucket bits.
+static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0) {
     const KbLayout& lo = ctx->lo;
     PartPlan pl;
     pl.fast = hash_fast_ok(ctx);
@@ -543,14 +546,16 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int min_bits0 = 0, 
         while (bb < 24 && (n_est >> bb) > target) bb++;
     }
     bb = std::min(bb, std::min(keybits, 24));
-    if (min_levels) bb = std::min(std::max(bb, min_bits0 + min_levels - 1), keybits);
-    pl.bb = bb;
-    pl.levels = std::max((bb + 8) / 9, min_levels);
-    if (min_levels && pl.levels) {
-        pl.bits[0] = std::max((bb + pl.levels - 1) / pl.levels, min_bits0);
-        const int rb = bb - pl.bits[0], rl = pl.levels - 1;
+    if (bits0) {
+        bb = std::min(std::max(bb, bits0 + 1), std::min(keybits, bits0 + 18));
+        const int rb = bb - bits0, rl = (rb + 8) / 9;
+        pl.bb = bb;
+        pl.levels = 1 + rl;
+        pl.bits[0] = bits0;
         for (int l = 1; l < pl.levels; l++) pl.bits[l] = rb / rl + (l - 1 < rb % rl ? 1 : 0);
     } else {
+        pl.bb = bb;
+        pl.levels = (bb + 8) / 9;
         for (int l = 0; l < pl.levels; l++) pl.bits[l] = bb / pl.levels + (l < bb % pl.levels ? 1 : 0);
     }
     const uint64_t max_tiles = n_est / KB_PT_TILE + ((uint64_t)1 << bb) + 2;
@@ -951,9 +956,18 @@ int kb_shard_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bas
     int min_bits0 = 0;
     while ((1 << min_bits0) < n_shards) min_bits0++;
     if (lo.FB < min_bits0 + 1) return fail(ctx, KB_EUNSUPPORTED, "flank key too short to shard over this many GPUs");
-    // every rank derives the same plan from the same numbers: records per shard ~ 2 * total bases / shards
-    PartPlan pl = make_plan(ctx, 2 * total_bases / (uint64_t)n_shards + 64, min_bits0, 2);
-    if (pl.levels < 2 || pl.bits[0] < min_bits0 || pl.bb > lo.FB) return fail(ctx, KB_EINTERNAL, "shard plan");
+    // every rank derives the same plan from the same numbers (records over all ranks ~ 2 * total bases).  Level 0 is the
+    // exchange: 4 digits per shard keep the digit runs of a tile long (efficient peer stores) and the piece table small.
+    // Measured at N = 2 (0.2 Gbp per GPU): 8 + 9 bits in two levels (256-byte runs, 450 GB/s of peer stores) beats 3 + 7 + 7 in
+    // three (8 KB runs, 570 GB/s, but one more pass): stay with two levels while the bucket bits allow it.
+    int bits0 = (int)ctx->opt_shard_bits0;
+    if (bits0 <= 0) {
+        const PartPlan probe = make_plan(ctx, 2 * total_bases + 64, 0);
+        bits0 = (probe.bb >= min_bits0 + 9 && probe.bb <= 17) ? probe.bb - 9 : min_bits0 + 2;
+    }
+    bits0 = std::max(std::max(min_bits0, 1), std::min(std::min(bits0, 9), lo.FB - 1));
+    PartPlan pl = make_plan(ctx, 2 * total_bases + 64, bits0);
+    if (pl.levels < 2 || pl.levels > 3 || pl.bits[0] < min_bits0 || pl.bb > lo.FB) return fail(ctx, KB_EINTERNAL, "shard plan");
     ctx->shard_plan = pl;
     ctx->shard_n = n_shards;
     ctx->shard_index = shard_index;
