@@ -683,16 +683,23 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
         const size_t fsmem = kb_hash_fast_smem(fb.slots_log2);
         KbHSizeArgs sz{};
         sz.ent = g.ent; sz.n_res = g.n_res; sz.cap = g.cap; sz.res_flank = g.res_flank; sz.res_run = g.res_run; sz.res_size = g.res_size; sz.lo = lo;
-        if (lo.D == 1) {
-            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bool spacer = lo.D == 1 && lo.FB == 54 && x.bb <= 22;
+        if (spacer) {
+            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CU(cudaFuncSetAttribute(kb_hash_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            kb_hash_stream_kernel<true><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);
+            kb_hash_stream_kernel<true, true><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);
+            CU(cudaGetLastError());
+            kb_hash_fast_kernel<true><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
+        } else if (lo.D == 1) {
+            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(kb_hash_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            kb_hash_stream_kernel<true, false><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);
             CU(cudaGetLastError());
             kb_hash_fast_kernel<true><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
         } else {
-            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CU(cudaFuncSetAttribute(kb_hash_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            kb_hash_stream_kernel<false><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);
+            kb_hash_stream_kernel<false, false><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);
             CU(cudaGetLastError());
             kb_hash_fast_kernel<false><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
         }

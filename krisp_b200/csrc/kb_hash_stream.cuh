@@ -84,7 +84,8 @@ __device__ __forceinline__ uint32_t kb_lower_bound(const unsigned long long* bst
 typedef KbKhSlot KbHsSlot;
 #define KB_HS_KEYMASK 0x00FFFFFFFFFFFFFFULL
 
-template <bool D1>
+// SPACER: the record layout is exactly 25/1/2-like (54 flank bits, D = 1): every shift is a compile-time constant.
+template <bool D1, bool SPACER>
 __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbHStreamArgs xs) {
     extern __shared__ __align__(16) unsigned char kb_smem_raw[];
     const KbHashArgs& x = xs.h;
@@ -135,12 +136,12 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
         }
     }
 
-    const uint32_t kshift = 64 - lo.FB;
-    const uint32_t D2 = 2 * lo.D;
-    const uint32_t mshift = 64 - lo.FB - D2;
+    const uint32_t kshift = SPACER ? 10u : 64 - lo.FB;
+    const uint32_t D2 = SPACER ? 2u : 2 * lo.D;
+    const uint32_t mshift = SPACER ? 8u : 64 - lo.FB - D2;
     const uint32_t colmask = lo.D ? (0xFFFFFFFFu << (4 * (8 - lo.D))) : 0u;
     const uint32_t limit = S - (S >> 2);
-    const uint32_t hmask = kb_kh_hmask((uint32_t)lo.FB, x.bb);
+    const uint32_t hmask = SPACER ? 0xFFFFFFFFu : kb_kh_hmask((uint32_t)lo.FB, x.bb);   // (SPACER: 54 - bb >= 32 key bits below the bucket bits)
     const uint32_t ing_lo = (uint32_t)x.ingroup64, ing_hi = (uint32_t)(x.ingroup64 >> 32);
     const uint32_t sshift = 32 - x.slots_log2;
     const uint32_t q_a = ring_a + (KB_HS_STAGES * KB_HS_CHUNK) * 8 + warp * (KB_HS_QCAP * 8);
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
     uint32_t par = 0;                    // parity of the current bucket
     uint32_t qn = 0;                     // records waiting in this warp's queue (warp-uniform)
 
-    const bool packed = D1 && lo.FB <= 54;       // base sets inside the key word
+    const bool packed = SPACER || (D1 && lo.FB <= 54);       // base sets inside the key word
     // record -> its bits in the table slot (sa = shared address of the slot, khi = high half of the key word as last read)
     auto accumulate = [&](uint32_t sa, uint64_t e, uint32_t khi) {
         const uint32_t id = (uint32_t)e & 0xFFu;
@@ -206,6 +207,21 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
         if (qn >= 32) drain();
     };
 
+    auto handle_full = [&](uint64_t e) {          // handle() for a record that is known to be in range
+        const uint64_t key = e >> kshift;
+        const uint32_t sa = tab_a + (kb_kh_bits(e, x.bb, hmask) >> sshift) * (uint32_t)sizeof(KbHsSlot);
+        const uint64_t k = kb_lds64(sa);
+        const bool hit = (packed ? (k & KB_HS_KEYMASK) : k) == key;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, !hit);
+        if (m) {
+            if (!hit) kb_sts64(q_a + (qn + __popc(m & lt_mask)) * 8, e);
+            qn += __popc(m);
+        }
+        if (hit) accumulate(sa, e, (uint32_t)(k >> 32));
+        __syncwarp();
+        if (qn >= 32) drain();
+    };
+
     if (tid < KB_HS_CONSUMERS) for (uint32_t i = tid; i < S; i += KB_HS_CONSUMERS) { tab[i].key = KB_KH_EMPTY; tab[i].msk[0] = 0; tab[i].msk[1] = 0; tab[i].pres[0] = 0; tab[i].pres[1] = 0; }
     __syncthreads();
     if (warp == KB_HS_WARPS) return;     // (spare warp of the launch shape; all work is done by the 8 consumer warps)
@@ -231,7 +247,7 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
 #pragma unroll
                     for (int j = 0; j < KB_HS_PER; j++) e[j] = kb_lds64(stage_a + (j * KB_HS_CONSUMERS + tid) * 8);
 #pragma unroll
-                    for (int j = 0; j < KB_HS_PER; j++) handle(e[j], true);
+                    for (int j = 0; j < KB_HS_PER; j++) handle_full(e[j]);
                 } else {
                     for (uint32_t j0 = o0 & ~31u; j0 < o1; j0 += KB_HS_CONSUMERS) {       // warp-uniform trip count
                         const uint32_t j = j0 + tid;

@@ -228,3 +228,42 @@ def test_group_sizes_and_gather_agree_with_sorted_path(searcher):
             assert int(res.group_size[g]) == mine.size
         out.append(per_group)
     assert out[0] == out[1] and len(out[0]) > 0
+
+
+def _valid_windows(genomes, k, omit_soft=False):
+    """2 x (windows without a bad base) over all records — what K1 must emit (S1-S4), computed with numpy prefix sums."""
+    total = 0
+    ok_tab = np.zeros(256, dtype=np.int64)
+    for ch in b"ACGT" + (b"" if omit_soft else b"acgt"):
+        ok_tab[ch] = 1
+    for g in genomes:
+        for r in g.records:
+            if len(r) < k:
+                continue
+            bad = 1 - ok_tab[r]
+            c = np.concatenate([[0], np.cumsum(bad)])
+            total += int(np.count_nonzero(c[k:] - c[:-k] == 0))
+    return 2 * total
+
+
+def test_full_size_panel_properties(searcher):
+    """BASELINE config 2 at full size (20+20 x 5 Mbp, 25/1/2; 4e8 records), through size-independent properties:
+    K1 emits exactly 2 x (valid windows); the two independent device paths (radix partition + bucket hash vs stable
+    radix sort + segmented pass) return the same rows; every row is a planted group SNP whose column separates the groups."""
+    from krisp_b200.panel import make_panel
+    gs = make_panel(20, 20, 5_000_000)
+    res = _search_panel(searcher, gs, 25, 1, 2)
+    assert res.n_records == _valid_windows(gs, 28)
+    rows = res.rows()
+    try:
+        res0 = _search_panel(searcher, gs, 25, 1, 2, options={"group_algo": 0})
+    finally:
+        searcher.set_option("group_algo", 1)
+    assert res0.n_records == res.n_records
+    assert res0.rows() == rows
+    assert 2500 < len(rows) < 4500                      # ~ 2 x 5000 sites x exp(-1e-3 x 27 x 40)
+    assert len(set(rows)) == len(rows)
+    # a surviving group is present in all 40 files, and its ingroup / outgroup base sets are disjoint in the one column
+    assert int(res.group_size.min()) >= 40
+    assert np.all((res.in_mask[:, 0] & res.out_mask[:, 0]) == 0)
+    assert res.stats["groups_in_every_file"] >= len(rows)
