@@ -43,7 +43,7 @@ struct PartPlan {
     uint32_t slots_log2 = 11;
     bool fast = false;
     // device tables inside ctx->plan (byte offsets), per level: counts/cursors [NC], starts [NC + 1], tile prefix [NC + 1]
-    size_t off_cnt[3] = {0, 0, 0}, off_start[3] = {0, 0, 0}, off_tile0[3] = {0, 0, 0}, off_tilemap = 0, bytes = 0;
+    size_t off_cnt[3] = {0, 0, 0}, off_start[3] = {0, 0, 0}, off_tile0[3] = {0, 0, 0}, off_part = 0, off_tilemap = 0, bytes = 0;
     uint32_t nc[3] = {0, 0, 0};          // children per level over the whole key space: 2^(bits[0] + ... + bits[l])
     uint32_t ncl[3] = {0, 0, 0};         // children per level this GPU works on (= nc on one GPU; its shard's part on several)
 };
@@ -76,6 +76,7 @@ struct kb_ctx {
     long long opt_bucket_bits = -1;      // -1 = from the input size
     long long opt_hash_slots_log2 = 0;   // 0 = default
     long long opt_hash_stream = 1;       // 1 = persistent TMA-fed bucket hash kernel for the fast shape
+    long long opt_fused_hist = 1;        // 1 = K1 also counts the level-1 children (single-GPU search path)
     long long opt_shard_bits0 = 0;       // multi-GPU: bits of partition level 0 (the exchange); 0 = log2(shards) + 2
 
     // sequences
@@ -228,6 +229,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "fast_group") ctx->opt_fast_group = value ? 1 : 0;
     else if (n == "group_algo") ctx->opt_group_algo = value ? 1 : 0;
     else if (n == "hash_stream") ctx->opt_hash_stream = value ? 1 : 0;
+    else if (n == "fused_hist") ctx->opt_fused_hist = value ? 1 : 0;
     else if (n == "shard_bits0") { if (value < 0 || value > 9) return fail(ctx, KB_EINVAL, "shard_bits0 must be in 0..9"); ctx->opt_shard_bits0 = value; }
     else if (n == "bucket_bits") { if (value < -1 || value > 24) return fail(ctx, KB_EINVAL, "bucket_bits must be in -1..24"); ctx->opt_bucket_bits = value; }
     else if (n == "hash_slots_log2") { if (value != 0 && (value < 4 || value > 12)) return fail(ctx, KB_EINVAL, "hash_slots_log2 must be 0 or in 4..12"); ctx->opt_hash_slots_log2 = value; }
@@ -387,7 +389,8 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
     a.tile0 = tile0; a.n_tiles = n_tiles;
     a.pos_lo = pos_lo; a.pos_hi = pos_hi;
     a.hist = hist; a.hist_shift = hist_shift; a.hist_bits = hist_bits;
-    const size_t smem = kb_extract_smem(lo.k);
+    const bool wide_hist = hist && hist_bits > 9;            // 4-group CTAs with the packed shared-memory histogram (<= 16 bits)
+    const size_t smem = wide_hist ? kb_extract_smem(lo.k, 4, (int)hist_bits) : kb_extract_smem(lo.k);
     prof_begin(ctx, "K1 extract");
     // Tile batches: when the sequences are still arriving from the host (copy stream), K1 runs on the tiles whose
     // bytes (+ halo) are resident while the later files are in flight; otherwise one launch covers everything.
@@ -419,12 +422,26 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
         const uint32_t nt = bt.first > t0 ? bt.first - t0 : 0;
         if (!nt) continue;
         a.tile0 = t0; a.n_tiles = nt;
-        const uint32_t grid = std::min<uint32_t>(nt, (uint32_t)ctx->n_sm * 8);
-        switch (lo.W) {
-            case 1: kb_extract_kernel<1><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
-            case 2: kb_extract_kernel<2><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
-            case 4: kb_extract_kernel<4><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
-            default: kb_extract_kernel<8><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
+        if (wide_hist) {
+            const uint32_t grid = std::min<uint32_t>((nt + 3) / 4, (uint32_t)ctx->n_sm);
+            switch (lo.W) {
+                case 1: CU(cudaFuncSetAttribute(kb_extract_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        kb_extract_kernel<1, 4><<<grid, KB_K1_THREADS * 4, smem, ctx->stream>>>(a); break;
+                case 2: CU(cudaFuncSetAttribute(kb_extract_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        kb_extract_kernel<2, 4><<<grid, KB_K1_THREADS * 4, smem, ctx->stream>>>(a); break;
+                case 4: CU(cudaFuncSetAttribute(kb_extract_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        kb_extract_kernel<4, 4><<<grid, KB_K1_THREADS * 4, smem, ctx->stream>>>(a); break;
+                default: CU(cudaFuncSetAttribute(kb_extract_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        kb_extract_kernel<8, 4><<<grid, KB_K1_THREADS * 4, smem, ctx->stream>>>(a); break;
+            }
+        } else {
+            const uint32_t grid = std::min<uint32_t>(nt, (uint32_t)ctx->n_sm * 8);
+            switch (lo.W) {
+                case 1: kb_extract_kernel<1, 1><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
+                case 2: kb_extract_kernel<2, 1><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
+                case 4: kb_extract_kernel<4, 1><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
+                default: kb_extract_kernel<8, 1><<<grid, KB_K1_THREADS, smem, ctx->stream>>>(a); break;
+            }
         }
         CU(cudaGetLastError());
         ctx->launches++;
@@ -569,6 +586,7 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0) {
         pl.off_start[l] = off; off += ((size_t)pl.nc[l] + 1) * 8;
         pl.off_tile0[l] = off; off += (((size_t)pl.nc[l] + 1) * 4 + 7) & ~(size_t)7;
     }
+    pl.off_part = off; off += ((((size_t)1 << bb) + KB_PLAN_BLOCK - 1) / KB_PLAN_BLOCK + 1) * 16;
     pl.off_tilemap = off; off += (max_tiles * 4 + 7) & ~(size_t)7;
     pl.bytes = off;
     return pl;
@@ -577,8 +595,23 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0) {
 // Partition levels [l_begin, l_end) of `in` (at most n elements) -> *parted, child table of the last level -> *bstart / *n_buckets.
 // l_begin == 0: the exact element count is K1's device counter and the level-0 histogram is already in the plan buffer;
 // l_begin > 0 needs `cp` (the parents of that level).
+static int launch_plan(kb_ctx* ctx, KbPlanArgs pa, const PartPlan& pl) {
+    pa.part = (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_part);
+    const uint32_t nb = (pa.nc + KB_PLAN_BLOCK - 1) / KB_PLAN_BLOCK;
+    kb_plan_reduce_kernel<<<nb, KB_PLAN_BLOCK, 0, ctx->stream>>>(pa);
+    CU(cudaGetLastError());
+    kb_plan_scan_kernel<<<1, KB_PLAN_BLOCK, 0, ctx->stream>>>(pa.part, nb);
+    CU(cudaGetLastError());
+    kb_plan_apply_kernel<<<nb, KB_PLAN_BLOCK, 0, ctx->stream>>>(pa);
+    CU(cudaGetLastError());
+    ctx->launches += 3;
+    return KB_OK;
+}
+
+// have_hist1: K1 already counted the level-1 children (plan buffer, level-1 counts); level 0's counts are their row sums.
 static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& other, uint64_t n, int l_begin, int l_end,
-                         const CustomParents* cp, uint64_t** parted, const unsigned long long** bstart, uint32_t* n_buckets) {
+                         const CustomParents* cp, uint64_t** parted, const unsigned long long** bstart, uint32_t* n_buckets,
+                         bool have_hist1 = false) {
     uint64_t* cur = (uint64_t*)in.p;
     uint8_t* P = (uint8_t*)ctx->plan.p;
     unsigned long long* root = (unsigned long long*)ctx->small.p + SM_ROOT;
@@ -620,7 +653,21 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
             grid = n / KB_PT_TILE + pl.ncl[l - 1] + 1;
         }
         prof_begin(ctx, hnames[l]);
-        if (l > 0) {
+        if (l == 0 && have_hist1) {
+            // level-1 offsets straight from K1's two-level histogram; its row sums are the level-0 counts
+            KbPlanArgs p1{};
+            p1.counts = (unsigned long long*)(P + pl.off_cnt[1]); p1.nc = pl.ncl[1];
+            p1.start = (unsigned long long*)(P + pl.off_start[1]);
+            p1.cursor = (unsigned long long*)(P + pl.off_cnt[1]);
+            p1.tile0 = (uint32_t*)(P + pl.off_tile0[1]);
+            p1.folded = a.cursor; p1.fold = 1u << pl.bits[1];
+            TRY(launch_plan(ctx, p1, pl));
+        }
+        if (l == 1 && have_hist1) {
+            kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, a.n_parents, (uint32_t*)(P + pl.off_tilemap));
+            CU(cudaGetLastError());
+            ctx->launches++;
+        } else if (l > 0) {
             kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, a.n_parents, (uint32_t*)(P + pl.off_tilemap));
             CU(cudaGetLastError());
             kb_part_hist_kernel<<<(unsigned)grid, KB_PT_THREADS, 0, ctx->stream>>>(a);
@@ -628,14 +675,14 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
             ctx->launches += 2;
             ctx->alg_rec_bytes += 8;
         }
-        KbPlanArgs pa{};
-        pa.counts = a.cursor; pa.nc = pl.ncl[l]; pa.base = 0;
-        pa.start = (unsigned long long*)(P + pl.off_start[l]);
-        pa.cursor = a.cursor;
-        pa.tile0 = (uint32_t*)(P + pl.off_tile0[l]);
-        kb_plan_kernel<<<1, 1024, 0, ctx->stream>>>(pa);
-        CU(cudaGetLastError());
-        ctx->launches++;
+        if (!(l == 1 && have_hist1)) {
+            KbPlanArgs pa{};
+            pa.counts = a.cursor; pa.nc = pl.ncl[l];
+            pa.start = (unsigned long long*)(P + pl.off_start[l]);
+            pa.cursor = a.cursor;
+            pa.tile0 = (uint32_t*)(P + pl.off_tile0[l]);
+            TRY(launch_plan(ctx, pa, pl));
+        }
         prof_end(ctx);
         prof_begin(ctx, pnames[l]);
         kb_part_kernel<2><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
@@ -929,13 +976,18 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
         const PartPlan pl = make_plan(ctx, 2 * ctx->n_bases + 64);
         TRY(ensure(ctx, ctx->plan, pl.bytes + 64));
         if (pl.levels) CU(cudaMemsetAsync(ctx->plan.p, 0, pl.bytes, ctx->stream));
-        unsigned long long* h0 = pl.levels ? (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[0]) : nullptr;
-        TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0], true));
+        // K1 counts the children of the first level — or of the first TWO levels at once (packed shared-memory histogram), which
+        // saves the pass that would re-read every record just to count level 1
+        const bool fused2 = ctx->opt_fused_hist && pl.levels >= 2 && pl.bits[0] + pl.bits[1] >= 10 && pl.bits[0] + pl.bits[1] <= 16;
+        const int hl = fused2 ? 1 : 0;
+        const uint32_t hbits = fused2 ? (uint32_t)(pl.bits[0] + pl.bits[1]) : (uint32_t)pl.bits[0];
+        unsigned long long* h0 = pl.levels ? (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[hl]) : nullptr;
+        TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, 64 - hbits, hbits, true));
         if (!lo.direct && n >= (1ULL << 32) + 64) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
         uint64_t* parted = nullptr;
         HashStage hs{};
         hs.pl = &pl;
-        TRY(run_partition(ctx, pl, ctx->entA, ctx->entB, n, 0, pl.levels, nullptr, &parted, &hs.bstart, &hs.n_buckets));
+        TRY(run_partition(ctx, pl, ctx->entA, ctx->entB, n, 0, pl.levels, nullptr, &parted, &hs.bstart, &hs.n_buckets, fused2));
         int rc = run_group(ctx, parted, n, out, &hs);
         prof_collect(ctx);
         return rc;

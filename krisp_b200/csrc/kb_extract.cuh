@@ -65,10 +65,30 @@ __device__ __forceinline__ uint32_t kb_pack4(uint32_t x, int soft_omit, uint32_t
     return packed;
 }
 
-template <int WN>   // WN = 1: DIRECT; 2/4/8: INDIRECT with WN words per record
-__global__ void __launch_bounds__(KB_K1_THREADS) kb_extract_kernel(const KbExtractArgs a) {
+// shared memory of one 256-thread group (bytes, multiple of 16)
+__host__ __device__ __forceinline__ size_t kb_extract_smem_dev(int k) {
+    const uint32_t halo = ((uint32_t)(k - 1) + 31u) & ~31u;
+    const uint32_t NWORD = (KB_K1_TB + halo) / 32;
+    const size_t s = (size_t)(NWORD + 1) * 8 * 2 + (size_t)((NWORD + 3) & ~1u) * 4 + (size_t)(KB_K1_TB / 32) * 4 * 2;
+    return (s + 31) & ~(size_t)15;
+}
+
+// WN = 1: DIRECT; 2/4/8: INDIRECT with WN words per record.
+// GROUPS = 1: one 256-thread group per CTA, digit histogram of <= 9 bits (512 shared-memory counters).
+// GROUPS = 4: FOUR independent 256-thread groups per CTA (named barriers), ONE CTA per SM, sharing a shared-memory histogram
+//             of up to 16 bits with 16-bit packed counters (128 KB): the child counts of the first TWO partition levels come out
+//             of K1 and the partition never re-reads the records just to count them.
+template <int GROUPS> __device__ __forceinline__ void kb_k1_sync(uint32_t group) {
+    if constexpr (GROUPS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "n"(KB_K1_THREADS) : "memory");
+}
+
+template <int WN, int GROUPS>
+__global__ void __launch_bounds__(KB_K1_THREADS * GROUPS) kb_extract_kernel(const KbExtractArgs a) {
     constexpr bool DIRECT = (WN == 1);
-    extern __shared__ __align__(16) unsigned char kb_smem_raw[];
+    extern __shared__ __align__(16) unsigned char kb_smem_all[];
+    const uint32_t group = GROUPS == 1 ? 0u : threadIdx.x / KB_K1_THREADS;
+    unsigned char* kb_smem_raw = kb_smem_all + (size_t)group * kb_extract_smem_dev(a.lo.k);
     const KbLayout& lo = a.lo;
     const uint32_t k = (uint32_t)lo.k;
     const uint32_t halo = ((k - 1) + 31u) & ~31u;
@@ -81,19 +101,38 @@ __global__ void __launch_bounds__(KB_K1_THREADS) kb_extract_kernel(const KbExtra
     uint32_t* bad = reinterpret_cast<uint32_t*>(rcs + NWORD + 1);        // NWORD + 2
     uint32_t* okw = bad + ((NWORD + 3) & ~1u);                           // NOK
     uint32_t* pre = okw + NOK;                                           // NOK exclusive popcount prefix
-    __shared__ unsigned long long s_base;
-    __shared__ int s_flo, s_fhi;
-    __shared__ uint32_t s_hist[512];
+    __shared__ unsigned long long s_base_g[GROUPS];
+    __shared__ int s_flo_g[GROUPS], s_fhi_g[GROUPS];
+    __shared__ uint32_t s_hist[GROUPS == 1 ? 512 : 1];
+    unsigned long long& s_base = s_base_g[group];
+    int& s_flo = s_flo_g[group];
+    int& s_fhi = s_fhi_g[group];
+    uint32_t* bh = reinterpret_cast<uint32_t*>(kb_smem_all + (size_t)GROUPS * kb_extract_smem_dev(a.lo.k));   // GROUPS > 1: 2^(hist_bits-1) packed words
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tid = GROUPS == 1 ? threadIdx.x : threadIdx.x % KB_K1_THREADS, lane = tid & 31, warp = tid >> 5;
     const uint32_t FB = (uint32_t)lo.FB;
     const bool do_hist = a.hist != nullptr;
     const uint32_t hmask = (1u << a.hist_bits) - 1u;
-    if (do_hist) for (uint32_t i = tid; i < 512; i += KB_K1_THREADS) s_hist[i] = 0;
+    if (do_hist) {
+        if constexpr (GROUPS == 1) { for (uint32_t i = tid; i < 512; i += KB_K1_THREADS) s_hist[i] = 0; }
+        else { for (uint32_t i = threadIdx.x; i < (1u << (a.hist_bits - 1)); i += KB_K1_THREADS * GROUPS) bh[i] = 0; __syncthreads(); }
+    }
+    auto hist_add = [&](uint64_t e) {
+        const uint32_t bin = (uint32_t)(e >> a.hist_shift) & hmask;
+        if constexpr (GROUPS == 1) atomicAdd(&s_hist[bin], 1u);
+        else {
+            const uint32_t sh = (bin & 1u) << 4;
+            const uint32_t old = atomicAdd(&bh[bin >> 1], 1u << sh);
+            if (((old >> sh) & 0xFFFFu) == 0x7FFFu) {            // half-way to the carry: move 2^15 counts to the global histogram
+                atomicSub(&bh[bin >> 1], 0x8000u << sh);
+                atomicAdd(a.hist + bin, 0x8000ULL);
+            }
+        }
+    };
 
-    for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile0 + a.n_tiles; tile += gridDim.x) {
+    for (uint32_t tile = a.tile0 + blockIdx.x * GROUPS + group; tile < a.tile0 + a.n_tiles; tile += gridDim.x * GROUPS) {
         const uint64_t tile_base = (uint64_t)tile * KB_K1_TB;
-        __syncthreads();   // previous tile's readers are done with shared memory
+        kb_k1_sync<GROUPS>(group);   // previous tile's readers are done with shared memory
 
         // ---- 1. pack: 32 bases per thread-iteration ------------------------------------------
         for (uint32_t wv = tid; wv < NWORD; wv += KB_K1_THREADS) {
@@ -121,7 +160,7 @@ __global__ void __launch_bounds__(KB_K1_THREADS) kb_extract_kernel(const KbExtra
             while (h1 - l1 > 1) { int m = (l1 + h1) >> 1; if (__ldg(a.file_starts + m) <= g1) l1 = m; else h1 = m; }
             s_flo = l0; s_fhi = l1;
         }
-        __syncthreads();
+        kb_k1_sync<GROUPS>(group);
 
         // ---- 2. window validity bitmap + dense offsets -----------------------------------------
         if (tid < NOK) {
@@ -138,7 +177,7 @@ __global__ void __launch_bounds__(KB_K1_THREADS) kb_extract_kernel(const KbExtra
             if (g + 32 > a.pos_hi) ok &= (g >= a.pos_hi) ? 0u : (0xFFFFFFFFu >> (uint32_t)(g + 32 - a.pos_hi));
             okw[tid] = ok;
         }
-        __syncthreads();
+        kb_k1_sync<GROUPS>(group);
         if (warp == 0) {
             uint32_t c[4], s = 0;
 #pragma unroll
@@ -151,7 +190,7 @@ __global__ void __launch_bounds__(KB_K1_THREADS) kb_extract_kernel(const KbExtra
             for (int i = 0; i < 4; i++) { pre[4 * lane + i] = ex; ex += c[i]; }
             if (lane == 31) s_base = inc ? atomicAdd(a.n_out, 2ULL * inc) : 0ULL;
         }
-        __syncthreads();
+        kb_k1_sync<GROUPS>(group);
         const uint64_t obase = s_base;
         const int flo = s_flo, fhi = s_fhi;
         const uint32_t gid_uniform = __ldg(a.file_gid + flo);
@@ -192,8 +231,8 @@ __global__ void __launch_bounds__(KB_K1_THREADS) kb_extract_kernel(const KbExtra
                 }
                 kb_st_stream128(a.out_entries + oidx, r[0], r[1]);
                 if (do_hist) {
-                    atomicAdd(&s_hist[(uint32_t)(r[0] >> a.hist_shift) & hmask], 1u);
-                    atomicAdd(&s_hist[(uint32_t)(r[1] >> a.hist_shift) & hmask], 1u);
+                    hist_add(r[0]);
+                    hist_add(r[1]);
                 }
             } else {
                 uint64_t ent[2];
@@ -218,24 +257,29 @@ __global__ void __launch_bounds__(KB_K1_THREADS) kb_extract_kernel(const KbExtra
                 }
                 kb_st_stream128(a.out_entries + oidx, ent[0], ent[1]);
                 if (do_hist) {
-                    atomicAdd(&s_hist[(uint32_t)(ent[0] >> a.hist_shift) & hmask], 1u);
-                    atomicAdd(&s_hist[(uint32_t)(ent[1] >> a.hist_shift) & hmask], 1u);
+                    hist_add(ent[0]);
+                    hist_add(ent[1]);
                 }
             }
         }
     }
     if (do_hist) {
         __syncthreads();
-        for (uint32_t i = tid; i <= hmask; i += KB_K1_THREADS) {
-            const uint32_t c = s_hist[i];
-            if (c) atomicAdd(a.hist + i, (unsigned long long)c);
+        if constexpr (GROUPS == 1) {
+            for (uint32_t i = tid; i <= hmask; i += KB_K1_THREADS) {
+                const uint32_t c = s_hist[i];
+                if (c) atomicAdd(a.hist + i, (unsigned long long)c);
+            }
+        } else {
+            for (uint32_t w = threadIdx.x; w < (1u << (a.hist_bits - 1)); w += KB_K1_THREADS * GROUPS) {
+                const uint32_t v = bh[w];
+                if (v & 0xFFFFu) atomicAdd(a.hist + 2 * w, (unsigned long long)(v & 0xFFFFu));
+                if (v >> 16) atomicAdd(a.hist + 2 * w + 1, (unsigned long long)(v >> 16));
+            }
         }
     }
 }
 
-static inline size_t kb_extract_smem(int k) {
-    uint32_t halo = ((uint32_t)(k - 1) + 31u) & ~31u;
-    uint32_t NWORD = (KB_K1_TB + halo) / 32;
-    size_t s = (size_t)(NWORD + 1) * 8 * 2 + (size_t)((NWORD + 3) & ~1u) * 4 + (size_t)(KB_K1_TB / 32) * 4 * 2;
-    return s + 16;
+static inline size_t kb_extract_smem(int k, int groups = 1, int hist_bits = 0) {
+    return (size_t)groups * kb_extract_smem_dev(k) + (groups > 1 ? ((size_t)1 << (hist_bits - 1)) * 4 : 0) + 16;
 }

@@ -75,29 +75,26 @@ __global__ void __launch_bounds__(KB_PT_THREADS) kb_part_hist_kernel(const KbPar
     }
 }
 
-// ---- counts -> offsets, cursors, tile prefix (ONE CTA) ----------------------------------------------
-// counts[nc] (u64) -> start[nc + 1] exclusive prefix (+ base), cursor[c] = start[c],
-// tile0[nc + 1] = exclusive prefix of ceil(count / TILE).
+// ---- counts -> offsets, cursors, tile prefix: three small launches (block sums, scan of the block sums, apply) -----------
+// counts[nc] (u64) -> start[nc + 1] exclusive prefix, cursor[c] = start[c], tile0[nc + 1] = exclusive prefix of ceil(count / TILE).
+// `cursor` may alias `counts` (each element is read before it is overwritten).
+#define KB_PLAN_BLOCK 1024
 struct KbPlanArgs {
     const unsigned long long* counts;
     uint32_t nc;
-    unsigned long long base;            // offset of the first child
     unsigned long long* start;          // [nc + 1]
     unsigned long long* cursor;         // [nc] (may be null)
     uint32_t* tile0;                    // [nc + 1] (may be null)
-    // optional: also fold groups of `fold` consecutive counts into parent counts (level-1 histogram from a
-    // fused finer histogram); null = off
+    unsigned long long* part;           // scratch: [2 * ceil(nc / 1024)] block sums of counts / of tile counts
+    // optional: also fold groups of `fold` consecutive counts (fold divides 1024) into parent counts: the level-0 histogram
+    // from K1's two-level histogram; null = off
     unsigned long long* folded; uint32_t fold;
 };
 
-__global__ void __launch_bounds__(1024) kb_plan_kernel(const KbPlanArgs a) {
-    __shared__ unsigned long long ws[32], wt[32];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (a.nc + 1023u) / 1024u;
-    const uint32_t c0 = min(a.nc, tid * per), c1 = min(a.nc, c0 + per);
-    unsigned long long sum = 0, tsum = 0;
-    for (uint32_t c = c0; c < c1; c++) { const unsigned long long v = a.counts[c]; sum += v; tsum += (v + KB_PT_TILE - 1) / KB_PT_TILE; }
-    unsigned long long x = sum, y = tsum;
+__device__ __forceinline__ void kb_block_scan2(unsigned long long& x, unsigned long long& y, unsigned long long* ws, unsigned long long* wt,
+                                               unsigned long long& tx, unsigned long long& ty) {
+    // inclusive scan of (x, y) over the 1024 threads of the CTA; (tx, ty) = CTA totals
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const unsigned long long ox = __shfl_up_sync(0xFFFFFFFFu, x, d), oy = __shfl_up_sync(0xFFFFFFFFu, y, d);
@@ -105,26 +102,60 @@ __global__ void __launch_bounds__(1024) kb_plan_kernel(const KbPlanArgs a) {
     }
     if (lane == 31) { ws[warp] = x; wt[warp] = y; }
     __syncthreads();
-    unsigned long long addx = 0, addy = 0;
-    for (uint32_t w = 0; w < warp; w++) { addx += ws[w]; addy += wt[w]; }
-    unsigned long long run = a.base + addx + x - sum, trun = addy + y - tsum;
+    unsigned long long ax = 0, ay = 0; tx = 0; ty = 0;
+    for (uint32_t w = 0; w < 32; w++) { if (w < warp) { ax += ws[w]; ay += wt[w]; } tx += ws[w]; ty += wt[w]; }
+    x += ax; y += ay;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(KB_PLAN_BLOCK) kb_plan_reduce_kernel(const KbPlanArgs a) {
+    __shared__ unsigned long long ws[32], wt[32], sv[KB_PLAN_BLOCK];
+    const uint32_t i = blockIdx.x * KB_PLAN_BLOCK + threadIdx.x;
+    const unsigned long long v = i < a.nc ? a.counts[i] : 0ULL;
+    unsigned long long x = v, y = (v + KB_PT_TILE - 1) / KB_PT_TILE, tx, ty;
+    if (a.folded) sv[threadIdx.x] = v;
+    kb_block_scan2(x, y, ws, wt, tx, ty);
+    if (threadIdx.x == 0) { a.part[2 * blockIdx.x] = tx; a.part[2 * blockIdx.x + 1] = ty; }
+    if (a.folded && (threadIdx.x % a.fold) == 0 && i < a.nc) {
+        unsigned long long s = 0;
+        for (uint32_t j = 0; j < a.fold; j++) s += sv[threadIdx.x + j];
+        a.folded[i / a.fold] = s;
+    }
+}
+
+// exclusive scan of the nb (count sum, tile sum) pairs in place; ONE CTA
+__global__ void __launch_bounds__(KB_PLAN_BLOCK) kb_plan_scan_kernel(unsigned long long* part, uint32_t nb) {
+    __shared__ unsigned long long ws[32], wt[32];
+    const uint32_t per = (nb + KB_PLAN_BLOCK - 1) / KB_PLAN_BLOCK;
+    const uint32_t c0 = min(nb, threadIdx.x * per), c1 = min(nb, c0 + per);
+    unsigned long long sx = 0, sy = 0;
+    for (uint32_t c = c0; c < c1; c++) { sx += part[2 * c]; sy += part[2 * c + 1]; }
+    unsigned long long x = sx, y = sy, tx, ty;
+    kb_block_scan2(x, y, ws, wt, tx, ty);
+    unsigned long long rx = x - sx, ry = y - sy;
     for (uint32_t c = c0; c < c1; c++) {
-        const unsigned long long v = a.counts[c];
-        a.start[c] = run;
-        if (a.cursor) a.cursor[c] = run;
-        if (a.tile0) a.tile0[c] = (uint32_t)trun;
-        run += v; trun += (v + KB_PT_TILE - 1) / KB_PT_TILE;
+        const unsigned long long vx = part[2 * c], vy = part[2 * c + 1];
+        part[2 * c] = rx; part[2 * c + 1] = ry;
+        rx += vx; ry += vy;
     }
-    if (tid == 1023) {
-        a.start[a.nc] = run;
-        if (a.tile0) a.tile0[a.nc] = (uint32_t)trun;
+}
+
+__global__ void __launch_bounds__(KB_PLAN_BLOCK) kb_plan_apply_kernel(const KbPlanArgs a) {
+    __shared__ unsigned long long ws[32], wt[32];
+    const uint32_t i = blockIdx.x * KB_PLAN_BLOCK + threadIdx.x;
+    const unsigned long long v = i < a.nc ? a.counts[i] : 0ULL;
+    const unsigned long long t = (v + KB_PT_TILE - 1) / KB_PT_TILE;
+    unsigned long long x = v, y = t, tx, ty;
+    kb_block_scan2(x, y, ws, wt, tx, ty);
+    const unsigned long long bx = a.part[2 * blockIdx.x], by = a.part[2 * blockIdx.x + 1];
+    if (i < a.nc) {
+        a.start[i] = bx + x - v;
+        if (a.cursor) a.cursor[i] = bx + x - v;
+        if (a.tile0) a.tile0[i] = (uint32_t)(by + y - t);
     }
-    if (a.folded) {
-        for (uint32_t p = tid; p < a.nc / a.fold; p += 1024) {
-            unsigned long long s = 0;
-            for (uint32_t j = 0; j < a.fold; j++) s += a.counts[(size_t)p * a.fold + j];
-            a.folded[p] = s;
-        }
+    if (i + 1 == a.nc) {
+        a.start[a.nc] = bx + x;
+        if (a.tile0) a.tile0[a.nc] = (uint32_t)(by + y);
     }
 }
 
