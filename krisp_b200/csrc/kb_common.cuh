@@ -55,22 +55,14 @@ __host__ __device__ constexpr uint64_t kb_inv64(uint64_t a) {   // inverse of od
 }
 __host__ __device__ __forceinline__ uint64_t kb_lowmask(int nb) { return nb >= 64 ? ~0ULL : ((1ULL << nb) - 1ULL); }
 
-// nb in 1..64, s = (nb+1)/2 (so that x ^= x >> s is an involution on nb bits)
-__host__ __device__ __forceinline__ uint64_t kb_mix(uint64_t x, int nb, uint32_t s) {
-    const uint64_t m = kb_lowmask(nb);
-    x = (x * KB_MIX_C1) & m;
-    x ^= x >> s;
-    x = (x * KB_MIX_C2) & m;
-    x ^= x >> s;
-    return x;
+// Multiplicative mixing mod 2^nb (nb in 1..64): a bijection whose TOP bits depend on every input bit — exactly what the
+// partition digits (top bits) and the hash-table slot (the bits below them) need; inverted only for survivors.
+// (An earlier two-round multiply / xor-shift version cost K1 13 more instructions per record for no measurable gain in balance.)
+__host__ __device__ __forceinline__ uint64_t kb_mix(uint64_t x, int nb, uint32_t /*s*/) {
+    return (x * KB_MIX_C1) & kb_lowmask(nb);
 }
-__host__ __device__ __forceinline__ uint64_t kb_unmix(uint64_t x, int nb, uint32_t s) {
-    const uint64_t m = kb_lowmask(nb);
-    x ^= x >> s;
-    x = (x * kb_inv64(KB_MIX_C2)) & m;
-    x ^= x >> s;
-    x = (x * kb_inv64(KB_MIX_C1)) & m;
-    return x;
+__host__ __device__ __forceinline__ uint64_t kb_unmix(uint64_t x, int nb, uint32_t /*s*/) {
+    return (x * kb_inv64(KB_MIX_C1)) & kb_lowmask(nb);
 }
 
 __host__ __device__ __forceinline__ uint64_t kb_mix64(uint64_t x) {

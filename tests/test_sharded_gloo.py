@@ -22,12 +22,7 @@ C1, C2 = 0x9E3779B97F4A7C15, 0xD6E8FEB86659FD93
 
 def kb_mix(x, nb):
     """csrc/kb_common.cuh kb_mix, restated."""
-    m, s = (1 << nb) - 1, (nb + 1) // 2
-    x = (x * C1) & m
-    x ^= x >> s
-    x = (x * C2) & m
-    x ^= x >> s
-    return x
+    return (x * C1) & ((1 << nb) - 1)
 
 
 class FakeSearcher:
@@ -107,9 +102,7 @@ class FakeSearcher:
             col = lambda m, c: (m >> (2 * (D - 1 - c))) & 3
             if D and not any({col(m, c) for m in ins}.isdisjoint({col(m, c) for m in outs}) for c in range(D)):
                 continue
-            m_, s_ = (1 << self.FB) - 1, (self.FB + 1) // 2
-            x = key
-            x ^= x >> s_; x = (x * inv2) & m_; x ^= x >> s_; x = (x * inv1) & m_
+            x = (key * inv1) & ((1 << self.FB) - 1)
             flank = "".join("ACGT"[(x >> (2 * (L + R - 1 - i))) & 3] for i in range(L + R))
             use = ins if have_outgroup else ins + outs
             cons = "".join(model.IUPAC_KEY[tuple(sorted({"ACGT"[col(m, c)] for m in use}))] for c in range(D))
