@@ -322,7 +322,7 @@ def run_ours(args):
                                f"with planted group SNPs, --conserved-left {L_} --diagnostic {D_} --conserved-right {R_} ({L_ + D_ + R_}-mer, "
                                f"{'one 64-bit record' if 2 * (L_ + D_ + R_) + 8 <= 64 else 'multi-word records'})",
                    "total_bases": total_bases, "records": int(n_rec) if world == 1 else None,
-                   "radix_passes": counters["radix_passes"], "rows": n_rows_total,
+                   "radix_passes": counters["radix_passes"], "rows": n_rows_total, "k3_stats": dict(last.stats),
                    "l2": "inputs larger than L2 (>= 0.2 GB of bases, 3.2 GB of records per GPU; 126 MB L2)",
                    "parallelism": f"flank-hash sharded x{world}" if world > 1 else "single GPU"},
         "e2e": {"value": total_bases / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
     // full probe (dense: called with the queued records of a whole warp): find the key or claim an empty slot
     auto insert = [&](uint64_t e) {
         const uint64_t key = e >> kshift;
-        uint32_t slot = kb_kh_bits(e, x.bb, hmask) >> sshift;
+        uint32_t slot = (kb_kh_bits(e, x.bb, hmask) * 0x9E3779B1u) >> sshift;   // (one more multiply: the key bits below the bucket bits are only lightly mixed)
         for (uint32_t step = 0; step <= S; step++) {
             const uint32_t sa = tab_a + slot * (uint32_t)sizeof(KbHsSlot);
             uint64_t k = kb_lds64(sa);
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
     // the common case inline: the key sits in its home slot; everything else goes through the queue
     auto handle = [&](uint64_t e, bool act) {
         const uint64_t key = e >> kshift;
-        const uint32_t sa = tab_a + (kb_kh_bits(e, x.bb, hmask) >> sshift) * (uint32_t)sizeof(KbHsSlot);
+        const uint32_t sa = tab_a + ((kb_kh_bits(e, x.bb, hmask) * 0x9E3779B1u) >> sshift) * (uint32_t)sizeof(KbHsSlot);
         const uint64_t k = kb_lds64(sa);
         const bool hit = act && (packed ? (k & KB_HS_KEYMASK) : k) == key;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, act && !hit);
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
 
     auto handle_full = [&](uint64_t e) {          // handle() for a record that is known to be in range
         const uint64_t key = e >> kshift;
-        const uint32_t sa = tab_a + (kb_kh_bits(e, x.bb, hmask) >> sshift) * (uint32_t)sizeof(KbHsSlot);
+        const uint32_t sa = tab_a + ((kb_kh_bits(e, x.bb, hmask) * 0x9E3779B1u) >> sshift) * (uint32_t)sizeof(KbHsSlot);
         const uint64_t k = kb_lds64(sa);
         const bool hit = (packed ? (k & KB_HS_KEYMASK) : k) == key;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, !hit);
