@@ -45,10 +45,17 @@ class SearchResult:
             return int(self.flank_words.shape[0])
         return 0 if self._left is None else int(self._left.shape[0])
 
+    def _decode_flanks(self):
+        both = _decode_bases(self.flank_words, 0, self.L + self.R)      # left and right are adjacent in the flank bits
+        if self._left is None:
+            self._left = both[:, :self.L]
+        if self._right is None:
+            self._right = both[:, self.L:]
+
     @property
     def left(self):
         if self._left is None:
-            self._left = _decode_bases(self.flank_words, 0, self.L)
+            self._decode_flanks()
         return self._left
 
     @left.setter
@@ -58,7 +65,7 @@ class SearchResult:
     @property
     def right(self):
         if self._right is None:
-            self._right = _decode_bases(self.flank_words, 2 * self.L, self.R)
+            self._decode_flanks()
         return self._right
 
     @right.setter
@@ -97,15 +104,34 @@ class SearchResult:
             return []
         cons = self.in_mask if self.have_outgroup else (self.in_mask | self.out_mask)
         width = self.L + 1 + self.D + 1 + self.R
-        m = np.empty((n, width), dtype=np.uint8)
+        m = np.empty((n, width + 1), dtype=np.uint8)               # row = text + "\n"
         m[:, :self.L] = self.left
         m[:, self.L] = ord(",")
         m[:, self.L + 1:self.L + 1 + self.D] = _IUPAC[cons]
         m[:, self.L + 1 + self.D] = ord(",")
-        m[:, self.L + 2 + self.D:] = self.right
-        flat = np.sort(np.ascontiguousarray(m).view(f"S{width}").ravel())      # bytewise order = str order for ASCII
-        text = flat.tobytes().decode("ascii")
-        return [text[i:i + width] for i in range(0, len(text), width)]
+        m[:, self.L + 2 + self.D:width] = self.right
+        m[:, width] = ord("\n")
+        # Canonical (str) order.  The flank words sort by (left, right); the row text sorts by (left, consensus, right): the two
+        # differ only inside runs of equal `left`, which are rare and are re-sorted as text.
+        fw = self.flank_words
+        if fw is None or fw.shape[0] != n:                         # (results assembled by hand: no packed flanks)
+            return sorted(m.tobytes().decode("ascii").split("\n")[:-1])
+        order = np.lexsort(tuple(fw[:, j] for j in range(fw.shape[1] - 1, -1, -1))) if fw.shape[1] > 1 else np.argsort(fw[:, 0], kind="stable")
+        ms = m[order]
+        rows = ms.tobytes().decode("ascii").split("\n")[:-1]
+        tie = np.flatnonzero(np.all(ms[1:, :self.L] == ms[:-1, :self.L], axis=1)) if n > 1 else ()
+        i = 0
+        while i < len(tie):
+            a = int(tie[i])
+            while i + 1 < len(tie) and tie[i + 1] == tie[i] + 1:
+                i += 1
+            b = int(tie[i]) + 2
+            rows[a:b] = sorted(rows[a:b])
+            i += 1
+        return rows
+
+
+_BYTE2LETTERS = _ACGT[(np.arange(256, dtype=np.uint16)[:, None] >> np.array([6, 4, 2, 0], dtype=np.uint16)[None, :]) & 3]   # [256, 4]
 
 
 def _decode_bases(words, first_bit, n_bases):
@@ -113,6 +139,13 @@ def _decode_bases(words, first_bit, n_bases):
     n = words.shape[0]
     if n == 0 or n_bases == 0:
         return np.zeros((n, n_bases), dtype=np.uint8)
+    if first_bit % 2 == 0:
+        # one table look-up per byte: 4 letters at a time
+        by = np.ascontiguousarray(words.astype(">u8")).view(np.uint8).reshape(n, -1)
+        b0, b1 = first_bit // 8, (first_bit + 2 * n_bases + 7) // 8
+        letters = _BYTE2LETTERS[by[:, b0:b1]].reshape(n, -1)
+        off = (first_bit % 8) // 2
+        return letters[:, off:off + n_bases]
     bits = np.unpackbits(np.ascontiguousarray(words.astype(">u8")).view(np.uint8).reshape(n, -1), axis=1)
     sel = bits[:, first_bit:first_bit + 2 * n_bases].reshape(n, n_bases, 2)
     return _ACGT[sel[:, :, 0] * 2 + sel[:, :, 1]]

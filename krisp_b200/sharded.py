@@ -91,6 +91,25 @@ def exchange(searcher, send_ptr, send_counts, digit_counts, device, group=None):
     return n_recv, pieces, {"sent": int(sum(send_counts) - send_counts[rank]), "received": n_recv}
 
 
+def piece_tables(table, rank):
+    """From the all-gathered digit counts ``table[source][digit]``: (records every shard receives, for `rank` the element offset
+    of its piece of every digit in the owner's receive buffer, the piece counts of `rank`'s own shard in arrival order).
+    A receive buffer is laid out by source rank, then digit."""
+    table = np.asarray(table, dtype=np.int64)
+    world, nd = table.shape
+    firsts = [first_digit(s, world, nd) for s in range(world + 1)]
+    need = [int(table[:, firsts[s]:firsts[s + 1]].sum()) for s in range(world)]
+    piece_base = [0] * nd
+    for s in range(world):
+        sub = table[:, firsts[s]:firsts[s + 1]]
+        flat = np.concatenate([[0], np.cumsum(sub.reshape(-1))])      # pieces in (source, digit) order
+        dps = firsts[s + 1] - firsts[s]
+        for j in range(dps):
+            piece_base[firsts[s] + j] = int(flat[rank * dps + j])
+    pieces = table[:, firsts[rank]:firsts[rank + 1]].reshape(-1).tolist()
+    return need, piece_base, pieces
+
+
 def direct_search(searcher, device, have_outgroup=True, group=None):
     """Steps 1-3 with the exchange FUSED into partition level 0: every rank stores each digit's run straight into the
     owner's receive buffer over NVLink peer memory (CUDA IPC mappings of library-owned buffers), so the only collectives
@@ -108,8 +127,7 @@ def direct_search(searcher, device, have_outgroup=True, group=None):
     dist.all_gather_into_tensor(alld, dg, group=group)
     table = alld.view(world, nd).cpu().numpy()                        # [source][digit]
     firsts = [first_digit(s, world, nd) for s in range(world + 1)]
-    # receive-buffer layout of shard s: pieces by source rank, then digit
-    need = [int(table[:, firsts[s]:firsts[s + 1]].sum()) for s in range(world)]
+    need, piece_base, pieces = piece_tables(table, rank)
     state = searcher.__dict__.setdefault("_ipc_state", {"cap": [0] * world, "world": world})
     if state["world"] != world or any(n > c for n, c in zip(need, state["cap"])):
         # some buffer is too small: every rank sees the same table, so every rank takes this branch together
@@ -120,19 +138,11 @@ def direct_search(searcher, device, have_outgroup=True, group=None):
         dist.all_gather_into_tensor(allh, mine, group=group)
         blob = allh.cpu().numpy().tobytes()
         searcher.shard_ipc_import([blob[64 * r:64 * (r + 1)] for r in range(world)])
-    piece_base = [0] * nd
-    for s in range(world):
-        sub = table[:, firsts[s]:firsts[s + 1]]
-        flat = np.concatenate([[0], np.cumsum(sub.reshape(-1))])      # pieces in (source, digit) order
-        dps = firsts[s + 1] - firsts[s]
-        for j in range(dps):
-            piece_base[firsts[s] + j] = int(flat[rank * dps + j])
     searcher.shard_scatter(piece_base)                                # partition level 0 -> peer stores
     prof += [p for p in searcher.last_profile() if p[0].startswith("K2 partition 0")]
     flag = torch.zeros(1, dtype=torch.int32, device=device)
     dist.all_reduce(flag, group=group)                                # every rank's stores have landed
     ev[1].record()
-    pieces = table[:, firsts[rank]:firsts[rank + 1]].reshape(-1).tolist()
     res = searcher.shard_search(need[rank], pieces, have_outgroup=have_outgroup)
     ev[1].synchronize()
     prof.append(("K4 count all-gather + partition/exchange + barrier", ev[0].elapsed_time(ev[1])))

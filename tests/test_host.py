@@ -134,3 +134,30 @@ def test_digit_ranges_partition_the_key_space():
     for n in (1, 2, 3, 8):
         firsts = [sharded.first_digit(s, n, 32) for s in range(n + 1)]
         assert firsts[0] == 0 and firsts[-1] == 32 and all(a < b for a, b in zip(firsts, firsts[1:]))
+
+
+def test_piece_tables_tile_every_receive_buffer_exactly():
+    """Fused partition + exchange: the pieces (source rank, digit) every rank writes into an owner's buffer must tile that buffer
+    without gaps or overlaps, in the order the owner's kb_shard_search expects (source-major, digit-minor)."""
+    rng = np.random.default_rng(7)
+    for world, nd in ((2, 8), (3, 16), (8, 32), (4, 256)):
+        table = rng.integers(0, 50, size=(world, nd))
+        table[rng.integers(0, world), rng.integers(0, nd)] = 0
+        per_rank = [sharded.piece_tables(table, r) for r in range(world)]
+        firsts = [sharded.first_digit(s, world, nd) for s in range(world + 1)]
+        for s in range(world):
+            need = per_rank[0][0][s]
+            cover = np.zeros(need, dtype=np.int64)
+            for src in range(world):
+                base = per_rank[src][1]
+                for d in range(firsts[s], firsts[s + 1]):
+                    cover[base[d]:base[d] + table[src, d]] += 1
+            assert np.all(cover == 1)
+            # arrival order at the owner: pieces listed by source, then digit, with these very counts
+            pieces = per_rank[s][2]
+            assert pieces == table[:, firsts[s]:firsts[s + 1]].reshape(-1).tolist() and sum(pieces) == need
+            pos = 0
+            for i, c in enumerate(pieces):
+                src, j = divmod(i, firsts[s + 1] - firsts[s])
+                assert per_rank[src][1][firsts[s] + j] == pos
+                pos += c
