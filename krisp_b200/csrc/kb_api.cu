@@ -41,7 +41,8 @@ struct kb_table {
 struct PartPlan {
     int levels = 0, bits[3] = {0, 0, 0}, bb = 0;
     uint32_t slots_log2 = 11;
-    bool fast = false;
+    bool fast = false;                   // kb_hash_fast_kernel applies (one-word records, <= 64 files, D <= 8)
+    bool stream = false;                 // kb_hash_stream_kernel applies (one-word records, D <= 8, any file count)
     // device tables inside ctx->plan (byte offsets), per level: counts/cursors [NC], starts [NC + 1], tile prefix [NC + 1]
     size_t off_cnt[3] = {0, 0, 0}, off_start[3] = {0, 0, 0}, off_tile0[3] = {0, 0, 0}, off_part = 0, off_tilemap = 0, bytes = 0;
     uint32_t nc[3] = {0, 0, 0};          // children per level over the whole key space: 2^(bits[0] + ... + bits[l])
@@ -545,8 +546,10 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0) {
     const KbLayout& lo = ctx->lo;
     PartPlan pl;
     pl.fast = hash_fast_ok(ctx);
+    pl.stream = ctx->opt_hash_stream && ctx->opt_fast_group && lo.direct && lo.FB >= 1 && lo.MW <= 1;
     if (ctx->opt_hash_slots_log2) pl.slots_log2 = (uint32_t)ctx->opt_hash_slots_log2;
-    else if (pl.fast) pl.slots_log2 = ctx->opt_hash_stream ? 10 : 11;   // 24 KB (+ 24 KB ring) / 48 KB of table: 4 CTAs per SM
+    else if (pl.stream) pl.slots_log2 = 10;                     // 24 - 56 KB of table + 28 KB ring and queues: 4 - 2 CTAs per SM
+    else if (pl.fast) pl.slots_log2 = 11;                       // 48 KB of table: 4 CTAs per SM
     else {
         const size_t sb = kb_hash_slot_bytes(lo);
         uint32_t l2 = 11;
@@ -714,43 +717,53 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
     x.full64 = (uint64_t)g.full[0] | ((uint64_t)g.full[1] << 32);
     x.err = (unsigned long long*)ctx->small.p + SM_ERR;
     const unsigned grid = (unsigned)std::min<uint32_t>(hs.n_buckets, 1u << 20);
-    if (hs.pl->fast && ctx->opt_hash_stream) {
+    if (hs.pl->stream) {
         TRY(ensure(ctx, ctx->deferred, (size_t)hs.n_buckets * 4 + 64));
         KbHStreamArgs xs{};
         xs.h = x; xs.n_ptr = (const unsigned long long*)ctx->small.p + SM_NOUT;
         xs.deferred = (uint32_t*)ctx->deferred.p;
         xs.n_deferred = (unsigned long long*)ctx->small.p + SM_NTAINT;       // zeroed with the result counters
-        const size_t smem = kb_hash_stream_smem(x.slots_log2);
+        const int pwn = lo.n_files <= 64 ? 2 : (lo.n_files <= 128 ? 4 : 8);
+        const size_t smem = kb_hash_stream_smem(x.slots_log2, pwn);
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (220 * 1024) / (smem + 1024)));
         const unsigned sgrid = (unsigned)std::min<uint64_t>((uint64_t)ctx->n_sm * per_sm, std::max<uint64_t>(1, g.n / 4096));
-        // fallback for the deferred buckets: the splitting kernel with a roomier table
-        KbHashArgs fb = x;
-        fb.slots_log2 = ctx->opt_hash_slots_log2 ? x.slots_log2 : std::max<uint32_t>(x.slots_log2, 11);
-        fb.list = xs.deferred; fb.n_list = xs.n_deferred;
-        const size_t fsmem = kb_hash_fast_smem(fb.slots_log2);
-        KbHSizeArgs sz{};
-        sz.ent = g.ent; sz.n_res = g.n_res; sz.cap = g.cap; sz.res_flank = g.res_flank; sz.res_run = g.res_run; sz.res_size = g.res_size; sz.lo = lo;
         const bool spacer = lo.D == 1 && lo.FB == 54 && x.bb <= 22;
-        if (spacer) {
-            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaFuncSetAttribute(kb_hash_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            kb_hash_stream_kernel<true, true><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);
-            CU(cudaGetLastError());
-            kb_hash_fast_kernel<true><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
-        } else if (lo.D == 1) {
-            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaFuncSetAttribute(kb_hash_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            kb_hash_stream_kernel<true, false><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);
-            CU(cudaGetLastError());
-            kb_hash_fast_kernel<true><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
-        } else {
-            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaFuncSetAttribute(kb_hash_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            kb_hash_stream_kernel<false, false><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);
-            CU(cudaGetLastError());
-            kb_hash_fast_kernel<false><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
+#define KB_LAUNCH_STREAM(D1_, SP_, PW_)                                                                                        \
+        do {                                                                                                                   \
+            CU(cudaFuncSetAttribute(kb_hash_stream_kernel<D1_, SP_, PW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            kb_hash_stream_kernel<D1_, SP_, PW_><<<sgrid, KB_HS_THREADS, smem, ctx->stream>>>(xs);                                \
+        } while (0)
+        if (pwn == 2) { if (spacer) KB_LAUNCH_STREAM(true, true, 2); else if (lo.D == 1) KB_LAUNCH_STREAM(true, false, 2); else KB_LAUNCH_STREAM(false, false, 2); }
+        else if (pwn == 4) { if (spacer) KB_LAUNCH_STREAM(true, true, 4); else if (lo.D == 1) KB_LAUNCH_STREAM(true, false, 4); else KB_LAUNCH_STREAM(false, false, 4); }
+        else { if (spacer) KB_LAUNCH_STREAM(true, true, 8); else if (lo.D == 1) KB_LAUNCH_STREAM(true, false, 8); else KB_LAUNCH_STREAM(false, false, 8); }
+#undef KB_LAUNCH_STREAM
+        CU(cudaGetLastError());
+        // fallback for the deferred buckets: the splitting kernels with a roomier table
+        KbHashArgs fb = x;
+        fb.list = xs.deferred; fb.n_list = xs.n_deferred;
+        if (hs.pl->fast) {
+            fb.slots_log2 = ctx->opt_hash_slots_log2 ? x.slots_log2 : std::max<uint32_t>(x.slots_log2, 11);
+            const size_t fsmem = kb_hash_fast_smem(fb.slots_log2);
+            if (lo.D == 1) {
+                CU(cudaFuncSetAttribute(kb_hash_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                kb_hash_fast_kernel<true><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
+            } else {
+                CU(cudaFuncSetAttribute(kb_hash_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                kb_hash_fast_kernel<false><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
+            }
+        } else {                                               // > 64 files: the generic kernel
+            if (!ctx->opt_hash_slots_log2) {
+                uint32_t l2 = 11;
+                while (l2 > 6 && ((size_t)1 << l2) * kb_hash_slot_bytes(lo) > 96 * 1024) l2--;
+                fb.slots_log2 = l2;
+            }
+            const size_t fsmem = kb_hash_smem(lo, fb.slots_log2);
+            CU(cudaFuncSetAttribute(kb_hash_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            kb_hash_kernel<1><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
         }
         CU(cudaGetLastError());
+        KbHSizeArgs sz{};
+        sz.ent = g.ent; sz.n_res = g.n_res; sz.cap = g.cap; sz.res_flank = g.res_flank; sz.res_run = g.res_run; sz.res_size = g.res_size; sz.lo = lo;
         kb_hsize_kernel<<<(unsigned)ctx->n_sm * 4, 256, 0, ctx->stream>>>(sz);
         CU(cudaGetLastError());
         ctx->launches += 3;

@@ -293,7 +293,9 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_kernel(const KbHashArgs
         return KB_KH_NONE;
     };
 
-    for (uint32_t b = blockIdx.x; b < x.n_buckets; b += gridDim.x) {
+    const uint32_t n_work = x.list ? (uint32_t)min((unsigned long long)x.n_buckets, *x.n_list) : x.n_buckets;
+    for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const uint32_t b = x.list ? x.list[wi] : wi;
         const uint64_t bs = x.bstart[b], be = x.bstart[b + 1];
         if (be == bs) continue;
         __syncthreads();

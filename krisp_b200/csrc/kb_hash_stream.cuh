@@ -81,12 +81,16 @@ __device__ __forceinline__ uint32_t kb_lower_bound(const unsigned long long* bst
 // 54 flank bits (the spacer shape 25/1/2) the two 4-bit base sets live in bits 56-63 of the KEY word instead
 // (ingroup 56-59, outgroup 60-63): the one LDS.64 that checks the key also tells whether the record's base is
 // already recorded, so a record costs two table accesses (key load, presence RED) instead of three.
-typedef KbKhSlot KbHsSlot;
+// PWN = 32-bit presence words (2 / 4 / 8: up to 64 / 128 / 256 files).  The slot size is kept at an odd number of 8-byte units
+// (24 / 40 / 56 bytes) so that slot addresses spread over all shared-memory banks.
+template <int PWN> struct KbHsSlotT { unsigned long long key; uint32_t pres[PWN]; uint32_t msk[2]; uint32_t pad[PWN == 2 ? 0 : 2]; };
+template <> struct KbHsSlotT<2> { unsigned long long key; uint32_t pres[2]; uint32_t msk[2]; };
 #define KB_HS_KEYMASK 0x00FFFFFFFFFFFFFFULL
 
 // SPACER: the record layout is exactly 25/1/2-like (54 flank bits, D = 1): every shift is a compile-time constant.
-template <bool D1, bool SPACER>
+template <bool D1, bool SPACER, int PWN>
 __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbHStreamArgs xs) {
+    typedef KbHsSlotT<PWN> KbHsSlot;
     extern __shared__ __align__(16) unsigned char kb_smem_raw[];
     const KbHashArgs& x = xs.h;
     const KbGroupArgs& a = x.g;
@@ -153,9 +157,9 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
     // record -> its bits in the table slot (sa = shared address of the slot, khi = high half of the key word as last read)
     auto accumulate = [&](uint32_t sa, uint64_t e, uint32_t khi) {
         const uint32_t id = (uint32_t)e & 0xFFu;
-        kb_reds_or(sa + 8 + ((id >> 3) & 4u), 1u << (id & 31));
+        kb_reds_or(sa + 8 + ((id >> 5) << 2), 1u << (id & 31));
         if (D2) {
-            const uint32_t isin = (((id & 32u) ? ing_hi : ing_lo) >> (id & 31)) & 1u;
+            const uint32_t isin = PWN == 2 ? ((((id & 32u) ? ing_hi : ing_lo) >> (id & 31)) & 1u) : ((a.ingroup[id >> 5] >> (id & 31)) & 1u);
             if (packed) {
                 const uint32_t bit = (isin ? 0x01000000u : 0x10000000u) << ((uint32_t)(e >> mshift) & 3u);   // bit 24 + code (in) / 28 + code (out) of the high half
                 if (!(khi & bit)) kb_reds_or(sa + 4, bit);
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
                 uint32_t oh;
                 if (D1) oh = 0x10000000u << ((uint32_t)(e >> mshift) & 3u);
                 else oh = kb_onehot8(((uint32_t)(e >> mshift) & ((1u << D2) - 1u)) << (16 - D2)) & colmask;
-                const uint32_t ma = sa + 20 - 4 * isin;
+                const uint32_t ma = sa + 8 + 4 * PWN + 4 - 4 * isin;
                 if ((kb_lds32(ma) & oh) != oh) kb_reds_or(ma, oh);
             }
         }
@@ -222,7 +226,12 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
         if (qn >= 32) drain();
     };
 
-    if (tid < KB_HS_CONSUMERS) for (uint32_t i = tid; i < S; i += KB_HS_CONSUMERS) { tab[i].key = KB_KH_EMPTY; tab[i].msk[0] = 0; tab[i].msk[1] = 0; tab[i].pres[0] = 0; tab[i].pres[1] = 0; }
+    auto clear_slot = [&](uint32_t i) {
+        tab[i].key = KB_KH_EMPTY; tab[i].msk[0] = 0; tab[i].msk[1] = 0;
+#pragma unroll
+        for (int j = 0; j < PWN; j++) tab[i].pres[j] = 0;
+    };
+    if (tid < KB_HS_CONSUMERS) for (uint32_t i = tid; i < S; i += KB_HS_CONSUMERS) clear_slot(i);
     __syncthreads();
     if (warp == KB_HS_WARPS) return;     // (spare warp of the launch shape; all work is done by the 8 consumer warps)
 
@@ -269,8 +278,10 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
                         const unsigned long long kk0 = tab[slot].key;
                         if (kk0 == KB_KH_EMPTY) continue;
                         n_closed++;
-                        const uint64_t P = (uint64_t)tab[slot].pres[0] | ((uint64_t)tab[slot].pres[1] << 32);
-                        if (P != x.full64) continue;
+                        bool present = true;
+#pragma unroll
+                        for (int j = 0; j < PWN; j++) present = present && (tab[slot].pres[j] == a.full[j]);
+                        if (!present) continue;
                         n_present++;
                         bool ok = true;
                         if (lo.D) {
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
                             a.res_size[gs] = 0xFFFFFFFFu;                    // filled by kb_hsize_kernel
                         }
                     }
-                    tab[slot].key = KB_KH_EMPTY; tab[slot].msk[0] = 0; tab[slot].msk[1] = 0; tab[slot].pres[0] = 0; tab[slot].pres[1] = 0;
+                    clear_slot(slot);
                 }
                 if (!defer) { n_closed_t += n_closed; n_present_t += n_present; }
                 if (tid == 0) {
@@ -345,9 +356,11 @@ __global__ void __launch_bounds__(KB_HS_THREADS) kb_hash_stream_kernel(const KbH
     }
 }
 
-static inline size_t kb_hash_stream_smem(uint32_t slots_log2) {
-    return (size_t)KB_HS_STAGES * KB_HS_CHUNK * 8 + (size_t)KB_HS_WARPS * KB_HS_QCAP * 8 + ((size_t)1 << slots_log2) * sizeof(KbHsSlot) + 64 + 8 * KB_HS_STAGES + 16;
+static inline size_t kb_hash_stream_smem(uint32_t slots_log2, int pwn) {
+    const size_t slot = pwn == 2 ? sizeof(KbHsSlotT<2>) : (pwn == 4 ? sizeof(KbHsSlotT<4>) : sizeof(KbHsSlotT<8>));
+    return (size_t)KB_HS_STAGES * KB_HS_CHUNK * 8 + (size_t)KB_HS_WARPS * KB_HS_QCAP * 8 + ((size_t)1 << slots_log2) * slot + 64 + 8 * KB_HS_STAGES + 16;
 }
+static_assert(sizeof(KbHsSlotT<2>) == 24 && sizeof(KbHsSlotT<4>) == 40 && sizeof(KbHsSlotT<8>) == 56, "odd multiples of 8 bytes");
 
 // ---- group sizes of the survivors emitted by the stream kernel: one warp per survivor ----------------------
 struct KbHSizeArgs {

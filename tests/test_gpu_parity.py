@@ -188,14 +188,15 @@ def _oracle_panel(genomes, L, D, R, omit_soft=False):
 
 @pytest.mark.parametrize("algo", [1, 0], ids=["hash", "sorted"])
 @pytest.mark.parametrize("shape", [(6, 6, 300_000, 25, 1, 2, False), (6, 6, 300_000, 25, 1, 2, True), (5, 4, 200_000, 32, 60, 32, False),
-                                   (3, 3, 400_000, 12, 3, 12, False), (20, 20, 100_000, 25, 1, 2, False), (40, 40, 40_000, 10, 4, 10, False)],
-                         ids=["spacer", "spacer_omit", "primer", "12_3_12", "bench_shape_small", "80_files"])
+                                   (3, 3, 400_000, 12, 3, 12, False), (20, 20, 100_000, 25, 1, 2, False), (40, 40, 40_000, 10, 4, 10, False),
+                                   (50, 50, 40_000, 25, 1, 2, False), (70, 70, 20_000, 10, 4, 10, False)],
+                         ids=["spacer", "spacer_omit", "primer", "12_3_12", "bench_shape_small", "80_files", "100_files_spacer", "140_files"])
 def test_seeded_panel_matches_oracle(shape, algo, searcher):
     """Seeded synthetic panels (bench.py's generator) at sizes the C oracle finishes in seconds:
     multi-level partitions, Ns, soft-masking, duplicated segments, > 64 files."""
     from krisp_b200.panel import make_panel
     n_in, n_out, glen, L, D, R, omit = shape
-    kw = dict(n_runs=1, run_len=30, noise=2e-4, dup_len=300, soft_block=100) if n_in + n_out > 64 else {}
+    kw = dict(n_runs=1, run_len=30, noise=2e-4 if n_in + n_out <= 80 else 1e-4, dup_len=300, soft_block=100) if n_in + n_out > 64 else {}
     gs = make_panel(n_in, n_out, glen, **kw)
     try:
         res = _search_panel(searcher, gs, L, D, R, omit, options={"group_algo": algo})
