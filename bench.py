@@ -144,7 +144,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": max(1, args.steps), "warmup": min(args.warmup, 1), "ms_per_step": cb["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"synthetic bacterial panel 20+20 genomes, {L_}/{D_}/{R_}; bounded sample: {cb['sample']}"},
+            "config": {"workload": f"synthetic bacterial panel {N_IN}+{N_OUT} genomes, {L_}/{D_}/{R_}; bounded sample: {cb['sample']}"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -346,13 +346,17 @@ def main():
     ap.add_argument("--genome-len", type=int, default=5_000_000, help="bases per genome per GPU (default: BASELINE config 2)")
     ap.add_argument("--cpu-sample-len", type=int, default=1_000_000, help="genome length of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--genomes", nargs=2, type=int, metavar=("N_IN", "N_OUT"), help="ingroup / outgroup genome counts (default 20 20; "
+                    "50 50 = the shape of BASELINE config 4, 5..100 each = the genome-count sweep of config 5)")
     ap.add_argument("--ldr", nargs=3, type=int, metavar=("L", "D", "R"), help="--conserved-left / --diagnostic / --conserved-right "
                     "(default 25 1 2 = BASELINE config 2; 32 60 32 = config 3, primer mode)")
     ap.add_argument("--option", nargs=2, action="append", metavar=("NAME", "VALUE"), help="kb_set_option passthrough")
     args = ap.parse_args()
+    global L_, D_, R_, N_IN, N_OUT
     if args.ldr:
-        global L_, D_, R_
         L_, D_, R_ = args.ldr
+    if args.genomes:
+        N_IN, N_OUT = args.genomes
     if args.impl == "reference":
         run_reference(args)
     else:
