@@ -82,13 +82,11 @@ struct KbAcc {
     }
 };
 
-// record of sort-element e -> rec words + flank key
+// record of sort-element e -> rec words (the loads) ...
 template <int WN>
-__device__ __forceinline__ void kb_fetch(const KbGroupArgs& a, uint64_t e, uint64_t (&rec)[WN], KbKey<WN>& key) {
-    const KbLayout& lo = a.lo;
+__device__ __forceinline__ void kb_fetch_rec(const KbGroupArgs& a, uint64_t e, uint64_t (&rec)[WN]) {
     if constexpr (WN == 1) {
         rec[0] = e;
-        key.w[0] = lo.FB ? (e >> (64 - lo.FB)) : 0ULL;
     } else {
         const uint64_t* p = a.recs + (e & 0xFFFFFFFFULL) * WN;
 #pragma unroll
@@ -97,6 +95,14 @@ __device__ __forceinline__ void kb_fetch(const KbGroupArgs& a, uint64_t e, uint6
             rec[j] = (uint64_t)v.x | ((uint64_t)v.y << 32);
             rec[j + 1] = (uint64_t)v.z | ((uint64_t)v.w << 32);
         }
+    }
+}
+// ... and its flank key
+template <int WN>
+__device__ __forceinline__ void kb_key_of(const KbLayout& lo, const uint64_t (&rec)[WN], KbKey<WN>& key) {
+    if constexpr (WN == 1) {
+        key.w[0] = lo.FB ? (rec[0] >> (64 - lo.FB)) : 0ULL;
+    } else {
         const int nb = lo.FB - 64 * (lo.FW - 1);      // flank bits in the last flank word (1..64)
 #pragma unroll
         for (int j = 0; j < WN; j++) {
@@ -105,6 +111,11 @@ __device__ __forceinline__ void kb_fetch(const KbGroupArgs& a, uint64_t e, uint6
             key.w[j] = w;
         }
     }
+}
+template <int WN>
+__device__ __forceinline__ void kb_fetch(const KbGroupArgs& a, uint64_t e, uint64_t (&rec)[WN], KbKey<WN>& key) {
+    kb_fetch_rec<WN>(a, e, rec);
+    kb_key_of<WN>(a.lo, rec, key);
 }
 
 template <int WN, int MWN>

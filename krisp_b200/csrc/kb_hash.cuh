@@ -312,21 +312,29 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_kernel(const KbHashArgs
             for (uint32_t i = tid; i < S * (uint32_t)(2 + PW + 2 * MW); i += KB_KH_THREADS) aux[i] = 0;   // aux, pres, min_, mout are contiguous
             __syncthreads();
 
-            for (uint64_t i0 = bs; i0 < be; i0 += KB_KH_THREADS) {
-                if (kb_ld_shared_volatile(&ctl.over)) break;
-                const uint64_t i = i0 + tid;
-                uint64_t e = 0;
-                uint32_t hh = 0;
-                bool act = i < be;
-                if (act) { e = kb_ld_stream(a.ent + i); hh = kb_kh_bits(e, x.bb, hmask); act = kb_kh_part(hh, nb) == part; }
-                uint64_t rec[WN]; KbKey<WN> key;
+            // software pipeline: the element and the (random, 8 W bytes) record of the NEXT round are in flight while the
+            // current one goes through the table
+            auto load = [&](uint64_t i, uint64_t& e, uint32_t& hh, bool& act, uint64_t (&rec)[WN]) {
+                act = i < be;
+                e = 0; hh = 0;
 #pragma unroll
-                for (int j = 0; j < WN; j++) { rec[j] = 0; key.w[j] = 0; }
+                for (int j = 0; j < WN; j++) rec[j] = 0;
+                if (act) { e = kb_ld_stream(a.ent + i); hh = kb_kh_bits(e, x.bb, hmask); act = kb_kh_part(hh, nb) == part; }
+                if (act) kb_fetch_rec<WN>(a, e, rec);
+            };
+            uint64_t e_n, rec_n[WN]; uint32_t hh_n; bool act_n;
+            load(bs + tid, e_n, hh_n, act_n, rec_n);
+            for (uint64_t i0 = bs; i0 < be; i0 += KB_KH_THREADS) {
+                const uint32_t hh = hh_n; const bool act = act_n;
+                uint64_t rec[WN];
+#pragma unroll
+                for (int j = 0; j < WN; j++) rec[j] = rec_n[j];
+                load(i0 + KB_KH_THREADS + tid, e_n, hh_n, act_n, rec_n);
+                if (kb_ld_shared_volatile(&ctl.over)) break;
+                KbKey<WN> key;
+                kb_key_of<WN>(lo, rec, key);
                 uint32_t slot = KB_KH_NONE;
-                if (act) {
-                    kb_fetch<WN>(a, e, rec, key);
-                    slot = find_or_insert(key, hh, kb_kh_slot(hh, nb, x.slots_log2), true);
-                }
+                if (act) slot = find_or_insert(key, hh, kb_kh_slot(hh, nb, x.slots_log2), true);
                 __syncwarp();
                 if (slot != KB_KH_NONE) {
                     const uint32_t id = (uint32_t)rec[WN - 1] & 0xFFu;
