@@ -49,6 +49,18 @@ struct PartPlan {
     uint32_t ncl[3] = {0, 0, 0};         // children per level this GPU works on (= nc on one GPU; its shard's part on several)
 };
 
+// Level 0 of the partition per batch of input files (host buffers still in flight): see kb_batch_*_kernel in kb_part.cuh.
+#define KB_MAX_BATCHES 16
+struct BatchL0 {
+    bool enabled = false;
+    int n_batches = 0;
+    uint32_t nc0 = 0, nc1 = 0, bits0 = 0, bits1 = 0;
+    unsigned long long *hist2 = nullptr, *total2 = nullptr, *counts_all = nullptr, *start_all = nullptr, *cursors = nullptr, *roots = nullptr;
+    uint32_t *roottiles = nullptr, *ptile0_all = nullptr, *prow = nullptr;
+    unsigned long long* scratch_start = nullptr;
+    uint64_t* out = nullptr;             // partition output (the other ping-pong buffer)
+};
+
 struct CustomParents {                  // parents of the first level run, when they are not the previous level's children
     const unsigned long long* pstart;   // [n + 1]
     const uint32_t* ptile0;             // [n + 1]
@@ -78,17 +90,20 @@ struct kb_ctx {
     long long opt_hash_slots_log2 = 0;   // 0 = default
     long long opt_hash_stream = 1;       // 1 = persistent TMA-fed bucket hash kernel for the fast shape
     long long opt_fused_hist = 1;        // 1 = K1 also counts the level-1 children (single-GPU search path)
+    long long opt_batch_level0 = 1;      // 1 = partition level 0 per batch of arriving files (hidden under the host -> device copy)
     long long opt_shard_bits0 = 0;       // multi-GPU: bits of partition level 0 (the exchange); 0 = log2(shards) + 2
 
     // sequences
     DevBuf bases;
     uint64_t n_bases = 0;
     std::vector<uint64_t> file_table_host;
+    std::vector<uint32_t> batch_rows_host;
     std::vector<uint64_t> file_starts;   // local files
     std::vector<uint32_t> file_gid;
     DevBuf d_file_starts, d_file_gid;
 
     // workspaces
+    DevBuf batchbuf;
     DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out, taint, plan, deferred;
     uint64_t* h_pinned = nullptr;        // 64 x u64 scratch for small D2H reads
     uint64_t result_cap = 0;
@@ -199,7 +214,7 @@ void kb_destroy(kb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->recs, &ctx->status,
                       &ctx->small, &ctx->res_flank, &ctx->res_in, &ctx->res_out, &ctx->res_size, &ctx->res_run,
-                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab};
+                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab, &ctx->batchbuf};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (size_t r = 0; r < ctx->peer_ptr.size(); r++) if (ctx->peer_ptr[r] && ctx->peer_ptr[r] != ctx->recvbuf.p) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
@@ -231,6 +246,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "group_algo") ctx->opt_group_algo = value ? 1 : 0;
     else if (n == "hash_stream") ctx->opt_hash_stream = value ? 1 : 0;
     else if (n == "fused_hist") ctx->opt_fused_hist = value ? 1 : 0;
+    else if (n == "batch_level0") ctx->opt_batch_level0 = value ? 1 : 0;
     else if (n == "shard_bits0") { if (value < 0 || value > 9) return fail(ctx, KB_EINVAL, "shard_bits0 must be in 0..9"); ctx->opt_shard_bits0 = value; }
     else if (n == "bucket_bits") { if (value < -1 || value > 24) return fail(ctx, KB_EINVAL, "bucket_bits must be in -1..24"); ctx->opt_bucket_bits = value; }
     else if (n == "hash_slots_log2") { if (value != 0 && (value < 4 || value > 12)) return fail(ctx, KB_EINVAL, "hash_slots_log2 must be 0 or in 4..12"); ctx->opt_hash_slots_log2 = value; }
@@ -366,7 +382,8 @@ static int prepare_small(kb_ctx* ctx) {
 
 // K1 over tiles [tile0, tile0+n_tiles), windows starting in [pos_lo, pos_hi); *n_out = records written
 static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint64_t* n_out,
-                       unsigned long long* hist = nullptr, uint32_t hist_shift = 0, uint32_t hist_bits = 0, bool no_sync = false) {
+                       unsigned long long* hist = nullptr, uint32_t hist_shift = 0, uint32_t hist_bits = 0, bool no_sync = false,
+                       BatchL0* bl = nullptr) {
     const uint64_t n_max = 2 * (std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo) + 64;
     TRY(ensure(ctx, ctx->entA, (n_max + 2048) * 8));   // slack: bulk copies of the stream kernel read whole 4 KB stages
     if (!lo.direct) TRY(ensure(ctx, ctx->recs, n_max * 8 * lo.W));
@@ -418,11 +435,14 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
         }
     }
     uint32_t t0 = tile0;
+    const bool batched_l0 = bl && bl->enabled && wide_hist && batches.size() > 1 && batches.size() <= KB_MAX_BATCHES;
+    if (batched_l0) CU(cudaFuncSetAttribute(kb_part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb_part_smem()));
     for (auto& bt : batches) {
         if (bt.second) CU(cudaStreamWaitEvent(ctx->stream, bt.second, 0));
         const uint32_t nt = bt.first > t0 ? bt.first - t0 : 0;
         if (!nt) continue;
         a.tile0 = t0; a.n_tiles = nt;
+        if (batched_l0) a.hist = bl->hist2 + (size_t)bl->n_batches * bl->nc1;
         if (wide_hist) {
             const uint32_t grid = std::min<uint32_t>((nt + 3) / 4, (uint32_t)ctx->n_sm);
             switch (lo.W) {
@@ -446,6 +466,25 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
         }
         CU(cudaGetLastError());
         ctx->launches++;
+        if (batched_l0) {
+            // level 0 of this batch right away: its records are the tail of the element array
+            const int b = bl->n_batches++;
+            unsigned long long* c0 = bl->counts_all + (size_t)b * bl->nc0;
+            kb_batch_fold_kernel<<<bl->nc0, 512, 0, ctx->stream>>>(a.hist, bl->total2, c0, 1u << bl->bits1);
+            CU(cudaGetLastError());
+            kb_batch_plan_kernel<<<1, 512, 0, ctx->stream>>>(c0, bl->nc0, bl->start_all + (size_t)b * bl->nc0, bl->start_all + (size_t)b * bl->nc0,
+                                                            bl->cursors + (size_t)b * bl->nc0, bl->roots + 2 * b, bl->roottiles + 2 * b);
+            CU(cudaGetLastError());
+            KbPartArgs pa{};
+            pa.in = (const uint64_t*)ctx->entA.p; pa.out = bl->out;
+            pa.pstart = bl->roots + 2 * b; pa.ptile0 = bl->roottiles + 2 * b; pa.n_parents = 1;
+            pa.shift = 64 - bl->bits0; pa.bits = bl->bits0;
+            pa.cursor = bl->cursors + (size_t)b * bl->nc0; pa.hist = pa.cursor;
+            const uint64_t bound = 2ull * nt * KB_K1_TB / KB_PT_TILE + 2;
+            kb_part_kernel<2><<<(unsigned)bound, KB_PT_THREADS, kb_part_smem(), ctx->stream>>>(pa);
+            CU(cudaGetLastError());
+            ctx->launches += 3;
+        }
         t0 = bt.first;
     }
     prof_end(ctx);
@@ -500,7 +539,7 @@ static int run_sort(kb_ctx* ctx, DevBuf& in, DevBuf& other, uint64_t n, int P, u
     *sorted = cur;
     if (n == 0 || P == 0) return KB_OK;
     if (P > 8) return fail(ctx, KB_EINTERNAL, "more than 8 radix passes");
-    TRY(ensure(ctx, other, in.cap));
+    TRY(ensure(ctx, other, (size_t)(n + 2048) * 8));        // (not in.cap: capacities carry growth slack and would chase each other)
     uint64_t* alt = (uint64_t*)other.p;
     const bool wide = n >= (1ULL << 30);
     const uint32_t shift0 = 64 - 8 * P;
@@ -625,7 +664,7 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
     ctx->launches++;
     *parted = cur; *bstart = root; *n_buckets = 1;
     if (l_end <= l_begin || n == 0) return KB_OK;
-    TRY(ensure(ctx, other, in.cap));
+    TRY(ensure(ctx, other, (size_t)(n + 2048) * 8));        // (not in.cap: capacities carry growth slack and would chase each other)
     uint64_t* alt = (uint64_t*)other.p;
     const size_t smem = kb_part_smem();
     CU(cudaFuncSetAttribute(kb_part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -995,7 +1034,59 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
         const int hl = fused2 ? 1 : 0;
         const uint32_t hbits = fused2 ? (uint32_t)(pl.bits[0] + pl.bits[1]) : (uint32_t)pl.bits[0];
         unsigned long long* h0 = pl.levels ? (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[hl]) : nullptr;
-        TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, 64 - hbits, hbits, true));
+        BatchL0 bl;
+        if (fused2 && ctx->opt_batch_level0 && pl.levels == 2 && lo.direct) {
+            // carve the batch tables: [B][nc1] two-level counts | [B*nc0] level-0 counts | [B*nc0+1] offsets (x2) | [B][nc0] cursors | roots | tiles | rows
+            bl.nc0 = pl.nc[0]; bl.nc1 = pl.nc[1]; bl.bits0 = (uint32_t)pl.bits[0]; bl.bits1 = (uint32_t)pl.bits[1];
+            const size_t B = KB_MAX_BATCHES, np = B * bl.nc0;
+            const size_t words = B * bl.nc1 + np + 2 * (np + 1) + np + 2 * B + B + (np + 2) / 2 + (np + 1) / 2 + 8;
+            TRY(ensure(ctx, ctx->batchbuf, words * 8));
+            TRY(ensure(ctx, ctx->entA, (size_t)(2 * ctx->n_bases + 64 + 2048) * 8));      // (what run_extract will ask for)
+            TRY(ensure(ctx, ctx->entB, (size_t)(2 * ctx->n_bases + 64 + 2048) * 8));
+            CU(cudaMemsetAsync(ctx->batchbuf.p, 0, words * 8, ctx->stream));
+            unsigned long long* q = (unsigned long long*)ctx->batchbuf.p;
+            bl.hist2 = q; q += B * bl.nc1;
+            bl.counts_all = q; q += np;
+            bl.start_all = q; q += np + 1;
+            bl.scratch_start = q; q += np + 1;
+            bl.cursors = q; q += np;
+            bl.roots = q; q += 2 * B;
+            bl.roottiles = (uint32_t*)q; q += B;
+            bl.ptile0_all = (uint32_t*)q; q += (np + 2) / 2;
+            bl.prow = (uint32_t*)q;
+            bl.total2 = (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[1]);
+            bl.out = (uint64_t*)ctx->entB.p;
+            bl.enabled = true;
+        }
+        TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, 64 - hbits, hbits, true, bl.enabled ? &bl : nullptr));
+        if (bl.n_batches > 0) {
+            // level 0 is done batch by batch: the (batch, digit) pieces are the parents of level 1 (rows = digits)
+            uint8_t* P = (uint8_t*)ctx->plan.p;
+            const uint32_t np = (uint32_t)bl.n_batches * bl.nc0;
+            KbPlanArgs pp{};
+            pp.counts = bl.counts_all; pp.nc = np; pp.start = bl.scratch_start; pp.cursor = nullptr; pp.tile0 = bl.ptile0_all;
+            TRY(launch_plan(ctx, pp, pl));
+            KbPlanArgs p1{};
+            p1.counts = bl.total2; p1.nc = pl.ncl[1];
+            p1.start = (unsigned long long*)(P + pl.off_start[1]); p1.cursor = bl.total2; p1.tile0 = (uint32_t*)(P + pl.off_tile0[1]);
+            TRY(launch_plan(ctx, p1, pl));
+            std::vector<uint32_t>& rows = ctx->batch_rows_host;
+            rows.resize(np);
+            for (uint32_t i = 0; i < np; i++) rows[i] = i % bl.nc0;
+            CU(cudaMemcpyAsync(bl.prow, rows.data(), (size_t)np * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CustomParents cp{};
+            cp.pstart = bl.start_all; cp.ptile0 = bl.ptile0_all; cp.prow = bl.prow; cp.n = np;
+            cp.max_tiles = n / KB_PT_TILE + np + 2;
+            ctx->alg_rec_bytes += 16;
+            ctx->passes += 1;
+            uint64_t* parted = nullptr;
+            HashStage hs{};
+            hs.pl = &pl;
+            TRY(run_partition(ctx, pl, ctx->entB, ctx->entA, n, 1, pl.levels, &cp, &parted, &hs.bstart, &hs.n_buckets, true));
+            int rc = run_group(ctx, parted, n, out, &hs);
+            prof_collect(ctx);
+            return rc;
+        }
         if (!lo.direct && n >= (1ULL << 32) + 64) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
         uint64_t* parted = nullptr;
         HashStage hs{};

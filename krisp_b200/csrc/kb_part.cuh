@@ -168,6 +168,46 @@ __global__ void kb_root_kernel(const unsigned long long* n_ptr, unsigned long lo
     }
 }
 
+// ---- level 0 per batch of input files (sequences still arriving from the host) -------------------------------------------
+// K1 runs per batch and counts the two-level children of the batch (hist2_b).  kb_batch_fold_kernel: level-0 counts of the
+// batch = row sums, and the whole search's level-1 counts accumulate in total2.  One block per level-0 digit.
+__global__ void __launch_bounds__(512) kb_batch_fold_kernel(const unsigned long long* hist2_b, unsigned long long* total2,
+                                                            unsigned long long* counts0, uint32_t fold) {
+    __shared__ unsigned long long ws[16];
+    const uint32_t d0 = blockIdx.x, t = threadIdx.x;
+    unsigned long long v = 0;
+    if (t < fold) { v = hist2_b[(size_t)d0 * fold + t]; total2[(size_t)d0 * fold + t] += v; }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if ((t & 31) == 0) ws[t >> 5] = v;
+    __syncthreads();
+    if (t == 0) { unsigned long long s = 0; for (int w = 0; w < 16; w++) s += ws[w]; counts0[d0] = s; }
+}
+
+// offsets of the batch's level-0 buckets: the batch's records are [*base, *base + sum) of the element array (K1 appends batch
+// after batch), its bucket d starts at start[d]; start[nc0] = end = the next batch's base.  One block, nc0 <= 512.
+__global__ void __launch_bounds__(512) kb_batch_plan_kernel(const unsigned long long* counts0, uint32_t nc0, const unsigned long long* base,
+                                                            unsigned long long* start, unsigned long long* cursor,
+                                                            unsigned long long* root, uint32_t* roottile) {
+    __shared__ unsigned long long ws[16];
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned long long v = t < nc0 ? counts0[t] : 0ULL;
+    unsigned long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (uint32_t)d) x += o; }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    unsigned long long add = *base, tot = 0;
+    for (uint32_t w = 0; w < 16; w++) { if (w < warp) add += ws[w]; tot += ws[w]; }
+    if (t < nc0) { start[t] = add + x - v; cursor[t] = add + x - v; }
+    if (t == 0) {
+        const unsigned long long b0 = *base;
+        start[nc0] = b0 + tot;
+        root[0] = b0; root[1] = b0 + tot;
+        roottile[0] = 0; roottile[1] = (uint32_t)((tot + KB_PT_TILE - 1) / KB_PT_TILE);
+    }
+}
+
 // tile -> parent map: one warp per parent
 __global__ void __launch_bounds__(256) kb_tilemap_kernel(const uint32_t* tile0, uint32_t n_parents, uint32_t* tile_parent) {
     const uint32_t lane = threadIdx.x & 31;
