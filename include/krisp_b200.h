@@ -89,6 +89,19 @@ int kb_add_sequence(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_b
 int kb_synchronize(kb_ctx* ctx);
 
 /*
+ * GPU-side FASTA de-lining.  Replaces the host loop of kstream._parse_FASTA (kstream/kstream.py:556-583; plain input:
+ * _parse_seqs :539-554): `bytes` = the whole decompressed file as read (host pointer, borrowed for the call).  The first
+ * line is the reference's FASTA probe (kstream.py:510-537: a '>' in it means FASTA; it is consumed either way, :450); header
+ * lines, line breaks and CRs before them are removed on the device and every header becomes one record separator.
+ * kb_fasta_flags: bit 0 = a 'U'/'u' was seen (RNA, kstream.py:481), bit 1 = whitespace that str.strip() would remove but the
+ * device path does not — since the last kb_clear_sequences; when a bit is set the caller re-ingests with its host parser
+ * (kb_add_sequence).  kb_get_sequence reads a file's bytes back as K1 will see them (tests / debugging; out == NULL: size only).
+ */
+int kb_add_fasta(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_bytes);
+int kb_fasta_flags(kb_ctx* ctx, unsigned int* flags);
+int kb_get_sequence(kb_ctx* ctx, int local_index, uint8_t* out, uint64_t cap, uint64_t* n_bytes);
+
+/*
  * The whole search on one GPU.  Replaces, in one call:
  *   extractSortedKmers  krisp_fasta.py:16  (kstream.write + GNU sort, kstream.py:250-325, :83-119)
  *   mergeFiles          intersectAmplicons.py:232 (tree of intersectSortedStreams, shared.py:321)

@@ -15,7 +15,8 @@ _ERRNAMES = {KB_EINVAL: "KB_EINVAL", KB_ECUDA: "KB_ECUDA", KB_ENOMEM: "KB_ENOMEM
 
 # every symbol include/krisp_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = ["kb_version", "kb_create", "kb_destroy", "kb_last_error", "kb_set_stream", "kb_configure",
-           "kb_set_option", "kb_clear_sequences", "kb_reserve", "kb_add_sequence", "kb_synchronize",
+           "kb_set_option", "kb_clear_sequences", "kb_reserve", "kb_add_sequence", "kb_add_fasta", "kb_fasta_flags",
+           "kb_get_sequence", "kb_synchronize",
            "kb_search", "kb_shard_plan", "kb_shard_ipc_export", "kb_shard_ipc_import", "kb_shard_count",
            "kb_shard_scatter", "kb_shard_extract", "kb_shard_recv_buffer", "kb_shard_search", "kb_result_get",
            "kb_result_free", "kb_last_profile", "kb_last_counters", "kb_extract_sorted", "kb_table_get",
@@ -70,6 +71,9 @@ def load():
     L.kb_clear_sequences.argtypes = [vp]
     L.kb_reserve.argtypes = [vp, u64]
     L.kb_add_sequence.argtypes = [vp, i, vp, u64, i]
+    L.kb_add_fasta.argtypes = [vp, i, vp, u64]
+    L.kb_fasta_flags.argtypes = [vp, ctypes.POINTER(ctypes.c_uint)]
+    L.kb_get_sequence.argtypes = [vp, i, vp, u64, ctypes.POINTER(u64)]
     L.kb_synchronize.argtypes = [vp]
     L.kb_search.argtypes = [vp, pvp]
     L.kb_shard_plan.argtypes = [vp, i, i, u64, ctypes.POINTER(i)]

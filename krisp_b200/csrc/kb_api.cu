@@ -17,6 +17,7 @@
 #include "kb_part.cuh"
 #include "kb_hash.cuh"
 #include "kb_hash_stream.cuh"
+#include "kb_ingest.cuh"
 
 #define KB_VERSION_STR "krisp_b200 0.1.0 sm_100a"
 
@@ -103,7 +104,7 @@ struct kb_ctx {
     DevBuf d_file_starts, d_file_gid;
 
     // workspaces
-    DevBuf batchbuf;
+    DevBuf batchbuf, rawbuf, fa_work, fa_flags;   // FASTA de-lining: raw file bytes, tile tables, flag word
     DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out, taint, plan, deferred;
     uint64_t* h_pinned = nullptr;        // 64 x u64 scratch for small D2H reads
     uint64_t result_cap = 0;
@@ -142,6 +143,8 @@ static int fail(kb_ctx* ctx, int code, const std::string& msg) {
             return fail(ctx, e__ == cudaErrorMemoryAllocation ? KB_ENOMEM : KB_ECUDA,                    \
                         std::string(#call) + ": " + cudaGetErrorString(e__));                            \
     } while (0)
+
+static int launch_plan(kb_ctx* ctx, KbPlanArgs pa, const PartPlan& pl);
 
 static int ensure(kb_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false) {
     if (bytes <= b.cap) return KB_OK;
@@ -214,7 +217,7 @@ void kb_destroy(kb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->recs, &ctx->status,
                       &ctx->small, &ctx->res_flank, &ctx->res_in, &ctx->res_out, &ctx->res_size, &ctx->res_run,
-                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab, &ctx->batchbuf};
+                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab, &ctx->batchbuf, &ctx->rawbuf, &ctx->fa_work, &ctx->fa_flags};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (size_t r = 0; r < ctx->peer_ptr.size(); r++) if (ctx->peer_ptr[r] && ctx->peer_ptr[r] != ctx->recvbuf.p) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
@@ -299,6 +302,7 @@ int kb_clear_sequences(kb_ctx* ctx) {
     ctx->file_starts.clear();
     ctx->file_gid.clear();
     ctx->file_event.clear();
+    if (ctx->fa_flags.p) { cudaSetDevice(ctx->device); cudaMemsetAsync(ctx->fa_flags.p, 0, 8, ctx->stream); }
     return KB_OK;
 }
 
@@ -348,6 +352,88 @@ int kb_add_sequence(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_b
     ctx->file_gid.push_back((uint32_t)file_id);
     ctx->file_event.push_back(ev);
     ctx->n_bases += n_bytes + 1;
+    return KB_OK;
+}
+
+int kb_add_fasta(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_bytes) {
+    if (!ctx) return KB_EINVAL;
+    if (file_id < 0 || file_id >= KB_MAX_FILES) return fail(ctx, KB_EINVAL, "file_id out of range");
+    if (n_bytes && !bytes) return fail(ctx, KB_EINVAL, "null file pointer");
+    CU(cudaSetDevice(ctx->device));
+    // the first line decides FASTA vs plain and is consumed by the probe (kstream.py:447-452, :510-537)
+    const uint8_t* nl = n_bytes ? (const uint8_t*)memchr(bytes, '\n', n_bytes) : nullptr;
+    const uint64_t first = nl ? (uint64_t)(nl - bytes) + 1 : n_bytes;
+    const int fasta = (n_bytes && memchr(bytes, '>', nl ? (size_t)(nl - bytes) : (size_t)n_bytes)) ? 1 : 0;
+    const uint8_t* body = bytes + first;
+    const uint64_t nb = n_bytes - first;
+    if (ctx->bases.cap < padded_len(ctx->n_bases + nb + 1)) {
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        TRY(ensure(ctx, ctx->bases, padded_len(ctx->n_bases + nb + 1), true));
+    }
+    uint8_t* slot = (uint8_t*)ctx->bases.p + ctx->n_bases;
+    CU(cudaMemsetAsync(slot, '\n', nb + 1, ctx->stream));               // separators wherever the packed bytes do not reach
+    if (nb) {
+        const uint32_t tiles = (uint32_t)((nb + KB_FA_TILE - 1) / KB_FA_TILE);
+        TRY(ensure(ctx, ctx->rawbuf, nb + 64));
+        const uint32_t nblk = (tiles + KB_PLAN_BLOCK - 1) / KB_PLAN_BLOCK;
+        const size_t words = (size_t)tiles * 3 + 2 + 2 * (size_t)nblk + (tiles + 7) / 8 + 8;
+        TRY(ensure(ctx, ctx->fa_work, words * 8));
+        if (!ctx->fa_flags.p) { TRY(ensure(ctx, ctx->fa_flags, 8)); CU(cudaMemsetAsync(ctx->fa_flags.p, 0, 8, ctx->stream)); }
+        CU(cudaMemcpyAsync(ctx->rawbuf.p, body, nb, cudaMemcpyHostToDevice, ctx->stream));
+        KbFastaArgs a{};
+        a.in = (const uint8_t*)ctx->rawbuf.p; a.n = nb; a.fasta = fasta;
+        unsigned long long* q = (unsigned long long*)ctx->fa_work.p;
+        a.last_nl = q; q += tiles;
+        a.counts = q; q += tiles;
+        unsigned long long* start = q; q += tiles + 1;
+        unsigned long long* part = q; q += 2 * (size_t)nblk + 1;
+        a.hdr0 = (uint8_t*)q;
+        a.start = start;
+        a.out = slot;
+        a.flags = (unsigned int*)ctx->fa_flags.p;
+        kb_fa_lastnl_kernel<<<tiles, KB_FA_THREADS, 0, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        kb_fa_scan_kernel<<<1, 1024, 0, ctx->stream>>>(a, tiles);
+        CU(cudaGetLastError());
+        kb_fa_pack_kernel<false><<<tiles, KB_FA_THREADS, 0, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        KbPlanArgs pa{};
+        pa.counts = a.counts; pa.nc = tiles; pa.start = start; pa.cursor = nullptr; pa.tile0 = nullptr; pa.part = part;
+        PartPlan none;
+        TRY(launch_plan(ctx, pa, none));
+        kb_fa_pack_kernel<true><<<tiles, KB_FA_THREADS, 0, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));                           // `bytes` is borrowed only for the call; rawbuf is reused by the next file
+    }
+    ctx->file_starts.push_back(ctx->n_bases);
+    ctx->file_gid.push_back((uint32_t)file_id);
+    ctx->file_event.push_back(nullptr);
+    ctx->n_bases += nb + 1;
+    return KB_OK;
+}
+
+int kb_fasta_flags(kb_ctx* ctx, unsigned int* flags) {
+    if (!ctx || !flags) return KB_EINVAL;
+    *flags = 0;
+    if (!ctx->fa_flags.p) return KB_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(ctx->h_pinned + 16, ctx->fa_flags.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *flags = (unsigned int)ctx->h_pinned[16];
+    return KB_OK;
+}
+
+int kb_get_sequence(kb_ctx* ctx, int local_index, uint8_t* out, uint64_t cap, uint64_t* n_bytes) {
+    if (!ctx || !n_bytes) return KB_EINVAL;
+    if (local_index < 0 || local_index >= (int)ctx->file_starts.size()) return fail(ctx, KB_EINVAL, "no such sequence");
+    const uint64_t lo = ctx->file_starts[local_index];
+    const uint64_t hi = local_index + 1 < (int)ctx->file_starts.size() ? ctx->file_starts[local_index + 1] : ctx->n_bases;
+    *n_bytes = hi - lo;
+    if (!out || cap < hi - lo) return KB_OK;                              // size query
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    CU(cudaMemcpyAsync(out, (const uint8_t*)ctx->bases.p + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return KB_OK;
 }
 
@@ -638,7 +724,7 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0) {
 // l_begin == 0: the exact element count is K1's device counter and the level-0 histogram is already in the plan buffer;
 // l_begin > 0 needs `cp` (the parents of that level).
 static int launch_plan(kb_ctx* ctx, KbPlanArgs pa, const PartPlan& pl) {
-    pa.part = (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_part);
+    if (!pa.part) pa.part = (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_part);
     const uint32_t nb = (pa.nc + KB_PLAN_BLOCK - 1) / KB_PLAN_BLOCK;
     kb_plan_reduce_kernel<<<nb, KB_PLAN_BLOCK, 0, ctx->stream>>>(pa);
     CU(cudaGetLastError());

@@ -226,6 +226,27 @@ class Searcher:
         self._keep.append(arr)
         self._check(self._L.kb_add_sequence(self._ctx, int(file_id), ctypes.c_void_p(arr.ctypes.data), int(arr.size), 0))
 
+    def add_fasta(self, file_id, raw):
+        """`raw`: the decompressed file content (bytes): headers and line breaks are removed on the device (kb_add_fasta)."""
+        arr = np.frombuffer(raw, dtype=np.uint8)
+        self.bases_added += int(arr.size)
+        self._check(self._L.kb_add_fasta(self._ctx, int(file_id), ctypes.c_void_p(arr.ctypes.data if arr.size else 0), int(arr.size)))
+
+    def fasta_flags(self):
+        """Bit 0: RNA letters seen, bit 1: whitespace only the host parser handles — since the last clear_sequences."""
+        f = ctypes.c_uint()
+        self._check(self._L.kb_fasta_flags(self._ctx, ctypes.byref(f)))
+        return int(f.value)
+
+    def get_sequence(self, local_index):
+        """A file's bytes as K1 will see them (tests / debugging)."""
+        n = ctypes.c_uint64()
+        self._check(self._L.kb_get_sequence(self._ctx, int(local_index), None, 0, ctypes.byref(n)))
+        out = np.zeros(int(n.value), dtype=np.uint8)
+        if out.size:
+            self._check(self._L.kb_get_sequence(self._ctx, int(local_index), ctypes.c_void_p(out.ctypes.data), int(out.size), ctypes.byref(n)))
+        return out
+
     def synchronize(self):
         self._check(self._L.kb_synchronize(self._ctx))
         self._keep = []
@@ -378,16 +399,25 @@ def search_files(ingroup_files, outgroup_files, L, D, R, omit_soft=False, want_r
         for k, v in (options or {}).items():
             s.set_option(k, v)
         s.clear_sequences()
-        packed = []
-        for f in files:
-            arr, rna = ingest.load_file(f)
-            if rna:
-                raise RNAInputError(f"{f}: RNA input — the reference's krisp_fasta output is undefined for it "
-                                    "(U-tables never intersect DNA tables and the renderer raises KeyError)")
-            packed.append(arr)
-        s.reserve(sum(a.size + 1 for a in packed))
-        for i, arr in enumerate(packed):
-            s.add_sequence(i, arr)
+        # de-lining on the device; inputs it does not reproduce exactly (RNA, stray whitespace) raise a flag and are
+        # re-ingested with the host restatement of the reference parser
+        raws = [ingest.read_bytes(f) for f in files]
+        s.reserve(sum(len(r) + 1 for r in raws))
+        for i, raw in enumerate(raws):
+            s.add_fasta(i, raw)
+        if s.fasta_flags():
+            s.clear_sequences()
+            packed = []
+            for f, raw in zip(files, raws):
+                arr = ingest.pack_bytes(raw)
+                if ingest.detect_rna(arr):
+                    raise RNAInputError(f"{f}: RNA input — the reference's krisp_fasta output is undefined for it "
+                                        "(U-tables never intersect DNA tables and the renderer raises KeyError)")
+                packed.append(arr)
+            s.reserve(sum(a.size + 1 for a in packed))
+            for i, arr in enumerate(packed):
+                s.add_sequence(i, arr)
+        del raws
         res = s.search(have_outgroup=have_out)
         res.labels = labels
         res.is_ingroup = is_in

@@ -268,3 +268,39 @@ def test_full_size_panel_properties(searcher):
     assert int(res.group_size.min()) >= 40
     assert np.all((res.in_mask[:, 0] & res.out_mask[:, 0]) == 0)
     assert res.stats["groups_in_every_file"] >= len(rows)
+
+
+def _fasta_inputs():
+    import glob
+    import os
+    from tests.helpers import GOLDEN_DIR
+    files = sorted(set(glob.glob(os.path.join(GOLDEN_DIR, "**", "*.fa*"), recursive=True) +
+                       glob.glob(os.path.join(GOLDEN_DIR, "**", "*.fna*"), recursive=True)))
+    return files
+
+
+_EDGE_TEXTS = {
+    "empty": b"", "only_header": b">only header", "headerless": b"ACGT\nGGCC\nTTAA\n", "crlf": b">a\r\nACGT\r\nTT\r\n>b\r\n>c\r\nGG\r\n",
+    "gt_inside": b">a\nAC>GT\nTT\n", "no_final_newline": b">a\nACGT\nGG", "long_line": b">a\n" + b"ACGTN" * 5000 + b"\n>b\n" + b"G" * 9000 + b"\n",
+    "many_headers": b"".join(b">h%d some text\nAC\n" % i for i in range(3000)), "blank_lines": b">a\n\nAC\n\n\nGT\n",
+    "header_crosses_tiles": b">a\n" + b"A" * 4090 + b"\n>" + b"x" * 9000 + b"\nCC\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(_EDGE_TEXTS) + ["@" + str(i) for i in range(len(_fasta_inputs()))])
+def test_device_fasta_delining_matches_host_parser(name, searcher):
+    """kb_add_fasta (header / newline removal on the GPU) == ingest.pack_bytes (the restated reference parser), up to runs of separators."""
+    import re
+    from krisp_b200 import ingest
+    raw = _EDGE_TEXTS[name] if not name.startswith("@") else ingest.read_bytes(_fasta_inputs()[int(name[1:])])
+    searcher.configure(5, 1, 2, [1])
+    searcher.clear_sequences()
+    searcher.add_fasta(0, raw)
+    flags = searcher.fasta_flags()
+    got = searcher.get_sequence(0).tobytes()
+    want = ingest.pack_bytes(raw).tobytes()
+    norm = lambda b: re.sub(rb"\n+", b"\n", b.strip(b"\n"))
+    if flags & 2:
+        pytest.skip("stray whitespace: the host parser takes over (flag raised)")
+    assert norm(got) == norm(want)
+    assert bool(flags & 1) == bool(re.search(rb"[Uu]", want))
