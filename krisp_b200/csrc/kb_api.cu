@@ -18,6 +18,7 @@
 #include "kb_hash.cuh"
 #include "kb_hash_stream.cuh"
 #include "kb_ingest.cuh"
+#include "kb_prefilter.cuh"
 
 #define KB_VERSION_STR "krisp_b200 0.1.0 sm_100a"
 
@@ -92,6 +93,8 @@ struct kb_ctx {
     long long opt_hash_stream = 1;       // 1 = persistent TMA-fed bucket hash kernel for the fast shape
     long long opt_fused_hist = 1;        // 1 = K1 also counts the level-1 children (single-GPU search path)
     long long opt_batch_level0 = 1;      // 1 = partition level 0 per batch of arriving files (hidden under the host -> device copy)
+    long long opt_lazy_records = 1;      // multi-word records: 1 = filter by flank hash, build records only for what is left (kb_prefilter.cuh)
+    bool lazy_now = false;               // the running search uses it
     long long opt_shard_bits0 = 0;       // multi-GPU: bits of partition level 0 (the exchange); 0 = log2(shards) + 2
 
     // sequences
@@ -104,6 +107,7 @@ struct kb_ctx {
     DevBuf d_file_starts, d_file_gid;
 
     // workspaces
+    DevBuf brun;                         // lazy records: per bucket (start, length) of the kept elements
     DevBuf batchbuf, rawbuf, fa_work, fa_flags;   // FASTA de-lining: raw file bytes, tile tables, flag word
     DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out, taint, plan, deferred;
     uint64_t* h_pinned = nullptr;        // 64 x u64 scratch for small D2H reads
@@ -217,7 +221,7 @@ void kb_destroy(kb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->recs, &ctx->status,
                       &ctx->small, &ctx->res_flank, &ctx->res_in, &ctx->res_out, &ctx->res_size, &ctx->res_run,
-                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab, &ctx->batchbuf, &ctx->rawbuf, &ctx->fa_work, &ctx->fa_flags};
+                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab, &ctx->batchbuf, &ctx->rawbuf, &ctx->fa_work, &ctx->fa_flags, &ctx->brun};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (size_t r = 0; r < ctx->peer_ptr.size(); r++) if (ctx->peer_ptr[r] && ctx->peer_ptr[r] != ctx->recvbuf.p) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
@@ -250,6 +254,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "hash_stream") ctx->opt_hash_stream = value ? 1 : 0;
     else if (n == "fused_hist") ctx->opt_fused_hist = value ? 1 : 0;
     else if (n == "batch_level0") ctx->opt_batch_level0 = value ? 1 : 0;
+    else if (n == "lazy_records") ctx->opt_lazy_records = value ? 1 : 0;
     else if (n == "shard_bits0") { if (value < 0 || value > 9) return fail(ctx, KB_EINVAL, "shard_bits0 must be in 0..9"); ctx->opt_shard_bits0 = value; }
     else if (n == "bucket_bits") { if (value < -1 || value > 24) return fail(ctx, KB_EINVAL, "bucket_bits must be in -1..24"); ctx->opt_bucket_bits = value; }
     else if (n == "hash_slots_log2") { if (value != 0 && (value < 4 || value > 12)) return fail(ctx, KB_EINVAL, "hash_slots_log2 must be 0 or in 4..12"); ctx->opt_hash_slots_log2 = value; }
@@ -472,7 +477,7 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
                        BatchL0* bl = nullptr) {
     const uint64_t n_max = 2 * (std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo) + 64;
     TRY(ensure(ctx, ctx->entA, (n_max + 2048) * 8));   // slack: bulk copies of the stream kernel read whole 4 KB stages
-    if (!lo.direct) TRY(ensure(ctx, ctx->recs, n_max * 8 * lo.W));
+    if (!lo.direct && !ctx->lazy_now) TRY(ensure(ctx, ctx->recs, n_max * 8 * lo.W));
     // separator padding past the data
     const size_t plen = padded_len(ctx->n_bases);
     TRY(ensure(ctx, ctx->bases, plen, true));
@@ -489,6 +494,7 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
     a.lo = lo;
     a.out_entries = (uint64_t*)ctx->entA.p;
     a.out_recs = (uint64_t*)ctx->recs.p;
+    a.lazy = ctx->lazy_now ? 1 : 0;
     a.n_out = (unsigned long long*)ctx->small.p + SM_NOUT;
     a.tile0 = tile0; a.n_tiles = n_tiles;
     a.pos_lo = pos_lo; a.pos_hi = pos_hi;
@@ -577,7 +583,7 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
     if (no_sync) {                                         // the count stays on the device; the caller sizes grids with the bound
         *n_out = n_max;
         ctx->alg_bytes += std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo;
-        ctx->alg_rec_bytes += 8 * (lo.direct ? 1 : (1 + lo.W));
+        ctx->alg_rec_bytes += 8 * ((lo.direct || ctx->lazy_now) ? 1 : (1 + lo.W));
         return KB_OK;
     }
     CU(cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NOUT, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -831,16 +837,20 @@ struct HashStage {            // what run_group needs to run the bucket-hash ker
     const PartPlan* pl;
     const unsigned long long* bstart;
     uint32_t n_buckets;
+    const unsigned long long* brun = nullptr;   // lazy records: (start, length) per bucket instead of bstart
+    uint32_t slots_log2 = 0;                     // != 0: table size of the exact pass (else the plan's)
+    uint64_t n_kept = 0;                         // lazy records: elements the exact pass reads
 };
 
 static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
     const KbLayout& lo = g.lo;
     KbHashArgs x{};
     x.g = g;
-    x.bstart = hs.bstart; x.n_buckets = hs.n_buckets; x.slots_log2 = hs.pl->slots_log2; x.bb = (uint32_t)hs.pl->bb;
+    x.bstart = hs.bstart; x.n_buckets = hs.n_buckets; x.slots_log2 = hs.slots_log2 ? hs.slots_log2 : hs.pl->slots_log2; x.bb = (uint32_t)hs.pl->bb;
     x.ingroup64 = (uint64_t)g.ingroup[0] | ((uint64_t)g.ingroup[1] << 32);
     x.full64 = (uint64_t)g.full[0] | ((uint64_t)g.full[1] << 32);
     x.err = (unsigned long long*)ctx->small.p + SM_ERR;
+    x.brun = hs.brun;
     const unsigned grid = (unsigned)std::min<uint32_t>(hs.n_buckets, 1u << 20);
     if (hs.pl->stream) {
         TRY(ensure(ctx, ctx->deferred, (size_t)hs.n_buckets * 4 + 64));
@@ -1016,9 +1026,10 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
                 res->v.n_records = n;
                 ctx->alg_bytes += n * ctx->alg_rec_bytes;
             }
-            ctx->alg_bytes += n * 8 * (lo.direct ? 1 : (1 + lo.W));
+            if (hs && hs->brun) ctx->alg_bytes += n * 8 + hs->n_kept * (uint64_t)(32 + 16 * lo.W + lo.k);   // K3a read, K3a/b/c on what is kept
+            else ctx->alg_bytes += n * 8 * (lo.direct ? 1 : (1 + lo.W));
             if (hs && ctx->h_pinned[7]) { delete res; return fail(ctx, KB_EINTERNAL, "bucket hash: a bucket could not be resolved (hash table split limit)"); }
-            if (hs && !lo.direct && n >= (1ULL << 32)) { delete res; return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode"); }
+            if (hs && !hs->brun && !lo.direct && n >= (1ULL << 32)) { delete res; return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode"); }
             if (!hs && allow_fast && fast_group_ok(ctx) && ctx->h_pinned[6] > KB_TAINT_CAP) { allow_fast = false; continue; }   // taint list overflow: generic kernel
             if (n_res <= ctx->result_cap) break;
             rc = ensure_results(ctx, n_res + n_res / 8 + 16);       // table too small: grow and re-run the pass
@@ -1092,7 +1103,74 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
     return KB_OK;
 }
 
+// Lazy records (kb_prefilter.cuh): K3a drops the occurrences whose hash-table entry misses a file, K3b builds the records of the rest.
+// On return *kept = the compacted elements [hash32 | index] and hs carries their per-bucket runs.
+static int run_prefilter(kb_ctx* ctx, const PartPlan& pl, uint64_t* parted, uint64_t n_bound, HashStage* hs, uint64_t** kept) {
+    const KbLayout& lo = ctx->lo;
+    DevBuf& other = parted == (uint64_t*)ctx->entA.p ? ctx->entB : ctx->entA;
+    TRY(ensure(ctx, other, (size_t)(n_bound + 2048) * 8));
+    TRY(ensure(ctx, ctx->brun, (size_t)hs->n_buckets * 16 + 16));
+    unsigned long long* n_kept_dev = (unsigned long long*)ctx->small.p + SM_NTAINT;      // zero since prepare_small
+    KbPrefilterArgs a{};
+    a.ent = parted; a.bstart = hs->bstart; a.n_buckets = hs->n_buckets; a.bb = (uint32_t)pl.bb;
+    a.tb = kb_prefilter_tb(lo.PW, a.bb);
+    a.file_starts = (const uint64_t*)ctx->d_file_starts.p; a.file_gid = (const uint32_t*)ctx->d_file_gid.p;
+    a.n_local_files = (int)ctx->file_gid.size();
+    a.blk_shift = 0;
+    while ((ctx->n_bases >> a.blk_shift) >= KB_PF_BLOCKS) a.blk_shift++;
+    for (int f = 0; f < lo.n_files; f++) a.full[f >> 5] |= 1u << (f & 31);
+    a.out = (uint64_t*)other.p; a.n_out = n_kept_dev; a.brun = (unsigned long long*)ctx->brun.p;
+    const size_t smem = kb_prefilter_smem(lo.PW, a.tb);
+    const unsigned pgrid = (unsigned)std::min<uint32_t>(hs->n_buckets, (uint32_t)ctx->n_sm * 6);
+    prof_begin(ctx, "K3a hash prefilter");
+    switch (kb_prefilter_pwn(lo.PW)) {
+        case 2: CU(cudaFuncSetAttribute(kb_prefilter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kb_prefilter_kernel<2><<<pgrid, KB_PF_THREADS, smem, ctx->stream>>>(a); break;
+        case 4: CU(cudaFuncSetAttribute(kb_prefilter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kb_prefilter_kernel<4><<<pgrid, KB_PF_THREADS, smem, ctx->stream>>>(a); break;
+        default: CU(cudaFuncSetAttribute(kb_prefilter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kb_prefilter_kernel<8><<<pgrid, KB_PF_THREADS, smem, ctx->stream>>>(a); break;
+    }
+    CU(cudaGetLastError());
+    prof_end(ctx);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(ctx->h_pinned + 8, n_kept_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const uint64_t n_kept = ctx->h_pinned[8];
+    if (n_kept >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 candidate records per GPU in multi-word mode");
+    TRY(ensure(ctx, ctx->recs, std::max<uint64_t>(n_kept, 1) * 8 * lo.W));
+    if (n_kept) {
+        KbMatArgs m{};
+        m.ent = (uint64_t*)other.p; m.n = n_kept; m.bases = (const uint8_t*)ctx->bases.p;
+        m.file_starts = a.file_starts; m.file_gid = a.file_gid; m.n_local_files = a.n_local_files;
+        m.lo = lo; m.recs = (uint64_t*)ctx->recs.p;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_kept + 255) / 256, (uint64_t)ctx->n_sm * 16);
+        prof_begin(ctx, "K3b build records");
+        switch (lo.W) {
+            case 2: kb_materialize_kernel<2><<<grid, 256, 0, ctx->stream>>>(m); break;
+            case 4: kb_materialize_kernel<4><<<grid, 256, 0, ctx->stream>>>(m); break;
+            default: kb_materialize_kernel<8><<<grid, 256, 0, ctx->stream>>>(m); break;
+        }
+        CU(cudaGetLastError());
+        prof_end(ctx);
+        ctx->launches++;
+    }
+    hs->brun = (const unsigned long long*)ctx->brun.p;
+    hs->n_kept = n_kept;
+    if (!ctx->opt_hash_slots_log2) {
+        // exact pass: every kept table entry holds all files, so a bucket keeps about (kept records / files) keys — usually a
+        // handful; a table sized for them (not for the whole bucket) is cleared in no time, and an overflow only splits the bucket
+        const uint64_t keys = n_kept / std::max<uint64_t>(1, (uint64_t)hs->n_buckets * (uint64_t)std::max(lo.n_files, 1)) + 1;
+        uint32_t l2 = 6;
+        while (l2 < hs->pl->slots_log2 && ((uint64_t)1 << l2) < 4 * keys) l2++;
+        hs->slots_log2 = l2;
+    }
+    *kept = (uint64_t*)other.p;
+    return KB_OK;
+}
+
 static void begin_search(kb_ctx* ctx) {
+    ctx->lazy_now = false;
     ctx->launches = 0; ctx->alg_bytes = 0; ctx->alg_rec_bytes = 0; ctx->passes = 0;
     for (auto& e : ctx->prof_events) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
     ctx->prof_events.clear();
@@ -1110,6 +1188,7 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
     const KbLayout& lo = ctx->lo;
     uint64_t n = 0;
     const uint32_t n_tiles = (uint32_t)((ctx->n_bases + KB_K1_TB - 1) / KB_K1_TB);
+    ctx->lazy_now = ctx->opt_group_algo && ctx->opt_lazy_records && !lo.direct && padded_len(ctx->n_bases) < (1ULL << 32);
     if (ctx->opt_group_algo) {
         const PartPlan pl = make_plan(ctx, 2 * ctx->n_bases + 64);
         TRY(ensure(ctx, ctx->plan, pl.bytes + 64));
@@ -1173,11 +1252,12 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
             prof_collect(ctx);
             return rc;
         }
-        if (!lo.direct && n >= (1ULL << 32) + 64) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
+        if (!lo.direct && !ctx->lazy_now && n >= (1ULL << 32) + 64) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
         uint64_t* parted = nullptr;
         HashStage hs{};
         hs.pl = &pl;
         TRY(run_partition(ctx, pl, ctx->entA, ctx->entB, n, 0, pl.levels, nullptr, &parted, &hs.bstart, &hs.n_buckets, fused2));
+        if (ctx->lazy_now && n > 0) TRY(run_prefilter(ctx, pl, parted, n, &hs, &parted));
         int rc = run_group(ctx, parted, n, out, &hs);
         prof_collect(ctx);
         return rc;

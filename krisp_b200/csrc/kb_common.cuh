@@ -72,6 +72,17 @@ __host__ __device__ __forceinline__ uint64_t kb_mix64(uint64_t x) {
     return x;
 }
 
+// Hash of the flank key (left, right) read straight from a 2-bit base stream, in 64-bit chunks of each field: used by the lazy
+// multi-word path (K1 computes it without building the record, kb_materialize_kernel recomputes it from the sequence bytes).
+// get(bit position, n bits <= 64) returns the bits right-aligned.  The TOP bits are the partition digits / table slots.
+template <class G>
+__device__ __forceinline__ uint64_t kb_flank_hash(G get, uint32_t lpos, uint32_t rpos, uint32_t L2, uint32_t R2) {
+    uint64_t h = 0x243F6A8885A308D3ULL;
+    for (uint32_t d = 0; d < L2; d += 64) { h = (h ^ get(lpos + d, min(64u, L2 - d))) * KB_MIX_C1; h ^= h >> 32; }
+    for (uint32_t d = 0; d < R2; d += 64) { h = (h ^ get(rpos + d, min(64u, R2 - d))) * KB_MIX_C1; h ^= h >> 32; }
+    return h * KB_MIX_C2;
+}
+
 // ---- MSB-first bit strings -------------------------------------------------------------------
 // nbits (1..64) starting at bit `pos` of the word array `s` (word pos/64+1 must be readable).
 __device__ __forceinline__ uint64_t kb_get_bits(const uint64_t* s, uint32_t pos, uint32_t nbits) {

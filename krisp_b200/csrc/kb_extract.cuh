@@ -10,6 +10,7 @@
 // Output : packed records (kb_common.cuh), dense, in no particular order:
 //          DIRECT   out_entries[i] = record word
 //          INDIRECT out_recs[i*WN .. ] = record words, out_entries[i] = hash32(flank)<<32 | i
+//          INDIRECT, lazy: no records; out_entries[i] = hash31(flank)<<33 | strand<<32 | window start (kb_prefilter.cuh)
 //
 // One CTA processes tiles of KB_K1_TB window-start positions (persistent, grid-strided).  Per tile:
 //   1. the tile's bases (+ k-1 halo) are packed once into shared memory: forward 2-bit stream,
@@ -39,6 +40,7 @@ struct KbExtractArgs {
     KbLayout lo;
     uint64_t* out_entries;
     uint64_t* out_recs;          // INDIRECT only
+    int lazy;                    // INDIRECT only: 1 = no records, element = [flank hash 31][strand 1][window start 32] (kb_prefilter.cuh)
     unsigned long long* n_out;   // global record counter (claimed per tile)
     uint32_t tile0, n_tiles;     // tiles [tile0, tile0 + n_tiles)
     uint64_t pos_lo, pos_hi;     // only windows starting in [pos_lo, pos_hi) are emitted (one-file tables)
@@ -240,6 +242,12 @@ __global__ void __launch_bounds__(KB_K1_THREADS * GROUPS) kb_extract_kernel(cons
                 for (int st = 0; st < 2; st++) {
                     const uint64_t* s = st ? rcs : fwd;
                     const uint32_t o = st ? (NB - (p + k)) : p;      // first base of the window in that stream
+                    if (a.lazy) {                                     // the record is built later, and only if it can still matter
+                        const uint64_t h = kb_flank_hash([&](uint32_t pos, uint32_t n) { return kb_get_bits(s, pos, n); },
+                                                         2 * o, 2 * (o + lo.L + lo.D), 2 * lo.L, 2 * lo.R);
+                        ent[st] = (h & 0xFFFFFFFE00000000ULL) | ((uint64_t)st << 32) | (uint64_t)(uint32_t)(tile_base + p);
+                        continue;
+                    }
                     uint64_t rec[WN];
 #pragma unroll
                     for (int j = 0; j < WN; j++) rec[j] = 0;

@@ -35,6 +35,7 @@ struct KbHashArgs {
     unsigned long long* err;             // != 0: a bucket could not be resolved
     const uint32_t* list;                // != null: process only the buckets list[0 .. *n_list)
     const unsigned long long* n_list;
+    const unsigned long long* brun;      // != null (generic kernel): bucket b = elements [brun[2b], brun[2b] + brun[2b+1]) (kb_prefilter.cuh)
 };
 
 // The 32 key (or flank-hash) bits right below the bucket bits, left-aligned.  Mixed keys (kb_mix) and flank
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_kernel(const KbHashArgs
     const uint32_t n_work = x.list ? (uint32_t)min((unsigned long long)x.n_buckets, *x.n_list) : x.n_buckets;
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const uint32_t b = x.list ? x.list[wi] : wi;
-        const uint64_t bs = x.bstart[b], be = x.bstart[b + 1];
+        const uint64_t bs = x.brun ? x.brun[2 * (size_t)b] : x.bstart[b], be = x.brun ? bs + x.brun[2 * (size_t)b + 1] : x.bstart[b + 1];
         if (be == bs) continue;
         __syncthreads();
         if (tid == 0) { ctl.sp = 1; ctl.stack[0] = 0; }

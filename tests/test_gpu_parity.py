@@ -111,6 +111,62 @@ def test_bucket_hash_is_exact_for_any_bucket_and_table_size(name, bucket_bits, s
         assert res.stats["mixed_runs"] > 0          # = bucket splits
 
 
+@pytest.mark.parametrize("lazy", [0, 1], ids=["eager", "lazy"])
+@pytest.mark.parametrize("bucket_bits,slots", [(0, 0), (5, 5), (12, 0), (24, 4)])
+@pytest.mark.parametrize("name", ["p_primer_3x3", "p_30_40_30", "c1_primer_32_60_32"])
+def test_multiword_records_lazy_and_eager_agree(name, bucket_bits, slots, lazy, searcher):
+    """k > 28: 'lazy' = K1 writes 8-byte (hash, strand, position) elements, K3a drops what provably misses a file, K3b builds
+    the records of the rest (kb_prefilter.cuh); 'eager' = K1 writes every record.  Both must give the reference's rows."""
+    from krisp_b200.search import search_files
+    cases = [c for c in _G["cases"] if c["name"] == name]
+    if not cases:
+        pytest.skip("no such golden case")
+    case = cases[0]
+    ins, outs = golden_paths(case)
+    L, D, R = deduce_ldr(case["flags"])
+    try:
+        res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher,
+                           options={"bucket_bits": bucket_bits, "hash_slots_log2": slots, "lazy_records": lazy})
+    finally:
+        searcher.set_option("lazy_records", 1)
+        searcher.set_option("bucket_bits", -1)
+        searcher.set_option("hash_slots_log2", 0)
+    rows = res.rows()
+    assert len(rows) == case["n_rows"]
+    assert hashlib.sha256("\n".join(rows).encode()).hexdigest() == case["rows_sha256"]
+
+
+@pytest.mark.parametrize("shape", [(5, 4, 200_000, 32, 60, 32, False), (5, 4, 200_000, 32, 60, 32, True), (3, 3, 150_000, 20, 10, 17, False),
+                                   (40, 40, 30_000, 20, 30, 20, False), (6, 5, 100_000, 100, 20, 100, False)],
+                         ids=["primer", "primer_omit", "20_10_17", "80_files", "k220"])
+def test_lazy_records_panel_matches_oracle_and_eager(shape, searcher):
+    """Multi-word records on seeded panels: lazy == eager == C oracle, and the gathered records (--out_align input) agree."""
+    from krisp_b200.panel import make_panel
+    n_in, n_out, glen, L, D, R, omit = shape
+    kw = dict(n_runs=1, run_len=30, noise=2e-4, dup_len=300, soft_block=100) if n_in + n_out > 64 else {}
+    gs = make_panel(n_in, n_out, glen, **kw)
+    got = {}
+    for lazy in (1, 0):
+        try:
+            res = _search_panel(searcher, gs, L, D, R, omit, options={"lazy_records": lazy}, want_records=True)
+        finally:
+            searcher.set_option("lazy_records", 1)
+            searcher.set_option("want_records", 0)
+        W = res.records.shape[1]
+        groups = []
+        for g in range(res.n_groups):
+            a, b = int(res.run_offset[g]), int(res.run_offset[g + 1])
+            assert b - a == int(res.group_size[g])
+            recs = res.records[a:b]
+            order = np.lexsort([recs[:, j] for j in range(W - 1, -1, -1)])
+            groups.append((res.flank_words[g].tobytes(), recs[order].tobytes()))
+        got[lazy] = (res.rows(), sorted(groups))
+    want = _oracle_panel(gs, L, D, R, omit)
+    assert got[1][0] == want
+    assert got[0][0] == want
+    assert got[1][1] == got[0][1]
+
+
 _TABLES = _G["tables"]
 
 
