@@ -22,7 +22,7 @@
 #define KB_PF_THREADS 512
 #define KB_PF_ITEMS 8
 #define KB_PF_CAP (KB_PF_THREADS * KB_PF_ITEMS)      // buckets up to this size stay in registers between the three steps
-#define KB_PF_BLOCKS 4096                            // coarse position -> file table
+#define KB_PF_BLOCKS 1024                            // coarse position -> file table
 
 struct KbPrefilterArgs {
     const uint64_t* ent;                 // partitioned lazy elements
@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(KB_PF_THREADS) kb_prefilter_kernel(const KbPre
     uint32_t* tab = reinterpret_cast<uint32_t*>(kb_smem_raw);
     __shared__ uint32_t s_fs[KB_MAX_FILES + 1];
     __shared__ uint8_t s_gid[KB_MAX_FILES];
-    __shared__ uint8_t s_blk[KB_PF_BLOCKS];                // file of the first position of every coarse block
+    // coarse block of positions -> { first file start after the block's first position, ids of the files before / after it, bit 16:
+    // more than one file starts inside the block }: ONE random shared-memory read per record
+    __shared__ uint2 s_blk[KB_PF_BLOCKS];
     __shared__ uint32_t s_count, s_cursor;
     __shared__ unsigned long long s_base;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -61,7 +63,14 @@ __global__ void __launch_bounds__(KB_PF_THREADS) kb_prefilter_kernel(const KbPre
     for (int i = (int)tid; i <= nf; i += KB_PF_THREADS) s_fs[i] = (uint32_t)min((unsigned long long)a.file_starts[i], 0xFFFFFFFFull);
     for (int i = (int)tid; i < nf; i += KB_PF_THREADS) s_gid[i] = (uint8_t)a.file_gid[i];
     __syncthreads();
-    for (uint32_t i = tid; i < KB_PF_BLOCKS; i += KB_PF_THREADS) s_blk[i] = (uint8_t)kb_pf_file(s_fs, nf, i << a.blk_shift);
+    for (uint32_t i = tid; i < KB_PF_BLOCKS; i += KB_PF_THREADS) {
+        const uint32_t p0 = i << a.blk_shift, p1 = p0 + ((1u << a.blk_shift) - 1u);
+        const uint32_t f = kb_pf_file(s_fs, nf, p0);                      // file of the block's first position
+        const uint32_t next = s_fs[min(f + 1, (uint32_t)nf)];             // where the following file starts (or the data end)
+        const uint32_t f1 = min(f + 1, (uint32_t)max(nf - 1, 0));
+        const bool many = f + 2 < (uint32_t)nf && s_fs[f + 2] <= p1;      // a third file starts inside the block
+        s_blk[i] = make_uint2(next, (uint32_t)s_gid[f] | ((uint32_t)s_gid[f1] << 8) | (many ? 0x10000u : 0u));
+    }
 
     auto slot_of = [&](uint64_t e) -> uint32_t* { return tab + (size_t)((uint32_t)((e << a.bb) >> (64 - a.tb))) * PWN; };
     auto alive = [&](uint64_t e) -> bool {
@@ -76,12 +85,10 @@ __global__ void __launch_bounds__(KB_PF_THREADS) kb_prefilter_kernel(const KbPre
     };
     auto mark = [&](uint64_t e) {
         const uint32_t pos = (uint32_t)e;
-        uint32_t f = s_blk[pos >> a.blk_shift];
-        while (s_fs[f + 1] <= pos) f++;                    // (files shorter than a block: a few steps)
-        const uint32_t id = s_gid[f];
-        uint32_t* p = slot_of(e) + (id >> 5);
-        const uint32_t bit = 1u << (id & 31);
-        if (!(kb_ld_shared_volatile(p) & bit)) atomicOr(p, bit);
+        const uint2 blk = s_blk[pos >> a.blk_shift];
+        uint32_t id = pos < blk.x ? (blk.y & 0xFFu) : ((blk.y >> 8) & 0xFFu);
+        if ((blk.y & 0x10000u) && pos >= blk.x) id = s_gid[kb_pf_file(s_fs, nf, pos)];   // several files start in this block (tiny files)
+        atomicOr(slot_of(e) + (id >> 5), 1u << (id & 31));
     };
 
     for (uint32_t b = blockIdx.x; b < a.n_buckets; b += gridDim.x) {
@@ -209,53 +216,53 @@ __global__ void __launch_bounds__(256) kb_materialize_kernel(const KbMatArgs a) 
     for (int i = (int)threadIdx.x; i < nf; i += 256) s_gid[i] = a.file_gid[i];
     __syncthreads();
     const uint32_t k = (uint32_t)lo.k;
-    const uint32_t nq = (k + 3) / 4;                              // groups of 4 bases
+    constexpr int NV = 2 * WN + 1;          // 16-byte pieces that hold a window of <= 32 WN - 4 bases at any alignment
+    constexpr int SN = WN + 2;              // 2-bit stream: 32 bases per word, + one readable pad word
     for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * 256) {
         const uint64_t e = a.ent[i];
         const uint32_t pos = (uint32_t)e;
         const uint32_t strand = (uint32_t)(e >> 32) & 1u;
-        // the window's k bases as a 2-bit stream, first base in the top bits of s[0]
-        uint64_t s[WN + 1];
+        // the aligned 16-byte pieces around the window as a 2-bit stream (first base in the top bits of s[0]); the window
+        // starts `off` bases into it
+        const uint4* v16 = reinterpret_cast<const uint4*>(a.bases + (pos & ~15u));
+        const uint32_t off = pos & 15u;
+        const uint32_t nld = (off + k + 15u) >> 4;
+        uint64_t s[SN];
 #pragma unroll
-        for (int j = 0; j <= WN; j++) s[j] = 0;
-        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(a.bases + (pos & ~3u));
-        const uint32_t sh = 8 * (pos & 3u);
-        uint32_t prev = __ldg(w32);
+        for (int j = 0; j < SN; j++) s[j] = 0;
 #pragma unroll
-        for (int q = 0; q < 8 * WN; q++) {
-            if (q < (int)nq) {
-                const uint32_t next = __ldg(w32 + q + 1);
-                const uint32_t x = __funnelshift_r(prev, next, sh);
-                prev = next;
-                const uint32_t u = x & 0xDFDFDFDFu;
-                const uint32_t c = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
-                const uint64_t pk = (c * 0x40100401u) >> 24;
-                s[q >> 3] |= pk << (56 - 8 * (q & 7));
+        for (int j = 0; j < NV; j++) {
+            if (j < (int)nld) {
+                const uint4 v = __ldg(v16 + j);
+                const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+                uint32_t pk = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t u = wd[t] & 0xDFDFDFDFu;
+                    const uint32_t c = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
+                    pk = (pk << 8) | ((c * 0x40100401u) >> 24);
+                }
+                s[j >> 1] |= (uint64_t)pk << ((j & 1) ? 0 : 32);
             }
         }
-        {   // bases past the window (the rest of its last group of 4) are not part of it
-            const uint32_t w = (2 * k) >> 6, o = (2 * k) & 63;
+        uint32_t o0 = off;                                        // first base of the occurrence in the stream
+        if (strand) {                                             // reverse complement of the whole stream (32 (WN + 1) bases)
+            uint64_t t[SN];
 #pragma unroll
-            for (int j = 0; j < WN; j++) if (j == (int)w) s[j] &= o ? (~0ULL << (64 - o)) : 0ULL;
-        }
-        uint32_t o0 = 0;                                          // first base of the occurrence in the stream
-        if (strand) {
-            uint64_t t[WN + 1];
+            for (int j = 0; j <= WN; j++) t[j] = kb_rc64(s[WN - j]);
+            t[WN + 1] = 0;
 #pragma unroll
-            for (int j = 0; j < WN; j++) t[j] = kb_rc64(s[WN - 1 - j]);
-            t[WN] = 0;
-#pragma unroll
-            for (int j = 0; j <= WN; j++) s[j] = t[j];
-            o0 = 32u * WN - k;
+            for (int j = 0; j < SN; j++) s[j] = t[j];
+            o0 = 32u * (WN + 1) - (off + k);
         }
         uint64_t rec[WN];
 #pragma unroll
         for (int j = 0; j < WN; j++) rec[j] = 0;
-        if (lo.L) kb_mat_copy<WN, WN + 1>(rec, 0, s, 2 * o0, 2 * lo.L);
-        if (lo.R) kb_mat_copy<WN, WN + 1>(rec, 2 * lo.L, s, 2 * (o0 + lo.L + lo.D), 2 * lo.R);
-        const uint64_t h = kb_flank_hash([&](uint32_t p, uint32_t n) { return kb_mat_bits<WN + 1>(s, p, n); },      // = K1's (lazy)
+        if (lo.L) kb_mat_copy<WN, SN>(rec, 0, s, 2 * o0, 2 * lo.L);
+        if (lo.R) kb_mat_copy<WN, SN>(rec, 2 * lo.L, s, 2 * (o0 + lo.L + lo.D), 2 * lo.R);
+        const uint64_t h = kb_flank_hash([&](uint32_t p, uint32_t n) { return kb_mat_bits<SN>(s, p, n); },      // = K1's (lazy)
                                          2 * o0, 2 * (o0 + lo.L + lo.D), 2 * lo.L, 2 * lo.R);
-        if (lo.D) kb_mat_copy<WN, WN + 1>(rec, lo.FB, s, 2 * (o0 + lo.L), 2 * lo.D);
+        if (lo.D) kb_mat_copy<WN, SN>(rec, lo.FB, s, 2 * (o0 + lo.L), 2 * lo.D);
         rec[WN - 1] |= (uint64_t)s_gid[kb_pf_file(s_fs, nf, pos)];
         uint64_t* dst = a.recs + i * WN;
 #pragma unroll
