@@ -114,6 +114,32 @@ def render_alignment(left, right, amps, ingroup=None, dot=False):
     return "\n".join(result)
 
 
+def interchange_lines(res, labels, order=None):
+    """The survivors in the reference's interchange text (Amplicon.write, Amplicon.py:330-348; label grammar :170-206): one line
+    ``left,mid,right,label(n);label...`` per distinct sequence, groups in ascending (left, right) order — the content of the
+    reference's ``filtered.txt`` (``merged_file.txt`` when D == 0; krisp_fasta.py:256-283), which its unchanged renderer
+    (``render_output``, outputAlignments.py:101; ``--out_align``, ``--dot-alignment``, ``--primer3``) reads back.
+    Inside a group the reference's line order follows its merge tree; here lines are sorted by middle (readers do not care:
+    alignmentStream shared.py:442-475 collects the whole group).  Needs a search run with want_records."""
+    order = _group_order(res) if order is None else order
+    out = []
+    for g in order:
+        left, right = res.left[g].tobytes().decode(), res.right[g].tobytes().decode()
+        amps = group_amplicons(res, g, labels)
+        for mid in sorted(amps):
+            out.append(f"{left},{mid},{right},{_labels_to_string(amps[mid])}")
+    return out
+
+
+def write_interchange(res, labels, filename):
+    """Write interchange_lines to `filename`; returns the number of lines (what the reference's stage functions return)."""
+    lines = interchange_lines(res, labels)
+    with open(filename, "w") as fh:
+        for ln in lines:
+            fh.write(ln + "\n")
+    return len(lines)
+
+
 def render_output(res, labels, ingroup=None, out_csv=None, out_align=None, dot=False):
     """Write the CSV (stdout when out_csv is None) and, if asked, the alignment file.  Returns the number of regions."""
     order = _group_order(res)

@@ -58,3 +58,35 @@ def rows_of(stdout):
     lines = [ln for ln in stdout.splitlines() if ln]
     assert lines and lines[0].startswith("left_seq,diag_seq,right_seq"), lines[:1]
     return sorted(lines[1:])
+
+
+_SPY = r"""
+import shutil, sys
+import krisp.krisp_fasta.krisp_fasta as m
+_dest = sys.argv.pop(1)
+_real = m.render_output
+def _spy(kmerfile, *a, **k):
+    shutil.copyfile(kmerfile, _dest)          # observe the interchange file; the reference code itself is untouched
+    return _real(kmerfile, *a, **k)
+m.render_output = _spy
+m.main()
+"""
+
+
+def krisp_fasta_interchange(argv, cwd=None, timeout=3600):
+    """``krisp_fasta <argv>`` -> (stdout, text of the k-mer file handed to render_output).
+
+    That file (``filtered.txt``, or ``merged_file.txt`` when D == 0; krisp_fasta.py:256-283) is the reference's
+    interchange format ``left,mid,right,label(n);label...`` restricted to the surviving groups."""
+    argv = list(map(str, argv))
+    with tempfile.TemporaryDirectory() as wd:
+        dest = os.path.join(wd, "interchange.txt")
+        if "--workdir" not in argv and "-w" not in argv:
+            argv += ["--workdir", wd]
+        p = subprocess.run([sys.executable, "-c", _SPY, dest] + argv, cwd=cwd, env=_env(), capture_output=True, text=True,
+                           timeout=timeout)
+        if p.returncode != 0:
+            raise RuntimeError(f"reference krisp_fasta failed rc={p.returncode}\n{p.stderr}")
+        with open(dest) as fh:
+            text = fh.read()
+    return p.stdout, text

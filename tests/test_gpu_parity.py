@@ -360,3 +360,45 @@ def test_device_fasta_delining_matches_host_parser(name, searcher):
         pytest.skip("stray whitespace: the host parser takes over (flag raised)")
     assert norm(got) == norm(want)
     assert bool(flags & 1) == bool(re.search(rb"[Uu]", want))
+
+
+def _interchange_golden():
+    import json
+    import os
+    from tests.helpers import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "interchange.json")) as fh:
+        return json.load(fh)
+
+
+def _groups_of(lines):
+    """Interchange lines -> ordered list of ((left, right), sorted lines of the group)."""
+    out = []
+    for ln in lines:
+        l, _m, r, _labs = ln.split(",")
+        if out and out[-1][0] == (l, r):
+            out[-1][1].append(ln)
+        else:
+            out.append(((l, r), [ln]))
+    return [(k, sorted(v)) for k, v in out]
+
+
+@pytest.mark.parametrize("name", sorted(_interchange_golden()))
+def test_interchange_file_matches_reference(name, searcher, tmp_path):
+    """The survivors written in the reference's interchange text == the file the unmodified reference hands to its renderer
+    (tests/golden/interchange.json, made by make_interchange.py): same groups in the same order, same lines per group."""
+    from krisp_b200.search import search_files
+    from krisp_b200.render import write_interchange
+    case = next(c for c in _G["cases"] if c["name"] == name)
+    ins, outs = golden_paths(case)
+    L, D, R = deduce_ldr(case["flags"])
+    try:
+        res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher, want_records=True)
+    finally:
+        searcher.set_option("want_records", 0)
+    path = str(tmp_path / "filtered.txt")
+    n = write_interchange(res, res.labels, path)
+    with open(path) as fh:
+        got = fh.read().splitlines()
+    want = _interchange_golden()[name].splitlines()
+    assert n == len(got) == len(want)
+    assert _groups_of(got) == _groups_of(want)

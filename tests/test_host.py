@@ -161,3 +161,61 @@ def test_piece_tables_tile_every_receive_buffer_exactly():
                 src, j = divmod(i, firsts[s + 1] - firsts[s])
                 assert per_rank[src][1][firsts[s] + j] == pos
                 pos += c
+
+
+def _pack_words(bits_value, nbits, words):
+    """MSB-first bit string of `nbits` bits -> `words` uint64 words (zero padded at the end)."""
+    v = bits_value << (64 * words - nbits)
+    return [(v >> (64 * (words - 1 - j))) & 0xFFFFFFFFFFFFFFFF for j in range(words)]
+
+
+def test_interchange_lines_round_trip_golden_files():
+    """render.interchange_lines on results assembled from the reference's own interchange files (tests/golden/interchange.json)
+    reproduces them: record layout [left | right | mid | pad | file id], label grammar name / name(n), group order."""
+    import json
+    import re
+    from krisp_b200.search import labels_for
+    with open(os.path.join(GOLDEN_DIR, "interchange.json")) as fh:
+        inter = json.load(fh)
+    assert len(inter) >= 10
+    for name, text in inter.items():
+        case = next(c for c in _G["cases"] if c["name"] == name)
+        L, D, R = deduce_ldr(case["flags"])
+        ins = [os.path.join(GOLDEN_DIR, p) for p in case["ingroup"]]
+        outs = [os.path.join(GOLDEN_DIR, p) for p in case["outgroup"]]
+        labels, _ = labels_for(ins, outs)
+        k = L + D + R
+        W = 1 if 2 * k + 8 <= 64 else (2 if 2 * k + 8 <= 128 else (4 if 2 * k + 8 <= 256 else 8))
+        FW = max(1, (2 * (L + R) + 63) // 64)
+        groups = []
+        for ln in text.splitlines():
+            l, m, r, labs = ln.split(",")
+            if not groups or groups[-1][0] != (l, r):
+                groups.append(((l, r), []))
+            for item in labs.split(";"):
+                mt = re.fullmatch(r"(.+?)(?:\((\d+)\))?", item)
+                groups[-1][1].extend([(m, mt.group(1))] * int(mt.group(2) or 1))
+        res = SearchResult(L=L, D=D, R=R, have_outgroup=bool(outs))
+        flank, recs, off = [], [], [0]
+        for (l, r), occ in groups:
+            flank.append(_pack_words(_pack(l + r), 2 * (L + R), FW) if L + R else [0] * FW)
+            for m, lab in occ:
+                words = _pack_words(_pack(l + r + m), 2 * k, W)
+                words[-1] |= labels.index(lab)
+                recs.append(words)
+            off.append(len(recs))
+        res.flank_words = np.array(flank, dtype=np.uint64).reshape(len(groups), FW)
+        res.records = np.array(recs, dtype=np.uint64).reshape(len(recs), W)
+        res.run_offset = np.array(off, dtype=np.uint64)
+        got = render.interchange_lines(res, labels)
+
+        def grouped(lines):
+            out = []
+            for ln in lines:
+                l, _m, r, _x = ln.split(",")
+                if out and out[-1][0] == (l, r):
+                    out[-1][1].append(ln)
+                else:
+                    out.append(((l, r), [ln]))
+            return [(kk, sorted(v)) for kk, v in out]
+        assert grouped(got) == grouped(text.splitlines()), name
