@@ -130,6 +130,17 @@ int kb_search(kb_ctx* ctx, kb_result** out);
  *                         this shard = first(shard_index + 1) - first(shard_index), first(s) = s * n_digits / n_shards.
  */
 int kb_shard_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bases, int* n_digits);
+/*
+ * Multi-word records (k > 28) on several GPUs: the 8-byte elements that travel carry (flank hash, strand, window start), and
+ * the owner rebuilds the records of the occurrences that are left after the hash filter from the sequence bytes — so every
+ * rank holds ALL sequences (the host layer all-gathers them, krisp_b200/sharded.py:replicate_sequences, and adds them in the
+ * same order everywhere) and extracts only its own files:
+ *   kb_sequence_buffer    device pointer / size of this rank's concatenated sequence bytes (every file followed by one separator)
+ *   kb_shard_own_files    K1 of the kb_shard_* calls covers only local files [first_local, first_local + n_local)
+ *                         (n_local < 0: all; reset by kb_clear_sequences)
+ */
+int kb_sequence_buffer(kb_ctx* ctx, void** device_bytes, uint64_t* n_bytes);
+int kb_shard_own_files(kb_ctx* ctx, int first_local, int n_local);
 
 /*
  * Fused partition + exchange over NVLink peer memory (the GPUs of one box; one process per GPU).  Instead of partitioning

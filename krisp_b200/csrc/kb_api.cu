@@ -127,6 +127,7 @@ struct kb_ctx {
     DevBuf recvbuf;                      // IPC-exported receive buffer of the fused partition + exchange
     std::vector<void*> peer_ptr;         // peer_ptr[r] = rank r's receive buffer mapped here (own entry = recvbuf.p)
     std::vector<uint64_t> scatter_host;  // staging of the per-digit tables of kb_shard_scatter
+    int own_first = 0, own_count = -1;   // replicated sequences: K1 of the shard calls covers only these local files (-1: all)
     int shard_direct = 0;                // the last exchange went through kb_shard_scatter (input of kb_shard_search = recvbuf)
     uint64_t shard_n_records = 0;
     int shard_send_in_B = 0;             // partitioned records are in entB (else entA)
@@ -307,6 +308,7 @@ int kb_clear_sequences(kb_ctx* ctx) {
     ctx->file_starts.clear();
     ctx->file_gid.clear();
     ctx->file_event.clear();
+    ctx->own_first = 0; ctx->own_count = -1;
     if (ctx->fa_flags.p) { cudaSetDevice(ctx->device); cudaMemsetAsync(ctx->fa_flags.p, 0, 8, ctx->stream); }
     return KB_OK;
 }
@@ -1134,9 +1136,9 @@ static int run_prefilter(kb_ctx* ctx, const PartPlan& pl, uint64_t* parted, uint
     CU(cudaGetLastError());
     prof_end(ctx);
     ctx->launches++;
-    CU(cudaMemcpyAsync(ctx->h_pinned + 8, n_kept_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_pinned + 9, n_kept_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    const uint64_t n_kept = ctx->h_pinned[8];
+    const uint64_t n_kept = ctx->h_pinned[9];
     if (n_kept >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 candidate records per GPU in multi-word mode");
     TRY(ensure(ctx, ctx->recs, std::max<uint64_t>(n_kept, 1) * 8 * lo.W));
     if (n_kept) {
@@ -1281,7 +1283,8 @@ int kb_shard_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bas
     if (!ctx || n_shards < 1 || n_shards > 256 || shard_index < 0 || shard_index >= n_shards) return KB_EINVAL;
     if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
     const KbLayout& lo = ctx->lo;
-    if (!lo.direct) return fail(ctx, KB_EUNSUPPORTED, "multi-GPU sharding of multi-word records is not built yet");
+    if (!lo.direct && !(ctx->opt_lazy_records && ctx->opt_group_algo))
+        return fail(ctx, KB_EUNSUPPORTED, "multi-GPU sharding of multi-word records needs lazy_records = 1 and group_algo = 1");
     int min_bits0 = 0;
     while ((1 << min_bits0) < n_shards) min_bits0++;
     if (lo.FB < min_bits0 + 1) return fail(ctx, KB_EUNSUPPORTED, "flank key too short to shard over this many GPUs");
@@ -1304,6 +1307,41 @@ int kb_shard_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bas
     return KB_OK;
 }
 
+int kb_sequence_buffer(kb_ctx* ctx, void** device_bytes, uint64_t* n_bytes) {
+    if (!ctx || !device_bytes || !n_bytes) return KB_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *device_bytes = ctx->bases.p;
+    *n_bytes = ctx->n_bases;
+    return KB_OK;
+}
+
+int kb_shard_own_files(kb_ctx* ctx, int first_local, int n_local) {
+    if (!ctx) return KB_EINVAL;
+    const int nf = (int)ctx->file_starts.size();
+    if (n_local >= 0 && (first_local < 0 || first_local + n_local > nf)) return fail(ctx, KB_EINVAL, "own file range outside the added sequences");
+    ctx->own_first = n_local < 0 ? 0 : first_local;
+    ctx->own_count = n_local;
+    return KB_OK;
+}
+
+// positions / K1 tiles of this rank's own files, and the lazy-records switch of the shard calls
+static int shard_extract_range(kb_ctx* ctx, uint64_t* pos_lo, uint64_t* pos_hi, uint32_t* tile0, uint32_t* n_tiles) {
+    const int nf = (int)ctx->file_starts.size();
+    *pos_lo = 0; *pos_hi = ctx->n_bases;
+    if (ctx->own_count >= 0) {
+        *pos_lo = ctx->own_first < nf ? ctx->file_starts[ctx->own_first] : ctx->n_bases;
+        *pos_hi = ctx->own_first + ctx->own_count < nf ? ctx->file_starts[ctx->own_first + ctx->own_count] : ctx->n_bases;
+    }
+    *tile0 = (uint32_t)(*pos_lo / KB_K1_TB);
+    *n_tiles = (uint32_t)((*pos_hi + KB_K1_TB - 1) / KB_K1_TB) - *tile0;
+    ctx->lazy_now = !ctx->lo.direct;
+    if (ctx->lazy_now && padded_len(ctx->n_bases) >= (1ULL << 32))
+        return fail(ctx, KB_EUNSUPPORTED, "multi-word records on several GPUs: more than 2^32 sequence bytes over all ranks");
+    return KB_OK;
+}
+
 int kb_shard_extract(kb_ctx* ctx, void** records, uint64_t* shard_counts, uint64_t* digit_counts) {
     if (!ctx || !records || !shard_counts || !digit_counts) return KB_EINVAL;
     if (!ctx->configured || ctx->shard_n < 1) return fail(ctx, KB_EINVAL, "kb_configure / kb_shard_plan have not been called");
@@ -1316,10 +1354,11 @@ int kb_shard_extract(kb_ctx* ctx, void** records, uint64_t* shard_counts, uint64
     const size_t tilemap_extra = (size_t)((2 * ctx->n_bases + 64) / KB_PT_TILE + 2) * 4;
     TRY(ensure(ctx, ctx->plan, pl.bytes + tilemap_extra + 64));
     CU(cudaMemsetAsync(ctx->plan.p, 0, pl.bytes, ctx->stream));
-    uint64_t n = 0;
-    const uint32_t n_tiles = (uint32_t)((ctx->n_bases + KB_K1_TB - 1) / KB_K1_TB);
+    uint64_t n = 0, pos_lo = 0, pos_hi = 0;
+    uint32_t tile0 = 0, n_tiles = 0;
+    TRY(shard_extract_range(ctx, &pos_lo, &pos_hi, &tile0, &n_tiles));
     unsigned long long* h0 = (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[0]);
-    TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0], true));
+    TRY(run_extract(ctx, lo, tile0, n_tiles, pos_lo, pos_hi, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0], true));
     uint64_t* parted = nullptr;
     const unsigned long long* start0 = nullptr;
     uint32_t nd = 0;
@@ -1391,10 +1430,11 @@ int kb_shard_count(kb_ctx* ctx, uint64_t* digit_counts) {
     const size_t tilemap_extra = (size_t)((2 * ctx->n_bases + 64) / KB_PT_TILE + 2) * 4;
     TRY(ensure(ctx, ctx->plan, pl.bytes + tilemap_extra + 64));
     CU(cudaMemsetAsync(ctx->plan.p, 0, pl.bytes, ctx->stream));
-    uint64_t n = 0;
-    const uint32_t n_tiles = (uint32_t)((ctx->n_bases + KB_K1_TB - 1) / KB_K1_TB);
+    uint64_t n = 0, pos_lo = 0, pos_hi = 0;
+    uint32_t tile0 = 0, n_tiles = 0;
+    TRY(shard_extract_range(ctx, &pos_lo, &pos_hi, &tile0, &n_tiles));
     unsigned long long* h0 = (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[0]);
-    TRY(run_extract(ctx, lo, 0, n_tiles, 0, ctx->n_bases, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0], true));
+    TRY(run_extract(ctx, lo, tile0, n_tiles, pos_lo, pos_hi, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0], true));
     std::vector<uint64_t>& st = ctx->scatter_host;
     st.assign(pl.nc[0], 0);
     CU(cudaMemcpyAsync(st.data(), h0, (size_t)pl.nc[0] * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1492,7 +1532,6 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_count
     }
     h_start[np] = run; h_tile0[np] = (uint32_t)trun;
     if (run != n_records) return fail(ctx, KB_EINVAL, "piece counts do not add up to the number of received records");
-    if (!ctx->lo.direct && n_records >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode");
     TRY(ensure(ctx, ctx->shard_tab, hp.size() * 8));
     CU(cudaMemcpyAsync(ctx->shard_tab.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h_pinned[8] = n_records;                            // the "record counter" the stream kernel and the root table read
@@ -1512,6 +1551,8 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_count
     HashStage hs{};
     hs.pl = &pl;
     TRY(run_partition(ctx, pl, in, other, n_records, 1, pl.levels, &cp, &parted, &hs.bstart, &hs.n_buckets));
+    ctx->lazy_now = !ctx->lo.direct;
+    if (ctx->lazy_now && n_records > 0) TRY(run_prefilter(ctx, pl, parted, n_records, &hs, &parted));
     int rc = run_group(ctx, parted, n_records, out, &hs);
     prof_collect(ctx);
     return rc;

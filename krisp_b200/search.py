@@ -178,6 +178,7 @@ class Searcher:
             self._check(self._L.kb_set_stream(self._ctx, ctypes.c_void_p(int(stream))))
         self._keep = []          # host buffers that must outlive the async copies
         self.bases_added = 0     # bytes handed to add_sequence since the last clear_sequences
+        self.added_ids = []      # global file ids in the order they were added
         self.lo = None
 
     def close(self):
@@ -210,6 +211,7 @@ class Searcher:
         self._check(self._L.kb_clear_sequences(self._ctx))
         self._keep = []
         self.bases_added = 0
+        self.added_ids = []
 
     def reserve(self, total_bytes):
         self._check(self._L.kb_reserve(self._ctx, int(total_bytes)))
@@ -219,10 +221,12 @@ class Searcher:
         if isinstance(data, tuple):
             ptr, n = data
             self.bases_added += int(n)
+            self.added_ids.append(int(file_id))
             self._check(self._L.kb_add_sequence(self._ctx, int(file_id), ctypes.c_void_p(int(ptr)), int(n), 1))
             return
         arr = np.ascontiguousarray(data, dtype=np.uint8)
         self.bases_added += int(arr.size)
+        self.added_ids.append(int(file_id))
         self._keep.append(arr)
         self._check(self._L.kb_add_sequence(self._ctx, int(file_id), ctypes.c_void_p(arr.ctypes.data), int(arr.size), 0))
 
@@ -230,6 +234,7 @@ class Searcher:
         """`raw`: the decompressed file content (bytes): headers and line breaks are removed on the device (kb_add_fasta)."""
         arr = np.frombuffer(raw, dtype=np.uint8)
         self.bases_added += int(arr.size)
+        self.added_ids.append(int(file_id))
         self._check(self._L.kb_add_fasta(self._ctx, int(file_id), ctypes.c_void_p(arr.ctypes.data if arr.size else 0), int(arr.size)))
 
     def fasta_flags(self):
@@ -246,6 +251,24 @@ class Searcher:
         if out.size:
             self._check(self._L.kb_get_sequence(self._ctx, int(local_index), ctypes.c_void_p(out.ctypes.data), int(out.size), ctypes.byref(n)))
         return out
+
+    def sequence_buffer(self):
+        """(device pointer, bytes) of this context's concatenated sequences (every file followed by one separator)."""
+        ptr, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(self._L.kb_sequence_buffer(self._ctx, ctypes.byref(ptr), ctypes.byref(n)))
+        return int(ptr.value or 0), int(n.value)
+
+    def sequence_sizes(self):
+        """Bytes of every added file in the sequence buffer (separator included), in the order they were added."""
+        out = []
+        for i in range(len(self.added_ids)):
+            n = ctypes.c_uint64()
+            self._check(self._L.kb_get_sequence(self._ctx, i, None, 0, ctypes.byref(n)))
+            out.append(int(n.value))
+        return out
+
+    def shard_own_files(self, first_local, n_local):
+        self._check(self._L.kb_shard_own_files(self._ctx, int(first_local), int(n_local)))
 
     def synchronize(self):
         self._check(self._L.kb_synchronize(self._ctx))

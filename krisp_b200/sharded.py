@@ -151,6 +151,47 @@ def direct_search(searcher, device, have_outgroup=True, group=None):
     return res
 
 
+def replicate_sequences(searcher, device, group=None):
+    """Multi-word records (k > 28): every rank gets ALL sequences, in the same order (rank 0's files, rank 1's files, ...), and
+    keeps extracting only its own.  The 8-byte elements that travel then carry a position that means the same on every GPU, and
+    the owner of a key can rebuild the records it still needs from the bytes (csrc/kb_prefilter.cuh).
+    One all-gather of the sequence bytes over NCCL (padded to the longest rank), then device-to-device adds."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ptr, n = searcher.sequence_buffer()
+    table = [None] * world
+    dist.all_gather_object(table, (list(searcher.added_ids), searcher.sequence_sizes(), n), group=group)
+    longest = max(t[2] for t in table)
+    mine = torch.zeros(max(longest, 1), dtype=torch.uint8, device=device)
+    if n:
+        mine[:n] = torch.as_tensor(_DeviceBytes(ptr, n), device=device)
+    allb = torch.empty(world * max(longest, 1), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(allb, mine, group=group)
+    torch.cuda.current_stream().synchronize() if device.type == "cuda" else None
+    searcher.clear_sequences()
+    searcher.reserve(sum(t[2] for t in table) + 64)
+    first = count = 0
+    base = allb.data_ptr()
+    n_added = 0
+    for r, (ids, sizes, _) in enumerate(table):
+        off = r * max(longest, 1)
+        if r == rank:
+            first, count = n_added, len(ids)
+        for gid, sz in zip(ids, sizes):
+            searcher.add_sequence(gid, (base + off, sz - 1))          # (the library appends the separator itself)
+            off += sz
+            n_added += 1
+    searcher.synchronize()                                            # the adds copy out of `allb`, which dies with this frame
+    searcher.shard_own_files(first, count)
+    return sum(t[2] for t in table)
+
+
+class _DeviceBytes:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 def sharded_search(searcher, device, have_outgroup=True, group=None, total_bases=None, exchange_mode=None):
     """Steps 0-3 on the sequences this rank has added to `searcher`.  Returns this rank's SearchResult.
     `total_bases` = bases over all ranks (all-reduced from ``searcher.bases_added`` when not given).
@@ -158,6 +199,12 @@ def sharded_search(searcher, device, have_outgroup=True, group=None, total_bases
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo = getattr(searcher, "lo", None)
+    if lo is not None and 2 * sum(lo) + 8 > 64 and hasattr(searcher, "sequence_buffer"):
+        if getattr(searcher, "_replicated", None) is not searcher.added_ids:
+            replicate_sequences(searcher, device, group)
+            searcher._replicated = searcher.added_ids                 # (a second search on the same sequences does not gather again)
+        total_bases = int(searcher.bases_added)                       # every rank now holds everything
     if total_bases is None:
         t = torch.tensor([int(getattr(searcher, "bases_added", 0))], dtype=torch.int64, device=device)
         dist.all_reduce(t, group=group)

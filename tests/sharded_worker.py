@@ -23,8 +23,8 @@ def main():
     bad = 0
     for case in load_golden()["cases"]:
         L, D, R = deduce_ldr(case["flags"])
-        if 2 * (L + D + R) + 8 > 64 or (R == 0 and D > 0):
-            continue                                   # multi-word records are not sharded yet
+        if R == 0 and D > 0:
+            continue                                   # quirk S9: the host answers without a search
         ins, outs = golden_paths(case)
         files = ins + outs
         _, is_in = labels_for(ins, outs)
