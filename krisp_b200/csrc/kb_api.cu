@@ -1585,7 +1585,6 @@ int kb_extract_sorted(kb_ctx* ctx, int local_index, kb_table** out) {
     *out = nullptr;
     if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
     if (local_index < 0 || local_index >= (int)ctx->file_starts.size()) return fail(ctx, KB_EINVAL, "no such sequence");
-    if (!ctx->lo.direct) return fail(ctx, KB_EUNSUPPORTED, "sorted tables of k-mers longer than 28 bases are not built yet");
     CU(cudaSetDevice(ctx->device));
     begin_search(ctx);
     TRY(prepare_small(ctx));
@@ -1599,6 +1598,46 @@ int kb_extract_sorted(kb_ctx* ctx, int local_index, kb_table** out) {
     uint64_t n = 0;
     TRY(run_extract(ctx, lo, tile0, tile1 - tile0, pos_lo, pos_hi, &n));
     uint64_t* sorted = nullptr;
+    if (!lo.direct) {
+        // multi-word records: K1 wrote them in extraction order; sort their indices by 32-bit chunks of the base bits, least
+        // significant chunk first (stable LSD), then write the records out in that order
+        if (n >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records in a multi-word table");
+        const uint32_t key_bits = 2 * (uint32_t)lo.k, chunks = (key_bits + 31) / 32;
+        DevBuf* in = &ctx->entA; DevBuf* other = &ctx->entB;
+        sorted = (uint64_t*)in->p;
+        const unsigned cgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->n_sm * 16));
+        for (int c = (int)chunks - 1; c >= 0 && n > 0; c--) {
+            KbChunkKeyArgs ck{};
+            ck.ent = (uint64_t*)in->p; ck.n = n; ck.recs = (const uint64_t*)ctx->recs.p; ck.W = (uint32_t)lo.W;
+            ck.bit_pos = 32u * (uint32_t)c; ck.nbits = std::min<uint32_t>(32, key_bits - ck.bit_pos);
+            kb_chunk_key_kernel<<<cgrid, 256, 0, ctx->stream>>>(ck);
+            CU(cudaGetLastError());
+            ctx->launches++;
+            CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_HIST, 0, 9 * 256 * 8, ctx->stream));     // run_sort accumulates its histograms
+            CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_TICKET, 0, 8 * 8, ctx->stream));
+            TRY(run_sort(ctx, *in, *other, n, 4, &sorted));
+            if (sorted != (uint64_t*)in->p) std::swap(in, other);
+        }
+        kb_table* t = new (std::nothrow) kb_table();
+        if (!t) return fail(ctx, KB_ENOMEM, "host allocation failed");
+        t->records.resize(n * lo.W);
+        t->record_words = lo.W;
+        if (n) {
+            int rc = ensure(ctx, ctx->gather_out, n * lo.W * 8);
+            if (rc) { delete t; return rc; }
+            KbTableGatherArgs g{};
+            g.ent = sorted; g.n = n; g.recs = (const uint64_t*)ctx->recs.p; g.W = (uint32_t)lo.W; g.out = (uint64_t*)ctx->gather_out.p;
+            kb_table_gather_kernel<<<cgrid * 4, 256, 0, ctx->stream>>>(g);
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(t->records.data(), ctx->gather_out.p, n * lo.W * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { delete t; return fail(ctx, KB_ECUDA, std::string("table download: ") + cudaGetErrorString(e)); }
+            ctx->launches++;
+        }
+        prof_collect(ctx);
+        *out = t;
+        return KB_OK;
+    }
     TRY(run_sort(ctx, ctx->entA, ctx->entB, n, lo.P, &sorted));
     kb_table* t = new (std::nothrow) kb_table();
     if (!t) return fail(ctx, KB_ENOMEM, "host allocation failed");
@@ -1617,7 +1656,7 @@ int kb_extract_sorted(kb_ctx* ctx, int local_index, kb_table** out) {
 int kb_table_get(const kb_table* t, const uint64_t** records, uint64_t* n_records, int* record_words) {
     if (!t) return KB_EINVAL;
     if (records) *records = t->records.data();
-    if (n_records) *n_records = t->records.size();
+    if (n_records) *n_records = t->records.size() / (size_t)std::max(t->record_words, 1);
     if (record_words) *record_words = t->record_words;
     return KB_OK;
 }

@@ -263,3 +263,43 @@ template <int THREADS, int ITEMS>
 static inline size_t kb_onesweep_smem() {
     return (size_t)THREADS * ITEMS * 8 + KB_RADIX * 8 + (size_t)(THREADS / 32) * KB_RADIX * 4 + 8 * 4 + 16;
 }
+
+// ---- sorted tables of multi-word records (k > 28): LSD over 32-bit chunks of the record's base bits -----------------------
+// The element is [chunk : 32][record index : 32]; one round = re-key every element with the next more significant chunk of its
+// record (kb_chunk_key_kernel), then a stable 4-pass radix sort on the chunk (the onesweep above).  After the most significant
+// chunk the indices are in the reference's LC_ALL=C order (left, right, middle: kstream.py:83-119); kb_table_gather_kernel
+// writes the records out in that order.
+struct KbChunkKeyArgs {
+    uint64_t* ent;
+    uint64_t n;
+    const uint64_t* recs;
+    uint32_t W, bit_pos, nbits;      // chunk = bits [bit_pos, bit_pos + nbits) of the record, nbits <= 32, inside one or two words
+};
+
+__global__ void __launch_bounds__(256) kb_chunk_key_kernel(const KbChunkKeyArgs a) {
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * 256) {
+        const uint64_t idx = a.ent[i] & 0xFFFFFFFFULL;
+        const uint64_t* r = a.recs + idx * a.W;
+        const uint32_t w = a.bit_pos >> 6, o = a.bit_pos & 63;
+        uint64_t v = r[w] << o;
+        if (o && w + 1 < a.W) v |= r[w + 1] >> (64 - o);
+        const uint64_t chunk = (v >> (64 - a.nbits)) << (32 - a.nbits);          // left-aligned in 32 bits
+        a.ent[i] = (chunk << 32) | idx;
+    }
+}
+
+struct KbTableGatherArgs {
+    const uint64_t* ent;
+    uint64_t n;
+    const uint64_t* recs;
+    uint32_t W;
+    uint64_t* out;
+};
+
+__global__ void __launch_bounds__(256) kb_table_gather_kernel(const KbTableGatherArgs a) {
+    const uint64_t total = a.n * a.W;
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
+        const uint64_t i = t / a.W, j = t % a.W;
+        a.out[t] = a.recs[(a.ent[i] & 0xFFFFFFFFULL) * a.W + j];
+    }
+}

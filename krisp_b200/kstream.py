@@ -3,8 +3,9 @@
 Mirrors the reference's ``kstream`` class / CLI (kstream/kstream.py:122-248, :835-952) for the
 configuration ``krisp_fasta`` drives it with (``extractSortedKmers``, krisp_fasta/krisp_fasta.py:16-43):
 ``kmers=k, complements=True, disallow="Nn", mapsoft | omitsoft, split=[L,-R], sort=True, sortcols=[0,2]``.
-That configuration is one K1 launch + one radix sort on the device (``kb_extract_sorted``); the lines
-come back in the reference's ``LC_ALL=C sort -t, -k1,1 -k3,3`` order.  Other option combinations
+That configuration is one K1 launch + one radix sort on the device (``kb_extract_sorted``; for k > 28 an
+LSD sort of the record indices over 32-bit chunks of the multi-word records); the lines come back in the
+reference's ``LC_ALL=C sort -t, -k1,1 -k3,3`` order.  Other option combinations
 (``--canonicals``, ``--allow``, ``--expand-iupac``, several k, unsorted streaming) are the reference's
 generic text pipeline and are not on the hot path: they raise ``UnsupportedError`` here (no CPU fallback).
 """
@@ -19,14 +20,14 @@ from .search import Searcher, _decode_bases
 
 
 def decode_table(records, L, D, R, rna=False):
-    """Packed sorted records (uint64, layout [left][right][mid][pad][id]) -> list of ``left,mid,right`` lines.
+    """Packed sorted records (uint64 [n] or [n, W], layout [left][right][mid][pad][id]) -> list of ``left,mid,right`` lines.
 
     Reproduces ``_split([L,-R])`` including its R == 0 quirk (kstream.py:824-830: the remainder lands in the
     third field and the middle stays empty)."""
     n = records.shape[0]
     if n == 0:
         return []
-    w = records.reshape(n, 1)
+    w = records.reshape(n, -1)                   # one word per record, or W words for k > 28
     left = _decode_bases(w, 0, L)
     right = _decode_bases(w, 2 * L, R)
     mid = _decode_bases(w, 2 * (L + R), D)

@@ -362,15 +362,16 @@ class Searcher:
 
     # ---- kstream path ------------------------------------------------------------------------------
     def extract_sorted(self, local_index):
-        """One file's k-mer table as packed 64-bit records in the reference's sorted order."""
+        """One file's k-mer table as packed records in the reference's sorted order: [n] uint64, or [n, W] for k > 28."""
         tab = ctypes.c_void_p()
         self._check(self._L.kb_extract_sorted(self._ctx, int(local_index), ctypes.byref(tab)))
         try:
             ptr, n, w = ctypes.POINTER(ctypes.c_uint64)(), ctypes.c_uint64(), ctypes.c_int()
             self._check(self._L.kb_table_get(tab, ctypes.byref(ptr), ctypes.byref(n), ctypes.byref(w)))
             if n.value == 0:
-                return np.zeros(0, dtype=np.uint64)
-            return np.ctypeslib.as_array(ptr, shape=(n.value * w.value,)).copy()
+                return np.zeros(0 if w.value == 1 else (0, w.value), dtype=np.uint64)
+            flat = np.ctypeslib.as_array(ptr, shape=(n.value * w.value,)).copy()
+            return flat if w.value == 1 else flat.reshape(n.value, w.value)
         finally:
             self._L.kb_table_free(tab)
 

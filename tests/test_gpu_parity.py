@@ -182,10 +182,6 @@ def test_kstream_sorted_table_matches_reference(tab):
     ks = kstream(kmers=L + D + R, complements=True, disallow="Nn", omitsoft=tab["omit_soft"], mapsoft=not tab["omit_soft"],
                  split=[L, -R], sort=True, sortcols=[0, 2])
     path = os.path.join(GOLDEN_DIR, tab["file"])
-    if 2 * (L + D + R) + 8 > 64:
-        with pytest.raises(UnsupportedError):
-            list(ks(path))
-        return
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "t.kmers")
         n = ks.write(out, path)
@@ -194,6 +190,25 @@ def test_kstream_sorted_table_matches_reference(tab):
     assert n == tab["count"] == len(lines)
     assert lines[:5] == tab["head"] and lines[-5:] == tab["tail"]
     assert hashlib.sha256(text.encode()).hexdigest() == tab["sha256"]
+
+
+@pytest.mark.parametrize("shape", [(25, 1, 2, False), (20, 10, 17, False), (32, 60, 32, False), (32, 60, 32, True), (100, 20, 100, False), (0, 30, 10, False)],
+                         ids=["25_1_2", "20_10_17", "32_60_32", "32_60_32_omit", "100_20_100", "0_30_10"])
+def test_kstream_sorted_table_matches_oracle_on_a_seeded_genome(shape):
+    """Sorted k-mer tables (kb_extract_sorted; multi-word records for k > 28) == the C oracle's table of the same records:
+    Ns, soft-masked blocks, several records, a duplicated segment (equal lines must all be there)."""
+    from krisp_b200.kstream import kstream
+    from krisp_b200.panel import make_genome
+    from oracle import oracle
+    L, D, R, omit = shape
+    g = make_genome(3, True, True, "g", 120_000)
+    recs = [r.tobytes().decode() for r in g.records]
+    ks = kstream(kmers=L + D + R, complements=True, disallow="Nn", omitsoft=omit, mapsoft=not omit, split=[L, -R], sort=True, sortcols=[0, 2])
+    got = list(ks([">probe"] + [x for r in recs for x in (">rec", r)][1:]))
+    want, n = oracle.table_text(recs, L, D, R, omit)
+    want = want.splitlines()
+    assert n == len(want) == len(got)
+    assert got == want
 
 
 _ALIGN = [c for c in _G["cases"] if "out_align" in c]
