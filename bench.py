@@ -231,14 +231,14 @@ def run_ours(args):
             res = search()
             t_c = time.perf_counter()
             if collect_rows:
-                results["rows"] = res.rows()
+                results["rows"] = res.csv_rows_text()          # the CSV body krisp_fasta prints (rendered + ordered on the device)
             t_d = time.perf_counter()
             for nm, dt in (("load", t_b - t_a), ("search", t_c - t_b), ("rows", t_d - t_c)):
                 host_ms[nm] = host_ms.get(nm, 0.0) + dt * 1e3 / steps
             launches += s.last_counters()["kernel_launches"]
             for name, ms in res.profile:
                 prof_acc.setdefault(name, []).append(ms)
-            d2h = res.n_groups * (8 + 2 * 4 + 4 + 16) + 48
+            d2h = res.n_groups * (8 * res.flank_words.shape[1] + 2 * 4 * res.in_words.shape[1] + 4 + 16 + res.row_bytes) + 64
             results["last"] = res
         e1.record(stream)
         barrier()
@@ -269,7 +269,8 @@ def run_ours(args):
     e2e_host_ms = dict(host_ms)
     e2e_stage_ms = {k: sum(v) / len(v) for k, v in prof_e2e.items()}
     rows = results["rows"]
-    n_rows_total = len(rows)
+    n_rows_total = rows.count("\n")
+    assert sorted(rows.splitlines()) == results["last"].rows(), "device-rendered rows differ from the host decoder's"   # (outside the timed region)
     if world > 1:
         t = torch.tensor([n_rows_total], device=dev)
         dist.all_reduce(t)

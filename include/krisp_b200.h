@@ -163,7 +163,9 @@ int kb_shard_extract(kb_ctx* ctx, void** records, uint64_t* shard_counts, uint64
 int kb_shard_recv_buffer(kb_ctx* ctx, uint64_t n_records, void** buffer);
 int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_counts, kb_result** out);
 
-/* Result accessors (borrowed pointers, valid until kb_result_free). */
+/* Result accessors: borrowed pointers.  The survivor table (flank, masks, group sizes) and the rows live in the context's pinned
+ * result arena — valid until kb_result_free OR the next search on the same context, whichever comes first (copy what must outlive
+ * it); run_offset / records (want_records) belong to the result and live until kb_result_free. */
 typedef struct {
     uint64_t n_groups;          /* surviving (left,right) groups                                  */
     uint64_t n_records;         /* valid k-mer occurrences processed (both strands, all files)    */
@@ -183,6 +185,14 @@ typedef struct {
     uint64_t stats[4];          /* groups, buckets (or queued runs), groups present in every file, bucket splits (or mixed runs) */
 } kb_result_view;
 int kb_result_get(const kb_result* res, kb_result_view* view);
+/*
+ * The survivors as CSV rows `left,consensus,right\n` (render_csv, Amplicon.py:663-671; consensus :550-558), rendered on the device in
+ * ascending (left, right) order — the row order of the reference with --cores 1 (outputAlignments.py:101-162).  Fixed width:
+ * *row_bytes = L + D + R + 3, *n_bytes = n_groups * row_bytes (no header, not NUL-terminated).  Option "render_rows" (default 1)
+ * switches it off; option "have_outgroup" (default 1) = an --outgroup was given: the consensus is the ingroup's, else every
+ * occurrence's (krisp_fasta.py:282-283).  Empty when R == 0 < D (the reference prints no rows then, kstream.py:824-830).
+ */
+int kb_result_rows(const kb_result* res, const char** text, uint64_t* n_bytes, int* row_bytes);
 void kb_result_free(kb_result* res);
 
 /* Per-stage device times of the last search in ms (needs option "profile"=1): fills up to `cap`

@@ -19,6 +19,7 @@
 #include "kb_hash_stream.cuh"
 #include "kb_ingest.cuh"
 #include "kb_prefilter.cuh"
+#include "kb_rows.cuh"
 
 #define KB_VERSION_STR "krisp_b200 0.1.0 sm_100a"
 
@@ -30,8 +31,11 @@ struct DevBuf {
 
 struct kb_result {
     kb_result_view v;
-    std::vector<uint64_t> flank, run_offset, records;
-    std::vector<uint32_t> in_mask, out_mask, group_size;
+    // flank / masks / group sizes / rows live in the context's pinned result arena (valid until the next search on that context)
+    std::vector<uint64_t> run_offset, records;
+    const char* rows = nullptr;          // CSV rows, ascending (left, right)
+    size_t rows_len = 0;
+    int row_bytes = 0;
 };
 
 struct kb_table {
@@ -93,6 +97,8 @@ struct kb_ctx {
     long long opt_hash_stream = 1;       // 1 = persistent TMA-fed bucket hash kernel for the fast shape
     long long opt_fused_hist = 1;        // 1 = K1 also counts the level-1 children (single-GPU search path)
     long long opt_batch_level0 = 1;      // 1 = partition level 0 per batch of arriving files (hidden under the host -> device copy)
+    long long opt_render_rows = 1;       // CSV rows of the survivors rendered + ordered on the device (kb_result_rows)
+    long long opt_have_outgroup = 1;     // consensus letters: ingroup only (an outgroup was given) / every occurrence
     long long opt_lazy_records = 1;      // multi-word records: 1 = filter by flank hash, build records only for what is left (kb_prefilter.cuh)
     bool lazy_now = false;               // the running search uses it
     long long opt_shard_bits0 = 0;       // multi-GPU: bits of partition level 0 (the exchange); 0 = log2(shards) + 2
@@ -107,10 +113,13 @@ struct kb_ctx {
     DevBuf d_file_starts, d_file_gid;
 
     // workspaces
+    DevBuf rowkeyA, rowkeyB, rowtext;    // row rendering: survivor indices being sorted, the text
     DevBuf brun;                         // lazy records: per bucket (start, length) of the kept elements
     DevBuf batchbuf, rawbuf, fa_work, fa_flags;   // FASTA de-lining: raw file bytes, tile tables, flag word
     DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out, taint, plan, deferred;
     uint64_t* h_pinned = nullptr;        // 64 x u64 scratch for small D2H reads
+    uint8_t* h_arena = nullptr;          // pinned result arena: survivor table + rows of the LAST search (no pageable copies)
+    size_t h_arena_cap = 0;
     uint64_t result_cap = 0;
 
     // last-search bookkeeping
@@ -222,9 +231,10 @@ void kb_destroy(kb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->recs, &ctx->status,
                       &ctx->small, &ctx->res_flank, &ctx->res_in, &ctx->res_out, &ctx->res_size, &ctx->res_run,
-                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab, &ctx->batchbuf, &ctx->rawbuf, &ctx->fa_work, &ctx->fa_flags, &ctx->brun};
+                      &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab, &ctx->batchbuf, &ctx->rawbuf, &ctx->fa_work, &ctx->fa_flags, &ctx->brun, &ctx->rowkeyA, &ctx->rowkeyB, &ctx->rowtext};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
     for (size_t r = 0; r < ctx->peer_ptr.size(); r++) if (ctx->peer_ptr[r] && ctx->peer_ptr[r] != ctx->recvbuf.p) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
     if (ctx->recvbuf.p) cudaFree(ctx->recvbuf.p);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -256,6 +266,8 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "fused_hist") ctx->opt_fused_hist = value ? 1 : 0;
     else if (n == "batch_level0") ctx->opt_batch_level0 = value ? 1 : 0;
     else if (n == "lazy_records") ctx->opt_lazy_records = value ? 1 : 0;
+    else if (n == "render_rows") ctx->opt_render_rows = value ? 1 : 0;
+    else if (n == "have_outgroup") ctx->opt_have_outgroup = value ? 1 : 0;
     else if (n == "shard_bits0") { if (value < 0 || value > 9) return fail(ctx, KB_EINVAL, "shard_bits0 must be in 0..9"); ctx->opt_shard_bits0 = value; }
     else if (n == "bucket_bits") { if (value < -1 || value > 24) return fail(ctx, KB_EINVAL, "bucket_bits must be in -1..24"); ctx->opt_bucket_bits = value; }
     else if (n == "hash_slots_log2") { if (value != 0 && (value < 4 || value > 12)) return fail(ctx, KB_EINVAL, "hash_slots_log2 must be 0 or in 4..12"); ctx->opt_hash_slots_log2 = value; }
@@ -984,6 +996,51 @@ static int launch_group(kb_ctx* ctx, const KbGroupArgs& a, bool allow_fast) {
     return KB_OK;
 }
 
+// CSV rows of the n_res survivors in the result table: order by flank words (chunked LSD sort of the indices), render, download
+static int render_rows(kb_ctx* ctx, kb_result* res, uint64_t n_res, char* host_dst) {
+    const KbLayout& lo = ctx->lo;
+    if (!n_res || (lo.R == 0 && lo.D > 0)) return KB_OK;
+    if (n_res >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 survivors");
+    const long long prof = ctx->opt_profile;
+    const int passes = ctx->passes;
+    const uint64_t alg = ctx->alg_bytes;
+    ctx->opt_profile = 0;                                    // (the sort below is bookkeeping on kilobytes, not a stage of the search)
+    TRY(ensure(ctx, ctx->rowkeyA, (size_t)(n_res + 2048) * 8));
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_res + 255) / 256, (uint64_t)ctx->n_sm * 8));
+    kb_iota_kernel<<<grid, 256, 0, ctx->stream>>>((uint64_t*)ctx->rowkeyA.p, n_res);
+    CU(cudaGetLastError());
+    DevBuf* in = &ctx->rowkeyA; DevBuf* other = &ctx->rowkeyB;
+    uint64_t* sorted = (uint64_t*)in->p;
+    const uint32_t chunks = ((uint32_t)lo.FB + 31) / 32;
+    for (int c = (int)chunks - 1; c >= 0; c--) {
+        KbChunkKeyArgs ck{};
+        ck.ent = (uint64_t*)in->p; ck.n = n_res; ck.recs = (const uint64_t*)ctx->res_flank.p; ck.W = (uint32_t)lo.FW;
+        ck.bit_pos = 32u * (uint32_t)c; ck.nbits = std::min<uint32_t>(32, (uint32_t)lo.FB - ck.bit_pos);
+        kb_chunk_key_kernel<<<grid, 256, 0, ctx->stream>>>(ck);
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_HIST, 0, 9 * 256 * 8, ctx->stream));
+        CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_TICKET, 0, 8 * 8, ctx->stream));
+        TRY(run_sort(ctx, *in, *other, n_res, 4, &sorted));
+        if (sorted != (uint64_t*)in->p) std::swap(in, other);
+        ctx->launches++;
+    }
+    ctx->opt_profile = prof; ctx->passes = passes; ctx->alg_bytes = alg;
+    const size_t bytes = (size_t)n_res * (size_t)res->row_bytes;
+    TRY(ensure(ctx, ctx->rowtext, bytes));
+    KbRowsArgs ra{};
+    ra.order = sorted; ra.n = n_res; ra.flank = (const uint64_t*)ctx->res_flank.p;
+    ra.in_mask = (const uint32_t*)ctx->res_in.p; ra.out_mask = (const uint32_t*)ctx->res_out.p;
+    ra.L = lo.L; ra.D = lo.D; ra.R = lo.R; ra.FW = lo.FW; ra.MW = std::max(lo.MW, 1);
+    ra.all_occurrences = ctx->opt_have_outgroup ? 0 : 1;
+    ra.out = (char*)ctx->rowtext.p;
+    kb_rows_kernel<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((bytes + 255) / 256, (uint64_t)ctx->n_sm * 16)), 256, 0, ctx->stream>>>(ra);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    CU(cudaMemcpyAsync(host_dst, ctx->rowtext.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    res->rows = host_dst; res->rows_len = bytes;
+    return KB_OK;                                            // (the caller synchronises with the other result copies)
+}
+
 // K3 over sorted[0..n) + result download
 static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result** out, const HashStage* hs = nullptr) {
     // (hs != null: n is an upper bound; the exact count arrives with the first read-back)
@@ -1040,23 +1097,39 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
         if (n_res > ctx->result_cap) { delete res; return fail(ctx, KB_EINTERNAL, "survivor table overflow"); }
     }
     res->v.n_groups = n_res;
-    res->flank.resize(n_res * lo.FW);
-    res->in_mask.resize(n_res * std::max(lo.MW, 1));
-    res->out_mask.resize(n_res * std::max(lo.MW, 1));
-    res->group_size.resize(n_res);
     res->run_offset.assign(n_res + 1, 0);
-    std::vector<uint64_t> runs(2 * n_res);
+    res->row_bytes = lo.L + lo.D + lo.R + 3;
+    // pinned arena: flank | ingroup masks | outgroup masks | group sizes | runs (want_records, sorted path) | rows
+    const size_t mw = (size_t)std::max(lo.MW, 1);
+    const bool rows_on = ctx->opt_render_rows && !(lo.R == 0 && lo.D > 0);
+    const bool need_runs = ctx->opt_want_records && !hs;
+    auto up = [](size_t x) { return (x + 63) & ~(size_t)63; };
+    const size_t o_flank = 0, o_in = o_flank + up(n_res * lo.FW * 8), o_out = o_in + up(n_res * mw * 4), o_size = o_out + up(n_res * mw * 4),
+                 o_runs = o_size + up(n_res * 4), o_rows = o_runs + up(need_runs ? n_res * 16 : 0),
+                 total_bytes = o_rows + up(rows_on ? n_res * (size_t)res->row_bytes : 0) + 64;
+    if (total_bytes > ctx->h_arena_cap) {
+        if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
+        ctx->h_arena = nullptr; ctx->h_arena_cap = 0;
+        const size_t want = total_bytes + total_bytes / 4 + (1 << 20);
+        if (cudaHostAlloc((void**)&ctx->h_arena, want, cudaHostAllocDefault) != cudaSuccess) { delete res; return fail(ctx, KB_ENOMEM, "pinned result arena"); }
+        ctx->h_arena_cap = want;
+    }
+    uint8_t* A = ctx->h_arena;
+    if (lo.MW == 0) memset(A + o_in, 0, (o_size - o_in));
+    const uint32_t* h_size = (const uint32_t*)(A + o_size);
+    const uint64_t* runs = (const uint64_t*)(A + o_runs);
+    if (rows_on) { int rc = render_rows(ctx, res, n_res, (char*)(A + o_rows)); if (rc) { delete res; return rc; } }
     if (n_res) {
-        cudaError_t e = cudaMemcpyAsync(res->flank.data(), ctx->res_flank.p, n_res * lo.FW * 8, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess && lo.MW) e = cudaMemcpyAsync(res->in_mask.data(), ctx->res_in.p, n_res * lo.MW * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess && lo.MW) e = cudaMemcpyAsync(res->out_mask.data(), ctx->res_out.p, n_res * lo.MW * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(res->group_size.data(), ctx->res_size.p, n_res * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(runs.data(), ctx->res_run.p, n_res * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(A + o_flank, ctx->res_flank.p, n_res * lo.FW * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && lo.MW) e = cudaMemcpyAsync(A + o_in, ctx->res_in.p, n_res * lo.MW * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && lo.MW) e = cudaMemcpyAsync(A + o_out, ctx->res_out.p, n_res * lo.MW * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(A + o_size, ctx->res_size.p, n_res * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && need_runs) e = cudaMemcpyAsync(A + o_runs, ctx->res_run.p, n_res * 16, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("result download: ") + cudaGetErrorString(e)); }
     }
     if (ctx->opt_want_records && n_res) {
-        for (uint64_t g = 0; g < n_res; g++) res->run_offset[g + 1] = res->run_offset[g] + (hs ? (uint64_t)res->group_size[g] : runs[2 * g + 1]);
+        for (uint64_t g = 0; g < n_res; g++) res->run_offset[g + 1] = res->run_offset[g] + (hs ? (uint64_t)h_size[g] : runs[2 * g + 1]);
         const uint64_t total = res->run_offset[n_res];
         int rc = ensure(ctx, ctx->gather_off, n_res * 8);
         if (!rc) rc = ensure(ctx, ctx->gather_out, total * lo.W * 8);
@@ -1095,10 +1168,10 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
         if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("record gather: ") + cudaGetErrorString(e)); }
         res->v.n_run_records = total;
     }
-    res->v.flank = res->flank.data();
-    res->v.in_mask = res->in_mask.data();
-    res->v.out_mask = res->out_mask.data();
-    res->v.group_size = res->group_size.data();
+    res->v.flank = (const uint64_t*)(A + o_flank);
+    res->v.in_mask = (const uint32_t*)(A + o_in);
+    res->v.out_mask = (const uint32_t*)(A + o_out);
+    res->v.group_size = h_size;
     res->v.run_offset = res->run_offset.data();
     res->v.records = res->records.data();
     *out = res;
@@ -1561,6 +1634,13 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_count
 int kb_result_get(const kb_result* res, kb_result_view* view) {
     if (!res || !view) return KB_EINVAL;
     *view = res->v;
+    return KB_OK;
+}
+int kb_result_rows(const kb_result* res, const char** text, uint64_t* n_bytes, int* row_bytes) {
+    if (!res || !text || !n_bytes) return KB_EINVAL;
+    *text = res->rows;
+    *n_bytes = res->rows_len;
+    if (row_bytes) *row_bytes = res->row_bytes;
     return KB_OK;
 }
 void kb_result_free(kb_result* res) { delete res; }

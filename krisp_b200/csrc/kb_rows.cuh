@@ -1,0 +1,50 @@
+// kb_rows.cuh — CSV rows of the survivors, rendered and ordered on the device.
+//
+// Replaces ConservedEndAmplicons.render_csv (krisp_fasta/Amplicon.py:663-671) with consensus (:550-558) and collapse_to_iupac
+// (:42-66) for every survivor, and the row order of render_output with --cores 1 (outputAlignments.py:101-162: ascending
+// (left, right), the order of the sorted k-mer file).  One row = left ',' consensus ',' right '\n' (fixed width L + D + R + 3):
+// bases come from the survivor's flank words (MSB-first 2-bit codes), the consensus letter of column c from its 4-bit base set
+// (bit 0 A .. bit 3 T; the inverse of Bio.Data.IUPACData.ambiguous_dna_values as Amplicon.py:10-12 builds it, 4 bases -> N):
+// the ingroup set when an outgroup was given, every occurrence otherwise (krisp_fasta.py:282-283).
+// Order: the survivors' indices are sorted by their flank words with the chunked LSD sort of kb_sort.cuh (kb_chunk_key_kernel).
+#pragma once
+#include "kb_common.cuh"
+
+struct KbRowsArgs {
+    const uint64_t* order;       // [n] sorted elements, low 32 bits = survivor index
+    uint64_t n;
+    const uint64_t* flank;       // [n][FW]
+    const uint32_t* in_mask;     // [n][MW]
+    const uint32_t* out_mask;    // [n][MW]
+    int L, D, R, FW, MW;
+    int all_occurrences;         // 1: consensus over ingroup and outgroup (no --outgroup given)
+    char* out;                   // [n][L + D + R + 3]
+};
+
+__global__ void __launch_bounds__(256) kb_rows_kernel(const KbRowsArgs a) {
+    const uint32_t width = (uint32_t)(a.L + a.D + a.R + 3);
+    const uint64_t total = a.n * width;
+    for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
+        const uint64_t r = t / width;
+        const uint32_t p = (uint32_t)(t % width);
+        const uint64_t g = a.order[r] & 0xFFFFFFFFULL;
+        char ch;
+        if (p == (uint32_t)a.L || p == (uint32_t)(a.L + 1 + a.D)) ch = ',';
+        else if (p == width - 1) ch = '\n';
+        else if (p > (uint32_t)a.L && p < (uint32_t)(a.L + 1 + a.D)) {
+            const uint32_t c = p - (uint32_t)a.L - 1;
+            uint32_t m = a.in_mask[g * a.MW + (c >> 3)];
+            if (a.all_occurrences) m |= a.out_mask[g * a.MW + (c >> 3)];
+            ch = "?ACMGRSVTWYHKDBN"[(m >> (28 - 4 * (c & 7))) & 0xFu];
+        } else {
+            const uint32_t b = p < (uint32_t)a.L ? p : p - 2 - (uint32_t)a.D;      // base index inside the flank bits
+            const uint64_t w = a.flank[g * a.FW + (b >> 5)];
+            ch = "ACGT"[(w >> (62 - 2 * (b & 31))) & 3ULL];
+        }
+        a.out[t] = ch;
+    }
+}
+
+__global__ void __launch_bounds__(256) kb_iota_kernel(uint64_t* ent, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) ent[i] = i;
+}

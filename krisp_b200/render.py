@@ -142,17 +142,16 @@ def write_interchange(res, labels, filename):
 
 def render_output(res, labels, ingroup=None, out_csv=None, out_align=None, dot=False):
     """Write the CSV (stdout when out_csv is None) and, if asked, the alignment file.  Returns the number of regions."""
-    order = _group_order(res)
-    rows = csv_rows(res, order)
+    text = res.csv_rows_text()                   # rendered and ordered on the device (ascending (left, right))
+    n_rows = text.count("\n")
     stream = sys.stdout if out_csv is None else open(out_csv, "w")
     try:
-        print(CSV_HEADER, file=stream)
-        for r in rows:
-            print(r, file=stream)
+        stream.write(CSV_HEADER + "\n" + text)
     finally:
         if out_csv is not None:
             stream.close()
     if out_align is not None:
+        order = _group_order(res)
         if os.path.isfile(out_align):
             os.remove(out_align)
         ing = frozenset(ingroup) if ingroup is not None else None
@@ -160,4 +159,4 @@ def render_output(res, labels, ingroup=None, out_csv=None, out_align=None, dot=F
             for g in order:
                 amps = group_amplicons(res, g, labels)
                 print(render_alignment(res.left[g].tobytes().decode(), res.right[g].tobytes().decode(), amps, ing, dot), file=fh)
-    return len(rows)
+    return n_rows

@@ -38,6 +38,7 @@ class SearchResult:
         self.in_words, self.out_words = in_words, out_words
         self.group_size, self.flank_words, self.run_offset, self.records = group_size, flank_words, run_offset, records
         self.stats, self.profile, self.have_outgroup = stats or {}, profile or [], have_outgroup
+        self.rows_blob, self.row_bytes = None, 0      # CSV rows rendered on the device, ascending (left, right) (kb_result_rows)
 
     @property
     def n_groups(self):
@@ -91,6 +92,15 @@ class SearchResult:
     @out_mask.setter
     def out_mask(self, value):
         self._out_mask = value
+
+    def csv_rows_text(self):
+        """The CSV body exactly as ``krisp_fasta --cores 1`` prints it after the header: one ``left,consensus,right`` line per
+        region in ascending (left, right) order — rendered and ordered on the device (kb_result_rows), no host work.
+        Falls back to the host decoder for results assembled by hand."""
+        if self.rows_blob is not None and (self.rows_blob or self.n_groups == 0 or (self.R == 0 and self.D > 0)):
+            return self.rows_blob.decode("ascii")
+        from . import render
+        return "".join(r + "\n" for r in render.csv_rows(self))
 
     def rows(self):
         """CSV rows ``left,consensus,right`` (render_csv, Amplicon.py:663-671), canonically sorted.
@@ -297,6 +307,10 @@ class Searcher:
             nrr = int(view.n_run_records)
             out.records = arr(view.records, nrr * W, np.uint64).reshape(nrr, W)
             out.stats = dict(zip(("runs", "queued_runs", "groups_in_every_file", "mixed_runs"), [int(x) for x in view.stats]))
+            text, nb, rb = ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_int()
+            self._check(self._L.kb_result_rows(res_ptr, ctypes.byref(text), ctypes.byref(nb), ctypes.byref(rb)))
+            out.rows_blob = ctypes.string_at(text.value, int(nb.value)) if nb.value else b""
+            out.row_bytes = int(rb.value)
         finally:
             self._L.kb_result_free(res_ptr)
         out.profile = self.last_profile()
@@ -305,9 +319,15 @@ class Searcher:
     def search(self, have_outgroup=True):
         """Run K1 -> K2 -> K3 on the sequences added so far."""
         res = ctypes.c_void_p()
+        self._set_have_outgroup(have_outgroup)
         self._check(self._L.kb_search(self._ctx, ctypes.byref(res)))
         self._keep = []
         return self._collect(res, have_outgroup)
+
+    def _set_have_outgroup(self, have_outgroup):
+        if getattr(self, "_have_outgroup", None) != bool(have_outgroup):       # (the option re-derives the plan: only on change)
+            self.set_option("have_outgroup", 1 if have_outgroup else 0)
+            self._have_outgroup = bool(have_outgroup)
 
     # ---- multi-GPU pieces (see krisp_b200/sharded.py) -------------------------------------------------
     def shard_plan(self, n_shards, shard_index, total_bases):
@@ -357,6 +377,7 @@ class Searcher:
         """piece_counts: flat [source rank][digit of this shard] record counts, in arrival order."""
         arr = (ctypes.c_uint64 * max(1, len(piece_counts)))(*[int(c) for c in piece_counts])
         res = ctypes.c_void_p()
+        self._set_have_outgroup(have_outgroup)
         self._check(self._L.kb_shard_search(self._ctx, int(n_records), arr, ctypes.byref(res)))
         return self._collect(res, have_outgroup)
 

@@ -417,3 +417,20 @@ def test_interchange_file_matches_reference(name, searcher, tmp_path):
     want = _interchange_golden()[name].splitlines()
     assert n == len(got) == len(want)
     assert _groups_of(got) == _groups_of(want)
+
+
+@pytest.mark.parametrize("case", _G["cases"], ids=[c["name"] for c in _G["cases"]])
+def test_device_rendered_rows_equal_host_decoder(case, searcher):
+    """kb_result_rows (rows rendered + ordered on the device) == the host decoder's rows, in the reference's --cores 1 order
+    (ascending (left, right)), and as a set == the golden rows of the unmodified reference."""
+    from krisp_b200 import render
+    from krisp_b200.search import search_files
+    ins, outs = golden_paths(case)
+    L, D, R = deduce_ldr(case["flags"])
+    res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher)
+    got = res.csv_rows_text().splitlines()
+    assert res.rows_blob is not None or (R == 0 and D > 0)        # (quirk S9: the host answers without a search)
+    assert got == render.csv_rows(res)
+    assert sorted(got) == res.rows()
+    assert len(got) == case["n_rows"]
+    assert hashlib.sha256("\n".join(sorted(got)).encode()).hexdigest() == case["rows_sha256"]
