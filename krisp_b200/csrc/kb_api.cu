@@ -136,6 +136,8 @@ struct kb_ctx {
     DevBuf recvbuf;                      // IPC-exported receive buffer of the fused partition + exchange
     std::vector<void*> peer_ptr;         // peer_ptr[r] = rank r's receive buffer mapped here (own entry = recvbuf.p)
     std::vector<uint64_t> scatter_host;  // staging of the per-digit tables of kb_shard_scatter
+    bool sep_filled = false;             // the sequence buffer holds separators in [n_bases, sep_upto) (host-buffer adds rely on it)
+    uint64_t sep_upto = 0, reserve_hint = 0;
     int own_first = 0, own_count = -1;   // replicated sequences: K1 of the shard calls covers only these local files (-1: all)
     int shard_direct = 0;                // the last exchange went through kb_shard_scatter (input of kb_shard_search = recvbuf)
     uint64_t shard_n_records = 0;
@@ -321,6 +323,7 @@ int kb_clear_sequences(kb_ctx* ctx) {
     ctx->file_gid.clear();
     ctx->file_event.clear();
     ctx->own_first = 0; ctx->own_count = -1;
+    ctx->sep_filled = false;
     if (ctx->fa_flags.p) { cudaSetDevice(ctx->device); cudaMemsetAsync(ctx->fa_flags.p, 0, 8, ctx->stream); }
     return KB_OK;
 }
@@ -333,6 +336,8 @@ int kb_reserve(kb_ctx* ctx, uint64_t total_bytes) {
     if (!ctx) return KB_EINVAL;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->reserve_hint = total_bytes + KB_MAX_FILES;
+    ctx->sep_filled = false;
     return ensure(ctx, ctx->bases, padded_len(total_bytes + KB_MAX_FILES), true);
 }
 
@@ -344,6 +349,7 @@ int kb_add_sequence(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_b
     if (ctx->bases.cap < padded_len(ctx->n_bases + n_bytes + 1)) {
         CU(cudaStreamSynchronize(ctx->copy_stream));                 // the buffer moves: no copy may be in flight
         TRY(ensure(ctx, ctx->bases, padded_len(ctx->n_bases + n_bytes + 1), true));
+        ctx->sep_filled = false;
     }
     uint8_t* dst = (uint8_t*)ctx->bases.p + ctx->n_bases;
     cudaEvent_t ev = nullptr;
@@ -353,7 +359,13 @@ int kb_add_sequence(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_b
     } else {
         // host buffers go over the copy stream; kb_search launches K1 on the files that have arrived
         const size_t idx = ctx->file_starts.size();
-        if (idx == 0) {                                              // the copy stream starts after whatever the main stream still does with the buffer
+        if (idx == 0 || !ctx->sep_filled || ctx->n_bases + n_bytes + 1 > ctx->sep_upto) {
+            // the copy stream starts after whatever the main stream still does with the buffer.
+            // The region the files will land in becomes separators ONCE, so that the copy stream carries nothing but the file
+            // copies (a one-byte memset between two copies costs the DMA engine a bubble per file)
+            const uint64_t upto = std::min<uint64_t>(ctx->bases.cap, std::max<uint64_t>(ctx->n_bases + n_bytes + 1 + 4096, ctx->reserve_hint));
+            CU(cudaMemsetAsync(dst, '\n', upto - ctx->n_bases, ctx->stream));
+            ctx->sep_filled = true; ctx->sep_upto = upto;
             CU(cudaEventRecord(ctx->main_event, ctx->stream));
             CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->main_event, 0));
         }
@@ -364,7 +376,6 @@ int kb_add_sequence(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_b
         }
         ev = ctx->copy_events[idx];
         if (n_bytes) CU(cudaMemcpyAsync(dst, bytes, n_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CU(cudaMemsetAsync(dst + n_bytes, '\n', 1, ctx->copy_stream));
         CU(cudaEventRecord(ev, ctx->copy_stream));
     }
     ctx->file_starts.push_back(ctx->n_bases);
