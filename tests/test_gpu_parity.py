@@ -167,6 +167,21 @@ def test_lazy_records_panel_matches_oracle_and_eager(shape, searcher):
     assert got[1][1] == got[0][1]
 
 
+@pytest.mark.parametrize("shape", [(4, 4, 120_000, 32, 60, 32, 0.0, 5000), (3, 2, 80_000, 40, 30, 40, 0.0, 20000), (6, 6, 60_000, 20, 10, 17, 1e-2, 300)],
+                         ids=["identical_genomes", "long_repeats", "noisy"])
+def test_lazy_records_when_the_filter_keeps_everything_or_nothing(shape, searcher):
+    """Extremes of the hash filter (kb_prefilter.cuh): genomes without private differences (every key is in every file, K3a keeps
+    all records and the exact pass works on full buckets, with long duplicated segments = many records per key) and very noisy
+    genomes (almost nothing survives).  Rows == C oracle either way."""
+    from krisp_b200.panel import make_panel
+    n_in, n_out, glen, L, D, R, noise, dup = shape
+    gs = make_panel(n_in, n_out, glen, noise=noise, dup_len=dup)
+    res = _search_panel(searcher, gs, L, D, R)
+    want = _oracle_panel(gs, L, D, R)
+    assert res.rows() == want
+    assert res.csv_rows_text().count("\n") == len(want)
+
+
 _TABLES = _G["tables"]
 
 
