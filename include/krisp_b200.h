@@ -139,6 +139,16 @@ int kb_shard_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bas
  *   kb_shard_own_files    K1 of the kb_shard_* calls covers only local files [first_local, first_local + n_local)
  *                         (n_local < 0: all; reset by kb_clear_sequences)
  */
+/*
+ * Optional: level-1 child counts travel with the digit counts, and the owner skips its histogram pass over the received records.
+ *   kb_shard_child_counts      after kb_shard_count: this rank's records per child of level 1 over the WHOLE key space
+ *                              (*n = n_digits << bits of level 1 entries, child = digit << bits1 | next digit; *n = 0 when K1 did not
+ *                              count them: the first two levels must have 10..16 bits together; counts == NULL: size only)
+ *   kb_shard_set_child_counts  before kb_shard_search: the counts of THIS shard's digits summed over all source ranks
+ *                              (dps << bits1 entries, in digit order); cleared by kb_shard_search and kb_shard_count
+ */
+int kb_shard_child_counts(kb_ctx* ctx, uint64_t* counts, uint64_t cap, uint64_t* n);
+int kb_shard_set_child_counts(kb_ctx* ctx, const uint64_t* counts, uint64_t n);
 int kb_sequence_buffer(kb_ctx* ctx, void** device_bytes, uint64_t* n_bytes);
 int kb_shard_own_files(kb_ctx* ctx, int first_local, int n_local);
 
@@ -157,6 +167,9 @@ int kb_shard_own_files(kb_ctx* ctx, int first_local, int n_local);
  */
 int kb_shard_ipc_export(kb_ctx* ctx, uint64_t capacity_records, uint8_t* handle64);
 int kb_shard_ipc_import(kb_ctx* ctx, int n_ranks, const uint8_t* handles);
+/* Unmap the peers' buffers.  When a receive buffer has to grow: every rank closes, barrier, then export / import again (exported
+ * memory must not be freed while another process maps it). */
+int kb_shard_ipc_close(kb_ctx* ctx);
 int kb_shard_count(kb_ctx* ctx, uint64_t* digit_counts);
 int kb_shard_scatter(kb_ctx* ctx, const uint64_t* piece_base);
 int kb_shard_extract(kb_ctx* ctx, void** records, uint64_t* shard_counts, uint64_t* digit_counts);

@@ -17,7 +17,7 @@ _ERRNAMES = {KB_EINVAL: "KB_EINVAL", KB_ECUDA: "KB_ECUDA", KB_ENOMEM: "KB_ENOMEM
 EXPORTS = ["kb_version", "kb_create", "kb_destroy", "kb_last_error", "kb_set_stream", "kb_configure",
            "kb_set_option", "kb_clear_sequences", "kb_reserve", "kb_add_sequence", "kb_add_fasta", "kb_fasta_flags",
            "kb_get_sequence", "kb_synchronize",
-           "kb_search", "kb_shard_plan", "kb_sequence_buffer", "kb_shard_own_files", "kb_shard_ipc_export", "kb_shard_ipc_import", "kb_shard_count",
+           "kb_search", "kb_shard_plan", "kb_shard_child_counts", "kb_shard_set_child_counts", "kb_sequence_buffer", "kb_shard_own_files", "kb_shard_ipc_export", "kb_shard_ipc_import", "kb_shard_ipc_close", "kb_shard_count",
            "kb_shard_scatter", "kb_shard_extract", "kb_shard_recv_buffer", "kb_shard_search", "kb_result_get", "kb_result_rows",
            "kb_result_free", "kb_last_profile", "kb_last_counters", "kb_extract_sorted", "kb_table_get",
            "kb_table_free"]
@@ -77,6 +77,9 @@ def load():
     L.kb_synchronize.argtypes = [vp]
     L.kb_search.argtypes = [vp, pvp]
     L.kb_shard_plan.argtypes = [vp, i, i, u64, ctypes.POINTER(i)]
+    L.kb_shard_child_counts.argtypes = [vp, vp, u64, ctypes.POINTER(u64)]
+    L.kb_shard_set_child_counts.argtypes = [vp, vp, u64]
+    L.kb_shard_ipc_close.argtypes = [vp]
     L.kb_sequence_buffer.argtypes = [vp, pvp, ctypes.POINTER(u64)]
     L.kb_shard_own_files.argtypes = [vp, i, i]
     L.kb_shard_ipc_export.argtypes = [vp, u64, ctypes.c_char_p]

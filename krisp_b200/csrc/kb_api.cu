@@ -136,6 +136,8 @@ struct kb_ctx {
     DevBuf recvbuf;                      // IPC-exported receive buffer of the fused partition + exchange
     std::vector<void*> peer_ptr;         // peer_ptr[r] = rank r's receive buffer mapped here (own entry = recvbuf.p)
     std::vector<uint64_t> scatter_host;  // staging of the per-digit tables of kb_shard_scatter
+    std::vector<uint64_t> shard_child_host;   // kb_shard_count: K1's two-level histogram (children of level 1 over the whole key space), if counted
+    std::vector<uint64_t> shard_child_set;    // kb_shard_set_child_counts: level-1 child counts of this shard's digits, summed over the source ranks
     bool sep_filled = false;             // the sequence buffer holds separators in [n_bases, sep_upto) (host-buffer adds rely on it)
     uint64_t sep_upto = 0, reserve_hint = 0;
     int own_first = 0, own_count = -1;   // replicated sequences: K1 of the shard calls covers only these local files (-1: all)
@@ -237,7 +239,7 @@ void kb_destroy(kb_ctx* ctx) {
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
-    for (size_t r = 0; r < ctx->peer_ptr.size(); r++) if (ctx->peer_ptr[r] && ctx->peer_ptr[r] != ctx->recvbuf.p) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
+    for (size_t r = 0; r < ctx->peer_ptr.size(); r++) if (ctx->peer_ptr[r] && (int)r != ctx->shard_index) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
     if (ctx->recvbuf.p) cudaFree(ctx->recvbuf.p);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (cudaEvent_t ev : ctx->copy_events) cudaEventDestroy(ev);
@@ -770,7 +772,7 @@ static int launch_plan(kb_ctx* ctx, KbPlanArgs pa, const PartPlan& pl) {
 // have_hist1: K1 already counted the level-1 children (plan buffer, level-1 counts); level 0's counts are their row sums.
 static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& other, uint64_t n, int l_begin, int l_end,
                          const CustomParents* cp, uint64_t** parted, const unsigned long long** bstart, uint32_t* n_buckets,
-                         bool have_hist1 = false) {
+                         bool have_hist1 = false, bool counts_given = false) {
     uint64_t* cur = (uint64_t*)in.p;
     uint8_t* P = (uint8_t*)ctx->plan.p;
     unsigned long long* root = (unsigned long long*)ctx->small.p + SM_ROOT;
@@ -829,10 +831,13 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
         } else if (l > 0) {
             kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, a.n_parents, (uint32_t*)(P + pl.off_tilemap));
             CU(cudaGetLastError());
-            kb_part_hist_kernel<<<(unsigned)grid, KB_PT_THREADS, 0, ctx->stream>>>(a);
-            CU(cudaGetLastError());
-            ctx->launches += 2;
-            ctx->alg_rec_bytes += 8;
+            ctx->launches++;
+            if (!(l == l_begin && counts_given)) {           // (multi-GPU: the child counts of the first level came with the exchange)
+                kb_part_hist_kernel<<<(unsigned)grid, KB_PT_THREADS, 0, ctx->stream>>>(a);
+                CU(cudaGetLastError());
+                ctx->launches++;
+                ctx->alg_rec_bytes += 8;
+            }
         }
         if (!(l == 1 && have_hist1)) {
             KbPlanArgs pa{};
@@ -1485,12 +1490,23 @@ int kb_shard_ipc_export(kb_ctx* ctx, uint64_t capacity_records, uint8_t* handle6
     return KB_OK;
 }
 
-int kb_shard_ipc_import(kb_ctx* ctx, int n_ranks, const uint8_t* handles) {
-    if (!ctx || !handles || n_ranks < 1 || n_ranks != ctx->shard_n) return KB_EINVAL;
+// Unmap every peer's receive buffer.  Exported memory must not be freed while another process still maps it, so when a buffer has
+// to grow ALL ranks close first (then a barrier), and only then the owners reallocate and export again.
+int kb_shard_ipc_close(kb_ctx* ctx) {
+    if (!ctx) return KB_EINVAL;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
-    for (size_t r = 0; r < ctx->peer_ptr.size(); r++)
-        if (ctx->peer_ptr[r] && ctx->peer_ptr[r] != ctx->recvbuf.p) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
+    for (size_t r = 0; r < ctx->peer_ptr.size(); r++) {
+        if (!ctx->peer_ptr[r] || (int)r == ctx->shard_index) continue;
+        if (cudaIpcCloseMemHandle(ctx->peer_ptr[r]) != cudaSuccess) cudaGetLastError();     // (do not leave a latent error behind)
+    }
+    ctx->peer_ptr.clear();
+    return KB_OK;
+}
+
+int kb_shard_ipc_import(kb_ctx* ctx, int n_ranks, const uint8_t* handles) {
+    if (!ctx || !handles || n_ranks < 1 || n_ranks != ctx->shard_n) return KB_EINVAL;
+    TRY(kb_shard_ipc_close(ctx));
     ctx->peer_ptr.assign((size_t)n_ranks, nullptr);
     for (int r = 0; r < n_ranks; r++) {
         if (r == ctx->shard_index) { ctx->peer_ptr[r] = ctx->recvbuf.p; continue; }
@@ -1517,18 +1533,44 @@ int kb_shard_count(kb_ctx* ctx, uint64_t* digit_counts) {
     uint64_t n = 0, pos_lo = 0, pos_hi = 0;
     uint32_t tile0 = 0, n_tiles = 0;
     TRY(shard_extract_range(ctx, &pos_lo, &pos_hi, &tile0, &n_tiles));
-    unsigned long long* h0 = (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[0]);
-    TRY(run_extract(ctx, lo, tile0, n_tiles, pos_lo, pos_hi, &n, h0, (uint32_t)(64 - pl.bits[0]), (uint32_t)pl.bits[0], true));
+    // K1 counts the level-0 digits — or, when the first two levels have 10..16 bits together, the children of level 1 as well
+    // (packed shared-memory histogram): the owners then get the level-1 counts with the digit counts and skip the histogram pass
+    const int hb2 = pl.levels >= 2 ? pl.bits[0] + pl.bits[1] : 0;
+    const bool two = ctx->opt_fused_hist && hb2 >= 10 && hb2 <= 16;
+    const int hl = two ? 1 : 0;
+    const uint32_t hbits = two ? (uint32_t)hb2 : (uint32_t)pl.bits[0];
+    unsigned long long* h0 = (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[hl]);
+    TRY(run_extract(ctx, lo, tile0, n_tiles, pos_lo, pos_hi, &n, h0, 64 - hbits, hbits, true));
     std::vector<uint64_t>& st = ctx->scatter_host;
-    st.assign(pl.nc[0], 0);
-    CU(cudaMemcpyAsync(st.data(), h0, (size_t)pl.nc[0] * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    st.assign(pl.nc[hl], 0);
+    CU(cudaMemcpyAsync(st.data(), h0, (size_t)pl.nc[hl] * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     uint64_t n_local = 0;
-    for (uint32_t d = 0; d < pl.nc[0]; d++) { digit_counts[d] = st[d]; n_local += st[d]; }
+    const uint32_t fold = two ? (1u << pl.bits[1]) : 1u;
+    for (uint32_t d = 0; d < pl.nc[0]; d++) {
+        uint64_t c = 0;
+        for (uint32_t j = 0; j < fold; j++) c += st[(size_t)d * fold + j];
+        digit_counts[d] = c; n_local += c;
+    }
+    if (two) ctx->shard_child_host = st; else ctx->shard_child_host.clear();
+    ctx->shard_child_set.clear();
     ctx->alg_bytes += n_local * ctx->alg_rec_bytes;
     ctx->alg_rec_bytes = 0;
     ctx->shard_n_records = n_local;
     prof_collect(ctx);
+    return KB_OK;
+}
+
+int kb_shard_child_counts(kb_ctx* ctx, uint64_t* counts, uint64_t cap, uint64_t* n) {
+    if (!ctx || !n) return KB_EINVAL;
+    *n = ctx->shard_child_host.size();
+    if (counts && cap >= *n && *n) memcpy(counts, ctx->shard_child_host.data(), *n * 8);
+    return KB_OK;
+}
+
+int kb_shard_set_child_counts(kb_ctx* ctx, const uint64_t* counts, uint64_t n) {
+    if (!ctx || (n && !counts)) return KB_EINVAL;
+    ctx->shard_child_set.assign(counts, counts + n);
     return KB_OK;
 }
 
@@ -1634,7 +1676,16 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_count
     uint64_t* parted = nullptr;
     HashStage hs{};
     hs.pl = &pl;
-    TRY(run_partition(ctx, pl, in, other, n_records, 1, pl.levels, &cp, &parted, &hs.bstart, &hs.n_buckets));
+    // level-1 child counts that came with the exchange (K1's two-level histograms, summed over the source ranks by the host layer)
+    const bool counts_given = pl.levels >= 2 && ctx->shard_child_set.size() == (size_t)pl.ncl[1] && n_records > 0;
+    if (counts_given) {
+        uint64_t total = 0;
+        for (uint64_t c : ctx->shard_child_set) total += c;
+        if (total != n_records) return fail(ctx, KB_EINVAL, "level-1 child counts do not add up to the number of received records");
+        CU(cudaMemcpyAsync((uint8_t*)ctx->plan.p + pl.off_cnt[1], ctx->shard_child_set.data(), (size_t)pl.ncl[1] * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TRY(run_partition(ctx, pl, in, other, n_records, 1, pl.levels, &cp, &parted, &hs.bstart, &hs.n_buckets, false, counts_given));
+    ctx->shard_child_set.clear();
     ctx->lazy_now = !ctx->lo.direct;
     if (ctx->lazy_now && n_records > 0) TRY(run_prefilter(ctx, pl, parted, n_records, &hs, &parted));
     int rc = run_group(ctx, parted, n_records, out, &hs);

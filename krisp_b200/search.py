@@ -357,12 +357,29 @@ class Searcher:
         blob = b"".join(handles)
         self._check(self._L.kb_shard_ipc_import(self._ctx, len(handles), blob))
 
+    def shard_ipc_close(self):
+        self._check(self._L.kb_shard_ipc_close(self._ctx))
+
     def shard_count(self):
         n_shards, _, nd = self._shard
         digits = (ctypes.c_uint64 * nd)()
         self._check(self._L.kb_shard_count(self._ctx, digits))
         self._keep = []
         return [int(c) for c in digits]
+
+    def shard_child_counts(self):
+        """This rank's records per level-1 child over the whole key space (after shard_count), or None when K1 did not count them."""
+        n = ctypes.c_uint64()
+        self._check(self._L.kb_shard_child_counts(self._ctx, None, 0, ctypes.byref(n)))
+        if n.value == 0:
+            return None
+        out = np.zeros(int(n.value), dtype=np.uint64)
+        self._check(self._L.kb_shard_child_counts(self._ctx, ctypes.c_void_p(out.ctypes.data), int(out.size), ctypes.byref(n)))
+        return out
+
+    def shard_set_child_counts(self, counts):
+        arr = np.ascontiguousarray(counts, dtype=np.uint64)
+        self._check(self._L.kb_shard_set_child_counts(self._ctx, ctypes.c_void_p(arr.ctypes.data), int(arr.size)))
 
     def shard_scatter(self, piece_base):
         arr = (ctypes.c_uint64 * len(piece_base))(*[int(c) for c in piece_base])

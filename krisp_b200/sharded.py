@@ -122,17 +122,30 @@ def direct_search(searcher, device, have_outgroup=True, group=None):
     nd = len(digits)
     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     ev[0].record()
-    dg = torch.tensor(digits, dtype=torch.int64, device=device)
-    alld = torch.empty(world * nd, dtype=torch.int64, device=device)
+    # K1's two-level histogram, when it has one: the level-1 child counts travel with the digit counts, so that the owner does not
+    # have to re-read the records it received just to count them
+    child = searcher.shard_child_counts() if hasattr(searcher, "shard_child_counts") else None
+    nch = 0 if child is None else int(child.size)
+    payload = list(digits) + ([] if child is None else child.astype(np.int64).tolist())
+    dg = torch.tensor(payload, dtype=torch.int64, device=device)
+    alld = torch.empty(world * (nd + nch), dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(alld, dg, group=group)
-    table = alld.view(world, nd).cpu().numpy()                        # [source][digit]
+    both = alld.view(world, nd + nch).cpu().numpy()
+    table = both[:, :nd]                                              # [source][digit]
     firsts = [first_digit(s, world, nd) for s in range(world + 1)]
     need, piece_base, pieces = piece_tables(table, rank)
+    if nch:
+        per = nch // nd                                               # children per digit
+        own = both[:, nd + firsts[rank] * per: nd + firsts[rank + 1] * per].sum(axis=0)
+        searcher.shard_set_child_counts(own.astype(np.uint64))
     state = searcher.__dict__.setdefault("_ipc_state", {"cap": [0] * world, "world": world})
     if state["world"] != world or any(n > c for n, c in zip(need, state["cap"])):
         # some buffer is too small: every rank sees the same table, so every rank takes this branch together
         state["cap"] = [max(c, n + n // 4 + 4096) for n, c in zip(need, state["cap"])]
         state["world"] = world
+        if hasattr(searcher, "shard_ipc_close"):
+            searcher.shard_ipc_close()                                # nobody maps a buffer that is about to be reallocated
+            dist.barrier(group=group)
         mine = torch.frombuffer(bytearray(searcher.shard_ipc_export(state["cap"][rank])), dtype=torch.uint8).to(device)
         allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(allh, mine, group=group)

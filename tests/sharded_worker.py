@@ -6,6 +6,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
@@ -41,6 +42,35 @@ def main():
             if rank == 0:
                 print(("ok   " if ok else "FAIL ") + case["name"], mode, len(rows), flush=True)
             bad += 0 if ok else 1
+    # seeded panels, big enough for multi-level plans; options force the plan shapes of the large runs: (4, 6, 6) bits = K1 counts the
+    # level-1 children too and the counts travel with the exchange; rows must equal the single-GPU search of the whole panel
+    from krisp_b200.panel import make_panel
+    for (L, D, R), opts in [((25, 1, 2), {}), ((25, 1, 2), {"bucket_bits": 16, "shard_bits0": 4}), ((25, 1, 2), {"bucket_bits": 16, "shard_bits0": 4, "fused_hist": 0}),
+                            ((32, 60, 32), {}), ((32, 60, 32), {"bucket_bits": 16, "shard_bits0": 4})]:
+        gs = make_panel(5, 4, 200_000)
+        is_in = [1 if g.is_ingroup else 0 for g in gs]
+        s.configure(L, D, R, is_in)
+        s.clear_sequences()
+        for i, g in enumerate(gs):
+            s.add_sequence(i, np.frombuffer(g.joined(), dtype=np.uint8))
+        want = s.search(have_outgroup=True).rows()
+        for k, v in opts.items():
+            s.set_option(k, v)
+        try:
+            s.clear_sequences()
+            for i, g in enumerate(gs):
+                if i % world == rank:
+                    s.add_sequence(i, np.frombuffer(g.joined(), dtype=np.uint8))
+            res = sharded.sharded_search(s, dev, have_outgroup=True)
+            rows = sharded.gather_rows(res.rows())
+        finally:
+            s.set_option("bucket_bits", -1)
+            s.set_option("shard_bits0", 0)
+            s.set_option("fused_hist", 1)
+        ok = rows == want and len(want) > 0
+        if rank == 0:
+            print(("ok   " if ok else "FAIL ") + f"panel {L}/{D}/{R} {opts}", len(rows), flush=True)
+        bad += 0 if ok else 1
     s.close()
     dist.barrier()
     dist.destroy_process_group()
