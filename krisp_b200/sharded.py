@@ -126,8 +126,8 @@ def direct_search(searcher, device, have_outgroup=True, group=None):
     # have to re-read the records it received just to count them
     child = searcher.shard_child_counts() if hasattr(searcher, "shard_child_counts") else None
     nch = 0 if child is None else int(child.size)
-    payload = list(digits) + ([] if child is None else child.astype(np.int64).tolist())
-    dg = torch.tensor(payload, dtype=torch.int64, device=device)
+    payload = np.asarray(digits, dtype=np.int64) if child is None else np.concatenate([np.asarray(digits, dtype=np.int64), child.astype(np.int64)])
+    dg = torch.from_numpy(payload).to(device)
     alld = torch.empty(world * (nd + nch), dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(alld, dg, group=group)
     both = alld.view(world, nd + nch).cpu().numpy()
