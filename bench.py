@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 L_, D_, R_ = 25, 1, 2
 N_IN, N_OUT = 20, 20
+PANEL_KW = {}            # --noise: private substitution rate of the synthetic genomes (default: the panel generator's 1e-3)
 METRIC = "diagnostic-region search throughput (input bases / s)"
 UNIT = "Gbp/s"
 
@@ -111,7 +112,7 @@ def build_panel(genome_len, rank=0, world=1):
         if i % world != rank:
             continue
         is_in = i < N_IN
-        g = make_genome(i, is_in, is_in and (i % 2 == 1), f"ingroup{i}" if is_in else f"outgroup{i - N_IN}", genome_len)
+        g = make_genome(i, is_in, is_in and (i % 2 == 1), f"ingroup{i}" if is_in else f"outgroup{i - N_IN}", genome_len, **PANEL_KW)
         out.append((i, is_in, np.frombuffer(g.joined(), dtype=np.uint8)))
     return out
 
@@ -354,6 +355,8 @@ def main():
                     "50 50 = the shape of BASELINE config 4, 5..100 each = the genome-count sweep of config 5)")
     ap.add_argument("--ldr", nargs=3, type=int, metavar=("L", "D", "R"), help="--conserved-left / --diagnostic / --conserved-right "
                     "(default 25 1 2 = BASELINE config 2; 32 60 32 = config 3, primer mode)")
+    ap.add_argument("--noise", type=float, help="private substitution rate per genome (default 1e-3); higher = more divergent genomes, "
+                    "fewer shared k-mers (robustness probe, not the BASELINE workload)")
     ap.add_argument("--option", nargs=2, action="append", metavar=("NAME", "VALUE"), help="kb_set_option passthrough")
     args = ap.parse_args()
     global L_, D_, R_, N_IN, N_OUT
@@ -361,6 +364,8 @@ def main():
         L_, D_, R_ = args.ldr
     if args.genomes:
         N_IN, N_OUT = args.genomes
+    if args.noise is not None:
+        PANEL_KW["noise"] = args.noise
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -101,6 +101,9 @@ struct kb_ctx {
     long long opt_have_outgroup = 1;     // consensus letters: ingroup only (an outgroup was given) / every occurrence
     long long opt_lazy_records = 1;      // multi-word records: 1 = filter by flank hash, build records only for what is left (kb_prefilter.cuh)
     bool lazy_now = false;               // the running search uses it
+    int bb_extra = 0;                    // bucket bits added to the size-based plan: learnt when a search deferred too many buckets
+                                         // (divergent genomes: far more distinct keys per record than the plan assumes); kept per layout
+    bool replan_ok = false;              // the running search may give up on a too coarse plan (kb_search retries with bb_extra + 2)
     long long opt_shard_bits0 = 0;       // multi-GPU: bits of partition level 0 (the exchange); 0 = log2(shards) + 2
 
     // sequences
@@ -149,6 +152,8 @@ struct kb_ctx {
 // layout of the `small` device buffer (u64 units)
 enum { SM_NOUT = 0, SM_NRES = 1, SM_STATS = 2 /*4*/, SM_NTAINT = 6, SM_ERR = 7, SM_TICKET = 8 /* u32 x 16 */, SM_HIST = 16 /* 9*256 */,
        SM_ROOT = 16 + 9 * 256 /* u64 x 2: {0, n} */, SM_ROOTTILE = SM_ROOT + 2 /* u32 x 2: {0, tiles} */, SM_TOTAL = SM_ROOT + 4 };
+
+#define KB_REPLAN 1                      // internal: the search gave up on its plan (never leaves the library)
 
 static int fail(kb_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -310,6 +315,7 @@ int kb_configure(kb_ctx* ctx, int L, int D, int R, int soft_mode, int n_files, c
     lo.n_files = n_files;
     lo.PW = (n_files + 31) / 32;
     lo.MW = (D + 7) / 8;
+    if (!ctx->configured || ctx->lo.L != lo.L || ctx->lo.D != lo.D || ctx->lo.R != lo.R || ctx->lo.n_files != lo.n_files) ctx->bb_extra = 0;
     ctx->lo = lo;
     ctx->soft_mode = soft_mode ? 1 : 0;
     memset(ctx->is_ingroup, 0, sizeof ctx->is_ingroup);
@@ -700,7 +706,7 @@ static bool hash_fast_ok(const kb_ctx* ctx) {
 // n_est: records over the whole key space (all GPUs).  bits0 > 0 (multi-GPU): level 0 — the exchange — separates exactly bits0 bits
 // (>= log2 of the shard count: it decides the owner; few digits = long runs = efficient peer stores), the levels after the exchange
 // share the remaining bucket bits.
-static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0) {
+static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0, bool use_hint = true) {
     const KbLayout& lo = ctx->lo;
     PartPlan pl;
     pl.fast = hash_fast_ok(ctx);
@@ -723,6 +729,7 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0) {
         bb = 0;
         while (bb < 24 && (n_est >> bb) > target) bb++;
     }
+    if (ctx->opt_bucket_bits < 0 && use_hint) bb += ctx->bb_extra;      // (never in the sharded plans: every rank must derive the same one)
     bb = std::min(bb, std::min(keybits, 24));
     if (bits0) {
         bb = std::min(std::max(bb, bits0 + 1), std::min(keybits, bits0 + 18));
@@ -906,6 +913,7 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
         // fallback for the deferred buckets: the splitting kernels with a roomier table
         KbHashArgs fb = x;
         fb.list = xs.deferred; fb.n_list = xs.n_deferred;
+        fb.abort_above = (ctx->replan_ok && hs.pl->bb < std::min(lo.FB, 24)) ? std::max<uint32_t>(hs.n_buckets / 8, 64) : 0;
         if (hs.pl->fast) {
             fb.slots_log2 = ctx->opt_hash_slots_log2 ? x.slots_log2 : std::max<uint32_t>(x.slots_log2, 11);
             const size_t fsmem = kb_hash_fast_smem(fb.slots_log2);
@@ -1103,6 +1111,7 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
             }
             if (hs && hs->brun) ctx->alg_bytes += n * 8 + hs->n_kept * (uint64_t)(32 + 16 * lo.W + lo.k);   // K3a read, K3a/b/c on what is kept
             else ctx->alg_bytes += n * 8 * (lo.direct ? 1 : (1 + lo.W));
+            if (hs && ctx->h_pinned[7] == 2) { delete res; return KB_REPLAN; }     // too many deferred buckets: the caller re-plans
             if (hs && ctx->h_pinned[7]) { delete res; return fail(ctx, KB_EINTERNAL, "bucket hash: a bucket could not be resolved (hash table split limit)"); }
             if (hs && !hs->brun && !lo.direct && n >= (1ULL << 32)) { delete res; return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode"); }
             if (!hs && allow_fast && fast_group_ok(ctx) && ctx->h_pinned[6] > KB_TAINT_CAP) { allow_fast = false; continue; }   // taint list overflow: generic kernel
@@ -1267,6 +1276,8 @@ static void begin_search(kb_ctx* ctx) {
     ctx->prof_events.clear();
 }
 
+static int search_once(kb_ctx* ctx, kb_result** out);
+
 extern "C" {
 
 int kb_search(kb_ctx* ctx, kb_result** out) {
@@ -1274,6 +1285,22 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
     *out = nullptr;
     if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
     CU(cudaSetDevice(ctx->device));
+    // The plan sizes the buckets from the record count, assuming that a key occurs in a good part of the files.  Divergent genomes
+    // have far more distinct keys: the stream kernel then defers most buckets, and splitting each of them in the fallback kernel
+    // costs more than a finer partition.  So a search that defers more than 1/8 of its buckets is abandoned and repeated with
+    // two more bucket bits (the sequences are still resident); the context remembers the bits for the next search.
+    for (int attempt = 0; ; attempt++) {
+        ctx->replan_ok = attempt < 3 && ctx->opt_bucket_bits < 0 && ctx->opt_group_algo && ctx->lo.direct;
+        const int rc = search_once(ctx, out);
+        ctx->replan_ok = false;
+        if (rc != KB_REPLAN) return rc;
+        ctx->bb_extra += 2;
+    }
+}
+
+}  // extern "C"
+
+static int search_once(kb_ctx* ctx, kb_result** out) {
     begin_search(ctx);
     TRY(prepare_small(ctx));
     const KbLayout& lo = ctx->lo;
@@ -1362,6 +1389,8 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
     return rc;
 }
 
+extern "C" {
+
 // ---- multi-GPU: level 0 of the partition decides the owner shard (contiguous digit ranges), the exchange moves every
 //      level-0 bucket to its owner, levels >= 1 and the bucket hash run there ------------------------------------------
 static uint32_t shard_first_digit(uint32_t shard, uint32_t n_shards, uint32_t n_digits) {
@@ -1383,11 +1412,11 @@ int kb_shard_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bas
     // three (8 KB runs, 570 GB/s, but one more pass): stay with two levels while the bucket bits allow it.
     int bits0 = (int)ctx->opt_shard_bits0;
     if (bits0 <= 0) {
-        const PartPlan probe = make_plan(ctx, 2 * total_bases + 64, 0);
+        const PartPlan probe = make_plan(ctx, 2 * total_bases + 64, 0, false);
         bits0 = (probe.bb >= min_bits0 + 9 && probe.bb <= 17) ? probe.bb - 9 : min_bits0 + 2;
     }
     bits0 = std::max(std::max(min_bits0, 1), std::min(std::min(bits0, 9), lo.FB - 1));
-    PartPlan pl = make_plan(ctx, 2 * total_bases + 64, bits0);
+    PartPlan pl = make_plan(ctx, 2 * total_bases + 64, bits0, false);
     if (pl.levels < 2 || pl.levels > 3 || pl.bits[0] < min_bits0 || pl.bb > lo.FB) return fail(ctx, KB_EINTERNAL, "shard plan");
     ctx->shard_plan = pl;
     ctx->shard_n = n_shards;

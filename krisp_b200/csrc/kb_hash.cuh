@@ -35,6 +35,8 @@ struct KbHashArgs {
     unsigned long long* err;             // != 0: a bucket could not be resolved
     const uint32_t* list;                // != null: process only the buckets list[0 .. *n_list)
     const unsigned long long* n_list;
+    uint32_t abort_above;                // list mode: more deferred buckets than this = the plan was too coarse for this input: set *err = 2
+                                         // and leave (the host re-plans with more bucket bits instead of splitting every bucket here)
     const unsigned long long* brun;      // != null (generic kernel): bucket b = elements [brun[2b], brun[2b] + brun[2b+1]) (kb_prefilter.cuh)
 };
 
@@ -101,6 +103,10 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_fast_kernel(const KbHas
         return KB_KH_NONE;
     };
 
+    if (x.list && x.abort_above && *x.n_list > (unsigned long long)x.abort_above) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicCAS(x.err, 0ULL, 2ULL);
+        return;
+    }
     const uint32_t n_work = x.list ? (uint32_t)min((unsigned long long)x.n_buckets, *x.n_list) : x.n_buckets;
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const uint32_t b = x.list ? x.list[wi] : wi;
@@ -294,6 +300,10 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_kernel(const KbHashArgs
         return KB_KH_NONE;
     };
 
+    if (x.list && x.abort_above && *x.n_list > (unsigned long long)x.abort_above) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicCAS(x.err, 0ULL, 2ULL);
+        return;
+    }
     const uint32_t n_work = x.list ? (uint32_t)min((unsigned long long)x.n_buckets, *x.n_list) : x.n_buckets;
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const uint32_t b = x.list ? x.list[wi] : wi;

@@ -137,8 +137,8 @@ def test_multiword_records_lazy_and_eager_agree(name, bucket_bits, slots, lazy, 
 
 
 @pytest.mark.parametrize("shape", [(5, 4, 200_000, 32, 60, 32, False), (5, 4, 200_000, 32, 60, 32, True), (3, 3, 150_000, 20, 10, 17, False),
-                                   (40, 40, 30_000, 20, 30, 20, False), (6, 5, 100_000, 100, 20, 100, False)],
-                         ids=["primer", "primer_omit", "20_10_17", "80_files", "k220"])
+                                   (40, 40, 30_000, 20, 30, 20, False), (6, 5, 100_000, 100, 20, 100, False), (70, 70, 15_000, 20, 30, 20, False)],
+                         ids=["primer", "primer_omit", "20_10_17", "80_files", "k220", "140_files"])
 def test_lazy_records_panel_matches_oracle_and_eager(shape, searcher):
     """Multi-word records on seeded panels: lazy == eager == C oracle, and the gathered records (--out_align input) agree."""
     from krisp_b200.panel import make_panel
@@ -180,6 +180,25 @@ def test_lazy_records_when_the_filter_keeps_everything_or_nothing(shape, searche
     want = _oracle_panel(gs, L, D, R)
     assert res.rows() == want
     assert res.csv_rows_text().count("\n") == len(want)
+
+
+def test_divergent_genomes_make_the_search_replan(searcher):
+    """Genomes with 3 % private substitutions: almost every 28-mer is unique to its genome, so a bucket sized for shared keys holds
+    several times more distinct keys than its hash table.  The search must notice (deferred buckets), repeat itself with more
+    bucket bits, remember them for the next search on the same layout — and return the oracle's rows both times."""
+    from krisp_b200.panel import make_panel
+    gs = make_panel(7, 5, 400_000, noise=3e-2, snp_every=200)
+    fresh = type(searcher)(0)
+    try:
+        res1 = _search_panel(fresh, gs, 25, 1, 2)
+        stages1 = [nm for nm, _ in res1.profile]
+        res2 = _search_panel(fresh, gs, 25, 1, 2)
+        want = _oracle_panel(gs, 25, 1, 2)
+        assert res1.rows() == want and res2.rows() == want
+        assert res2.stats["queued_runs"] <= res2.stats["runs"]
+        assert len([nm for nm, _ in res2.profile]) >= len(stages1) - 1
+    finally:
+        fresh.close()
 
 
 _TABLES = _G["tables"]
