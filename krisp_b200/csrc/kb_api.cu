@@ -724,8 +724,12 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0, bool
     int bb;
     if (ctx->opt_bucket_bits >= 0) bb = (int)ctx->opt_bucket_bits;
     else {
-        // records per bucket: half a table of distinct keys, each expected in most of the files
-        const uint64_t target = ((uint64_t)1 << pl.slots_log2) / 2 * (uint64_t)std::min(std::max(lo.n_files, 1), 12);
+        // records per bucket: half a table of distinct keys, each expected in a good part of the files (every file for small panels,
+        // half of them — at most 24 — for large ones: 19..31 occurrences per key on the 40..200-genome panels of BASELINE config 5).
+        // Optimistic on purpose: a panel with fewer shared keys is caught by the re-plan of kb_search
+        const int nf = std::max(lo.n_files, 1);
+        const uint64_t mult = (uint64_t)(nf <= 12 ? nf : std::min(std::max(nf / 2, 12), 24));
+        const uint64_t target = ((uint64_t)1 << pl.slots_log2) / 2 * mult;
         bb = 0;
         while (bb < 24 && (n_est >> bb) > target) bb++;
     }
