@@ -110,6 +110,17 @@ def piece_tables(table, rank):
     return need, piece_base, pieces
 
 
+def shard_child_counts(children, n_digits, rank):
+    """From the all-gathered two-level histograms ``children[source][digit << bits1 | next digit]`` (every rank's K1 counts over the
+    whole key space): the level-1 child counts of the digits `rank` owns, summed over the sources, in digit order — what
+    kb_shard_set_child_counts expects (the owner then needs no histogram pass over the records it received)."""
+    children = np.asarray(children, dtype=np.int64)
+    world, nch = children.shape
+    per = nch // n_digits                                             # children per level-0 digit
+    lo, hi = first_digit(rank, world, n_digits), first_digit(rank + 1, world, n_digits)
+    return children[:, lo * per:hi * per].sum(axis=0).astype(np.uint64)
+
+
 def direct_search(searcher, device, have_outgroup=True, group=None):
     """Steps 1-3 with the exchange FUSED into partition level 0: every rank stores each digit's run straight into the
     owner's receive buffer over NVLink peer memory (CUDA IPC mappings of library-owned buffers), so the only collectives
@@ -135,9 +146,7 @@ def direct_search(searcher, device, have_outgroup=True, group=None):
     firsts = [first_digit(s, world, nd) for s in range(world + 1)]
     need, piece_base, pieces = piece_tables(table, rank)
     if nch:
-        per = nch // nd                                               # children per digit
-        own = both[:, nd + firsts[rank] * per: nd + firsts[rank + 1] * per].sum(axis=0)
-        searcher.shard_set_child_counts(own.astype(np.uint64))
+        searcher.shard_set_child_counts(shard_child_counts(both[:, nd:], nd, rank))
     state = searcher.__dict__.setdefault("_ipc_state", {"cap": [0] * world, "world": world})
     if state["world"] != world or any(n > c for n, c in zip(need, state["cap"])):
         # some buffer is too small: every rank sees the same table, so every rank takes this branch together

@@ -219,3 +219,26 @@ def test_interchange_lines_round_trip_golden_files():
                     out.append(((l, r), [ln]))
             return [(kk, sorted(v)) for kk, v in out]
         assert grouped(got) == grouped(text.splitlines()), name
+
+
+def test_shard_child_counts_are_the_owned_slice_summed_over_sources():
+    """sharded.shard_child_counts: K1's two-level histograms of all ranks -> level-1 child counts of one shard's digits (what the
+    owner would count over the records it receives)."""
+    from krisp_b200 import sharded
+    rng = np.random.default_rng(5)
+    for world, bits0, bits1 in [(2, 3, 4), (4, 4, 7), (8, 5, 7), (3, 3, 2)]:
+        nd, per = 1 << bits0, 1 << bits1
+        # records as (source, digit, child) triples
+        src = rng.integers(0, world, 5000)
+        key = rng.integers(0, nd * per, 5000)
+        children = np.zeros((world, nd * per), dtype=np.int64)
+        np.add.at(children, (src, key), 1)
+        covered = 0
+        for rank in range(world):
+            got = sharded.shard_child_counts(children, nd, rank)
+            lo, hi = sharded.first_digit(rank, world, nd), sharded.first_digit(rank + 1, world, nd)
+            mine = key[(key >> bits1 >= lo) & (key >> bits1 < hi)]            # every source's records of the digits this rank owns
+            want = np.bincount(mine - lo * per, minlength=(hi - lo) * per)
+            assert got.dtype == np.uint64 and got.tolist() == want.tolist()
+            covered += int(got.sum())
+        assert covered == 5000
