@@ -242,3 +242,25 @@ def test_shard_child_counts_are_the_owned_slice_summed_over_sources():
             assert got.dtype == np.uint64 and got.tolist() == want.tolist()
             covered += int(got.sum())
         assert covered == 5000
+
+
+def test_decode_table_handles_one_word_and_multi_word_records():
+    """kstream.decode_table on hand-packed records ([left | right | mid | pad | id], 1 / 2 / 4 / 8 words) == the C oracle's sorted
+    table lines of the same sequence, including the R == 0 quirk (middle lands in the third field)."""
+    from krisp_b200.kstream import decode_table
+    from oracle import oracle
+    rng = np.random.default_rng(11)
+    seq = "".join("ACGT"[i] for i in rng.integers(0, 4, 600))
+    for L, D, R in [(25, 1, 2), (9, 1, 0), (20, 10, 17), (32, 60, 32), (100, 20, 100), (0, 30, 10)]:
+        text, n = oracle.table_text([seq], L, D, R)
+        want = text.splitlines()
+        k = L + D + R
+        W = 1 if 2 * k + 8 <= 64 else (2 if 2 * k + 8 <= 128 else (4 if 2 * k + 8 <= 256 else 8))
+        recs = []
+        for ln in want:
+            f = ln.split(",")
+            left, mid, right = (f[0], f[2], "") if R == 0 else (f[0], f[1], f[2])      # quirk S9: `left,,mid`
+            recs.append(_pack_words(_pack(left + right + mid), 2 * k, W))
+        arr = np.array(recs, dtype=np.uint64).reshape(len(recs), W)
+        got = decode_table(arr if W > 1 else arr[:, 0], L, D, R)
+        assert got == want and len(got) == n, (L, D, R)
