@@ -51,6 +51,7 @@ struct PartPlan {
     bool stream = false;                 // kb_hash_stream_kernel applies (one-word records, D <= 8, any file count)
     // device tables inside ctx->plan (byte offsets), per level: counts/cursors [NC], starts [NC + 1], tile prefix [NC + 1]
     size_t off_cnt[3] = {0, 0, 0}, off_start[3] = {0, 0, 0}, off_tile0[3] = {0, 0, 0}, off_part = 0, off_tilemap = 0, bytes = 0;
+    size_t off_pair = 0;                 // pair mode (17 bits in two levels): 2^16 pair counts | 2^16 + 1 pair offsets
     uint32_t nc[3] = {0, 0, 0};          // children per level over the whole key space: 2^(bits[0] + ... + bits[l])
     uint32_t ncl[3] = {0, 0, 0};         // children per level this GPU works on (= nc on one GPU; its shard's part on several)
 };
@@ -95,6 +96,7 @@ struct kb_ctx {
     long long opt_bucket_bits = -1;      // -1 = from the input size
     long long opt_hash_slots_log2 = 0;   // 0 = default
     long long opt_hash_stream = 1;       // 1 = persistent TMA-fed bucket hash kernel for the fast shape
+    long long opt_pair_hist = 1;         // 1 = 17 bucket bits in two levels run on K1's 16-bit histogram (sibling pairs fill their range from both ends)
     long long opt_fused_hist = 1;        // 1 = K1 also counts the level-1 children (single-GPU search path)
     long long opt_batch_level0 = 1;      // 1 = partition level 0 per batch of arriving files (hidden under the host -> device copy)
     long long opt_render_rows = 1;       // CSV rows of the survivors rendered + ordered on the device (kb_result_rows)
@@ -273,6 +275,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "group_algo") ctx->opt_group_algo = value ? 1 : 0;
     else if (n == "hash_stream") ctx->opt_hash_stream = value ? 1 : 0;
     else if (n == "fused_hist") ctx->opt_fused_hist = value ? 1 : 0;
+    else if (n == "pair_hist") ctx->opt_pair_hist = value ? 1 : 0;
     else if (n == "batch_level0") ctx->opt_batch_level0 = value ? 1 : 0;
     else if (n == "lazy_records") ctx->opt_lazy_records = value ? 1 : 0;
     else if (n == "render_rows") ctx->opt_render_rows = value ? 1 : 0;
@@ -746,6 +749,8 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0, bool
         pl.bb = bb;
         pl.levels = (bb + 8) / 9;
         for (int l = 0; l < pl.levels; l++) pl.bits[l] = bb / pl.levels + (l < bb % pl.levels ? 1 : 0);
+        if (pl.levels == 2 && bb == 17) { pl.bits[0] = 8; pl.bits[1] = 9; }     // a 256-way level runs faster than a 512-way one: give level 0,
+                                                                                  // which cannot use the pair trick, the narrow digit
     }
     const uint64_t max_tiles = n_est / KB_PT_TILE + ((uint64_t)1 << bb) + 2;
     size_t off = 0;
@@ -760,6 +765,7 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0, bool
     }
     pl.off_part = off; off += ((((size_t)1 << bb) + KB_PLAN_BLOCK - 1) / KB_PLAN_BLOCK + 1) * 16;
     pl.off_tilemap = off; off += (max_tiles * 4 + 7) & ~(size_t)7;
+    pl.off_pair = off; off += ((size_t)2 << 16) * 8 + 64;
     pl.bytes = off;
     return pl;
 }
@@ -783,7 +789,7 @@ static int launch_plan(kb_ctx* ctx, KbPlanArgs pa, const PartPlan& pl) {
 // have_hist1: K1 already counted the level-1 children (plan buffer, level-1 counts); level 0's counts are their row sums.
 static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& other, uint64_t n, int l_begin, int l_end,
                          const CustomParents* cp, uint64_t** parted, const unsigned long long** bstart, uint32_t* n_buckets,
-                         bool have_hist1 = false, bool counts_given = false) {
+                         bool have_hist1 = false, bool counts_given = false, bool pair = false) {
     uint64_t* cur = (uint64_t*)in.p;
     uint8_t* P = (uint8_t*)ctx->plan.p;
     unsigned long long* root = (unsigned long long*)ctx->small.p + SM_ROOT;
@@ -825,7 +831,21 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
             grid = n / KB_PT_TILE + pl.ncl[l - 1] + 1;
         }
         prof_begin(ctx, hnames[l]);
-        if (l == 0 && have_hist1) {
+        if (l == 0 && pair) {
+            // K1 counted 16 bits, level 0 + 1 have 17: the counts are those of sibling pairs.  Pair offsets -> the cursors of both
+            // siblings (left end / right end) and the even entries of the bucket table; row sums = the level-0 counts
+            unsigned long long* h16 = (unsigned long long*)(P + pl.off_pair);
+            unsigned long long* s16 = h16 + ((size_t)1 << 16);
+            const uint32_t n_pairs = pl.ncl[1] / 2;
+            KbPlanArgs pp{};
+            pp.counts = h16; pp.nc = n_pairs; pp.start = s16; pp.cursor = nullptr; pp.tile0 = nullptr;
+            pp.folded = a.cursor; pp.fold = 1u << (pl.bits[1] - 1);
+            TRY(launch_plan(ctx, pp, pl));
+            kb_pair_expand_kernel<<<(n_pairs + 255) / 256, 256, 0, ctx->stream>>>(s16, n_pairs, (unsigned long long*)(P + pl.off_cnt[1]),
+                                                                                (unsigned long long*)(P + pl.off_start[1]));
+            CU(cudaGetLastError());
+            ctx->launches++;
+        } else if (l == 0 && have_hist1) {
             // level-1 offsets straight from K1's two-level histogram; its row sums are the level-0 counts
             KbPlanArgs p1{};
             p1.counts = (unsigned long long*)(P + pl.off_cnt[1]); p1.nc = pl.ncl[1];
@@ -860,9 +880,20 @@ static int run_partition(kb_ctx* ctx, const PartPlan& pl, DevBuf& in, DevBuf& ot
         }
         prof_end(ctx);
         prof_begin(ctx, pnames[l]);
-        kb_part_kernel<2><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
+        a.pair_mode = (pair && l == 1) ? 1 : 0;
+        if (a.pair_mode) {
+            CU(cudaFuncSetAttribute(kb_part_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kb_part_kernel<2, true><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
+        } else {
+            kb_part_kernel<2><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
+        }
         CU(cudaGetLastError());
         ctx->launches++;
+        if (a.pair_mode) {
+            kb_pair_fix_kernel<<<(pl.ncl[1] / 2 + 255) / 256, 256, 0, ctx->stream>>>(a.cursor, pl.ncl[1] / 2, (unsigned long long*)(P + pl.off_start[1]));
+            CU(cudaGetLastError());
+            ctx->launches++;
+        }
         prof_end(ctx);
         ctx->alg_rec_bytes += 16;
         std::swap(cur, alt);
@@ -1318,9 +1349,12 @@ static int search_once(kb_ctx* ctx, kb_result** out) {
         // K1 counts the children of the first level — or of the first TWO levels at once (packed shared-memory histogram), which
         // saves the pass that would re-read every record just to count level 1
         const bool fused2 = ctx->opt_fused_hist && pl.levels >= 2 && pl.bits[0] + pl.bits[1] >= 10 && pl.bits[0] + pl.bits[1] <= 16;
+        // 17 bits in two levels: K1 still counts 16 — the sizes of sibling pairs of level-1 children, which is all the pass needs when
+        // the two siblings fill their common range from both ends (KbPartArgs::pair_mode)
+        const bool pair = ctx->opt_fused_hist && ctx->opt_pair_hist && pl.levels == 2 && pl.bits[0] + pl.bits[1] == 17;
         const int hl = fused2 ? 1 : 0;
-        const uint32_t hbits = fused2 ? (uint32_t)(pl.bits[0] + pl.bits[1]) : (uint32_t)pl.bits[0];
-        unsigned long long* h0 = pl.levels ? (unsigned long long*)((uint8_t*)ctx->plan.p + pl.off_cnt[hl]) : nullptr;
+        const uint32_t hbits = pair ? 16u : (fused2 ? (uint32_t)(pl.bits[0] + pl.bits[1]) : (uint32_t)pl.bits[0]);
+        unsigned long long* h0 = pl.levels ? (unsigned long long*)((uint8_t*)ctx->plan.p + (pair ? pl.off_pair : pl.off_cnt[hl])) : nullptr;
         BatchL0 bl;
         if (fused2 && ctx->opt_batch_level0 && pl.levels == 2 && lo.direct) {
             // carve the batch tables: [B][nc1] two-level counts | [B*nc0] level-0 counts | [B*nc0+1] offsets (x2) | [B][nc0] cursors | roots | tiles | rows
@@ -1378,7 +1412,7 @@ static int search_once(kb_ctx* ctx, kb_result** out) {
         uint64_t* parted = nullptr;
         HashStage hs{};
         hs.pl = &pl;
-        TRY(run_partition(ctx, pl, ctx->entA, ctx->entB, n, 0, pl.levels, nullptr, &parted, &hs.bstart, &hs.n_buckets, fused2));
+        TRY(run_partition(ctx, pl, ctx->entA, ctx->entB, n, 0, pl.levels, nullptr, &parted, &hs.bstart, &hs.n_buckets, fused2 || pair, false, pair));
         if (ctx->lazy_now && n > 0) TRY(run_prefilter(ctx, pl, parted, n, &hs, &parted));
         int rc = run_group(ctx, parted, n, out, &hs);
         prof_collect(ctx);

@@ -38,6 +38,10 @@ struct KbPartArgs {
     uint32_t shift, bits;               // digit = (e >> shift) & (2^bits - 1)
     unsigned long long* cursor;         // [n_parents << bits] absolute output offsets, advanced atomically
     unsigned long long* hist;           // kb_part_hist_kernel: [n_parents << bits] child counts (zeroed)
+    int pair_mode;                      // 1: only the sizes of sibling PAIRS of children (2p, 2p + 1) are known (one bit more than the
+                                        // histogram K1 could count): the pair's range is exact, the even child fills it from the left end,
+                                        // the odd child from the right end — cursor[2p] starts at the pair's start and grows, cursor[2p+1]
+                                        // starts at its end and shrinks; where they meet is the boundary (kb_pair_fix_kernel)
     const unsigned long long* out_elems; // != null: child c is written to the buffer at element address out_elems[c] (= pointer / 8)
                                         // instead of `out` — multi-GPU: the owner's receive buffer, a peer mapping over NVLink; the
                                         // cursor of c then counts from the first element of this rank's piece in that buffer
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(256) kb_tilemap_kernel(const uint32_t* tile0, 
 }
 
 // ---- one partition level -------------------------------------------------------------------------------
-template <int MINB>
+template <int MINB, bool PAIR = false>
 __global__ void __launch_bounds__(KB_PT_THREADS, MINB) kb_part_kernel(const KbPartArgs a) {
     extern __shared__ __align__(16) unsigned char kb_smem_raw[];
     uint64_t* skeys = reinterpret_cast<uint64_t*>(kb_smem_raw);                   // TILE
@@ -259,7 +263,10 @@ __global__ void __launch_bounds__(KB_PT_THREADS, MINB) kb_part_kernel(const KbPa
     unsigned long long g = 0;
     if (tid < KB_PT_MAXR) {
         c = cnt[tid];
-        if (c) g = atomicAdd(a.cursor + (((size_t)parent << a.bits) | tid), (unsigned long long)c);
+        if (c) {
+            if (PAIR && (tid & 1u)) g = atomicAdd(a.cursor + (((size_t)parent << a.bits) | tid), 0ULL - (unsigned long long)c) - (unsigned long long)c;   // claim downwards
+            else g = atomicAdd(a.cursor + (((size_t)parent << a.bits) | tid), (unsigned long long)c);
+        }
     }
     {
         uint32_t x = c;
@@ -299,6 +306,21 @@ __global__ void __launch_bounds__(KB_PT_THREADS, MINB) kb_part_kernel(const KbPa
             *reinterpret_cast<uint64_t*>((dbase[(uint32_t)(kv >> a.shift) & dmask] + pos) << 3) = kv;
         }
     }
+}
+
+// pair mode: cursors and bucket table from the exclusive prefix of the PAIR counts (pstart[n_pairs + 1])
+__global__ void __launch_bounds__(256) kb_pair_expand_kernel(const unsigned long long* pstart, uint32_t n_pairs, unsigned long long* cursor,
+                                                             unsigned long long* start) {
+    for (uint32_t p = blockIdx.x * 256 + threadIdx.x; p < n_pairs; p += gridDim.x * 256) {
+        const unsigned long long s0 = pstart[p], s1 = pstart[p + 1];
+        cursor[2 * (size_t)p] = s0; cursor[2 * (size_t)p + 1] = s1;
+        start[2 * (size_t)p] = s0; start[2 * (size_t)p + 1] = s1;        // (odd entries: fixed after the pass)
+        if (p == n_pairs - 1) start[2 * (size_t)n_pairs] = s1;
+    }
+}
+// after the pass the even child's cursor stands at the boundary between the two siblings
+__global__ void __launch_bounds__(256) kb_pair_fix_kernel(const unsigned long long* cursor, uint32_t n_pairs, unsigned long long* start) {
+    for (uint32_t p = blockIdx.x * 256 + threadIdx.x; p < n_pairs; p += gridDim.x * 256) start[2 * (size_t)p + 1] = cursor[2 * (size_t)p];
 }
 
 static inline size_t kb_part_smem() { return (size_t)KB_PT_TILE * 8 + KB_PT_MAXR * 8 + KB_PT_MAXR * 4 + (KB_PT_MAXR / 32) * 4 + 16; }
