@@ -15,6 +15,23 @@ from .render import render_output
 from .search import search_files
 
 
+def extractSortedKmers(fasta, primer_left, primer_right, ampl_len, output, sortmem=None, parallel=1, verbose=True, omit=True):
+    """Fasta file -> sorted ``left,mid,right`` k-mer table written to `output` — the reference's stage function
+    (krisp_fasta/krisp_fasta.py:16-62) with the same arguments and the same progress lines on stderr; extraction and sort run on
+    the device (``krisp_b200.kstream``: K1 + radix sort).  `sortmem` / `parallel` tuned GNU sort and are accepted for compatibility."""
+    import time
+    from .kstream import kstream
+    kmers = kstream(fasta, kmers=ampl_len, disallow="Nn", complements=True, omitsoft=bool(omit), mapsoft=not omit,
+                    split=[primer_left, -primer_right], sort=True, sortmem=sortmem, sortcols=[0, 2], sortnp=parallel, parallel=parallel)
+    if not verbose:
+        kmers.write(output)
+        return
+    start_t = time.time()
+    print(f"Extracting {ampl_len}-mers from {fasta} and saving to {output}", end="\n", file=sys.stderr)
+    found = kmers.write(output)
+    print(f"=> Extracted and sorted {found:,} {ampl_len}-kmers from {fasta} in {time.time() - start_t:.2f}s", file=sys.stderr)
+
+
 def build_parser():
     parser = argparse.ArgumentParser(
         description="Find diagnostic alignments for a set of fasta files",

@@ -245,6 +245,19 @@ def test_kstream_sorted_table_matches_oracle_on_a_seeded_genome(shape):
     assert got == want
 
 
+def test_extractSortedKmers_stage_function_writes_the_reference_table(tmp_path, capsys):
+    """The reference's stage function signature (krisp_fasta.py:16): same table file, same 'Extracted and sorted N k-kmers' line."""
+    import os
+    from krisp_b200.krisp_fasta import extractSortedKmers
+    from tests.helpers import GOLDEN_DIR
+    tab = next(t for t in _TABLES if t["L"] == 25 and not t["omit_soft"])
+    out = str(tmp_path / "x.28mers")
+    extractSortedKmers(os.path.join(GOLDEN_DIR, tab["file"]), 25, 2, 28, out, None, parallel=1, verbose=True, omit=False)
+    text = open(out).read()
+    assert hashlib.sha256(text.encode()).hexdigest() == tab["sha256"]
+    assert f"=> Extracted and sorted {tab['count']:,} 28-kmers" in capsys.readouterr().err
+
+
 _ALIGN = [c for c in _G["cases"] if "out_align" in c]
 
 
