@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -17,6 +18,8 @@
 #include "kb_part.cuh"
 #include "kb_hash.cuh"
 #include "kb_hash_stream.cuh"
+#include "kb_hash_warp.cuh"
+#include "kb_extract_part.cuh"
 #include "kb_ingest.cuh"
 #include "kb_prefilter.cuh"
 #include "kb_rows.cuh"
@@ -102,6 +105,10 @@ struct kb_ctx {
     long long opt_render_rows = 1;       // CSV rows of the survivors rendered + ordered on the device (kb_result_rows)
     long long opt_have_outgroup = 1;     // consensus letters: ingroup only (an outgroup was given) / every occurrence
     long long opt_lazy_records = 1;      // multi-word records: 1 = filter by flank hash, build records only for what is left (kb_prefilter.cuh)
+    long long opt_slab = 1;              // one-word records: 1 = K1 fused with partition level 0 into fixed-capacity slabs (kb_extract_part.cuh)
+    long long opt_hash_warp = 1;         // 1 = warp-private bucket hash kernel (kb_hash_warp.cuh) instead of the CTA-wide stream kernel
+    long long opt_slab_cap = 0;          // != 0: force the capacity of every slab (tests: overflow -> exact path)
+    bool slab_off = false;               // a slab overflowed on these sequences: searches use the exact path until they change
     bool lazy_now = false;               // the running search uses it
     int bb_extra = 0;                    // bucket bits added to the size-based plan: learnt when a search deferred too many buckets
                                          // (divergent genomes: far more distinct keys per record than the plan assumes); kept per layout
@@ -152,10 +159,11 @@ struct kb_ctx {
 };
 
 // layout of the `small` device buffer (u64 units)
-enum { SM_NOUT = 0, SM_NRES = 1, SM_STATS = 2 /*4*/, SM_NTAINT = 6, SM_ERR = 7, SM_TICKET = 8 /* u32 x 16 */, SM_HIST = 16 /* 9*256 */,
-       SM_ROOT = 16 + 9 * 256 /* u64 x 2: {0, n} */, SM_ROOTTILE = SM_ROOT + 2 /* u32 x 2: {0, tiles} */, SM_TOTAL = SM_ROOT + 4 };
+enum { SM_NOUT = 0, SM_NRES = 1, SM_STATS = 2 /*4*/, SM_NTAINT = 6, SM_ERR = 7, SM_OVF = 8 /* a slab overflowed */, SM_TICKET = 16 /* u32 x 16 */,
+       SM_HIST = 24 /* 9*256 */, SM_ROOT = SM_HIST + 9 * 256 /* u64 x 2: {0, n} */, SM_ROOTTILE = SM_ROOT + 2 /* u32 x 2: {0, tiles} */, SM_TOTAL = SM_ROOT + 4 };
 
 #define KB_REPLAN 1                      // internal: the search gave up on its plan (never leaves the library)
+#define KB_SLABOVF 2                     // internal: a slab overflowed; repeat on the exact path
 
 static int fail(kb_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -278,6 +286,9 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "pair_hist") ctx->opt_pair_hist = value ? 1 : 0;
     else if (n == "batch_level0") ctx->opt_batch_level0 = value ? 1 : 0;
     else if (n == "lazy_records") ctx->opt_lazy_records = value ? 1 : 0;
+    else if (n == "slab") { ctx->opt_slab = value ? 1 : 0; ctx->slab_off = false; }
+    else if (n == "hash_warp") ctx->opt_hash_warp = value ? 1 : 0;
+    else if (n == "slab_cap") { if (value < 0) return fail(ctx, KB_EINVAL, "slab_cap must be >= 0"); ctx->opt_slab_cap = value; ctx->slab_off = false; }
     else if (n == "render_rows") ctx->opt_render_rows = value ? 1 : 0;
     else if (n == "have_outgroup") ctx->opt_have_outgroup = value ? 1 : 0;
     else if (n == "shard_bits0") { if (value < 0 || value > 9) return fail(ctx, KB_EINVAL, "shard_bits0 must be in 0..9"); ctx->opt_shard_bits0 = value; }
@@ -318,7 +329,7 @@ int kb_configure(kb_ctx* ctx, int L, int D, int R, int soft_mode, int n_files, c
     lo.n_files = n_files;
     lo.PW = (n_files + 31) / 32;
     lo.MW = (D + 7) / 8;
-    if (!ctx->configured || ctx->lo.L != lo.L || ctx->lo.D != lo.D || ctx->lo.R != lo.R || ctx->lo.n_files != lo.n_files) ctx->bb_extra = 0;
+    if (!ctx->configured || ctx->lo.L != lo.L || ctx->lo.D != lo.D || ctx->lo.R != lo.R || ctx->lo.n_files != lo.n_files) { ctx->bb_extra = 0; ctx->slab_off = false; }
     ctx->lo = lo;
     ctx->soft_mode = soft_mode ? 1 : 0;
     memset(ctx->is_ingroup, 0, sizeof ctx->is_ingroup);
@@ -335,6 +346,7 @@ int kb_clear_sequences(kb_ctx* ctx) {
     ctx->file_event.clear();
     ctx->own_first = 0; ctx->own_count = -1;
     ctx->sep_filled = false;
+    ctx->slab_off = false;
     if (ctx->fa_flags.p) { cudaSetDevice(ctx->device); cudaMemsetAsync(ctx->fa_flags.p, 0, 8, ctx->stream); }
     return KB_OK;
 }
@@ -507,6 +519,32 @@ static int prepare_small(kb_ctx* ctx) {
     return KB_OK;
 }
 
+// Tile batches of K1: when the sequences are still arriving from the host (copy stream), K1 runs on the tiles whose bytes
+// (+ halo) are resident while the later files are in flight; otherwise one launch covers everything.  (end tile, event to wait for)
+static std::vector<std::pair<uint32_t, cudaEvent_t>> extract_batches(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles) {
+    std::vector<std::pair<uint32_t, cudaEvent_t>> batches;
+    const size_t nf = ctx->file_starts.size();
+    const uint32_t t_end = tile0 + n_tiles;
+    const uint64_t step = std::max<uint64_t>(ctx->n_bases / 10, 8ull << 20);
+    uint64_t next = step;
+    for (size_t f = 0; f < nf; f++) {
+        if (!ctx->file_event[f]) continue;
+        const uint64_t resident = f + 1 < nf ? ctx->file_starts[f + 1] : ctx->n_bases;   // bytes [0, resident) are there once event f fired
+        if (f + 1 < nf && resident < next) continue;
+        next = resident + step;
+        uint32_t t1 = f + 1 < nf ? (uint32_t)std::min<uint64_t>(t_end, resident > KB_K1_PAD ? (resident - KB_K1_MAXHALO - 64) / KB_K1_TB : 0) : t_end;
+        if (f + 1 == nf) { batches.push_back({t_end, ctx->file_event[f]}); break; }
+        if (t1 > tile0 && (batches.empty() || t1 > batches.back().first)) batches.push_back({t1, ctx->file_event[f]});
+    }
+    if (batches.empty() || batches.back().first < t_end) {
+        // device-resident sequences (or none pending): everything at once, after every pending copy
+        cudaEvent_t last = nullptr;
+        for (size_t f = 0; f < nf; f++) if (ctx->file_event[f]) last = ctx->file_event[f];
+        batches.push_back({t_end, last});
+    }
+    return batches;
+}
+
 // K1 over tiles [tile0, tile0+n_tiles), windows starting in [pos_lo, pos_hi); *n_out = records written
 static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint64_t* n_out,
                        unsigned long long* hist = nullptr, uint32_t hist_shift = 0, uint32_t hist_bits = 0, bool no_sync = false,
@@ -538,30 +576,7 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
     const bool wide_hist = hist && hist_bits > 9;            // 4-group CTAs with the packed shared-memory histogram (<= 16 bits)
     const size_t smem = wide_hist ? kb_extract_smem(lo.k, 4, (int)hist_bits) : kb_extract_smem(lo.k);
     prof_begin(ctx, "K1 extract");
-    // Tile batches: when the sequences are still arriving from the host (copy stream), K1 runs on the tiles whose
-    // bytes (+ halo) are resident while the later files are in flight; otherwise one launch covers everything.
-    std::vector<std::pair<uint32_t, cudaEvent_t>> batches;      // (end tile, event to wait for)
-    {
-        const size_t nf = ctx->file_starts.size();
-        const uint32_t t_end = tile0 + n_tiles;
-        const uint64_t step = std::max<uint64_t>(ctx->n_bases / 10, 8ull << 20);
-        uint64_t next = step;
-        for (size_t f = 0; f < nf; f++) {
-            if (!ctx->file_event[f]) continue;
-            const uint64_t resident = f + 1 < nf ? ctx->file_starts[f + 1] : ctx->n_bases;   // bytes [0, resident) are there once event f fired
-            if (f + 1 < nf && resident < next) continue;
-            next = resident + step;
-            uint32_t t1 = f + 1 < nf ? (uint32_t)std::min<uint64_t>(t_end, resident > KB_K1_PAD ? (resident - KB_K1_MAXHALO - 64) / KB_K1_TB : 0) : t_end;
-            if (f + 1 == nf) { batches.push_back({t_end, ctx->file_event[f]}); break; }
-            if (t1 > tile0 && (batches.empty() || t1 > batches.back().first)) batches.push_back({t1, ctx->file_event[f]});
-        }
-        if (batches.empty() || batches.back().first < t_end) {
-            // device-resident sequences (or none pending): everything at once, after every pending copy
-            cudaEvent_t last = nullptr;
-            for (size_t f = 0; f < nf; f++) if (ctx->file_event[f]) last = ctx->file_event[f];
-            batches.push_back({t_end, last});
-        }
-    }
+    std::vector<std::pair<uint32_t, cudaEvent_t>> batches = extract_batches(ctx, tile0, n_tiles);
     uint32_t t0 = tile0;
     const bool batched_l0 = bl && bl->enabled && wide_hist && batches.size() > 1 && batches.size() <= KB_MAX_BATCHES;
     if (batched_l0) CU(cudaFuncSetAttribute(kb_part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb_part_smem()));
@@ -715,7 +730,7 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0, bool
     pl.fast = hash_fast_ok(ctx);
     pl.stream = ctx->opt_hash_stream && ctx->opt_fast_group && lo.direct && lo.FB >= 1 && lo.MW <= 1;
     if (ctx->opt_hash_slots_log2) pl.slots_log2 = (uint32_t)ctx->opt_hash_slots_log2;
-    else if (pl.stream) pl.slots_log2 = 10;                     // 24 - 56 KB of table + 28 KB ring and queues: 4 - 2 CTAs per SM
+    else if (pl.stream) pl.slots_log2 = ctx->opt_hash_warp ? 9 : 10;   // warp-private tables (4 - 16 KB each) / CTA-wide: 24 - 56 KB of table + 28 KB ring and queues
     else if (pl.fast) pl.slots_log2 = 11;                       // 48 KB of table: 4 CTAs per SM
     else {
         const size_t sb = kb_hash_slot_bytes(lo);
@@ -912,6 +927,8 @@ struct HashStage {            // what run_group needs to run the bucket-hash ker
     const unsigned long long* brun = nullptr;   // lazy records: (start, length) per bucket instead of bstart
     uint32_t slots_log2 = 0;                     // != 0: table size of the exact pass (else the plan's)
     uint64_t n_kept = 0;                         // lazy records: elements the exact pass reads
+    const unsigned long long* bend = nullptr;   // slab layout: fill level (absolute end) of every bucket
+    uint64_t bcap = 0;                           // slab layout: bucket b starts at b * bcap
 };
 
 static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
@@ -923,18 +940,42 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
     x.full64 = (uint64_t)g.full[0] | ((uint64_t)g.full[1] << 32);
     x.err = (unsigned long long*)ctx->small.p + SM_ERR;
     x.brun = hs.brun;
+    x.bend = hs.bend; x.bcap = hs.bcap;
     const unsigned grid = (unsigned)std::min<uint32_t>(hs.n_buckets, 1u << 20);
+    const bool warp_kernel = hs.pl->stream && (ctx->opt_hash_warp || hs.bcap);     // (the CTA-wide stream kernel needs contiguous buckets)
     if (hs.pl->stream) {
         TRY(ensure(ctx, ctx->deferred, (size_t)hs.n_buckets * 4 + 64));
+        const int pwn = lo.n_files <= 64 ? 2 : (lo.n_files <= 128 ? 4 : 8);
+        const bool spacer = lo.D == 1 && lo.FB == 54 && x.bb <= 22;
+        if (warp_kernel) {
+            KbHWarpArgs xw{};
+            xw.h = x;
+            xw.deferred = (uint32_t*)ctx->deferred.p;
+            xw.n_deferred = (unsigned long long*)ctx->small.p + SM_NTAINT;   // zeroed with the result counters
+            const bool packed = lo.D == 1 && lo.FB <= 54;
+            xw.wbytes = kb_hash_warp_wbytes(x.slots_log2, pwn, packed);
+            const uint32_t nwarps = std::max<uint32_t>(1, std::min<uint32_t>(KB_HW_MAXWARPS, (uint32_t)((224 * 1024) / xw.wbytes)));
+            const size_t smem = (size_t)nwarps * xw.wbytes + 16;
+            if (smem > 227 * 1024) return fail(ctx, KB_EINVAL, "hash_slots_log2 too large for the warp-private bucket hash");
+            const unsigned wgrid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->n_sm, (hs.n_buckets + nwarps - 1) / nwarps));
+#define KB_LAUNCH_WARP(D1_, SP_, PW_)                                                                                          \
+            do {                                                                                                               \
+                CU(cudaFuncSetAttribute(kb_hash_warp_kernel<D1_, SP_, PW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                kb_hash_warp_kernel<D1_, SP_, PW_><<<wgrid, 32 * nwarps, smem, ctx->stream>>>(xw);                               \
+            } while (0)
+            if (pwn == 2) { if (spacer) KB_LAUNCH_WARP(true, true, 2); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 2); else KB_LAUNCH_WARP(false, false, 2); }
+            else if (pwn == 4) { if (spacer) KB_LAUNCH_WARP(true, true, 4); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 4); else KB_LAUNCH_WARP(false, false, 4); }
+            else { if (spacer) KB_LAUNCH_WARP(true, true, 8); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 8); else KB_LAUNCH_WARP(false, false, 8); }
+#undef KB_LAUNCH_WARP
+            CU(cudaGetLastError());
+        } else {
         KbHStreamArgs xs{};
         xs.h = x; xs.n_ptr = (const unsigned long long*)ctx->small.p + SM_NOUT;
         xs.deferred = (uint32_t*)ctx->deferred.p;
         xs.n_deferred = (unsigned long long*)ctx->small.p + SM_NTAINT;       // zeroed with the result counters
-        const int pwn = lo.n_files <= 64 ? 2 : (lo.n_files <= 128 ? 4 : 8);
         const size_t smem = kb_hash_stream_smem(x.slots_log2, pwn);
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (220 * 1024) / (smem + 1024)));
         const unsigned sgrid = (unsigned)std::min<uint64_t>((uint64_t)ctx->n_sm * per_sm, std::max<uint64_t>(1, g.n / 4096));
-        const bool spacer = lo.D == 1 && lo.FB == 54 && x.bb <= 22;
 #define KB_LAUNCH_STREAM(D1_, SP_, PW_)                                                                                        \
         do {                                                                                                                   \
             CU(cudaFuncSetAttribute(kb_hash_stream_kernel<D1_, SP_, PW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -945,9 +986,10 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
         else { if (spacer) KB_LAUNCH_STREAM(true, true, 8); else if (lo.D == 1) KB_LAUNCH_STREAM(true, false, 8); else KB_LAUNCH_STREAM(false, false, 8); }
 #undef KB_LAUNCH_STREAM
         CU(cudaGetLastError());
+        }
         // fallback for the deferred buckets: the splitting kernels with a roomier table
         KbHashArgs fb = x;
-        fb.list = xs.deferred; fb.n_list = xs.n_deferred;
+        fb.list = (const uint32_t*)ctx->deferred.p; fb.n_list = (const unsigned long long*)ctx->small.p + SM_NTAINT;
         fb.abort_above = (ctx->replan_ok && hs.pl->bb < std::min(lo.FB, 24)) ? std::max<uint32_t>(hs.n_buckets / 8, 64) : 0;
         if (hs.pl->fast) {
             fb.slots_log2 = ctx->opt_hash_slots_log2 ? x.slots_log2 : std::max<uint32_t>(x.slots_log2, 11);
@@ -1134,7 +1176,7 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
             prof_end(ctx);
             if (rc) { delete res; return rc; }
             // one read-back: [0] K1's record count, [1] survivors, [2..5] stats, [6] taint / deferred count, [7] error flag
-            e = cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NOUT, 8 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            e = cudaMemcpyAsync(ctx->h_pinned, (uint64_t*)ctx->small.p + SM_NOUT, 9 * 8, cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("group pass: ") + cudaGetErrorString(e)); }
             n_res = ctx->h_pinned[1];
@@ -1146,6 +1188,7 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
             }
             if (hs && hs->brun) ctx->alg_bytes += n * 8 + hs->n_kept * (uint64_t)(32 + 16 * lo.W + lo.k);   // K3a read, K3a/b/c on what is kept
             else ctx->alg_bytes += n * 8 * (lo.direct ? 1 : (1 + lo.W));
+            if (hs && hs->bcap && ctx->h_pinned[8]) { delete res; return KB_SLABOVF; }   // a slab overflowed (records were dropped): exact path
             if (hs && ctx->h_pinned[7] == 2) { delete res; return KB_REPLAN; }     // too many deferred buckets: the caller re-plans
             if (hs && ctx->h_pinned[7]) { delete res; return fail(ctx, KB_EINTERNAL, "bucket hash: a bucket could not be resolved (hash table split limit)"); }
             if (hs && !hs->brun && !lo.direct && n >= (1ULL << 32)) { delete res; return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 records per GPU in multi-word mode"); }
@@ -1304,6 +1347,174 @@ static int run_prefilter(kb_ctx* ctx, const PartPlan& pl, uint64_t* parted, uint
     return KB_OK;
 }
 
+// ---- slab search path (one-word records): K1 fused with partition level 0 (kb_extract_part.cuh), further levels and the bucket
+//      hash on fixed-capacity slabs.  No histogram, no exact offsets: a level's cursors ARE its bucket table. ------------------------
+struct SlabPlan {
+    int levels = 0, bits[3] = {0, 0, 0};
+    uint32_t nc[3] = {0, 0, 0};
+    uint64_t cap[3] = {0, 0, 0};
+    size_t off_cur[3] = {0, 0, 0}, off_counts = 0, off_start = 0, off_part = 0, off_tab0 = 0, off_tile0[3] = {0, 0, 0}, off_tilemap = 0, bytes = 0;
+    uint64_t max_tiles = 0;
+};
+
+// capacity of one of `nc` slabs that share n_est records: mean + 6 sigma (a key's occurrences move together) + a little
+static uint64_t slab_capacity(const kb_ctx* ctx, uint64_t n_est, uint64_t nc) {
+    if (ctx->opt_slab_cap) return ((uint64_t)ctx->opt_slab_cap + 1) & ~1ULL;
+    const double mu = (double)n_est / (double)nc;
+    const double m = 2.0 * std::max(ctx->lo.n_files, 4);
+    const double cap = mu + 6.0 * std::sqrt(m * mu) + 0.02 * mu + 256.0;
+    return ((uint64_t)cap + 1) & ~1ULL;                         // even: every slab starts 16-byte aligned (bulk copies of K3)
+}
+
+static SlabPlan make_slab_plan(const kb_ctx* ctx, const PartPlan& pl, uint64_t n_est) {
+    SlabPlan sp;
+    sp.levels = pl.levels;
+    uint32_t maxnc = 0;
+    size_t off = 0;
+    for (int l = 0; l < pl.levels; l++) {
+        sp.bits[l] = pl.bits[l];
+        sp.nc[l] = pl.nc[l];
+        sp.cap[l] = slab_capacity(ctx, n_est, pl.nc[l]);
+        maxnc = std::max(maxnc, sp.nc[l]);
+        sp.off_cur[l] = off; off += (size_t)sp.nc[l] * 8;
+    }
+    sp.off_counts = off; off += (size_t)maxnc * 8;
+    sp.off_start = off; off += ((size_t)maxnc + 1) * 8;
+    sp.off_part = off; off += ((size_t)maxnc / KB_PLAN_BLOCK + 2) * 16;
+    sp.off_tab0 = off; off += (size_t)2 * KB_XP_MAXR * 8;       // level-0 slab ends | destination element addresses
+    for (int l = 0; l < pl.levels; l++) { sp.off_tile0[l] = off; off += (((size_t)sp.nc[l] + 2) * 4 + 7) & ~(size_t)7; }
+    sp.max_tiles = n_est / KB_PT_TILE + maxnc + 2;
+    sp.off_tilemap = off; off += ((size_t)sp.max_tiles * 4 + 7) & ~(size_t)7;
+    sp.bytes = off;
+    return sp;
+}
+
+static bool slab_ok(const kb_ctx* ctx, const PartPlan& pl) {
+    const KbLayout& lo = ctx->lo;
+    return ctx->opt_slab && !ctx->slab_off && ctx->opt_group_algo && lo.direct && pl.stream && pl.levels >= 1 && pl.bits[0] >= 1 && ctx->own_count < 0;
+}
+
+// K1 + level 0 over tiles [tile0, tile0 + n_tiles): cursor / limit / destination tables as in KbXPartArgs (device pointers)
+static int run_extract_part(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint32_t bits,
+                            unsigned long long* cursor, const unsigned long long* limit, const unsigned long long* out_elems) {
+    const KbLayout& lo = ctx->lo;
+    const size_t plen = padded_len(ctx->n_bases);
+    TRY(ensure(ctx, ctx->bases, plen, true));
+    CU(cudaMemsetAsync((uint8_t*)ctx->bases.p + ctx->n_bases, '\n', plen - ctx->n_bases, ctx->stream));
+    TRY(upload_file_table(ctx));
+    KbXPartArgs a{};
+    a.bases = (const uint8_t*)ctx->bases.p; a.n_bases = ctx->n_bases;
+    a.file_starts = (const uint64_t*)ctx->d_file_starts.p; a.file_gid = (const uint32_t*)ctx->d_file_gid.p;
+    a.n_local_files = (int)ctx->file_gid.size();
+    a.soft_omit = ctx->soft_mode;
+    a.lo = lo;
+    a.pos_lo = pos_lo; a.pos_hi = pos_hi;
+    a.bits = bits;
+    a.cursor = cursor; a.limit = limit; a.out_elems = out_elems;
+    a.n_out = (unsigned long long*)ctx->small.p + SM_NOUT;
+    a.ovf = (unsigned long long*)ctx->small.p + SM_OVF;
+    const bool spacer = lo.L == 25 && lo.D == 1 && lo.R == 2 && lo.mix;
+    const size_t smem = kb_xpart_smem();
+    if (spacer) CU(cudaFuncSetAttribute(kb_extract_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CU(cudaFuncSetAttribute(kb_extract_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(ctx, "K1 extract + partition 0");
+    uint32_t t0 = tile0;
+    for (auto& bt : extract_batches(ctx, tile0, n_tiles)) {
+        if (bt.second) CU(cudaStreamWaitEvent(ctx->stream, bt.second, 0));
+        const uint32_t nt = bt.first > t0 ? bt.first - t0 : 0;
+        if (!nt) continue;
+        a.tile0 = t0; a.n_tiles = nt;
+        if (spacer) kb_extract_part_kernel<true><<<nt, KB_XP_THREADS, smem, ctx->stream>>>(a);
+        else kb_extract_part_kernel<false><<<nt, KB_XP_THREADS, smem, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        t0 = bt.first;
+    }
+    prof_end(ctx);
+    ctx->alg_bytes += std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo;
+    ctx->alg_rec_bytes += 8;
+    return KB_OK;
+}
+
+// partition levels [l_begin, levels) on slabs; level l reads buf[(l - 1) & 1] and writes buf[l & 1]
+static int run_slab_levels(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl, int l_begin, uint64_t* bufs[2], uint64_t n_est) {
+    uint8_t* P = (uint8_t*)ctx->plan.p;
+    static const char* pnames[3] = {"K2 partition 0", "K2 partition 1", "K2 partition 2"};
+    static const char* hnames[3] = {"K2 plan 0", "K2 plan 1", "K2 plan 2"};
+    const size_t smem = kb_part_smem();
+    CU(cudaFuncSetAttribute(kb_part_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int shift = 64;
+    for (int l = 0; l < l_begin; l++) shift -= sp.bits[l];
+    for (int l = l_begin; l < sp.levels; l++) {
+        shift -= sp.bits[l];
+        KbPartArgs a{};
+        a.in = bufs[(l - 1) & 1]; a.out = bufs[l & 1];
+        a.pend = (const unsigned long long*)(P + sp.off_cur[l - 1]); a.pcap = sp.cap[l - 1];
+        a.ptile0 = (const uint32_t*)(P + sp.off_tile0[l - 1]);
+        a.tile_parent = (const uint32_t*)(P + sp.off_tilemap);
+        a.n_parents = sp.nc[l - 1];
+        a.shift = (uint32_t)shift; a.bits = (uint32_t)sp.bits[l];
+        a.cursor = (unsigned long long*)(P + sp.off_cur[l]);
+        a.ccap = sp.cap[l];
+        a.ovf = (unsigned long long*)ctx->small.p + SM_OVF;
+        prof_begin(ctx, hnames[l]);
+        unsigned long long* counts = (unsigned long long*)(P + sp.off_counts);
+        kb_slab_counts_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 255) / 256, 1024), 256, 0, ctx->stream>>>(a.pend, a.n_parents, a.pcap, counts);
+        CU(cudaGetLastError());
+        KbPlanArgs pa{};
+        pa.counts = counts; pa.nc = a.n_parents; pa.start = (unsigned long long*)(P + sp.off_start); pa.cursor = nullptr;
+        pa.tile0 = (uint32_t*)(P + sp.off_tile0[l - 1]); pa.part = (unsigned long long*)(P + sp.off_part);
+        TRY(launch_plan(ctx, pa, pl));
+        kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, a.n_parents, (uint32_t*)(P + sp.off_tilemap));
+        CU(cudaGetLastError());
+        ctx->launches += 2;
+        prof_end(ctx);
+        prof_begin(ctx, pnames[l]);
+        const uint64_t grid = n_est / KB_PT_TILE + a.n_parents + 1;
+        kb_part_kernel<2, false, true><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        prof_end(ctx);
+        ctx->alg_rec_bytes += 16;
+    }
+    return KB_OK;
+}
+
+static int search_slab(kb_ctx* ctx, const PartPlan& pl, kb_result** out) {
+    const uint64_t n_est = 2 * ctx->n_bases + 64;
+    const SlabPlan sp = make_slab_plan(ctx, pl, n_est);
+    size_t need[2] = {0, 0};
+    for (int l = 0; l < sp.levels; l++) need[l & 1] = std::max(need[l & 1], (size_t)sp.nc[l] * sp.cap[l] + 4096);
+    TRY(ensure(ctx, ctx->entA, need[0] * 8));
+    if (need[1]) TRY(ensure(ctx, ctx->entB, need[1] * 8));
+    TRY(ensure(ctx, ctx->plan, sp.bytes + 64));
+    uint8_t* P = (uint8_t*)ctx->plan.p;
+    uint64_t* bufs[2] = {(uint64_t*)ctx->entA.p, (uint64_t*)ctx->entB.p};
+    for (int l = 0; l < sp.levels; l++) {
+        kb_slab_init_kernel<<<(unsigned)std::min<uint32_t>((sp.nc[l] + 255) / 256, 1024), 256, 0, ctx->stream>>>((unsigned long long*)(P + sp.off_cur[l]), sp.nc[l], sp.cap[l]);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    // level-0 tables: slab ends, destination (this GPU's buffer for every digit)
+    std::vector<uint64_t>& t0 = ctx->scatter_host;
+    t0.assign((size_t)2 * KB_XP_MAXR, 0);
+    for (uint32_t d = 0; d < sp.nc[0]; d++) { t0[d] = (uint64_t)(d + 1) * sp.cap[0]; t0[KB_XP_MAXR + d] = (uint64_t)(reinterpret_cast<uintptr_t>(bufs[0]) >> 3); }
+    CU(cudaMemcpyAsync(P + sp.off_tab0, t0.data(), t0.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t n_tiles = (uint32_t)((ctx->n_bases + KB_K1_TB - 1) / KB_K1_TB);
+    TRY(run_extract_part(ctx, 0, n_tiles, 0, ctx->n_bases, (uint32_t)sp.bits[0], (unsigned long long*)(P + sp.off_cur[0]),
+                         (const unsigned long long*)(P + sp.off_tab0), (const unsigned long long*)(P + sp.off_tab0) + KB_XP_MAXR));
+    TRY(run_slab_levels(ctx, sp, pl, 1, bufs, n_est));
+    ctx->passes = sp.levels;
+    HashStage hs{};
+    hs.pl = &pl;
+    hs.n_buckets = sp.nc[sp.levels - 1];
+    hs.bend = (const unsigned long long*)(P + sp.off_cur[sp.levels - 1]);
+    hs.bcap = sp.cap[sp.levels - 1];
+    int rc = run_group(ctx, bufs[(sp.levels - 1) & 1], n_est, out, &hs);
+    prof_collect(ctx);
+    return rc;
+}
+
 static void begin_search(kb_ctx* ctx) {
     ctx->lazy_now = false;
     ctx->launches = 0; ctx->alg_bytes = 0; ctx->alg_rec_bytes = 0; ctx->passes = 0;
@@ -1328,6 +1539,7 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
         ctx->replan_ok = attempt < 3 && ctx->opt_bucket_bits < 0 && ctx->opt_group_algo && ctx->lo.direct;
         const int rc = search_once(ctx, out);
         ctx->replan_ok = false;
+        if (rc == KB_SLABOVF) { ctx->slab_off = true; attempt--; continue; }     // a slab overflowed: the exact path from now on
         if (rc != KB_REPLAN) return rc;
         ctx->bb_extra += 2;
     }
@@ -1344,6 +1556,7 @@ static int search_once(kb_ctx* ctx, kb_result** out) {
     ctx->lazy_now = ctx->opt_group_algo && ctx->opt_lazy_records && !lo.direct && padded_len(ctx->n_bases) < (1ULL << 32);
     if (ctx->opt_group_algo) {
         const PartPlan pl = make_plan(ctx, 2 * ctx->n_bases + 64);
+        if (slab_ok(ctx, pl)) return search_slab(ctx, pl, out);
         TRY(ensure(ctx, ctx->plan, pl.bytes + 64));
         if (pl.levels) CU(cudaMemsetAsync(ctx->plan.p, 0, pl.bytes, ctx->stream));
         // K1 counts the children of the first level — or of the first TWO levels at once (packed shared-memory histogram), which
@@ -1727,8 +1940,8 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_count
     if (run != n_records) return fail(ctx, KB_EINVAL, "piece counts do not add up to the number of received records");
     TRY(ensure(ctx, ctx->shard_tab, hp.size() * 8));
     CU(cudaMemcpyAsync(ctx->shard_tab.p, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->h_pinned[8] = n_records;                            // the "record counter" the stream kernel and the root table read
-    CU(cudaMemcpyAsync((uint64_t*)ctx->small.p + SM_NOUT, ctx->h_pinned + 8, 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_pinned[10] = n_records;                           // the "record counter" the stream kernel and the root table read
+    CU(cudaMemcpyAsync((uint64_t*)ctx->small.p + SM_NOUT, ctx->h_pinned + 10, 8, cudaMemcpyHostToDevice, ctx->stream));
     // local child counts: dps rows at level 0, then the usual fan-out
     { uint32_t c = dps; pl.ncl[0] = c; for (int l = 1; l < pl.levels; l++) { c <<= pl.bits[l]; pl.ncl[l] = c; } }
     const size_t tilemap_extra = (size_t)(trun + np + 2) * 4;

@@ -38,7 +38,17 @@ struct KbHashArgs {
     uint32_t abort_above;                // list mode: more deferred buckets than this = the plan was too coarse for this input: set *err = 2
                                          // and leave (the host re-plans with more bucket bits instead of splitting every bucket here)
     const unsigned long long* brun;      // != null (generic kernel): bucket b = elements [brun[2b], brun[2b] + brun[2b+1]) (kb_prefilter.cuh)
+    const unsigned long long* bend;      // != null: bucket b ends at bend[b] instead of bstart[b + 1]
+    uint64_t bcap;                       // != 0 (slab layout, kb_extract_part.cuh): bucket b = [b * bcap, min(bend[b], (b + 1) * bcap)), bstart unused
 };
+
+// element range of bucket b in every layout
+__device__ __forceinline__ void kb_bucket_range(const KbHashArgs& x, uint32_t b, uint64_t& bs, uint64_t& be) {
+    if (x.brun) { bs = x.brun[2 * (size_t)b]; be = bs + x.brun[2 * (size_t)b + 1]; }
+    else if (x.bcap) { bs = (uint64_t)b * x.bcap; be = min((uint64_t)x.bend[b], bs + x.bcap); }
+    else { bs = x.bstart[b]; be = x.bend ? x.bend[b] : x.bstart[b + 1]; }
+    if (be < bs) be = bs;
+}
 
 // The 32 key (or flank-hash) bits right below the bucket bits, left-aligned.  Mixed keys (kb_mix) and flank
 // hashes are uniform there, so these bits index the table directly: the first `nb` bits select the part of a
@@ -110,7 +120,8 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_fast_kernel(const KbHas
     const uint32_t n_work = x.list ? (uint32_t)min((unsigned long long)x.n_buckets, *x.n_list) : x.n_buckets;
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const uint32_t b = x.list ? x.list[wi] : wi;
-        const uint64_t bs = x.bstart[b], be = x.bstart[b + 1];
+        uint64_t bs, be;
+        kb_bucket_range(x, b, bs, be);
         if (be == bs) continue;
         __syncthreads();
         if (tid == 0) { ctl.sp = 1; ctl.stack[0] = 0; }
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_fast_kernel(const KbHas
                 uint64_t r[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) r[u] = (u * KB_KH_THREADS + tid < left) ? kb_ld_stream(a.ent + i0 + u * KB_KH_THREADS + tid) : 0ULL;
-                if (kb_ld_shared_volatile(&ctl.over)) break;
+                if (__any_sync(0xFFFFFFFFu, kb_ld_shared_volatile(&ctl.over))) break;      // (warp-uniform exit: the loop body has __syncwarp)
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const uint64_t e = r[u];
@@ -307,7 +318,8 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_kernel(const KbHashArgs
     const uint32_t n_work = x.list ? (uint32_t)min((unsigned long long)x.n_buckets, *x.n_list) : x.n_buckets;
     for (uint32_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const uint32_t b = x.list ? x.list[wi] : wi;
-        const uint64_t bs = x.brun ? x.brun[2 * (size_t)b] : x.bstart[b], be = x.brun ? bs + x.brun[2 * (size_t)b + 1] : x.bstart[b + 1];
+        uint64_t bs, be;
+        kb_bucket_range(x, b, bs, be);
         if (be == bs) continue;
         __syncthreads();
         if (tid == 0) { ctl.sp = 1; ctl.stack[0] = 0; }
@@ -341,7 +353,7 @@ __global__ void __launch_bounds__(KB_KH_THREADS) kb_hash_kernel(const KbHashArgs
 #pragma unroll
                 for (int j = 0; j < WN; j++) rec[j] = rec_n[j];
                 load(i0 + KB_KH_THREADS + tid, e_n, hh_n, act_n, rec_n);
-                if (kb_ld_shared_volatile(&ctl.over)) break;
+                if (__any_sync(0xFFFFFFFFu, kb_ld_shared_volatile(&ctl.over))) break;      // (warp-uniform exit: the loop body has __syncwarp)
                 KbKey<WN> key;
                 kb_key_of<WN>(lo, rec, key);
                 uint32_t slot = KB_KH_NONE;

@@ -45,13 +45,28 @@ struct KbPartArgs {
     const unsigned long long* out_elems; // != null: child c is written to the buffer at element address out_elems[c] (= pointer / 8)
                                         // instead of `out` — multi-GPU: the owner's receive buffer, a peer mapping over NVLink; the
                                         // cursor of c then counts from the first element of this rank's piece in that buffer
+    // Slab layout (kb_extract_part.cuh): buckets are fixed-capacity regions filled through their cursors, not exact ranges.
+    const unsigned long long* pend;     // != null: parent p = elements [p * pcap, min(pend[p], (p + 1) * pcap)) of `in` (pstart unused)
+    uint64_t pcap;
+    uint64_t ccap;                      // != 0: child c owns [c * ccap, (c + 1) * ccap) of `out` (its cursor starts at c * ccap); a run that
+    unsigned long long* ovf;            // does not fit is dropped and *ovf is raised (the host repeats the search on the exact path)
 };
+
+// element range of parent p
+__device__ __forceinline__ void kb_part_parent(const KbPartArgs& a, uint32_t parent, uint64_t& ps, uint64_t& pe) {
+    if (a.pend) {
+        ps = (uint64_t)parent * a.pcap;
+        pe = min((uint64_t)a.pend[parent], ps + a.pcap);
+        if (pe < ps) pe = ps;
+    } else { ps = a.pstart[parent]; pe = a.pstart[parent + 1]; }
+}
 
 // tile -> its range [s, s + n_tile) and the cursor row of its parent
 __device__ __forceinline__ bool kb_part_tile(const KbPartArgs& a, uint32_t tile, uint32_t& row, uint64_t& s, uint32_t& n_tile) {
     if (tile >= __ldg(a.ptile0 + a.n_parents)) return false;
     const uint32_t parent = a.n_parents == 1 ? 0u : __ldg(a.tile_parent + tile);
-    const uint64_t ps = a.pstart[parent], pe = a.pstart[parent + 1];
+    uint64_t ps, pe;
+    kb_part_parent(a, parent, ps, pe);
     s = ps + (uint64_t)(tile - __ldg(a.ptile0 + parent)) * KB_PT_TILE;
     n_tile = (uint32_t)min((uint64_t)KB_PT_TILE, pe - s);
     row = a.prow ? __ldg(a.prow + parent) : parent;
@@ -222,7 +237,8 @@ __global__ void __launch_bounds__(256) kb_tilemap_kernel(const uint32_t* tile0, 
 }
 
 // ---- one partition level -------------------------------------------------------------------------------
-template <int MINB, bool PAIR = false>
+#define KB_PT_DROP 0xFFFFFFFFFFFFFFFFULL
+template <int MINB, bool PAIR = false, bool SLAB = false>
 __global__ void __launch_bounds__(KB_PT_THREADS, MINB) kb_part_kernel(const KbPartArgs a) {
     extern __shared__ __align__(16) unsigned char kb_smem_raw[];
     uint64_t* skeys = reinterpret_cast<uint64_t*>(kb_smem_raw);                   // TILE
@@ -261,11 +277,13 @@ __global__ void __launch_bounds__(KB_PT_THREADS, MINB) kb_part_kernel(const KbPa
     // ---- per digit: claim the output range (global cursor), local start -----------------------------
     uint32_t c = 0, lstart = 0;
     unsigned long long g = 0;
+    bool drop = false;
     if (tid < KB_PT_MAXR) {
         c = cnt[tid];
         if (c) {
             if (PAIR && (tid & 1u)) g = atomicAdd(a.cursor + (((size_t)parent << a.bits) | tid), 0ULL - (unsigned long long)c) - (unsigned long long)c;   // claim downwards
             else g = atomicAdd(a.cursor + (((size_t)parent << a.bits) | tid), (unsigned long long)c);
+            if (SLAB && g + c > ((((unsigned long long)parent << a.bits) | tid) + 1ULL) * a.ccap) { drop = true; *a.ovf = 1ULL; }
         }
     }
     {
@@ -293,7 +311,7 @@ __global__ void __launch_bounds__(KB_PT_THREADS, MINB) kb_part_kernel(const KbPa
         // element address (pointer / 8) of the digit's run minus its position in the staged tile
         const unsigned long long base = a.out_elems ? (c ? a.out_elems[((size_t)parent << a.bits) | tid] : 0ULL)
                                                     : (unsigned long long)(reinterpret_cast<uintptr_t>(a.out) >> 3);
-        dbase[tid] = base + g - (unsigned long long)lstart;
+        dbase[tid] = (SLAB && drop) ? KB_PT_DROP : base + g - (unsigned long long)lstart;
     }
     __syncthreads();
 
@@ -303,7 +321,8 @@ __global__ void __launch_bounds__(KB_PT_THREADS, MINB) kb_part_kernel(const KbPa
         const uint32_t pos = i * KB_PT_THREADS + tid;
         if (n_tile == KB_PT_TILE || pos < n_tile) {
             const uint64_t kv = skeys[pos];
-            *reinterpret_cast<uint64_t*>((dbase[(uint32_t)(kv >> a.shift) & dmask] + pos) << 3) = kv;
+            const unsigned long long db = dbase[(uint32_t)(kv >> a.shift) & dmask];
+            if (!SLAB || db != KB_PT_DROP) *reinterpret_cast<uint64_t*>((db + pos) << 3) = kv;
         }
     }
 }
@@ -321,6 +340,19 @@ __global__ void __launch_bounds__(256) kb_pair_expand_kernel(const unsigned long
 // after the pass the even child's cursor stands at the boundary between the two siblings
 __global__ void __launch_bounds__(256) kb_pair_fix_kernel(const unsigned long long* cursor, uint32_t n_pairs, unsigned long long* start) {
     for (uint32_t p = blockIdx.x * 256 + threadIdx.x; p < n_pairs; p += gridDim.x * 256) start[2 * (size_t)p + 1] = cursor[2 * (size_t)p];
+}
+
+// ---- slab layout helpers ----------------------------------------------------------------------------------------------
+// cursors of nc slabs of `cap` elements: cursor[c] = c * cap
+__global__ void __launch_bounds__(256) kb_slab_init_kernel(unsigned long long* cursor, uint32_t nc, uint64_t cap) {
+    for (uint32_t c = blockIdx.x * 256 + threadIdx.x; c < nc; c += gridDim.x * 256) cursor[c] = (unsigned long long)c * cap;
+}
+// fill levels after a pass: counts[c] = min(cursor[c], (c + 1) * cap) - c * cap (input of kb_plan_*: tile prefix of the next level)
+__global__ void __launch_bounds__(256) kb_slab_counts_kernel(const unsigned long long* cursor, uint32_t nc, uint64_t cap, unsigned long long* counts) {
+    for (uint32_t c = blockIdx.x * 256 + threadIdx.x; c < nc; c += gridDim.x * 256) {
+        const unsigned long long s = (unsigned long long)c * cap, e = min(cursor[c], s + cap);
+        counts[c] = e > s ? e - s : 0ULL;
+    }
 }
 
 static inline size_t kb_part_smem() { return (size_t)KB_PT_TILE * 8 + KB_PT_MAXR * 8 + KB_PT_MAXR * 4 + (KB_PT_MAXR / 32) * 4 + 16; }

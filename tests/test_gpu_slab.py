@@ -1,0 +1,144 @@
+"""GPU parity of the slab search path (K1 fused with partition level 0, kb_extract_part.cuh; warp-private bucket hash,
+kb_hash_warp.cuh) against the C oracle, the golden vectors and the exact (histogram-based) path."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from tests.helpers import deduce_ldr, golden_paths, load_golden
+from tests.test_gpu_parity import _oracle_panel, _search_panel
+
+pytestmark = pytest.mark.gpu
+_G = load_golden()
+
+_RESET = {"slab": 1, "hash_warp": 1, "bucket_bits": -1, "hash_slots_log2": 0, "slab_cap": 0, "want_records": 0, "profile": 0}
+
+
+@pytest.fixture(scope="module")
+def searcher():
+    from krisp_b200.search import Searcher
+    s = Searcher()
+    yield s
+    s.close()
+
+
+def _reset(searcher):
+    for k, v in _RESET.items():
+        searcher.set_option(k, v)
+
+
+def _stages(res):
+    return [nm for nm, _ in res.profile]
+
+
+@pytest.mark.parametrize("mode", [(1, 1), (0, 1), (0, 0)], ids=["slab+warp", "exact+warp", "exact+stream"])
+@pytest.mark.parametrize("shape", [(6, 6, 300_000, 25, 1, 2, False), (6, 6, 300_000, 25, 1, 2, True), (3, 3, 400_000, 12, 3, 12, False),
+                                   (20, 20, 100_000, 25, 1, 2, False), (40, 40, 40_000, 10, 4, 10, False), (50, 50, 40_000, 25, 1, 2, False),
+                                   (70, 70, 20_000, 10, 4, 10, False), (2, 1, 40_000, 20, 0, 7, False), (3, 2, 300_000, 9, 8, 9, False)],
+                         ids=["spacer", "spacer_omit", "12_3_12", "bench_shape_small", "80_files", "100_files_spacer", "140_files", "D0", "D8"])
+def test_slab_and_exact_paths_match_oracle(shape, mode, searcher):
+    """Same rows, group sizes and gathered records whichever way the records were grouped."""
+    from krisp_b200.panel import make_panel
+    n_in, n_out, glen, L, D, R, omit = shape
+    kw = dict(n_runs=1, run_len=30, noise=2e-4 if n_in + n_out <= 80 else 1e-4, dup_len=300, soft_block=100) if n_in + n_out > 64 else {}
+    gs = make_panel(n_in, n_out, glen, **kw)
+    try:
+        res = _search_panel(searcher, gs, L, D, R, omit, options={"slab": mode[0], "hash_warp": mode[1], "profile": 1}, want_records=True)
+    finally:
+        _reset(searcher)
+    want = _oracle_panel(gs, L, D, R, omit)
+    assert len(want) > 0
+    assert res.rows() == want
+    assert ("K1 extract + partition 0" in _stages(res)) == bool(mode[0])
+    # every group's gathered records carry its flank key, and there are group_size of them
+    FB = 2 * (L + R)
+    for g in range(res.n_groups):
+        a, b = int(res.run_offset[g]), int(res.run_offset[g + 1])
+        recs = res.records[a:b, 0]
+        fw = res.flank_words[g, 0]
+        mine = recs[(recs >> np.uint64(64 - FB)) == (fw >> np.uint64(64 - FB))] if FB else recs
+        assert int(res.group_size[g]) == mine.size >= n_in + n_out
+
+
+@pytest.mark.parametrize("bucket_bits,slots", [(1, 0), (3, 5), (9, 0), (10, 6), (13, 4), (17, 0), (18, 7), (20, 0)])
+@pytest.mark.parametrize("name", ["c1_spacer_25_1_2", "p_spacer_3x3", "p_5_2_3", "p_6_1_2", "c1_single_file", "p_spacer_4x5"])
+def test_slab_path_on_golden_cases_for_any_depth(name, bucket_bits, slots, searcher):
+    """One to three slab levels and tiny hash tables (deferred buckets, splits) on the reference's golden cases."""
+    from krisp_b200.search import search_files
+    case = next(c for c in _G["cases"] if c["name"] == name)
+    ins, outs = golden_paths(case)
+    L, D, R = deduce_ldr(case["flags"])
+    try:
+        res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher,
+                           options={"bucket_bits": bucket_bits, "hash_slots_log2": slots, "profile": 1})
+    finally:
+        _reset(searcher)
+    rows = res.rows()
+    assert "K1 extract + partition 0" in _stages(res)
+    assert len(rows) == case["n_rows"]
+    assert hashlib.sha256("\n".join(rows).encode()).hexdigest() == case["rows_sha256"]
+
+
+def test_slab_overflow_falls_back_to_the_exact_path(searcher):
+    """Slabs of 2 records overflow at once: the search must notice, repeat itself on the exact path, stay there for these
+    sequences, and try slabs again once the sequences change."""
+    from krisp_b200.panel import make_panel
+    gs = make_panel(4, 4, 200_000)
+    want = _oracle_panel(gs, 25, 1, 2)
+    try:
+        res = _search_panel(searcher, gs, 25, 1, 2, options={"slab_cap": 2, "profile": 1})
+        assert res.rows() == want
+        assert "K1 extract" in _stages(res) and "K1 extract + partition 0" not in _stages(res)
+        res2 = searcher.search(have_outgroup=True)
+        assert res2.rows() == want and "K1 extract + partition 0" not in _stages(res2)
+        searcher.set_option("slab_cap", 0)
+        res3 = _search_panel(searcher, gs, 25, 1, 2, options={"profile": 1})
+        assert res3.rows() == want and "K1 extract + partition 0" in _stages(res3)
+    finally:
+        _reset(searcher)
+
+
+def test_repeats_overflow_one_slab_and_still_give_the_oracle_rows(searcher):
+    """A genome family full of one repeated unit: thousands of records share a few keys, far beyond a slab's slack."""
+    from krisp_b200.panel import Genome
+    rng = np.random.default_rng(7)
+    unit = rng.integers(0, 4, size=40, dtype=np.uint8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    gs = []
+    for i in range(6):
+        body = rng.integers(0, 4, size=150_000, dtype=np.uint8)
+        body[20_000:20_000 + 40 * 1500] = np.tile(unit, 1500)
+        if i < 3:
+            body[100::1000] = (body[100::1000] + 1) & 3
+        gs.append(Genome(name=f"g{i}", is_ingroup=i < 3, records=[acgt[body]]))
+    try:
+        res = _search_panel(searcher, gs, 25, 1, 2, options={"profile": 1})
+    finally:
+        _reset(searcher)
+    assert res.rows() == _oracle_panel(gs, 25, 1, 2)
+
+
+def test_host_buffers_in_batches_take_the_slab_path(searcher):
+    """Pinned host buffers: K1 + level 0 run per batch of arrived files and append to the same slabs."""
+    import torch
+    from krisp_b200.panel import make_panel
+    gs = make_panel(10, 10, 1_000_000)
+    want = _oracle_panel(gs, 25, 1, 2)
+    pinned = []
+    for g in gs:
+        t = torch.empty(len(g.joined()), dtype=torch.uint8, pin_memory=True)
+        t.numpy()[:] = np.frombuffer(g.joined(), dtype=np.uint8)
+        pinned.append(t)
+    try:
+        searcher.configure(25, 1, 2, [1 if g.is_ingroup else 0 for g in gs])
+        searcher.set_option("profile", 1)
+        for _ in range(2):
+            searcher.clear_sequences()
+            searcher.reserve(sum(t.numel() + 1 for t in pinned))
+            for i, t in enumerate(pinned):
+                searcher.add_sequence(i, t.numpy())
+            res = searcher.search(have_outgroup=True)
+            assert "K1 extract + partition 0" in _stages(res)
+            assert res.rows() == want
+    finally:
+        _reset(searcher)

@@ -1,0 +1,26 @@
+#!/bin/bash
+# first GPU run of round 2: parity of the slab path + bench variants
+set -x
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_slab.py -x -q -m gpu > gpurun_out/r04a_slab_tests.log 2>&1; echo "slab tests rc=$?" 
+tail -5 gpurun_out/r04a_slab_tests.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r04a_all_tests.log 2>&1; echo "all tests rc=$?"
+tail -5 gpurun_out/r04a_all_tests.log
+B="timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline"
+$B > gpurun_out/r04a_bench_default.json 2> gpurun_out/r04a_bench_default.err; echo "rc=$?"
+$B --option slab 0 --option hash_warp 0 > gpurun_out/r04a_bench_old.json 2> gpurun_out/r04a_bench_old.err; echo "rc=$?"
+$B --option slab 0 > gpurun_out/r04a_bench_exact_warp.json 2> gpurun_out/r04a_bench_exact_warp.err; echo "rc=$?"
+$B --option bucket_bits 16 > gpurun_out/r04a_bench_bb16.json 2> gpurun_out/r04a_bench_bb16.err; echo "rc=$?"
+$B --option bucket_bits 16 --option hash_slots_log2 10 > gpurun_out/r04a_bench_bb16_s10.json 2> gpurun_out/r04a_bench_bb16_s10.err; echo "rc=$?"
+$B --option bucket_bits 17 --option hash_slots_log2 8 > gpurun_out/r04a_bench_bb17_s8.json 2> gpurun_out/r04a_bench_bb17_s8.err; echo "rc=$?"
+$B --option bucket_bits 18 --option hash_slots_log2 8 > gpurun_out/r04a_bench_bb18_s8.json 2> gpurun_out/r04a_bench_bb18_s8.err; echo "rc=$?"
+for f in gpurun_out/r04a_bench_*.json; do python - "$f" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], "ms", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["ms_per_step"],3), {k:round(v,3) for k,v in d["stage_ms"].items()}, d["config"]["rows"], d["config"]["k3_stats"])
+except Exception as e:
+    print(sys.argv[1], "FAILED", e)
+PY
+done
