@@ -953,15 +953,15 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
             xw.deferred = (uint32_t*)ctx->deferred.p;
             xw.n_deferred = (unsigned long long*)ctx->small.p + SM_NTAINT;   // zeroed with the result counters
             const bool packed = lo.D == 1 && lo.FB <= 54;
-            xw.wbytes = kb_hash_warp_wbytes(x.slots_log2, pwn, packed);
-            const uint32_t nwarps = std::max<uint32_t>(1, std::min<uint32_t>(KB_HW_MAXWARPS, (uint32_t)((224 * 1024) / xw.wbytes)));
-            const size_t smem = (size_t)nwarps * xw.wbytes + 16;
-            if (smem > 227 * 1024) return fail(ctx, KB_EINVAL, "hash_slots_log2 too large for the warp-private bucket hash");
-            const unsigned wgrid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->n_sm, (hs.n_buckets + nwarps - 1) / nwarps));
+            while (xw.h.slots_log2 > 4 && (size_t)KB_HW_WARPS * kb_hash_warp_wbytes(xw.h.slots_log2, pwn, packed) + 16 > 224 * 1024) xw.h.slots_log2--;
+            xw.wbytes = kb_hash_warp_wbytes(xw.h.slots_log2, pwn, packed);
+            const size_t smem = (size_t)KB_HW_WARPS * xw.wbytes + 16;
+            const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(3, (224 * 1024) / (smem + 1024)));
+            const unsigned wgrid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->n_sm * per_sm, (hs.n_buckets + KB_HW_WARPS - 1) / KB_HW_WARPS));
 #define KB_LAUNCH_WARP(D1_, SP_, PW_)                                                                                          \
             do {                                                                                                               \
                 CU(cudaFuncSetAttribute(kb_hash_warp_kernel<D1_, SP_, PW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                kb_hash_warp_kernel<D1_, SP_, PW_><<<wgrid, 32 * nwarps, smem, ctx->stream>>>(xw);                               \
+                kb_hash_warp_kernel<D1_, SP_, PW_><<<wgrid, 32 * KB_HW_WARPS, smem, ctx->stream>>>(xw);                          \
             } while (0)
             if (pwn == 2) { if (spacer) KB_LAUNCH_WARP(true, true, 2); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 2); else KB_LAUNCH_WARP(false, false, 2); }
             else if (pwn == 4) { if (spacer) KB_LAUNCH_WARP(true, true, 4); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 4); else KB_LAUNCH_WARP(false, false, 4); }
@@ -1358,12 +1358,15 @@ struct SlabPlan {
 };
 
 // capacity of one of `nc` slabs that share n_est records: mean + 6 sigma (a key's occurrences move together) + a little
-static uint64_t slab_capacity(const kb_ctx* ctx, uint64_t n_est, uint64_t nc) {
+static uint64_t slab_capacity(const kb_ctx* ctx, uint64_t n_est, uint64_t nc, bool is_parent) {
     if (ctx->opt_slab_cap) return ((uint64_t)ctx->opt_slab_cap + 1) & ~1ULL;
     const double mu = (double)n_est / (double)nc;
     const double m = 2.0 * std::max(ctx->lo.n_files, 4);
-    const double cap = mu + 6.0 * std::sqrt(m * mu) + 0.02 * mu + 256.0;
-    return ((uint64_t)cap + 1) & ~1ULL;                         // even: every slab starts 16-byte aligned (bulk copies of K3)
+    const uint64_t cap = (uint64_t)(mu + 6.0 * std::sqrt(m * mu) + 0.02 * mu + 64.0);
+    // a level whose slabs are the parents of another level: a multiple of the partition tile, so that tiles map to parents by
+    // division (no tile map, no dependent loads at CTA start) — where that costs at most a few percent of memory
+    if (is_parent && cap >= 16 * (uint64_t)KB_PT_TILE) return (cap + KB_PT_TILE - 1) / KB_PT_TILE * KB_PT_TILE;
+    return (cap + 1) & ~1ULL;                                   // even: every slab starts 16-byte aligned
 }
 
 static SlabPlan make_slab_plan(const kb_ctx* ctx, const PartPlan& pl, uint64_t n_est) {
@@ -1374,7 +1377,7 @@ static SlabPlan make_slab_plan(const kb_ctx* ctx, const PartPlan& pl, uint64_t n
     for (int l = 0; l < pl.levels; l++) {
         sp.bits[l] = pl.bits[l];
         sp.nc[l] = pl.nc[l];
-        sp.cap[l] = slab_capacity(ctx, n_est, pl.nc[l]);
+        sp.cap[l] = slab_capacity(ctx, n_est, pl.nc[l], l + 1 < pl.levels);
         maxnc = std::max(maxnc, sp.nc[l]);
         sp.off_cur[l] = off; off += (size_t)sp.nc[l] * 8;
     }
@@ -1457,20 +1460,25 @@ static int run_slab_levels(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl, 
         a.cursor = (unsigned long long*)(P + sp.off_cur[l]);
         a.ccap = sp.cap[l];
         a.ovf = (unsigned long long*)ctx->small.p + SM_OVF;
-        prof_begin(ctx, hnames[l]);
-        unsigned long long* counts = (unsigned long long*)(P + sp.off_counts);
-        kb_slab_counts_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 255) / 256, 1024), 256, 0, ctx->stream>>>(a.pend, a.n_parents, a.pcap, counts);
-        CU(cudaGetLastError());
-        KbPlanArgs pa{};
-        pa.counts = counts; pa.nc = a.n_parents; pa.start = (unsigned long long*)(P + sp.off_start); pa.cursor = nullptr;
-        pa.tile0 = (uint32_t*)(P + sp.off_tile0[l - 1]); pa.part = (unsigned long long*)(P + sp.off_part);
-        TRY(launch_plan(ctx, pa, pl));
-        kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, a.n_parents, (uint32_t*)(P + sp.off_tilemap));
-        CU(cudaGetLastError());
-        ctx->launches += 2;
-        prof_end(ctx);
+        const bool by_division = sp.cap[l - 1] % KB_PT_TILE == 0;
+        uint64_t grid = (uint64_t)a.n_parents * (sp.cap[l - 1] / KB_PT_TILE);
+        if (by_division) { a.ptile0 = nullptr; a.tile_parent = nullptr; }
+        else {
+            prof_begin(ctx, hnames[l]);
+            unsigned long long* counts = (unsigned long long*)(P + sp.off_counts);
+            kb_slab_counts_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 255) / 256, 1024), 256, 0, ctx->stream>>>(a.pend, a.n_parents, a.pcap, counts);
+            CU(cudaGetLastError());
+            KbPlanArgs pa{};
+            pa.counts = counts; pa.nc = a.n_parents; pa.start = (unsigned long long*)(P + sp.off_start); pa.cursor = nullptr;
+            pa.tile0 = (uint32_t*)(P + sp.off_tile0[l - 1]); pa.part = (unsigned long long*)(P + sp.off_part);
+            TRY(launch_plan(ctx, pa, pl));
+            kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, a.n_parents, (uint32_t*)(P + sp.off_tilemap));
+            CU(cudaGetLastError());
+            ctx->launches += 2;
+            prof_end(ctx);
+            grid = n_est / KB_PT_TILE + a.n_parents + 1;
+        }
         prof_begin(ctx, pnames[l]);
-        const uint64_t grid = n_est / KB_PT_TILE + a.n_parents + 1;
         kb_part_kernel<2, false, true><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
         CU(cudaGetLastError());
         ctx->launches++;

@@ -49,21 +49,18 @@ struct KbExtractArgs {
 };
 
 // 4 ASCII bytes (little-endian in x) -> 8 bits of 2-bit codes (first base in the top bits) and 4 "bad" bits
-// (bit i = byte i).  A/C/G/T -> 0..3 via ((u>>1)^(u>>2))&3 on the upper-cased byte.
+// (bit i = byte i).  A/C/G/T -> 0..3 via ((u>>1)^(u>>2))&3 on the upper-cased byte; a byte is good iff the letter that
+// its code stands for ("ACGT"[code], one PRMT for all four bytes) is the byte itself.
 __device__ __forceinline__ uint32_t kb_pack4(uint32_t x, int soft_omit, uint32_t& bad4) {
     const uint32_t u = x & 0xDFDFDFDFu;
     const uint32_t c = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
     const uint32_t packed = (c * 0x40100401u) >> 24;     // b0<<6 | b1<<4 | b2<<2 | b3 (no carries)
-    uint32_t bad = 0;
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        const uint32_t ch = (x >> (8 * b)) & 0xFFu;
-        const uint32_t idx = (ch & 0xDFu) - 0x41u;        // 'A' -> 0, 'C' -> 2, 'G' -> 6, 'T' -> 19
-        bool ok = (idx < 20u) && ((0x80045u >> idx) & 1u);
-        if (soft_omit) ok = ok && !(ch & 0x20u);
-        bad |= (ok ? 0u : 1u) << b;
-    }
-    bad4 = bad;
+    const uint32_t t = (c | (c >> 4)) & 0x00FF00FFu;
+    const uint32_t sel = (t | (t >> 8)) & 0xFFFFu;       // one selector nibble per byte = its code
+    const uint32_t d = __byte_perm(0x54474341u, 0u, sel) ^ u;                    // zero byte <=> A, C, G or T (either case)
+    uint32_t m = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;          // bit 7 of every non-zero byte
+    if (soft_omit) m |= (x & 0x20202020u) << 2;                                  // --omit-soft: lower case is bad too
+    bad4 = (m * 0x00204081u) >> 28;                                              // bits 7, 15, 23, 31 -> 0..3
     return packed;
 }
 

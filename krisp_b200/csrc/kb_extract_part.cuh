@@ -17,7 +17,7 @@
 // Per tile of 4096 window starts (512 threads x 8 CONSECUTIVE windows — output order does not matter here, so the
 // windows of a thread slide over one 128-bit register pair instead of being re-read from shared memory):
 //   1. 16 bases per thread -> 2-bit forward stream + bad-base bitmap in shared memory;
-//   2. window validity bitmap (OR of the bad bitmap shifted 0..k-1);
+//   2. every thread derives the validity of its 8 windows from 64 bits of the bad bitmap (no bad base in [p, p + k));
 //   3. per window: forward record from the register pair, reverse-complement record from the pair's reverse
 //      complement (computed once per thread), digit rank by shared-memory atomicAdd;
 //   4. digit scan, slab claim, staging in digit order, coalesced stores.
@@ -51,7 +51,7 @@ struct KbXPartArgs {
 };
 
 static inline size_t kb_xpart_smem() {
-    return (size_t)2 * KB_XP_TB * 8 + KB_XP_MAXR * 8 + 144 * 8 + KB_XP_MAXR * 4 + 16 * 4 + 136 * 4 + 128 * 4 + 16;
+    return (size_t)2 * KB_XP_TB * 8 + KB_XP_MAXR * 8 + 144 * 8 + KB_XP_MAXR * 4 + 16 * 4 + 136 * 4 + 16;
 }
 
 // SPACER: the layout is 25/1/2-like with mixing (FB = 54, D = 1, R = 2, k = 28): every shift is a compile-time constant.
@@ -64,7 +64,6 @@ __global__ void __launch_bounds__(KB_XP_THREADS, 2) kb_extract_part_kernel(const
     uint32_t* cnt = reinterpret_cast<uint32_t*>(fwd + 144);                      // MAXR digit counters, then local starts
     uint32_t* wsum = cnt + KB_XP_MAXR;                                           // 16
     uint32_t* bad = wsum + 16;                                                   // NWORD + 2 (<= 131)
-    uint32_t* okw = bad + 136;                                                   // 128
     __shared__ int s_flo, s_fhi;
     __shared__ uint32_t s_total;
 
@@ -107,24 +106,19 @@ __global__ void __launch_bounds__(KB_XP_THREADS, 2) kb_extract_part_kernel(const
     }
     __syncthreads();
 
-    // ---- 2. window validity: no bad base in [p, p + k) -----------------------------------------------------------------
-    if (tid < KB_XP_TB / 32) {
-        uint32_t acc = 0, w = tid, lo_w = bad[w], hi_w = bad[w + 1];
-        for (uint32_t d = 0; d < k; d++) {
-            const uint32_t o = d & 31;
-            if (o == 0 && d) { w++; lo_w = hi_w; hi_w = bad[w + 1 <= NWORD + 1 ? w + 1 : NWORD + 1]; }
-            acc |= __funnelshift_r(lo_w, hi_w, o);
-        }
-        uint32_t ok = ~acc;
-        const uint64_t g = tile_base + 32ull * tid;
-        if (g < a.pos_lo) ok &= (a.pos_lo - g >= 32) ? 0u : (0xFFFFFFFFu << (uint32_t)(a.pos_lo - g));
-        if (g + 32 > a.pos_hi) ok &= (g >= a.pos_hi) ? 0u : (0xFFFFFFFFu >> (uint32_t)(g + 32 - a.pos_hi));
-        okw[tid] = ok;
+    // ---- 2. validity of this thread's 8 windows: no bad base in [p, p + k) ------------------------------------------------
+    uint32_t ok8 = 0;
+    {
+        const uint64_t B = ((((uint64_t)bad[(tid >> 2) + 1]) << 32) | bad[tid >> 2]) >> (8u * (tid & 3u));   // bit i = base 8 tid + i is bad
+        const uint32_t mk = 0xFFFFFFFFu >> (32 - k);                             // (k <= 28 on this path)
+#pragma unroll
+        for (int j = 0; j < KB_XP_WPT; j++) ok8 |= (((uint32_t)(B >> j) & mk) == 0u ? 1u : 0u) << j;
+        const uint64_t g = tile_base + (uint64_t)tid * KB_XP_WPT;                // restrict to [pos_lo, pos_hi)
+        if (g < a.pos_lo) ok8 &= (a.pos_lo - g >= 8) ? 0u : (0xFFu << (uint32_t)(a.pos_lo - g));
+        if (g + 8 > a.pos_hi) ok8 &= (g >= a.pos_hi) ? 0u : (0xFFu >> (uint32_t)(g + 8 - a.pos_hi));
     }
-    __syncthreads();
 
     // ---- 3. records of this thread's 8 windows + digit ranks -----------------------------------------------------------
-    const uint32_t ok8 = (okw[tid >> 2] >> (8u * (tid & 3u))) & 0xFFu;
     const uint32_t dshift = 64u - a.bits;
     uint64_t rec[2 * KB_XP_WPT];
     uint32_t rk[KB_XP_WPT];                                                      // ranks of (forward, reverse) as 16-bit halves
@@ -132,7 +126,16 @@ __global__ void __launch_bounds__(KB_XP_THREADS, 2) kb_extract_part_kernel(const
     for (int j = 0; j < KB_XP_WPT; j++) { rec[2 * j] = 0; rec[2 * j + 1] = 0; rk[j] = 0; }
     if (ok8) {
         const int flo = s_flo, fhi = s_fhi;
-        uint32_t gid = __ldg(a.file_gid + flo);
+        uint64_t gids = 0x0101010101010101ULL * (uint64_t)__ldg(a.file_gid + flo);   // file id of every window (one byte each)
+        if (flo != fhi) {                                                        // tile spans several files (rare)
+#pragma unroll 1
+            for (int j = 0; j < KB_XP_WPT; j++) {
+                const uint64_t gp = tile_base + (uint64_t)tid * KB_XP_WPT + j;
+                int l0 = flo, h0 = fhi + 1;
+                while (h0 - l0 > 1) { const int m = (l0 + h0) >> 1; if (__ldg(a.file_starts + m) <= gp) l0 = m; else h0 = m; }
+                gids = (gids & ~(0xFFULL << (8 * j))) | ((uint64_t)__ldg(a.file_gid + l0) << (8 * j));
+            }
+        }
         const uint32_t K2 = 2 * k;
         const uint32_t D2 = SPACER ? 2u : 2u * (uint32_t)lo.D, R2 = SPACER ? 4u : 2u * (uint32_t)lo.R, FB = SPACER ? 54u : (uint32_t)lo.FB;
         const uint64_t mD = kb_lowmask((int)D2), mR = kb_lowmask((int)R2), mK = kb_lowmask((int)K2);
@@ -146,12 +149,7 @@ __global__ void __launch_bounds__(KB_XP_THREADS, 2) kb_extract_part_kernel(const
 #pragma unroll
         for (int j = 0; j < KB_XP_WPT; j++) {
             if (!((ok8 >> j) & 1u)) continue;
-            if (flo != fhi) {                                                    // tile spans several files (rare)
-                const uint64_t gp = tile_base + (uint64_t)tid * KB_XP_WPT + j;
-                int l0 = flo, h0 = fhi + 1;
-                while (h0 - l0 > 1) { const int m = (l0 + h0) >> 1; if (__ldg(a.file_starts + m) <= gp) l0 = m; else h0 = m; }
-                gid = __ldg(a.file_gid + l0);
-            }
+            const uint32_t gid = (uint32_t)(gids >> (8 * j)) & 0xFFu;
             const uint64_t top = j ? ((x << (2 * j)) | (y >> (64 - 2 * j))) : x;  // window j left-aligned
             const uint64_t win = top >> (64 - K2);
             const uint64_t rcw = (j ? ((ry >> (2 * j)) | (rx << (64 - 2 * j))) : ry) & mK;

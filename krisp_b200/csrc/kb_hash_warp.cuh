@@ -3,11 +3,14 @@
 // Same contract and per-bucket algorithm as kb_hash_stream_kernel (kb_hash_stream.cuh; reference stages: simplifyStream /
 // alignmentStream shared.py:210-240,:442-475, intersectSortedStreams :321-347 folded by mergeFiles
 // intersectAmplicons.py:232-310, filterAlignments.py:4-28 + ingroupUniqueColumns Amplicon.py:495-521), but every WARP owns
-// its buckets, its hash table, its miss queue and its own ring of bulk-copy stages:
+// its buckets, its hash table and its miss queue:
 //   * no CTA barrier anywhere: a bucket end (scan + emit + clear) stalls one warp, not 256 threads;
-//   * a stage is 256 records and never straddles two buckets, so the hot loop has no boundary logic: eight records per
-//     lane are loaded, their eight home slots are loaded, then hit / miss is resolved (misses go to the warp's queue and
-//     are inserted 32 at a time, as before);
+//   * every warp streams its buckets through its own small ring (KB_HW_STAGES chunks of 128 records, filled with 16-byte
+//     cp.async copies that run two chunks ahead, across bucket boundaries): no mbarrier, no producer, and the shared
+//     memory of a warp stays small enough for 24 warps per SM;
+//   * a chunk never straddles two buckets, so the hot loop has no boundary logic: four records per lane, their four home
+//     slots are loaded together, hit / miss is resolved for all four, misses go to the warp's queue and are inserted 32 at a
+//     time, as before;
 //   * table in structure-of-arrays form (keys 8 B apart, presence words apart from them): key loads spread over all banks;
 //   * buckets may be exact ranges (bstart[b], bstart[b + 1]) or slabs (b * bcap, filled up to bend[b]) — kb_extract_part.cuh.
 // Buckets whose distinct keys overflow the table or that hold more than KB_HW_MAX_INLINE survivors are deferred to
@@ -15,12 +18,12 @@
 #pragma once
 #include "kb_hash_stream.cuh"
 
-#define KB_HW_CH 256                          // records per stage (2 KB)
-#define KB_HW_PER (KB_HW_CH / 32)
-#define KB_HW_STAGES 4
-#define KB_HW_QCAP 64
+#define KB_HW_PER 4                           // records per lane and chunk
+#define KB_HW_CH (32 * KB_HW_PER)             // 128 records per chunk
+#define KB_HW_STAGES 3
+#define KB_HW_QCAP (32 + KB_HW_CH)            // the queue is drained to < 32 entries after every chunk
 #define KB_HW_MAX_INLINE 8
-#define KB_HW_MAXWARPS 16
+#define KB_HW_WARPS 8                         // warps per CTA (independent of each other)
 
 struct KbHWarpArgs {
     KbHashArgs h;                        // g.ent = partitioned elements; buckets via h.bstart / h.bend / h.bcap
@@ -29,23 +32,22 @@ struct KbHWarpArgs {
     uint32_t wbytes;                     // shared memory per warp (kb_hash_warp_wbytes)
 };
 
-// bytes of one warp's region: ring | queue | keys | presence words | column sets (only when they do not fit the key word) | mbarriers
+// bytes of one warp's region: ring | queue | keys | presence words | column sets (only when they do not fit the key word)
 static inline uint32_t kb_hash_warp_wbytes(uint32_t slots_log2, int pwn, bool packed) {
     const uint32_t S = 1u << slots_log2;
-    const uint32_t b = 8u * (KB_HW_STAGES * KB_HW_CH + KB_HW_QCAP + S) + 4u * S * (uint32_t)pwn + (packed ? 0u : 8u * S) + 8u * KB_HW_STAGES;
+    const uint32_t b = 8u * (KB_HW_STAGES * KB_HW_CH + KB_HW_QCAP + S) + 4u * S * (uint32_t)pwn + (packed ? 0u : 8u * S);
     return (b + 15u) & ~15u;
 }
 
 template <bool D1, bool SPACER, int PWN>
-__global__ void __launch_bounds__(32 * KB_HW_MAXWARPS, 1) kb_hash_warp_kernel(const KbHWarpArgs xs) {
+__global__ void __launch_bounds__(32 * KB_HW_WARPS, 3) kb_hash_warp_kernel(const KbHWarpArgs xs) {
     extern __shared__ __align__(16) unsigned char kb_smem_raw[];
     const KbHashArgs& x = xs.h;
     const KbGroupArgs& a = x.g;
     const KbLayout& lo = a.lo;
     const uint32_t S = 1u << x.slots_log2, smask = S - 1u;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nw = blockDim.x >> 5;
-    const uint32_t wg = blockIdx.x * nw + warp, TW = gridDim.x * nw;
+    const uint32_t wg = blockIdx.x * KB_HW_WARPS + warp, TW = gridDim.x * KB_HW_WARPS;
     const bool packed = SPACER || (D1 && lo.FB <= 54);       // both 4-bit base sets inside the key word (bits 56-63)
 
     uint32_t smem_a = kb_smem_u32(kb_smem_raw) + warp * xs.wbytes;
@@ -55,12 +57,7 @@ __global__ void __launch_bounds__(32 * KB_HW_MAXWARPS, 1) kb_hash_warp_kernel(co
     const uint32_t keys_a = q_a + KB_HW_QCAP * 8;
     const uint32_t pres_a = keys_a + S * 8;
     const uint32_t msk_a = pres_a + S * 4 * PWN;              // [S][2] (unpacked sets only)
-    const uint32_t bars_a = msk_a + (packed ? 0u : S * 8);
 
-    if (lane == 0) {
-        for (int s = 0; s < KB_HW_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bars_a + 8 * s), "r"(1) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     for (uint32_t i = lane; i < S; i += 32) {
         kb_sts64(keys_a + i * 8, KB_KH_EMPTY);
 #pragma unroll
@@ -86,6 +83,15 @@ __global__ void __launch_bounds__(32 * KB_HW_MAXWARPS, 1) kb_hash_warp_kernel(co
         if (x.bcap) { s = (uint64_t)b * x.bcap; e = min((uint64_t)x.bend[b], s + x.bcap); }
         else { s = x.bstart[b]; e = x.bend ? x.bend[b] : x.bstart[b + 1]; }
         if (e < s) e = s;
+    };
+    // first non-empty bucket of this warp at or after `from` (stride TW); nb >= n_buckets: none
+    auto next_bucket = [&](uint32_t from, uint32_t& nb, uint64_t& s, uint64_t& e) {
+        nb = from; s = 0; e = 0;
+        while (nb < x.n_buckets) {
+            bucket_range(nb, s, e);
+            if (e > s) break;
+            nb += TW;
+        }
     };
     auto slot_of = [&](uint64_t e) -> uint32_t { return (kb_kh_bits(e, x.bb, hmask) * 0x9E3779B1u) >> sshift; };
 
@@ -134,76 +140,86 @@ __global__ void __launch_bounds__(32 * KB_HW_MAXWARPS, 1) kb_hash_warp_kernel(co
         if (__any_sync(0xFFFFFFFFu, st == 2u) || nkeys > limit) over = true;
     };
 
-    // ---- producer: the chunk sequence of this warp's buckets (wg, wg + TW, ...), bulk copies issued by lane 0 ----------------
+    // ---- producer side: the chunk sequence of this warp's buckets (wg, wg + TW, ...), 16-byte cp.async pieces, one commit
+    //      group per consumer iteration (empty once the buckets are exhausted, so that the group arithmetic stays put) --------
     const uint64_t* ent = a.ent;
-    uint32_t pb = wg, pk = 0, pnch = 0, pq = 0;
+    uint32_t pb, pk = 0, pnch = 0, pq = 0;
     uint64_t ps_al = 0, pn_al = 0;
-    auto prod_enter = [&]() {            // geometry of bucket pb
-        uint64_t s, e;
-        bucket_range(pb, s, e);
-        ps_al = s & ~1ULL;               // 16-byte aligned stream start
-        pn_al = e > s ? e - ps_al : 0ULL;
-        pnch = (uint32_t)((pn_al + KB_HW_CH - 1) / KB_HW_CH);
-        pk = 0;
-    };
-    if (pb < x.n_buckets) prod_enter();
-    auto issue = [&]() {
-        while (pb < x.n_buckets && pk >= pnch) { pb += TW; if (pb < x.n_buckets) prod_enter(); }
-        if (pb >= x.n_buckets) return;
-        const uint32_t cnt = (uint32_t)min((uint64_t)KB_HW_CH, pn_al - (uint64_t)pk * KB_HW_CH);
-        const uint32_t bytes = ((cnt + 1u) & ~1u) * 8u;
-        const uint32_t st = pq % KB_HW_STAGES;
-        if (lane == 0) {
-            kb_mbar_expect_tx(bars_a + 8 * st, bytes);
-            kb_bulk_g2s(ring_a + st * (KB_HW_CH * 8), ent + ps_al + (uint64_t)pk * KB_HW_CH, bytes, bars_a + 8 * st);
+    auto prod_enter = [&](uint32_t from) {      // first non-empty bucket at or after `from`
+        pb = from; pk = 0; pnch = 0;
+        while (pb < x.n_buckets) {
+            uint64_t s, e;
+            bucket_range(pb, s, e);
+            if (e > s) { ps_al = s & ~1ULL; pn_al = e - ps_al; pnch = (uint32_t)((pn_al + KB_HW_CH - 1) / KB_HW_CH); break; }
+            pb += TW;
         }
-        pk++; pq++;
+    };
+    prod_enter(wg);
+    auto issue = [&]() {
+        if (pb < x.n_buckets) {
+            const uint32_t here = (uint32_t)min((uint64_t)KB_HW_CH, pn_al - (uint64_t)pk * KB_HW_CH);
+            const uint64_t* src = ent + ps_al + (uint64_t)pk * KB_HW_CH;
+            const uint32_t dst = ring_a + (pq % KB_HW_STAGES) * (KB_HW_CH * 8);
+#pragma unroll
+            for (int h = 0; h < KB_HW_CH / 64; h++) {
+                const uint32_t piece = h * 32 + lane;                            // records 2 piece, 2 piece + 1
+                if (2 * piece < here)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + piece * 16), "l"(src + 2 * piece) : "memory");
+            }
+            pq++;
+            if (++pk >= pnch) prod_enter(pb + TW);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 #pragma unroll 1
-    for (int s = 0; s < KB_HW_STAGES; s++) issue();
+    for (int s = 0; s < KB_HW_STAGES - 1; s++) issue();
 
+    uint32_t b;
+    uint64_t bs, be;
+    next_bucket(wg, b, bs, be);
     uint32_t cq = 0;
     uint32_t n_closed_t = 0, n_present_t = 0, n_rounds = 0, n_defer = 0;
-    for (uint32_t b = wg; b < x.n_buckets; b += TW) {
-        uint64_t bs, be;
-        bucket_range(b, bs, be);
-        if (be <= bs) continue;
+    while (b < x.n_buckets) {
         const uint64_t s_al = bs & ~1ULL;
         const uint32_t skip = (uint32_t)(bs - s_al);
         const uint64_t n_al = be - s_al;
         const uint32_t nch = (uint32_t)((n_al + KB_HW_CH - 1) / KB_HW_CH);
         over = false; nkeys = 0; qn = 0;
         for (uint32_t ck = 0; ck < nch; ck++) {
-            const uint32_t st = cq % KB_HW_STAGES;
-            kb_mbar_wait(bars_a + 8 * st, (cq / KB_HW_STAGES) & 1u);
-            const uint32_t stage_a = ring_a + st * (KB_HW_CH * 8);
+            issue();                                                             // chunk cq + STAGES - 1 (into the stage freed last iteration)
+            asm volatile("cp.async.wait_group %0;" :: "n"(KB_HW_STAGES - 1) : "memory");
+            __syncwarp();
+            const uint32_t stage_a = ring_a + (cq % KB_HW_STAGES) * (KB_HW_CH * 8);
             const uint32_t cnt = (uint32_t)min((uint64_t)KB_HW_CH, n_al - (uint64_t)ck * KB_HW_CH);
             const uint32_t first = ck == 0 ? skip : 0u;
             if (!over) {
                 uint64_t e[KB_HW_PER], k[KB_HW_PER];
-                uint32_t sl[KB_HW_PER];
+                uint32_t sl[KB_HW_PER], m[KB_HW_PER];
+                bool hit[KB_HW_PER];
 #pragma unroll
                 for (int j = 0; j < KB_HW_PER; j++) e[j] = kb_lds64(stage_a + (j * 32 + lane) * 8);
 #pragma unroll
                 for (int j = 0; j < KB_HW_PER; j++) { sl[j] = slot_of(e[j]); k[j] = kb_lds64(keys_a + sl[j] * 8); }
-                const bool whole = first == 0 && cnt == KB_HW_CH;
 #pragma unroll
                 for (int j = 0; j < KB_HW_PER; j++) {
-                    const uint32_t idx = j * 32 + lane;
-                    const bool act = whole || (idx >= first && idx < cnt);
-                    const bool hit = act && (packed ? (k[j] & KB_HS_KEYMASK) : k[j]) == (e[j] >> kshift);
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, act && !hit);
-                    if (m) {
-                        if (act && !hit) kb_sts64(q_a + (qn + __popc(m & lt_mask)) * 8, e[j]);
-                        qn += __popc(m);
-                    }
-                    if (hit) accumulate(sl[j], e[j], (uint32_t)(k[j] >> 32));
-                    if (qn >= 32) { __syncwarp(); drain(); }
+                    const uint32_t idx = (uint32_t)(j * 32) + lane;
+                    const bool act = idx >= first && idx < cnt;
+                    hit[j] = act && (packed ? (k[j] & KB_HS_KEYMASK) : k[j]) == (e[j] >> kshift);
+                    m[j] = __ballot_sync(0xFFFFFFFFu, act && !hit[j]);
                 }
+#pragma unroll
+                for (int j = 0; j < KB_HW_PER; j++) {
+                    if (m[j]) {
+                        if ((m[j] >> lane) & 1u) kb_sts64(q_a + (qn + __popc(m[j] & lt_mask)) * 8, e[j]);
+                        qn += __popc(m[j]);
+                    }
+                    if (hit[j]) accumulate(sl[j], e[j], (uint32_t)(k[j] >> 32));
+                }
+                __syncwarp();
+                while (qn >= 32 && !over) drain();
             }
-            __syncwarp();                // every lane is done with the stage: refill it with the chunk STAGES ahead
+            __syncwarp();                                                        // every lane is done with this stage
             cq++;
-            issue();
         }
         // ---- bucket b is complete: flush the queue, evaluate, emit, clear ---------------------------------------------------
         __syncwarp();
@@ -264,7 +280,9 @@ __global__ void __launch_bounds__(32 * KB_HW_MAXWARPS, 1) kb_hash_warp_kernel(co
             if (lane == 0) { const unsigned long long d = atomicAdd(xs.n_deferred, 1ULL); xs.deferred[d] = b; }
         }
         __syncwarp();
+        next_bucket(b + TW, b, bs, be);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     n_closed_t = __reduce_add_sync(0xFFFFFFFFu, n_closed_t);
     n_present_t = __reduce_add_sync(0xFFFFFFFFu, n_present_t);

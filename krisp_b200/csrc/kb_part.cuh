@@ -63,6 +63,19 @@ __device__ __forceinline__ void kb_part_parent(const KbPartArgs& a, uint32_t par
 
 // tile -> its range [s, s + n_tile) and the cursor row of its parent
 __device__ __forceinline__ bool kb_part_tile(const KbPartArgs& a, uint32_t tile, uint32_t& row, uint64_t& s, uint32_t& n_tile) {
+    if (a.pend && !a.ptile0) {
+        // slab parents whose capacity is a multiple of the tile: tile -> parent by division, no tile map (tiles past the fill level leave)
+        const uint32_t tpp = (uint32_t)(a.pcap / KB_PT_TILE);
+        const uint32_t parent = tile / tpp;
+        if (parent >= a.n_parents) return false;
+        uint64_t ps, pe;
+        kb_part_parent(a, parent, ps, pe);
+        s = ps + (uint64_t)(tile - parent * tpp) * KB_PT_TILE;
+        if (s >= pe) return false;
+        n_tile = (uint32_t)min((uint64_t)KB_PT_TILE, pe - s);
+        row = a.prow ? __ldg(a.prow + parent) : parent;
+        return true;
+    }
     if (tile >= __ldg(a.ptile0 + a.n_parents)) return false;
     const uint32_t parent = a.n_parents == 1 ? 0u : __ldg(a.tile_parent + tile);
     uint64_t ps, pe;
