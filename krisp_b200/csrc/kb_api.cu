@@ -730,7 +730,7 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0, bool
     pl.fast = hash_fast_ok(ctx);
     pl.stream = ctx->opt_hash_stream && ctx->opt_fast_group && lo.direct && lo.FB >= 1 && lo.MW <= 1;
     if (ctx->opt_hash_slots_log2) pl.slots_log2 = (uint32_t)ctx->opt_hash_slots_log2;
-    else if (pl.stream) pl.slots_log2 = ctx->opt_hash_warp ? 9 : 10;   // warp-private tables (4 - 16 KB each) / CTA-wide: 24 - 56 KB of table + 28 KB ring and queues
+    else if (pl.stream) pl.slots_log2 = ctx->opt_hash_warp ? 8 : 10;   // warp-private tables (4 KB each: 24 warps per SM) / CTA-wide: 24 - 56 KB of table + 28 KB ring and queues
     else if (pl.fast) pl.slots_log2 = 11;                       // 48 KB of table: 4 CTAs per SM
     else {
         const size_t sb = kb_hash_slot_bytes(lo);
@@ -1353,7 +1353,7 @@ struct SlabPlan {
     int levels = 0, bits[3] = {0, 0, 0};
     uint32_t nc[3] = {0, 0, 0};
     uint64_t cap[3] = {0, 0, 0};
-    size_t off_cur[3] = {0, 0, 0}, off_counts = 0, off_start = 0, off_part = 0, off_tab0 = 0, off_tile0[3] = {0, 0, 0}, off_tilemap = 0, bytes = 0;
+    size_t off_cur[3] = {0, 0, 0}, off_counts = 0, off_start = 0, off_part = 0, off_tab0 = 0, off_tile0[3] = {0, 0, 0}, off_tilemap = 0, off_snap = 0, bytes = 0;
     uint64_t max_tiles = 0;
 };
 
@@ -1388,6 +1388,7 @@ static SlabPlan make_slab_plan(const kb_ctx* ctx, const PartPlan& pl, uint64_t n
     for (int l = 0; l < pl.levels; l++) { sp.off_tile0[l] = off; off += (((size_t)sp.nc[l] + 2) * 4 + 7) & ~(size_t)7; }
     sp.max_tiles = n_est / KB_PT_TILE + maxnc + 2;
     sp.off_tilemap = off; off += ((size_t)sp.max_tiles * 4 + 7) & ~(size_t)7;
+    sp.off_snap = off; off += (size_t)(KB_MAX_BATCHES + 2) * sp.nc[0] * 8;      // level-0 cursors after every batch of input files
     sp.bytes = off;
     return sp;
 }
@@ -1397,14 +1398,13 @@ static bool slab_ok(const kb_ctx* ctx, const PartPlan& pl) {
     return ctx->opt_slab && !ctx->slab_off && ctx->opt_group_algo && lo.direct && pl.stream && pl.levels >= 1 && pl.bits[0] >= 1 && ctx->own_count < 0;
 }
 
-// K1 + level 0 over tiles [tile0, tile0 + n_tiles): cursor / limit / destination tables as in KbXPartArgs (device pointers)
+// K1 + level 0 over tiles [tile0, tile0 + n_tiles): cursor / limit / destination tables as in KbXPartArgs (device pointers).
+// after_batch(i, n_batches, tiles of the batch) runs after the launch of every batch of arrived files (host buffers in flight).
+template <class F>
 static int run_extract_part(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint32_t bits,
-                            unsigned long long* cursor, const unsigned long long* limit, const unsigned long long* out_elems) {
+                            unsigned long long* cursor, const unsigned long long* limit, const unsigned long long* out_elems,
+                            const std::vector<std::pair<uint32_t, cudaEvent_t>>& batches, F after_batch) {
     const KbLayout& lo = ctx->lo;
-    const size_t plen = padded_len(ctx->n_bases);
-    TRY(ensure(ctx, ctx->bases, plen, true));
-    CU(cudaMemsetAsync((uint8_t*)ctx->bases.p + ctx->n_bases, '\n', plen - ctx->n_bases, ctx->stream));
-    TRY(upload_file_table(ctx));
     KbXPartArgs a{};
     a.bases = (const uint8_t*)ctx->bases.p; a.n_bases = ctx->n_bases;
     a.file_starts = (const uint64_t*)ctx->d_file_starts.p; a.file_gid = (const uint32_t*)ctx->d_file_gid.p;
@@ -1420,22 +1420,75 @@ static int run_extract_part(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles, uint6
     const size_t smem = kb_xpart_smem();
     if (spacer) CU(cudaFuncSetAttribute(kb_extract_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else CU(cudaFuncSetAttribute(kb_extract_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prof_begin(ctx, "K1 extract + partition 0");
     uint32_t t0 = tile0;
-    for (auto& bt : extract_batches(ctx, tile0, n_tiles)) {
+    int bi = 0;
+    for (auto& bt : batches) {
         if (bt.second) CU(cudaStreamWaitEvent(ctx->stream, bt.second, 0));
         const uint32_t nt = bt.first > t0 ? bt.first - t0 : 0;
-        if (!nt) continue;
-        a.tile0 = t0; a.n_tiles = nt;
-        if (spacer) kb_extract_part_kernel<true><<<nt, KB_XP_THREADS, smem, ctx->stream>>>(a);
-        else kb_extract_part_kernel<false><<<nt, KB_XP_THREADS, smem, ctx->stream>>>(a);
-        CU(cudaGetLastError());
-        ctx->launches++;
-        t0 = bt.first;
+        if (nt) {
+            a.tile0 = t0; a.n_tiles = nt;
+            if (spacer) kb_extract_part_kernel<true><<<nt, KB_XP_THREADS, smem, ctx->stream>>>(a);
+            else kb_extract_part_kernel<false><<<nt, KB_XP_THREADS, smem, ctx->stream>>>(a);
+            CU(cudaGetLastError());
+            ctx->launches++;
+            t0 = bt.first;
+        }
+        TRY(after_batch(bi, (int)batches.size(), nt));
+        bi++;
     }
-    prof_end(ctx);
     ctx->alg_bytes += std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo;
     ctx->alg_rec_bytes += 8;
+    return KB_OK;
+}
+
+// separator padding past the data + file table: what both K1 variants need before their first launch
+static int prepare_extract(kb_ctx* ctx) {
+    const size_t plen = padded_len(ctx->n_bases);
+    TRY(ensure(ctx, ctx->bases, plen, true));
+    CU(cudaMemsetAsync((uint8_t*)ctx->bases.p + ctx->n_bases, '\n', plen - ctx->n_bases, ctx->stream));
+    return upload_file_table(ctx);
+}
+
+// One slab level l >= 1: reads the slabs of level l - 1 in `in` (fill levels pend, optionally only the segments from pbegin on),
+// writes the slabs of level l into `out`.  rec_bound = records the pass can meet at most (sizes the grid in tile-map mode).
+static int launch_slab_level(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl, int l, const uint64_t* in, uint64_t* out,
+                             const unsigned long long* pend, const unsigned long long* pbegin, uint32_t n_parents, const uint32_t* prow,
+                             uint64_t rec_bound) {
+    uint8_t* P = (uint8_t*)ctx->plan.p;
+    const size_t smem = kb_part_smem();
+    CU(cudaFuncSetAttribute(kb_part_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int shift = 64;
+    for (int i = 0; i <= l; i++) shift -= sp.bits[i];
+    KbPartArgs a{};
+    a.in = in; a.out = out;
+    a.pend = pend; a.pbegin = pbegin; a.pcap = sp.cap[l - 1];
+    a.ptile0 = (const uint32_t*)(P + sp.off_tile0[l - 1]);
+    a.tile_parent = (const uint32_t*)(P + sp.off_tilemap);
+    a.prow = prow;
+    a.n_parents = n_parents;
+    a.shift = (uint32_t)shift; a.bits = (uint32_t)sp.bits[l];
+    a.cursor = (unsigned long long*)(P + sp.off_cur[l]);
+    a.ccap = sp.cap[l];
+    a.ovf = (unsigned long long*)ctx->small.p + SM_OVF;
+    const bool by_division = !pbegin && sp.cap[l - 1] % KB_PT_TILE == 0;
+    uint64_t grid = (uint64_t)n_parents * (sp.cap[l - 1] / KB_PT_TILE);
+    if (by_division) { a.ptile0 = nullptr; a.tile_parent = nullptr; }
+    else {
+        unsigned long long* counts = (unsigned long long*)(P + sp.off_counts);
+        kb_slab_counts_kernel<<<(unsigned)std::min<uint32_t>((n_parents + 255) / 256, 1024), 256, 0, ctx->stream>>>(pend, pbegin, n_parents, a.pcap, counts);
+        CU(cudaGetLastError());
+        KbPlanArgs pa{};
+        pa.counts = counts; pa.nc = n_parents; pa.start = (unsigned long long*)(P + sp.off_start); pa.cursor = nullptr;
+        pa.tile0 = (uint32_t*)(P + sp.off_tile0[l - 1]); pa.part = (unsigned long long*)(P + sp.off_part);
+        TRY(launch_plan(ctx, pa, pl));
+        kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((n_parents + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, n_parents, (uint32_t*)(P + sp.off_tilemap));
+        CU(cudaGetLastError());
+        ctx->launches += 2;
+        grid = rec_bound / KB_PT_TILE + n_parents + 1;
+    }
+    kb_part_kernel<2, false, true><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    ctx->launches++;
     return KB_OK;
 }
 
@@ -1443,45 +1496,10 @@ static int run_extract_part(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles, uint6
 static int run_slab_levels(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl, int l_begin, uint64_t* bufs[2], uint64_t n_est) {
     uint8_t* P = (uint8_t*)ctx->plan.p;
     static const char* pnames[3] = {"K2 partition 0", "K2 partition 1", "K2 partition 2"};
-    static const char* hnames[3] = {"K2 plan 0", "K2 plan 1", "K2 plan 2"};
-    const size_t smem = kb_part_smem();
-    CU(cudaFuncSetAttribute(kb_part_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int shift = 64;
-    for (int l = 0; l < l_begin; l++) shift -= sp.bits[l];
     for (int l = l_begin; l < sp.levels; l++) {
-        shift -= sp.bits[l];
-        KbPartArgs a{};
-        a.in = bufs[(l - 1) & 1]; a.out = bufs[l & 1];
-        a.pend = (const unsigned long long*)(P + sp.off_cur[l - 1]); a.pcap = sp.cap[l - 1];
-        a.ptile0 = (const uint32_t*)(P + sp.off_tile0[l - 1]);
-        a.tile_parent = (const uint32_t*)(P + sp.off_tilemap);
-        a.n_parents = sp.nc[l - 1];
-        a.shift = (uint32_t)shift; a.bits = (uint32_t)sp.bits[l];
-        a.cursor = (unsigned long long*)(P + sp.off_cur[l]);
-        a.ccap = sp.cap[l];
-        a.ovf = (unsigned long long*)ctx->small.p + SM_OVF;
-        const bool by_division = sp.cap[l - 1] % KB_PT_TILE == 0;
-        uint64_t grid = (uint64_t)a.n_parents * (sp.cap[l - 1] / KB_PT_TILE);
-        if (by_division) { a.ptile0 = nullptr; a.tile_parent = nullptr; }
-        else {
-            prof_begin(ctx, hnames[l]);
-            unsigned long long* counts = (unsigned long long*)(P + sp.off_counts);
-            kb_slab_counts_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 255) / 256, 1024), 256, 0, ctx->stream>>>(a.pend, a.n_parents, a.pcap, counts);
-            CU(cudaGetLastError());
-            KbPlanArgs pa{};
-            pa.counts = counts; pa.nc = a.n_parents; pa.start = (unsigned long long*)(P + sp.off_start); pa.cursor = nullptr;
-            pa.tile0 = (uint32_t*)(P + sp.off_tile0[l - 1]); pa.part = (unsigned long long*)(P + sp.off_part);
-            TRY(launch_plan(ctx, pa, pl));
-            kb_tilemap_kernel<<<(unsigned)std::min<uint32_t>((a.n_parents + 7) / 8, 4096), 256, 0, ctx->stream>>>(a.ptile0, a.n_parents, (uint32_t*)(P + sp.off_tilemap));
-            CU(cudaGetLastError());
-            ctx->launches += 2;
-            prof_end(ctx);
-            grid = n_est / KB_PT_TILE + a.n_parents + 1;
-        }
         prof_begin(ctx, pnames[l]);
-        kb_part_kernel<2, false, true><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
-        CU(cudaGetLastError());
-        ctx->launches++;
+        TRY(launch_slab_level(ctx, sp, pl, l, bufs[(l - 1) & 1], bufs[l & 1], (const unsigned long long*)(P + sp.off_cur[l - 1]), nullptr,
+                              sp.nc[l - 1], nullptr, n_est));
         prof_end(ctx);
         ctx->alg_rec_bytes += 16;
     }
@@ -1509,9 +1527,28 @@ static int search_slab(kb_ctx* ctx, const PartPlan& pl, kb_result** out) {
     for (uint32_t d = 0; d < sp.nc[0]; d++) { t0[d] = (uint64_t)(d + 1) * sp.cap[0]; t0[KB_XP_MAXR + d] = (uint64_t)(reinterpret_cast<uintptr_t>(bufs[0]) >> 3); }
     CU(cudaMemcpyAsync(P + sp.off_tab0, t0.data(), t0.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t n_tiles = (uint32_t)((ctx->n_bases + KB_K1_TB - 1) / KB_K1_TB);
-    TRY(run_extract_part(ctx, 0, n_tiles, 0, ctx->n_bases, (uint32_t)sp.bits[0], (unsigned long long*)(P + sp.off_cur[0]),
-                         (const unsigned long long*)(P + sp.off_tab0), (const unsigned long long*)(P + sp.off_tab0) + KB_XP_MAXR));
-    TRY(run_slab_levels(ctx, sp, pl, 1, bufs, n_est));
+    TRY(prepare_extract(ctx));
+    const auto batches = extract_batches(ctx, 0, n_tiles);
+    // Host buffers still arriving: level 1 runs per batch of files too, on the segment the batch appended to every level-0 slab
+    // (cursor snapshots), so that after the last copy only the last batch's share of K1 / level 0 / level 1 is left
+    const bool per_batch = ctx->opt_batch_level0 && sp.levels >= 2 && batches.size() > 1 && batches.size() <= KB_MAX_BATCHES;
+    unsigned long long* cur0 = (unsigned long long*)(P + sp.off_cur[0]);
+    unsigned long long* snap = (unsigned long long*)(P + sp.off_snap);
+    if (per_batch) CU(cudaMemcpyAsync(snap, cur0, (size_t)sp.nc[0] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    prof_begin(ctx, per_batch ? "K1 extract + partition 0 + partition 1 per batch" : "K1 extract + partition 0");
+    TRY(run_extract_part(ctx, 0, n_tiles, 0, ctx->n_bases, (uint32_t)sp.bits[0], cur0,
+                         (const unsigned long long*)(P + sp.off_tab0), (const unsigned long long*)(P + sp.off_tab0) + KB_XP_MAXR, batches,
+                         [&](int bi, int, uint32_t nt) -> int {
+                             if (!per_batch) return KB_OK;
+                             unsigned long long* s0 = snap + (size_t)bi * sp.nc[0];
+                             unsigned long long* s1 = s0 + sp.nc[0];
+                             CU(cudaMemcpyAsync(s1, cur0, (size_t)sp.nc[0] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                             if (!nt) return KB_OK;
+                             return launch_slab_level(ctx, sp, pl, 1, bufs[0], bufs[1], s1, s0, sp.nc[0], nullptr, 2ull * nt * KB_K1_TB);
+                         }));
+    prof_end(ctx);
+    if (per_batch) ctx->alg_rec_bytes += 16;
+    TRY(run_slab_levels(ctx, sp, pl, per_batch ? 2 : 1, bufs, n_est));
     ctx->passes = sp.levels;
     HashStage hs{};
     hs.pl = &pl;

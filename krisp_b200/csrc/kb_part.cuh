@@ -47,6 +47,7 @@ struct KbPartArgs {
                                         // cursor of c then counts from the first element of this rank's piece in that buffer
     // Slab layout (kb_extract_part.cuh): buckets are fixed-capacity regions filled through their cursors, not exact ranges.
     const unsigned long long* pend;     // != null: parent p = elements [p * pcap, min(pend[p], (p + 1) * pcap)) of `in` (pstart unused)
+    const unsigned long long* pbegin;   // != null (with pend): only the segment from pbegin[p] on — what a batch of input files appended to the slab
     uint64_t pcap;
     uint64_t ccap;                      // != 0: child c owns [c * ccap, (c + 1) * ccap) of `out` (its cursor starts at c * ccap); a run that
     unsigned long long* ovf;            // does not fit is dropped and *ovf is raised (the host repeats the search on the exact path)
@@ -57,13 +58,14 @@ __device__ __forceinline__ void kb_part_parent(const KbPartArgs& a, uint32_t par
     if (a.pend) {
         ps = (uint64_t)parent * a.pcap;
         pe = min((uint64_t)a.pend[parent], ps + a.pcap);
+        if (a.pbegin) ps = max(ps, (uint64_t)a.pbegin[parent]);
         if (pe < ps) pe = ps;
     } else { ps = a.pstart[parent]; pe = a.pstart[parent + 1]; }
 }
 
 // tile -> its range [s, s + n_tile) and the cursor row of its parent
 __device__ __forceinline__ bool kb_part_tile(const KbPartArgs& a, uint32_t tile, uint32_t& row, uint64_t& s, uint32_t& n_tile) {
-    if (a.pend && !a.ptile0) {
+    if (a.pend && !a.ptile0) {                                                    // (never together with pbegin)
         // slab parents whose capacity is a multiple of the tile: tile -> parent by division, no tile map (tiles past the fill level leave)
         const uint32_t tpp = (uint32_t)(a.pcap / KB_PT_TILE);
         const uint32_t parent = tile / tpp;
@@ -361,9 +363,12 @@ __global__ void __launch_bounds__(256) kb_slab_init_kernel(unsigned long long* c
     for (uint32_t c = blockIdx.x * 256 + threadIdx.x; c < nc; c += gridDim.x * 256) cursor[c] = (unsigned long long)c * cap;
 }
 // fill levels after a pass: counts[c] = min(cursor[c], (c + 1) * cap) - c * cap (input of kb_plan_*: tile prefix of the next level)
-__global__ void __launch_bounds__(256) kb_slab_counts_kernel(const unsigned long long* cursor, uint32_t nc, uint64_t cap, unsigned long long* counts) {
+__global__ void __launch_bounds__(256) kb_slab_counts_kernel(const unsigned long long* cursor, const unsigned long long* begin, uint32_t nc, uint64_t cap,
+                                                             unsigned long long* counts) {
     for (uint32_t c = blockIdx.x * 256 + threadIdx.x; c < nc; c += gridDim.x * 256) {
-        const unsigned long long s = (unsigned long long)c * cap, e = min(cursor[c], s + cap);
+        unsigned long long s = (unsigned long long)c * cap;
+        const unsigned long long e = min(cursor[c], s + cap);
+        if (begin) s = max(s, begin[c]);
         counts[c] = e > s ? e - s : 0ULL;
     }
 }
