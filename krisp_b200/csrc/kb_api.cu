@@ -106,7 +106,8 @@ struct kb_ctx {
     long long opt_have_outgroup = 1;     // consensus letters: ingroup only (an outgroup was given) / every occurrence
     long long opt_lazy_records = 1;      // multi-word records: 1 = filter by flank hash, build records only for what is left (kb_prefilter.cuh)
     long long opt_slab = 1;              // one-word records: 1 = K1 fused with partition level 0 into fixed-capacity slabs (kb_extract_part.cuh)
-    long long opt_hash_warp = 1;         // 1 = warp-private bucket hash kernel (kb_hash_warp.cuh) instead of the CTA-wide stream kernel
+    long long opt_hash_warp = 1;         // 1 = bucket hash kernel with per-warp streaming (kb_hash_warp.cuh) instead of the CTA-wide stream kernel
+    long long opt_hash_shared = -1;      // kb_hash_warp.cuh: 1 = one table per CTA, 0 = one per warp, -1 = by table size (>= 1024 slots: per CTA)
     long long opt_slab_cap = 0;          // != 0: force the capacity of every slab (tests: overflow -> exact path)
     bool slab_off = false;               // a slab overflowed on these sequences: searches use the exact path until they change
     bool lazy_now = false;               // the running search uses it
@@ -288,6 +289,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "lazy_records") ctx->opt_lazy_records = value ? 1 : 0;
     else if (n == "slab") { ctx->opt_slab = value ? 1 : 0; ctx->slab_off = false; }
     else if (n == "hash_warp") ctx->opt_hash_warp = value ? 1 : 0;
+    else if (n == "hash_shared") ctx->opt_hash_shared = value < 0 ? -1 : (value ? 1 : 0);
     else if (n == "slab_cap") { if (value < 0) return fail(ctx, KB_EINVAL, "slab_cap must be >= 0"); ctx->opt_slab_cap = value; ctx->slab_off = false; }
     else if (n == "render_rows") ctx->opt_render_rows = value ? 1 : 0;
     else if (n == "have_outgroup") ctx->opt_have_outgroup = value ? 1 : 0;
@@ -730,7 +732,8 @@ static PartPlan make_plan(const kb_ctx* ctx, uint64_t n_est, int bits0 = 0, bool
     pl.fast = hash_fast_ok(ctx);
     pl.stream = ctx->opt_hash_stream && ctx->opt_fast_group && lo.direct && lo.FB >= 1 && lo.MW <= 1;
     if (ctx->opt_hash_slots_log2) pl.slots_log2 = (uint32_t)ctx->opt_hash_slots_log2;
-    else if (pl.stream) pl.slots_log2 = ctx->opt_hash_warp ? 8 : 10;   // warp-private tables (4 KB each: 24 warps per SM) / CTA-wide: 24 - 56 KB of table + 28 KB ring and queues
+    else if (pl.stream) pl.slots_log2 = ctx->opt_hash_warp ? (lo.n_files <= 64 ? 11 : 10) : 10;   // kb_hash_warp.cuh, one table per CTA (32 - 40 KB,
+                                                                // fewer bucket bits = cheaper partition levels) / stream kernel: 24 - 56 KB of table + 28 KB ring and queues
     else if (pl.fast) pl.slots_log2 = 11;                       // 48 KB of table: 4 CTAs per SM
     else {
         const size_t sb = kb_hash_slot_bytes(lo);
@@ -953,15 +956,27 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
             xw.deferred = (uint32_t*)ctx->deferred.p;
             xw.n_deferred = (unsigned long long*)ctx->small.p + SM_NTAINT;   // zeroed with the result counters
             const bool packed = lo.D == 1 && lo.FB <= 54;
-            while (xw.h.slots_log2 > 4 && (size_t)KB_HW_WARPS * kb_hash_warp_wbytes(xw.h.slots_log2, pwn, packed) + 16 > 224 * 1024) xw.h.slots_log2--;
-            xw.wbytes = kb_hash_warp_wbytes(xw.h.slots_log2, pwn, packed);
-            const size_t smem = (size_t)KB_HW_WARPS * xw.wbytes + 16;
-            const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(3, (224 * 1024) / (smem + 1024)));
-            const unsigned wgrid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->n_sm * per_sm, (hs.n_buckets + KB_HW_WARPS - 1) / KB_HW_WARPS));
+            bool shared = ctx->opt_hash_shared < 0 ? xw.h.slots_log2 >= 10 : ctx->opt_hash_shared != 0;
+            if (!shared && xw.h.slots_log2 > 10) shared = true;                  // (a warp scans at most 32 x 32 slots)
+            auto smem_of = [&](uint32_t l2) {
+                return (size_t)(shared ? kb_hash_cta_tbytes(l2, pwn, packed) : 0) + (size_t)KB_HW_WARPS * kb_hash_warp_wbytes(l2, pwn, packed, shared) + 16;
+            };
+            while (xw.h.slots_log2 > 4 && (smem_of(xw.h.slots_log2) > 224 * 1024 || xw.h.slots_log2 > 13)) xw.h.slots_log2--;
+            xw.wbytes = kb_hash_warp_wbytes(xw.h.slots_log2, pwn, packed, shared);
+            xw.tbytes = shared ? kb_hash_cta_tbytes(xw.h.slots_log2, pwn, packed) : 0;
+            const size_t smem = smem_of(xw.h.slots_log2);
+            const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(shared ? 4 : 3, (224 * 1024) / (smem + 1024)));
+            const uint32_t units = shared ? hs.n_buckets : (hs.n_buckets + KB_HW_WARPS - 1) / KB_HW_WARPS;
+            const unsigned wgrid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->n_sm * per_sm, units));
 #define KB_LAUNCH_WARP(D1_, SP_, PW_)                                                                                          \
             do {                                                                                                               \
-                CU(cudaFuncSetAttribute(kb_hash_warp_kernel<D1_, SP_, PW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                kb_hash_warp_kernel<D1_, SP_, PW_><<<wgrid, 32 * KB_HW_WARPS, smem, ctx->stream>>>(xw);                          \
+                if (shared) {                                                                                                  \
+                    CU(cudaFuncSetAttribute(kb_hash_warp_kernel<D1_, SP_, PW_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                    kb_hash_warp_kernel<D1_, SP_, PW_, true><<<wgrid, KB_HW_THREADS, smem, ctx->stream>>>(xw);                   \
+                } else {                                                                                                       \
+                    CU(cudaFuncSetAttribute(kb_hash_warp_kernel<D1_, SP_, PW_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                    kb_hash_warp_kernel<D1_, SP_, PW_, false><<<wgrid, KB_HW_THREADS, smem, ctx->stream>>>(xw);                  \
+                }                                                                                                              \
             } while (0)
             if (pwn == 2) { if (spacer) KB_LAUNCH_WARP(true, true, 2); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 2); else KB_LAUNCH_WARP(false, false, 2); }
             else if (pwn == 4) { if (spacer) KB_LAUNCH_WARP(true, true, 4); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 4); else KB_LAUNCH_WARP(false, false, 4); }

@@ -1,18 +1,22 @@
-// kb_hash_warp.cuh — K3, warp-private version of the bucket hash aggregation (one-word records, D <= 8, up to 256 files).
+// kb_hash_warp.cuh — K3: bucket hash aggregation with per-warp streaming (one-word records, D <= 8, up to 256 files).
 //
 // Same contract and per-bucket algorithm as kb_hash_stream_kernel (kb_hash_stream.cuh; reference stages: simplifyStream /
 // alignmentStream shared.py:210-240,:442-475, intersectSortedStreams :321-347 folded by mergeFiles
-// intersectAmplicons.py:232-310, filterAlignments.py:4-28 + ingroupUniqueColumns Amplicon.py:495-521), but every WARP owns
-// its buckets, its hash table and its miss queue:
-//   * no CTA barrier anywhere: a bucket end (scan + emit + clear) stalls one warp, not 256 threads;
-//   * every warp streams its buckets through its own small ring (KB_HW_STAGES chunks of 128 records, filled with 16-byte
-//     cp.async copies that run two chunks ahead, across bucket boundaries): no mbarrier, no producer, and the shared
-//     memory of a warp stays small enough for 24 warps per SM;
+// intersectAmplicons.py:232-310, filterAlignments.py:4-28 + ingroupUniqueColumns Amplicon.py:495-521).  What differs:
+//   * every warp streams its share of the records through its own small ring (KB_HW_STAGES chunks of 128 records, filled
+//     with 16-byte cp.async copies that run two chunks ahead, across bucket boundaries): no mbarrier, no producer warp, and
+//     little shared memory per warp, so 24 warps fit an SM;
 //   * a chunk never straddles two buckets, so the hot loop has no boundary logic: four records per lane, their four home
 //     slots are loaded together, hit / miss is resolved for all four, misses go to the warp's queue and are inserted 32 at a
-//     time, as before;
+//     time;
 //   * table in structure-of-arrays form (keys 8 B apart, presence words apart from them): key loads spread over all banks;
 //   * buckets may be exact ranges (bstart[b], bstart[b + 1]) or slabs (b * bcap, filled up to bend[b]) — kb_extract_part.cuh.
+// Two table arrangements:
+//   SHARED = false  every WARP owns its buckets and a private table: no CTA barrier anywhere, a bucket end (scan + emit +
+//                   clear) stalls one warp.  Best for small buckets (a 256-slot table is 4 KB).
+//   SHARED = true   the 8 warps of a CTA share one table and one bucket at a time, warp w streams chunks w, w + 8, ... of it;
+//                   three named barriers per bucket.  For buckets too big for a private table (fewer bucket bits: two
+//                   partition levels still suffice when level 0 also has to separate the owner GPUs).
 // Buckets whose distinct keys overflow the table or that hold more than KB_HW_MAX_INLINE survivors are deferred to
 // kb_hash_fast_kernel / kb_hash_kernel exactly like in the stream kernel; group sizes come from kb_hsize_kernel.
 #pragma once
@@ -23,48 +27,66 @@
 #define KB_HW_STAGES 3
 #define KB_HW_QCAP (32 + KB_HW_CH)            // the queue is drained to < 32 entries after every chunk
 #define KB_HW_MAX_INLINE 8
-#define KB_HW_WARPS 8                         // warps per CTA (independent of each other)
+#define KB_HW_WARPS 8                         // warps per CTA
+#define KB_HW_THREADS (32 * KB_HW_WARPS)
 
 struct KbHWarpArgs {
     KbHashArgs h;                        // g.ent = partitioned elements; buckets via h.bstart / h.bend / h.bcap
     uint32_t* deferred;                  // [n_buckets] bucket ids left to the fallback kernel
     unsigned long long* n_deferred;
-    uint32_t wbytes;                     // shared memory per warp (kb_hash_warp_wbytes)
+    uint32_t wbytes;                     // shared memory per warp
+    uint32_t tbytes;                     // SHARED: bytes of the CTA's table + control words (in front of the warp regions)
 };
 
-// bytes of one warp's region: ring | queue | keys | presence words | column sets (only when they do not fit the key word)
-static inline uint32_t kb_hash_warp_wbytes(uint32_t slots_log2, int pwn, bool packed) {
+static inline uint32_t kb_hash_table_bytes(uint32_t slots_log2, int pwn, bool packed) {
     const uint32_t S = 1u << slots_log2;
-    const uint32_t b = 8u * (KB_HW_STAGES * KB_HW_CH + KB_HW_QCAP + S) + 4u * S * (uint32_t)pwn + (packed ? 0u : 8u * S);
+    return 8u * S + 4u * S * (uint32_t)pwn + (packed ? 0u : 8u * S);
+}
+// bytes of one warp's region: ring | queue (| private table)
+static inline uint32_t kb_hash_warp_wbytes(uint32_t slots_log2, int pwn, bool packed, bool shared) {
+    const uint32_t b = 8u * (KB_HW_STAGES * KB_HW_CH + KB_HW_QCAP) + (shared ? 0u : kb_hash_table_bytes(slots_log2, pwn, packed));
     return (b + 15u) & ~15u;
 }
+static inline uint32_t kb_hash_cta_tbytes(uint32_t slots_log2, int pwn, bool packed) { return kb_hash_table_bytes(slots_log2, pwn, packed) + 64u; }
 
-template <bool D1, bool SPACER, int PWN>
-__global__ void __launch_bounds__(32 * KB_HW_WARPS, 3) kb_hash_warp_kernel(const KbHWarpArgs xs) {
+__device__ __forceinline__ void kb_hw_bar() { asm volatile("bar.sync 1, %0;" :: "n"(KB_HW_THREADS) : "memory"); }
+
+template <bool D1, bool SPACER, int PWN, bool SHARED>
+__global__ void __launch_bounds__(KB_HW_THREADS, 3) kb_hash_warp_kernel(const KbHWarpArgs xs) {
     extern __shared__ __align__(16) unsigned char kb_smem_raw[];
     const KbHashArgs& x = xs.h;
     const KbGroupArgs& a = x.g;
     const KbLayout& lo = a.lo;
     const uint32_t S = 1u << x.slots_log2, smask = S - 1u;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t wg = blockIdx.x * KB_HW_WARPS + warp, TW = gridDim.x * KB_HW_WARPS;
+    // bucket / chunk ownership
+    const uint32_t b_first = SHARED ? blockIdx.x : blockIdx.x * KB_HW_WARPS + warp;
+    const uint32_t b_step = SHARED ? gridDim.x : gridDim.x * KB_HW_WARPS;
+    const uint32_t c_first = SHARED ? warp : 0u;
+    constexpr uint32_t c_step = SHARED ? KB_HW_WARPS : 1u;
     const bool packed = SPACER || (D1 && lo.FB <= 54);       // both 4-bit base sets inside the key word (bits 56-63)
 
-    uint32_t smem_a = kb_smem_u32(kb_smem_raw) + warp * xs.wbytes;
+    uint32_t smem_a = kb_smem_u32(kb_smem_raw);
     asm volatile("" : "+r"(smem_a));                          // opaque: keep the base in a register
-    const uint32_t ring_a = smem_a;
+    const uint32_t warp_a = smem_a + (SHARED ? xs.tbytes : 0u) + warp * xs.wbytes;
+    const uint32_t ring_a = warp_a;
     const uint32_t q_a = ring_a + KB_HW_STAGES * KB_HW_CH * 8;
-    const uint32_t keys_a = q_a + KB_HW_QCAP * 8;
+    const uint32_t keys_a = SHARED ? smem_a : q_a + KB_HW_QCAP * 8;
     const uint32_t pres_a = keys_a + S * 8;
     const uint32_t msk_a = pres_a + S * 4 * PWN;              // [S][2] (unpacked sets only)
+    const uint32_t ctl_a = msk_a + (packed ? 0u : S * 8);     // SHARED: per bucket parity p: [p] over, [2 + p] distinct keys, [4 + p] survivors
 
-    for (uint32_t i = lane; i < S; i += 32) {
+    // table slots this thread scans / clears
+    const uint32_t t_first = SHARED ? tid : lane;
+    constexpr uint32_t t_step = SHARED ? KB_HW_THREADS : 32u;
+    for (uint32_t i = t_first; i < S; i += t_step) {
         kb_sts64(keys_a + i * 8, KB_KH_EMPTY);
 #pragma unroll
         for (int j = 0; j < PWN; j++) kb_sts32(pres_a + (i * PWN + j) * 4, 0u);
         if (!packed) kb_sts64(msk_a + i * 8, 0ULL);
     }
-    __syncwarp();
+    if (SHARED) { if (tid < 16) kb_sts32(ctl_a + 4 * tid, 0u); __syncthreads(); }
+    else __syncwarp();
 
     const uint32_t kshift = SPACER ? 10u : 64 - lo.FB;
     const uint32_t D2 = SPACER ? 2u : 2 * lo.D;
@@ -76,21 +98,22 @@ __global__ void __launch_bounds__(32 * KB_HW_WARPS, 3) kb_hash_warp_kernel(const
     const uint32_t sshift = 32 - x.slots_log2;
     const uint32_t lt_mask = kb_lanemask_lt();
     uint32_t qn = 0;                     // records waiting in the queue (warp-uniform)
-    uint32_t nkeys = 0;                  // distinct keys in the table (warp-uniform)
+    uint32_t nkeys = 0;                  // private table: distinct keys in it (warp-uniform)
     bool over = false;                   // the current bucket is given up (warp-uniform)
+    uint32_t par = 0;                    // SHARED: parity of the current bucket (selects its control words)
 
     auto bucket_range = [&](uint32_t b, uint64_t& s, uint64_t& e) {
         if (x.bcap) { s = (uint64_t)b * x.bcap; e = min((uint64_t)x.bend[b], s + x.bcap); }
         else { s = x.bstart[b]; e = x.bend ? x.bend[b] : x.bstart[b + 1]; }
         if (e < s) e = s;
     };
-    // first non-empty bucket of this warp at or after `from` (stride TW); nb >= n_buckets: none
+    // first non-empty bucket at or after `from` (stride b_step); nb >= n_buckets: none
     auto next_bucket = [&](uint32_t from, uint32_t& nb, uint64_t& s, uint64_t& e) {
         nb = from; s = 0; e = 0;
         while (nb < x.n_buckets) {
             bucket_range(nb, s, e);
             if (e > s) break;
-            nb += TW;
+            nb += b_step;
         }
     };
     auto slot_of = [&](uint64_t e) -> uint32_t { return (kb_kh_bits(e, x.bb, hmask) * 0x9E3779B1u) >> sshift; };
@@ -136,25 +159,38 @@ __global__ void __launch_bounds__(32 * KB_HW_WARPS, 3) kb_hash_warp_kernel(const
         uint32_t st = 0;
         if (lane < cnt) st = insert(kb_lds64(q_a + (qn + lane) * 8));
         __syncwarp();
-        nkeys += __popc(__ballot_sync(0xFFFFFFFFu, st == 1u));
-        if (__any_sync(0xFFFFFFFFu, st == 2u) || nkeys > limit) over = true;
+        const uint32_t fresh = __popc(__ballot_sync(0xFFFFFFFFu, st == 1u));
+        const bool full = __any_sync(0xFFFFFFFFu, st == 2u);
+        if (SHARED) {
+            uint32_t total = 0;
+            if (lane == 0 && fresh) total = kb_atoms_add(ctl_a + 4 * (2 + par), fresh) + fresh;
+            if (lane == 0 && (full || total > limit)) kb_sts32(ctl_a + 4 * par, 1u);
+            __syncwarp();
+            over = over || full || __any_sync(0xFFFFFFFFu, kb_lds32(ctl_a + 4 * par));   // (another warp may have given the bucket up)
+        } else {
+            nkeys += fresh;
+            if (full || nkeys > limit) over = true;
+        }
     };
 
-    // ---- producer side: the chunk sequence of this warp's buckets (wg, wg + TW, ...), 16-byte cp.async pieces, one commit
-    //      group per consumer iteration (empty once the buckets are exhausted, so that the group arithmetic stays put) --------
+    // ---- producer side: this warp's chunk sequence over its buckets, 16-byte cp.async pieces, one commit group per consumer
+    //      iteration (empty once the chunks are exhausted, so that the group arithmetic stays put) -----------------------------
     const uint64_t* ent = a.ent;
     uint32_t pb, pk = 0, pnch = 0, pq = 0;
     uint64_t ps_al = 0, pn_al = 0;
-    auto prod_enter = [&](uint32_t from) {      // first non-empty bucket at or after `from`
-        pb = from; pk = 0; pnch = 0;
+    auto prod_enter = [&](uint32_t from) {      // first bucket at or after `from` that has a chunk for this warp
+        pb = from; pk = c_first; pnch = 0;
         while (pb < x.n_buckets) {
             uint64_t s, e;
             bucket_range(pb, s, e);
-            if (e > s) { ps_al = s & ~1ULL; pn_al = e - ps_al; pnch = (uint32_t)((pn_al + KB_HW_CH - 1) / KB_HW_CH); break; }
-            pb += TW;
+            if (e > s) {
+                ps_al = s & ~1ULL; pn_al = e - ps_al; pnch = (uint32_t)((pn_al + KB_HW_CH - 1) / KB_HW_CH);
+                if (pnch > c_first) break;
+            }
+            pb += b_step;
         }
     };
-    prod_enter(wg);
+    prod_enter(b_first);
     auto issue = [&]() {
         if (pb < x.n_buckets) {
             const uint32_t here = (uint32_t)min((uint64_t)KB_HW_CH, pn_al - (uint64_t)pk * KB_HW_CH);
@@ -167,7 +203,8 @@ __global__ void __launch_bounds__(32 * KB_HW_WARPS, 3) kb_hash_warp_kernel(const
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + piece * 16), "l"(src + 2 * piece) : "memory");
             }
             pq++;
-            if (++pk >= pnch) prod_enter(pb + TW);
+            pk += c_step;
+            if (pk >= pnch) prod_enter(pb + b_step);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -176,7 +213,7 @@ __global__ void __launch_bounds__(32 * KB_HW_WARPS, 3) kb_hash_warp_kernel(const
 
     uint32_t b;
     uint64_t bs, be;
-    next_bucket(wg, b, bs, be);
+    next_bucket(b_first, b, bs, be);
     uint32_t cq = 0;
     uint32_t n_closed_t = 0, n_present_t = 0, n_rounds = 0, n_defer = 0;
     while (b < x.n_buckets) {
@@ -185,10 +222,11 @@ __global__ void __launch_bounds__(32 * KB_HW_WARPS, 3) kb_hash_warp_kernel(const
         const uint64_t n_al = be - s_al;
         const uint32_t nch = (uint32_t)((n_al + KB_HW_CH - 1) / KB_HW_CH);
         over = false; nkeys = 0; qn = 0;
-        for (uint32_t ck = 0; ck < nch; ck++) {
+        for (uint32_t ck = c_first; ck < nch; ck += c_step) {
             issue();                                                             // chunk cq + STAGES - 1 (into the stage freed last iteration)
             asm volatile("cp.async.wait_group %0;" :: "n"(KB_HW_STAGES - 1) : "memory");
             __syncwarp();
+            if (SHARED) over = over || __any_sync(0xFFFFFFFFu, kb_lds32(ctl_a + 4 * par));
             const uint32_t stage_a = ring_a + (cq % KB_HW_STAGES) * (KB_HW_CH * 8);
             const uint32_t cnt = (uint32_t)min((uint64_t)KB_HW_CH, n_al - (uint64_t)ck * KB_HW_CH);
             const uint32_t first = ck == 0 ? skip : 0u;
@@ -221,15 +259,15 @@ __global__ void __launch_bounds__(32 * KB_HW_WARPS, 3) kb_hash_warp_kernel(const
             __syncwarp();                                                        // every lane is done with this stage
             cq++;
         }
-        // ---- bucket b is complete: flush the queue, evaluate, emit, clear ---------------------------------------------------
+        // ---- this warp's share of bucket b is done: flush the queue; then evaluate, emit, clear --------------------------------
         __syncwarp();
         while (qn && !over) drain();
         __syncwarp();
+        if (SHARED) { kb_hw_bar(); over = kb_lds32(ctl_a + 4 * par) != 0; }      // (uniform over the CTA from here on)
         n_rounds++;
-        uint32_t flags = 0, n_surv = 0;
+        uint32_t flags = 0, n_surv = 0, n_closed = 0, n_present = 0;
         if (!over) {
-            uint32_t n_closed = 0, n_present = 0;
-            for (uint32_t q = 0, slot = lane; slot < S; q++, slot += 32) {
+            for (uint32_t q = 0, slot = t_first; slot < S; q++, slot += t_step) {
                 const uint64_t kk0 = kb_lds64(keys_a + slot * 8);
                 if (kk0 == KB_KH_EMPTY) continue;
                 n_closed++;
@@ -249,10 +287,15 @@ __global__ void __launch_bounds__(32 * KB_HW_WARPS, 3) kb_hash_warp_kernel(const
                 if (ok) flags |= 1u << q;
             }
             n_surv = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(flags));
-            if (n_surv <= KB_HW_MAX_INLINE) { n_closed_t += n_closed; n_present_t += n_present; }
-        }
+            if (SHARED) {
+                if (lane == 0 && n_surv) kb_atoms_add(ctl_a + 4 * (4 + par), n_surv);
+                kb_hw_bar();
+                n_surv = kb_lds32(ctl_a + 4 * (4 + par));
+            }
+        } else if (SHARED) kb_hw_bar();
         const bool defer = over || n_surv > KB_HW_MAX_INLINE;
-        for (uint32_t q = 0, slot = lane; slot < S; q++, slot += 32) {
+        if (!defer) { n_closed_t += n_closed; n_present_t += n_present; }
+        for (uint32_t q = 0, slot = t_first; slot < S; q++, slot += t_step) {
             const uint64_t kk0 = kb_lds64(keys_a + slot * 8);
             if (kk0 == KB_KH_EMPTY) continue;
             if (!defer && ((flags >> q) & 1u)) {
@@ -275,12 +318,15 @@ __global__ void __launch_bounds__(32 * KB_HW_WARPS, 3) kb_hash_warp_kernel(const
             for (int j = 0; j < PWN; j++) kb_sts32(pres_a + (slot * PWN + j) * 4, 0u);
             if (!packed) kb_sts64(msk_a + slot * 8, 0ULL);
         }
-        if (defer) {
-            n_defer++;
-            if (lane == 0) { const unsigned long long d = atomicAdd(xs.n_deferred, 1ULL); xs.deferred[d] = b; }
-        }
-        __syncwarp();
-        next_bucket(b + TW, b, bs, be);
+        if (defer && (SHARED ? tid == 0 : lane == 0)) { const unsigned long long d = atomicAdd(xs.n_deferred, 1ULL); xs.deferred[d] = b; }
+        if (defer && (SHARED ? warp == 0 : true)) n_defer++;
+        if (SHARED) {
+            if (tid == 0) { kb_sts32(ctl_a + 4 * (par ^ 1u), 0u); kb_sts32(ctl_a + 4 * (2 + (par ^ 1u)), 0u); kb_sts32(ctl_a + 4 * (4 + (par ^ 1u)), 0u); }
+            kb_hw_bar();                                                         // table and the next bucket's control words are clean
+            par ^= 1u;
+            if (warp != 0) n_rounds--;                                           // (one count per CTA)
+        } else __syncwarp();
+        next_bucket(b + b_step, b, bs, be);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 
