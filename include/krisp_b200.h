@@ -72,6 +72,12 @@ int kb_configure(kb_ctx* ctx, int L, int D, int R, int soft_mode, int n_files, c
  *   "want_records"  1 = also return every record of the surviving groups' runs (for --out_align)
  *   "profile"       1 = time each stage with CUDA events (kb_last_profile)
  *   "result_cap"    initial capacity of the survivor table (it grows and the group pass re-runs on overflow)
+ *   "slab"          1 (default) = one-word records: K1 fused with partition level 0 into fixed-capacity slabs (kb_extract_part.cuh);
+ *                   a slab overflow (very repetitive input) repeats the search on the exact, histogram-based path.  "slab_cap" forces
+ *                   the slab capacity (tests).  "hash_warp" 1 (default) = bucket hash with per-warp streaming (kb_hash_warp.cuh),
+ *                   "hash_shared" 1 / 0 / -1 = one table per CTA / per warp / by table size
+ *   "batch_level0"  1 (default) = with host buffers in flight K1 (+ partition levels 0 and 1) run per batch of arrived files
+ *   "shard_bb_extra" bucket bits added to the sharded slab plan (kb_shard_slab_search status 1)
  */
 int kb_set_option(kb_ctx* ctx, const char* name, long long value);
 
@@ -175,6 +181,28 @@ int kb_shard_scatter(kb_ctx* ctx, const uint64_t* piece_base);
 int kb_shard_extract(kb_ctx* ctx, void** records, uint64_t* shard_counts, uint64_t* digit_counts);
 int kb_shard_recv_buffer(kb_ctx* ctx, uint64_t n_records, void** buffer);
 int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_counts, kb_result** out);
+
+/*
+ * Multi-GPU on slabs (one-word records; the default exchange): K1 is fused with partition level 0 (csrc/kb_extract_part.cuh) and
+ * stores every level-0 digit's run straight into a fixed-capacity slab of the OWNER's receive buffer over NVLink peer memory —
+ * slab (source rank, digit) — so the exchange is K1's store phase: no count exchange before the data, no separate partition pass.
+ * The fill levels (cursors) stay on the device and are all-gathered there (torch.distributed / NCCL on device tensors); the
+ * all-gather is also the barrier after which every rank's stores have landed.
+ *   kb_shard_slab_plan     same call on every rank (total_bases = bases over all ranks, max_rank_bases = the largest rank's share:
+ *                          it sizes the slabs).  *recv_capacity_records = what kb_shard_ipc_export must allocate.
+ *                          KB_EUNSUPPORTED for multi-word records / when the slab path is switched off: use kb_shard_count ... instead.
+ *   kb_shard_slab_extract  K1 + level 0 + peer stores on this rank's files; *cursors_dev = device array of n_digits u64 (this rank's
+ *                          fill level of its slab of every digit, in the owner's buffer) for the all-gather.
+ *   kb_shard_slab_search   gathered_cursors_dev = device array [n_ranks][n_digits] (all-gather result, rank-major).  Remaining
+ *                          partition levels + bucket hash on this rank's receive buffer.  *status: 0 = result in *out, 1 = the plan
+ *                          was too coarse for this input (option "shard_bb_extra" + 2 on EVERY rank, plan again), 2 = a slab
+ *                          overflowed (repetitive input: use the exact exchange, kb_shard_count ...).  The host layer all-reduces
+ *                          the status so that all ranks take the same decision (krisp_b200/sharded.py:slab_search).
+ */
+int kb_shard_slab_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bases, uint64_t max_rank_bases, int* n_digits,
+                       uint64_t* recv_capacity_records);
+int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev);
+int kb_shard_slab_search(kb_ctx* ctx, const void* gathered_cursors_dev, int* status, kb_result** out);
 
 /* Result accessors: borrowed pointers.  The survivor table (flank, masks, group sizes) and the rows live in the context's pinned
  * result arena — valid until kb_result_free OR the next search on the same context, whichever comes first (copy what must outlive

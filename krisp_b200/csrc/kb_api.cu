@@ -59,6 +59,15 @@ struct PartPlan {
     uint32_t ncl[3] = {0, 0, 0};         // children per level this GPU works on (= nc on one GPU; its shard's part on several)
 };
 
+// slab search path (kb_extract_part.cuh): per level the number of slabs, their capacity, and where their tables live in ctx->plan
+struct SlabPlan {
+    int levels = 0, bits[3] = {0, 0, 0};
+    uint32_t nc[3] = {0, 0, 0};
+    uint64_t cap[3] = {0, 0, 0};
+    size_t off_cur[3] = {0, 0, 0}, off_counts = 0, off_start = 0, off_part = 0, off_tab0 = 0, off_tile0[3] = {0, 0, 0}, off_tilemap = 0, off_snap = 0, bytes = 0;
+    uint64_t max_tiles = 0;
+};
+
 // Level 0 of the partition per batch of input files (host buffers still in flight): see kb_batch_*_kernel in kb_part.cuh.
 #define KB_MAX_BATCHES 16
 struct BatchL0 {
@@ -142,6 +151,7 @@ struct kb_ctx {
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
 
     // shard state
+    SlabPlan shard_sp;
     PartPlan shard_plan;
     int shard_n = 0, shard_index = 0;
     std::vector<uint64_t> shard_tab_host;
@@ -155,6 +165,9 @@ struct kb_ctx {
     uint64_t sep_upto = 0, reserve_hint = 0;
     int own_first = 0, own_count = -1;   // replicated sequences: K1 of the shard calls covers only these local files (-1: all)
     int shard_direct = 0;                // the last exchange went through kb_shard_scatter (input of kb_shard_search = recvbuf)
+    bool shard_slab = false;             // kb_shard_slab_plan succeeded: shard_sp / shard_plan describe the slab exchange
+    long long opt_shard_bb_extra = 0;    // bucket bits added to the sharded slab plan (set on every rank alike after a re-plan vote)
+    uint64_t shard_total_bases = 0;
     uint64_t shard_n_records = 0;
     int shard_send_in_B = 0;             // partitioned records are in entB (else entA)
 };
@@ -290,6 +303,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "slab") { ctx->opt_slab = value ? 1 : 0; ctx->slab_off = false; }
     else if (n == "hash_warp") ctx->opt_hash_warp = value ? 1 : 0;
     else if (n == "hash_shared") ctx->opt_hash_shared = value < 0 ? -1 : (value ? 1 : 0);
+    else if (n == "shard_bb_extra") { if (value < 0 || value > 12) return fail(ctx, KB_EINVAL, "shard_bb_extra must be in 0..12"); ctx->opt_shard_bb_extra = value; }
     else if (n == "slab_cap") { if (value < 0) return fail(ctx, KB_EINVAL, "slab_cap must be >= 0"); ctx->opt_slab_cap = value; ctx->slab_off = false; }
     else if (n == "render_rows") ctx->opt_render_rows = value ? 1 : 0;
     else if (n == "have_outgroup") ctx->opt_have_outgroup = value ? 1 : 0;
@@ -1364,13 +1378,6 @@ static int run_prefilter(kb_ctx* ctx, const PartPlan& pl, uint64_t* parted, uint
 
 // ---- slab search path (one-word records): K1 fused with partition level 0 (kb_extract_part.cuh), further levels and the bucket
 //      hash on fixed-capacity slabs.  No histogram, no exact offsets: a level's cursors ARE its bucket table. ------------------------
-struct SlabPlan {
-    int levels = 0, bits[3] = {0, 0, 0};
-    uint32_t nc[3] = {0, 0, 0};
-    uint64_t cap[3] = {0, 0, 0};
-    size_t off_cur[3] = {0, 0, 0}, off_counts = 0, off_start = 0, off_part = 0, off_tab0 = 0, off_tile0[3] = {0, 0, 0}, off_tilemap = 0, off_snap = 0, bytes = 0;
-    uint64_t max_tiles = 0;
-};
 
 // capacity of one of `nc` slabs that share n_est records: mean + 6 sigma (a key's occurrences move together) + a little
 static uint64_t slab_capacity(const kb_ctx* ctx, uint64_t n_est, uint64_t nc, bool is_parent) {
@@ -2030,6 +2037,171 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_count
     if (ctx->lazy_now && n_records > 0) TRY(run_prefilter(ctx, pl, parted, n_records, &hs, &parted));
     int rc = run_group(ctx, parted, n_records, out, &hs);
     prof_collect(ctx);
+    return rc;
+}
+
+// ---- multi-GPU on slabs: K1 + level 0 store straight into the owners' receive slabs (the exchange IS K1's store phase), the
+//      cursors are all-gathered on the device, levels >= 1 and the bucket hash run on the owner -----------------------------------
+__global__ void __launch_bounds__(256) kb_shard_pend_kernel(const unsigned long long* gathered, uint32_t n_ranks, uint32_t nd0, uint32_t d_lo, uint32_t dps,
+                                                            unsigned long long* pend, uint32_t* prow) {
+    for (uint32_t p = blockIdx.x * 256 + threadIdx.x; p < n_ranks * dps; p += gridDim.x * 256) {
+        const uint32_t src = p / dps, j = p - src * dps;
+        pend[p] = gathered[(size_t)src * nd0 + d_lo + j];              // the source's cursor of (its slab of) digit d_lo + j in this buffer
+        prow[p] = j;
+    }
+}
+
+int kb_shard_slab_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bases, uint64_t max_rank_bases, int* n_digits,
+                       uint64_t* recv_capacity_records) {
+    if (!ctx || n_shards < 1 || n_shards > 256 || shard_index < 0 || shard_index >= n_shards || !recv_capacity_records) return KB_EINVAL;
+    if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
+    const KbLayout& lo = ctx->lo;
+    ctx->shard_slab = false;
+    const uint64_t n_est = 2 * total_bases + 64;
+    const PartPlan probe = make_plan(ctx, n_est, 0, false);
+    if (!(ctx->opt_slab && ctx->opt_group_algo && lo.direct && probe.stream))
+        return fail(ctx, KB_EUNSUPPORTED, "the slab exchange needs one-word records and the bucket-hash path (slab = 1, group_algo = 1)");
+    int min_bits0 = 0;
+    while ((1 << min_bits0) < n_shards) min_bits0++;
+    const int keybits = lo.FB;
+    int bb = std::min(probe.bb + (int)ctx->opt_shard_bb_extra, std::min(keybits, 24));
+    bb = std::max(bb, min_bits0 + 1);
+    if (keybits < min_bits0 + 1) return fail(ctx, KB_EUNSUPPORTED, "flank key too short to shard over this many GPUs");
+    int bits0 = ctx->opt_shard_bits0 > 0 ? (int)ctx->opt_shard_bits0 : (bb + 1) / 2;
+    bits0 = std::max(std::max(min_bits0, 1), std::min(std::min(bits0, 9), bb - 1));
+    if (bb - bits0 > 18) bb = bits0 + 18;
+    // make_plan with a forced level 0: (bits0, then the rest in levels of <= 9 bits); the option bucket_bits, when set, still wins
+    const long long save_bb = ctx->opt_bucket_bits;
+    ctx->opt_bucket_bits = ctx->opt_bucket_bits >= 0 ? ctx->opt_bucket_bits : bb;
+    PartPlan pl = make_plan(ctx, n_est, bits0, false);
+    ctx->opt_bucket_bits = save_bb;
+    if (pl.levels < 2 || pl.levels > 3 || pl.bits[0] < min_bits0) return fail(ctx, KB_EINTERNAL, "shard slab plan");
+    const uint32_t nd0 = pl.nc[0];
+    const uint32_t d_lo = shard_first_digit((uint32_t)shard_index, (uint32_t)n_shards, nd0);
+    const uint32_t dps = shard_first_digit((uint32_t)shard_index + 1, (uint32_t)n_shards, nd0) - d_lo;
+    SlabPlan sp;
+    sp.levels = pl.levels;
+    size_t off = 0;
+    uint32_t maxnc = std::max<uint32_t>(nd0, (uint32_t)n_shards * dps);
+    uint32_t loc = dps;
+    for (int l = 0; l < pl.levels; l++) {
+        sp.bits[l] = pl.bits[l];
+        if (l == 0) { sp.nc[0] = nd0; sp.cap[0] = slab_capacity(ctx, 2 * max_rank_bases + 64, nd0, true); }
+        else { loc <<= pl.bits[l]; sp.nc[l] = loc; sp.cap[l] = slab_capacity(ctx, n_est, pl.nc[l], l + 1 < pl.levels); }
+        pl.ncl[l] = l == 0 ? dps : loc;
+        maxnc = std::max(maxnc, sp.nc[l]);
+        sp.off_cur[l] = off; off += (size_t)sp.nc[l] * 8;
+    }
+    sp.off_counts = off; off += (size_t)maxnc * 8;
+    sp.off_start = off; off += ((size_t)maxnc + 1) * 8;
+    sp.off_part = off; off += ((size_t)maxnc / KB_PLAN_BLOCK + 2) * 16;
+    sp.off_tab0 = off; off += (size_t)2 * KB_XP_MAXR * 8;
+    for (int l = 0; l < pl.levels; l++) { sp.off_tile0[l] = off; off += (((size_t)std::max<uint32_t>(sp.nc[l], (uint32_t)n_shards * dps) + 2) * 4 + 7) & ~(size_t)7; }
+    sp.max_tiles = (2 * total_bases / std::max(1, n_shards) * 2 + 64) / KB_PT_TILE + maxnc + (uint64_t)n_shards * dps + 2;
+    sp.off_tilemap = off; off += ((size_t)sp.max_tiles * 4 + 7) & ~(size_t)7;
+    sp.off_snap = off; off += ((size_t)n_shards * dps) * 8 + (((size_t)n_shards * dps * 4 + 7) & ~(size_t)7);   // parent fill levels | cursor rows
+    sp.bytes = off;
+    ctx->shard_sp = sp;
+    ctx->shard_plan = pl;
+    ctx->shard_n = n_shards;
+    ctx->shard_index = shard_index;
+    ctx->shard_total_bases = total_bases;
+    ctx->shard_slab = true;
+    if (n_digits) *n_digits = (int)nd0;
+    *recv_capacity_records = (uint64_t)n_shards * dps * sp.cap[0] + 4096;
+    return KB_OK;
+}
+
+int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev) {
+    if (!ctx || !cursors_dev) return KB_EINVAL;
+    if (!ctx->configured || !ctx->shard_slab) return fail(ctx, KB_EINVAL, "kb_shard_slab_plan has not been called");
+    if ((int)ctx->peer_ptr.size() != ctx->shard_n) return fail(ctx, KB_EINVAL, "kb_shard_ipc_import has not been called");
+    const SlabPlan& sp = ctx->shard_sp;
+    const uint32_t nd0 = sp.nc[0];
+    const int N = ctx->shard_n, me = ctx->shard_index;
+    CU(cudaSetDevice(ctx->device));
+    begin_search(ctx);
+    TRY(prepare_small(ctx));
+    TRY(ensure(ctx, ctx->plan, sp.bytes + 64));
+    uint8_t* P = (uint8_t*)ctx->plan.p;
+    // children levels on this GPU: level l writes buf[l & 1] (level 1 reads the receive buffer)
+    size_t need[2] = {0, 0};
+    for (int l = 1; l < sp.levels; l++) need[l & 1] = std::max(need[l & 1], (size_t)sp.nc[l] * sp.cap[l] + 4096);
+    if (need[0]) TRY(ensure(ctx, ctx->entA, need[0] * 8));
+    if (need[1]) TRY(ensure(ctx, ctx->entB, need[1] * 8));
+    for (int l = 1; l < sp.levels; l++) {
+        kb_slab_init_kernel<<<(unsigned)std::min<uint32_t>((sp.nc[l] + 255) / 256, 1024), 256, 0, ctx->stream>>>((unsigned long long*)(P + sp.off_cur[l]), sp.nc[l], sp.cap[l]);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    // level-0 tables: digit d lives in the receive buffer of its owner o, slab (this rank, d - first(o))
+    std::vector<uint64_t>& t0 = ctx->scatter_host;
+    t0.assign((size_t)3 * KB_XP_MAXR, 0);
+    for (int o = 0; o < N; o++) {
+        const uint32_t d0 = shard_first_digit((uint32_t)o, (uint32_t)N, nd0), d1 = shard_first_digit((uint32_t)o + 1, (uint32_t)N, nd0);
+        const uint64_t dps_o = d1 - d0;
+        for (uint32_t d = d0; d < d1; d++) {
+            const uint64_t first = ((uint64_t)me * dps_o + (d - d0)) * sp.cap[0];
+            t0[d] = first + sp.cap[0];                                                                   // slab end
+            t0[KB_XP_MAXR + d] = (uint64_t)(reinterpret_cast<uintptr_t>(ctx->peer_ptr[o]) >> 3);       // destination buffer
+            t0[2 * KB_XP_MAXR + d] = first;                                                              // cursor start
+        }
+    }
+    if ((uint64_t)N * (shard_first_digit((uint32_t)me + 1, (uint32_t)N, nd0) - shard_first_digit((uint32_t)me, (uint32_t)N, nd0)) * sp.cap[0] + 2048 > ctx->recvbuf.cap / 8)
+        return fail(ctx, KB_EINVAL, "the receive buffer is smaller than kb_shard_slab_plan asked for");
+    CU(cudaMemcpyAsync(P + sp.off_tab0, t0.data(), (size_t)2 * KB_XP_MAXR * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(P + sp.off_cur[0], t0.data() + 2 * KB_XP_MAXR, (size_t)nd0 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t pos_lo = 0, pos_hi = 0;
+    uint32_t tile0 = 0, n_tiles = 0;
+    TRY(shard_extract_range(ctx, &pos_lo, &pos_hi, &tile0, &n_tiles));
+    TRY(prepare_extract(ctx));
+    const auto batches = extract_batches(ctx, tile0, n_tiles);
+    prof_begin(ctx, "K1 extract + partition 0 + exchange (peer stores)");
+    TRY(run_extract_part(ctx, tile0, n_tiles, pos_lo, pos_hi, (uint32_t)sp.bits[0], (unsigned long long*)(P + sp.off_cur[0]),
+                         (const unsigned long long*)(P + sp.off_tab0), (const unsigned long long*)(P + sp.off_tab0) + KB_XP_MAXR, batches,
+                         [](int, int, uint32_t) -> int { return KB_OK; }));
+    prof_end(ctx);
+    *cursors_dev = P + sp.off_cur[0];
+    return KB_OK;
+}
+
+int kb_shard_slab_search(kb_ctx* ctx, const void* gathered_cursors_dev, int* status, kb_result** out) {
+    if (!ctx || !gathered_cursors_dev || !status || !out) return KB_EINVAL;
+    *out = nullptr; *status = 0;
+    if (!ctx->configured || !ctx->shard_slab) return fail(ctx, KB_EINVAL, "kb_shard_slab_plan has not been called");
+    const SlabPlan& sp = ctx->shard_sp;
+    PartPlan pl = ctx->shard_plan;
+    const uint32_t nd0 = sp.nc[0];
+    const uint32_t N = (uint32_t)ctx->shard_n, me = (uint32_t)ctx->shard_index;
+    const uint32_t d_lo = shard_first_digit(me, N, nd0), dps = shard_first_digit(me + 1, N, nd0) - d_lo;
+    const uint32_t np = N * dps;
+    CU(cudaSetDevice(ctx->device));
+    uint8_t* P = (uint8_t*)ctx->plan.p;
+    unsigned long long* pend = (unsigned long long*)(P + sp.off_snap);
+    uint32_t* prow = (uint32_t*)(pend + np);
+    kb_shard_pend_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)gathered_cursors_dev, N, nd0, d_lo, dps, pend, prow);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    const uint64_t n_est = 2 * ctx->shard_total_bases + 64;
+    uint64_t* bufs[2] = {(uint64_t*)ctx->entA.p, (uint64_t*)ctx->entB.p};
+    prof_begin(ctx, "K2 partition 1");
+    TRY(launch_slab_level(ctx, sp, pl, 1, (const uint64_t*)ctx->recvbuf.p, bufs[1], pend, nullptr, np, prow, std::min<uint64_t>(n_est, (uint64_t)np * sp.cap[0])));
+    prof_end(ctx);
+    ctx->alg_rec_bytes += 16;
+    // (launch_slab_level sized the tile tables by parents = np; deeper levels use the local child counts)
+    TRY(run_slab_levels(ctx, sp, pl, 2, bufs, sp.levels > 2 ? std::min<uint64_t>(n_est, (uint64_t)sp.nc[1] * sp.cap[1]) : n_est));
+    ctx->passes = sp.levels;
+    HashStage hs{};
+    hs.pl = &pl;
+    hs.n_buckets = sp.nc[sp.levels - 1];
+    hs.bend = (const unsigned long long*)(P + sp.off_cur[sp.levels - 1]);
+    hs.bcap = sp.cap[sp.levels - 1];
+    ctx->replan_ok = ctx->opt_bucket_bits < 0 && pl.bb < std::min(ctx->lo.FB, 24);
+    int rc = run_group(ctx, bufs[(sp.levels - 1) & 1], n_est, out, &hs);
+    ctx->replan_ok = false;
+    prof_collect(ctx);
+    if (rc == KB_REPLAN) { *status = 1; return KB_OK; }
+    if (rc == KB_SLABOVF) { *status = 2; return KB_OK; }
     return rc;
 }
 

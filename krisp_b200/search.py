@@ -385,6 +385,35 @@ class Searcher:
         arr = (ctypes.c_uint64 * len(piece_base))(*[int(c) for c in piece_base])
         self._check(self._L.kb_shard_scatter(self._ctx, arr))
 
+    # slab exchange (K1 fused with partition level 0, peer stores into the owners' slabs; see include/krisp_b200.h)
+    def shard_slab_plan(self, n_shards, shard_index, total_bases, max_rank_bases):
+        """-> (level-0 fan-out, receive-buffer capacity in records); raises UnsupportedError where the slab exchange does not apply."""
+        nd, cap = ctypes.c_int(), ctypes.c_uint64()
+        self._check(self._L.kb_shard_slab_plan(self._ctx, int(n_shards), int(shard_index), int(total_bases), int(max_rank_bases),
+                                               ctypes.byref(nd), ctypes.byref(cap)))
+        self._shard = (int(n_shards), int(shard_index), int(nd.value))
+        return int(nd.value), int(cap.value)
+
+    def shard_slab_extract(self):
+        """K1 + level 0 + peer stores; -> device pointer of this rank's n_digits slab cursors (u64)."""
+        ptr = ctypes.c_void_p()
+        self._check(self._L.kb_shard_slab_extract(self._ctx, ctypes.byref(ptr)))
+        self._keep = []
+        return int(ptr.value)
+
+    def shard_slab_search(self, gathered_ptr, have_outgroup=True):
+        """-> (SearchResult or None, status): status 1 = plan too coarse, 2 = slab overflow (see the header)."""
+        res, status = ctypes.c_void_p(), ctypes.c_int()
+        self._set_have_outgroup(have_outgroup)
+        self._check(self._L.kb_shard_slab_search(self._ctx, ctypes.c_void_p(int(gathered_ptr)), ctypes.byref(status), ctypes.byref(res)))
+        if status.value != 0 or not res.value:
+            return None, int(status.value)
+        return self._collect(res, have_outgroup), 0
+
+    def set_stream(self, stream):
+        """Launch on this raw cudaStream_t from now on (0 = the default stream)."""
+        self._check(self._L.kb_set_stream(self._ctx, ctypes.c_void_p(int(stream))))
+
     def shard_recv_buffer(self, n_records):
         buf = ctypes.c_void_p()
         self._check(self._L.kb_shard_recv_buffer(self._ctx, int(n_records), ctypes.byref(buf)))

@@ -147,19 +147,7 @@ def direct_search(searcher, device, have_outgroup=True, group=None):
     need, piece_base, pieces = piece_tables(table, rank)
     if nch:
         searcher.shard_set_child_counts(shard_child_counts(both[:, nd:], nd, rank))
-    state = searcher.__dict__.setdefault("_ipc_state", {"cap": [0] * world, "world": world})
-    if state["world"] != world or any(n > c for n, c in zip(need, state["cap"])):
-        # some buffer is too small: every rank sees the same table, so every rank takes this branch together
-        state["cap"] = [max(c, n + n // 4 + 4096) for n, c in zip(need, state["cap"])]
-        state["world"] = world
-        if hasattr(searcher, "shard_ipc_close"):
-            searcher.shard_ipc_close()                                # nobody maps a buffer that is about to be reallocated
-            dist.barrier(group=group)
-        mine = torch.frombuffer(bytearray(searcher.shard_ipc_export(state["cap"][rank])), dtype=torch.uint8).to(device)
-        allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
-        dist.all_gather_into_tensor(allh, mine, group=group)
-        blob = allh.cpu().numpy().tobytes()
-        searcher.shard_ipc_import([blob[64 * r:64 * (r + 1)] for r in range(world)])
+    _ensure_ipc(searcher, device, group, need)
     searcher.shard_scatter(piece_base)                                # partition level 0 -> peer stores
     prof += [p for p in searcher.last_profile() if p[0].startswith("K2 partition 0")]
     flag = torch.zeros(1, dtype=torch.int32, device=device)
@@ -171,6 +159,104 @@ def direct_search(searcher, device, have_outgroup=True, group=None):
     res.profile = prof + list(res.profile)
     res.exchange = {"sent": int(sum(digits) - sum(digits[firsts[rank]:firsts[rank + 1]])), "received": need[rank]}
     return res
+
+
+def _ensure_ipc(searcher, device, group, need):
+    """Every rank's receive buffer holds at least need[rank] records and is mapped by every peer (CUDA IPC).  `need` is the same
+    list on every rank, so all ranks take the (re)allocation branch together; buffers only grow."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    state = searcher.__dict__.setdefault("_ipc_state", {"cap": [0] * world, "world": world})
+    if state["world"] == world and all(n <= c for n, c in zip(need, state["cap"])):
+        return
+    state["cap"] = [max(c, n + n // 8 + 4096) for n, c in zip(need, state["cap"] if state["world"] == world else [0] * world)]
+    state["world"] = world
+    if hasattr(searcher, "shard_ipc_close"):
+        searcher.shard_ipc_close()                                    # nobody maps a buffer that is about to be reallocated
+        dist.barrier(group=group)
+    mine = torch.frombuffer(bytearray(searcher.shard_ipc_export(state["cap"][rank])), dtype=torch.uint8).to(device)
+    allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(allh, mine, group=group)
+    blob = allh.cpu().numpy().tobytes()
+    searcher.shard_ipc_import([blob[64 * r:64 * (r + 1)] for r in range(world)])
+
+
+def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=None):
+    """The exchange fused into K1 (one-word records): every rank's K1 + partition level 0 (csrc/kb_extract_part.cuh) store each
+    level-0 digit's run straight into a fixed-capacity slab of the owner's receive buffer over NVLink peer memory.  There is no count
+    exchange before the data and no separate partition pass; the slab fill levels stay on the device and are all-gathered there —
+    the all-gather doubles as the barrier after which every rank's stores have landed — and the owner runs level 1 + the bucket hash
+    on its slabs.  No host round trip between the stages.
+    Returns the SearchResult, or None when the slab exchange does not apply (multi-word records, slab overflow on a repetitive
+    input): the caller then uses the exact exchange (direct_search).  All ranks return the same kind of answer."""
+    import torch
+    import torch.distributed as dist
+    from ._lib import UnsupportedError
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = int(getattr(searcher, "bases_added", 0))
+    t = torch.tensor([mine, -mine], dtype=torch.int64, device=device)
+    if total_bases is None:
+        s = torch.tensor([mine], dtype=torch.int64, device=device)
+        dist.all_reduce(s, group=group)
+        total_bases = int(s.item())
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    max_rank_bases = int(t[0].item())
+    extra = int(searcher.__dict__.get("_shard_bb_extra", 0))
+    for _ in range(4):
+        searcher.set_option("shard_bb_extra", extra)
+        try:
+            nd, cap = searcher.shard_slab_plan(world, rank, total_bases, max_rank_bases)
+            ok = 1
+        except UnsupportedError:
+            nd, cap, ok = 0, 0, 0
+        caps = torch.tensor([cap if ok else -1], dtype=torch.int64, device=device)
+        allc = torch.empty(world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(allc, caps, group=group)
+        need = [int(c) for c in allc.tolist()]
+        if min(need) < 0:
+            return None                                               # (some rank cannot: nobody does)
+        _ensure_ipc(searcher, device, group, need)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        cur_ptr = searcher.shard_slab_extract()                       # K1 + level 0 + peer stores (asynchronous)
+        prof = list(searcher.last_profile())
+        ev[1].record()
+        cur = _wrap(cur_ptr, nd, device)
+        gathered = torch.empty(world * nd, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(gathered, cur, group=group)       # fill levels, on the device; every rank's stores have landed
+        ev[2].record()
+        res, status = searcher.shard_slab_search(gathered.data_ptr(), have_outgroup=have_outgroup)
+        st = torch.tensor([status], dtype=torch.int64, device=device)
+        dist.all_reduce(st, op=dist.ReduceOp.MAX, group=group)        # same decision everywhere; also: nobody starts the next
+        status = int(st.item())                                       # search's stores while a peer still reads its buffer
+        if status == 0:
+            ev[2].synchronize()
+            res.profile = [("K1 + partition 0 + exchange (launch to last store)", ev[0].elapsed_time(ev[1])),
+                           ("K4 cursor all-gather (barrier)", ev[1].elapsed_time(ev[2]))] + [p for p in res.profile]
+            res.profile = prof + res.profile
+            lo_d, hi_d = first_digit(rank, world, nd), first_digit(rank + 1, world, nd)
+            res.exchange = {"slab": True, "digits": nd, "records_extracted": int(res.n_records), "own_digits": [lo_d, hi_d],
+                            "sent": int(res.n_records) - int(res.n_records) * (hi_d - lo_d) // max(nd, 1)}   # (uniform digits: the share that stays)
+            return res
+        if status == 2:
+            return None                                               # a slab overflowed somewhere: exact exchange for everybody
+        extra += 2                                                    # plan too coarse somewhere: two more bucket bits for everybody
+        searcher.__dict__["_shard_bb_extra"] = extra
+    return None
+
+
+def shutdown(searcher, group=None):
+    """Collective teardown: every rank unmaps its peers' receive buffers, then a barrier, then the contexts may be destroyed
+    (exported memory must not be freed while a peer still maps it or still stores into it)."""
+    import torch.distributed as dist
+    if hasattr(searcher, "synchronize"):
+        searcher.synchronize()
+    if hasattr(searcher, "shard_ipc_close"):
+        searcher.shard_ipc_close()
+    dist.barrier(group=group)
+    searcher.__dict__.pop("_ipc_state", None)
+    searcher.close()
 
 
 def replicate_sequences(searcher, device, group=None):
@@ -221,7 +307,21 @@ def sharded_search(searcher, device, have_outgroup=True, group=None, total_bases
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    on_cuda = device is not None and getattr(device, "type", "cpu") == "cuda"
+    if on_cuda and hasattr(searcher, "set_stream"):
+        # the library's kernels must be ordered with the collectives issued here: both on torch's current stream
+        searcher.set_stream(torch.cuda.current_stream(device).cuda_stream)
     lo = getattr(searcher, "lo", None)
+    multiword = lo is not None and 2 * sum(lo) + 8 > 64
+    if exchange_mode is None:
+        exchange_mode = os.environ.get("KRISP_EXCHANGE")
+    if exchange_mode in (None, "slab") and on_cuda and not multiword and hasattr(searcher, "shard_slab_plan"):
+        res = slab_search(searcher, device, have_outgroup, group, total_bases)
+        if res is not None:
+            return res
+        exchange_mode = "p2p"                                         # slab exchange not applicable / overflowed: exact exchange
+    if exchange_mode == "slab":
+        exchange_mode = None
     if lo is not None and 2 * sum(lo) + 8 > 64 and hasattr(searcher, "sequence_buffer"):
         if getattr(searcher, "_replicated", None) is not searcher.added_ids:
             replicate_sequences(searcher, device, group)
@@ -232,9 +332,8 @@ def sharded_search(searcher, device, have_outgroup=True, group=None, total_bases
         dist.all_reduce(t, group=group)
         total_bases = int(t.item())
     searcher.shard_plan(world, rank, total_bases)
-    on_cuda = device is not None and getattr(device, "type", "cpu") == "cuda"
     if exchange_mode is None:
-        exchange_mode = os.environ.get("KRISP_EXCHANGE", "p2p" if on_cuda and hasattr(searcher, "shard_scatter") else "nccl")
+        exchange_mode = "p2p" if on_cuda and hasattr(searcher, "shard_scatter") else "nccl"
     if exchange_mode == "p2p":
         return direct_search(searcher, device, have_outgroup, group)
     _dbg("shard_extract")

@@ -20,7 +20,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    s = Searcher(device=local, stream=torch.cuda.current_stream().cuda_stream)
+    s = Searcher(device=local)                         # (own stream: sharded_search moves it onto torch's current stream itself)
     bad = 0
     for case in load_golden()["cases"]:
         L, D, R = deduce_ldr(case["flags"])
@@ -35,7 +35,7 @@ def main():
         for i, f in enumerate(files):
             if owner[i] == rank:
                 s.add_sequence(i, ingest.load_file(f)[0])
-        for mode in ("p2p", "nccl"):                   # fused partition + exchange over peer memory / NCCL all-to-all
+        for mode in ("slab", "p2p", "nccl"):           # K1-fused slab exchange / fused partition + exchange over peer memory / NCCL all-to-all
             res = sharded.sharded_search(s, dev, have_outgroup=len(outs) > 0, exchange_mode=mode)
             rows = sharded.gather_rows(res.rows())
             ok = len(rows) == case["n_rows"] and hashlib.sha256("\n".join(rows).encode()).hexdigest() == case["rows_sha256"]
@@ -46,6 +46,8 @@ def main():
     # level-1 children too and the counts travel with the exchange; rows must equal the single-GPU search of the whole panel
     from krisp_b200.panel import make_panel
     for (L, D, R), opts in [((25, 1, 2), {}), ((25, 1, 2), {"bucket_bits": 16, "shard_bits0": 4}), ((25, 1, 2), {"bucket_bits": 16, "shard_bits0": 4, "fused_hist": 0}),
+                            ((25, 1, 2), {"bucket_bits": 12}), ((25, 1, 2), {"bucket_bits": 20, "shard_bits0": 5}), ((25, 1, 2), {"bucket_bits": 14, "hash_shared": 0, "hash_slots_log2": 6}),
+                            ((25, 1, 2), {"slab_cap": 2}), ((25, 1, 2), {"slab": 0}), ((12, 3, 12), {"bucket_bits": 10}),
                             ((32, 60, 32), {}), ((32, 60, 32), {"bucket_bits": 16, "shard_bits0": 4})]:
         gs = make_panel(5, 4, 200_000)
         is_in = [1 if g.is_ingroup else 0 for g in gs]
@@ -64,15 +66,33 @@ def main():
             res = sharded.sharded_search(s, dev, have_outgroup=True)
             rows = sharded.gather_rows(res.rows())
         finally:
-            s.set_option("bucket_bits", -1)
-            s.set_option("shard_bits0", 0)
-            s.set_option("fused_hist", 1)
+            for k, v in (("bucket_bits", -1), ("shard_bits0", 0), ("fused_hist", 1), ("slab_cap", 0), ("slab", 1), ("hash_shared", -1), ("hash_slots_log2", 0)):
+                s.set_option(k, v)
         ok = rows == want and len(want) > 0
         if rank == 0:
             print(("ok   " if ok else "FAIL ") + f"panel {L}/{D}/{R} {opts}", len(rows), flush=True)
         bad += 0 if ok else 1
-    s.close()
-    dist.barrier()
+    # divergent genomes (3 % private substitutions): the sharded plan is too coarse at first; every rank must vote for the re-plan
+    # and the rows must still be the single-GPU rows
+    gs = make_panel(7, 5, 400_000, noise=3e-2, snp_every=200)
+    is_in = [1 if g.is_ingroup else 0 for g in gs]
+    s.configure(25, 1, 2, is_in)
+    s.clear_sequences()
+    for i, g in enumerate(gs):
+        s.add_sequence(i, np.frombuffer(g.joined(), dtype=np.uint8))
+    want = s.search(have_outgroup=True).rows()
+    s.clear_sequences()
+    for i, g in enumerate(gs):
+        if i % world == rank:
+            s.add_sequence(i, np.frombuffer(g.joined(), dtype=np.uint8))
+    for rep in range(2):
+        res = sharded.sharded_search(s, dev, have_outgroup=True)
+        rows = sharded.gather_rows(res.rows())
+        ok = rows == want                                 # (possibly no row at all: almost every 28-mer is private)
+        if rank == 0:
+            print(("ok   " if ok else "FAIL ") + f"divergent panel, search {rep}, exchange {getattr(res, 'exchange', None)}", len(rows), flush=True)
+        bad += 0 if ok else 1
+    sharded.shutdown(s)
     dist.destroy_process_group()
     sys.exit(1 if bad else 0)
 
