@@ -184,25 +184,37 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_count
 
 /*
  * Multi-GPU on slabs (one-word records; the default exchange): K1 is fused with partition level 0 (csrc/kb_extract_part.cuh) and
- * stores every level-0 digit's run straight into a fixed-capacity slab of the OWNER's receive buffer over NVLink peer memory —
- * slab (source rank, digit) — so the exchange is K1's store phase: no count exchange before the data, no separate partition pass.
- * The fill levels (cursors) stay on the device and are all-gathered there (torch.distributed / NCCL on device tensors); the
- * all-gather is also the barrier after which every rank's stores have landed.
+ * leaves every level-0 digit's records in a fixed-capacity slab — slab (source rank, digit) of the OWNER's receive buffer.  No
+ * count exchange before the data and no separate partition pass: the slabs of a group of digits travel as bulk peer copies over
+ * NVLink while the owner already runs level 1 + the bucket hash on the previous group.  The fill levels (cursors) stay on the
+ * device and are all-gathered there (torch.distributed / NCCL on device tensors).
  *   kb_shard_slab_plan     same call on every rank (total_bases = bases over all ranks, max_rank_bases = the largest rank's share:
- *                          it sizes the slabs).  *recv_capacity_records = what kb_shard_ipc_export must allocate.
+ *                          it sizes the slabs).  *recv_capacity_records = what kb_shard_ipc_export must allocate; *max_groups = into how
+ *                          many digit groups the exchange may be cut (1 = no pipelining: small inputs, three-level plans).
  *                          KB_EUNSUPPORTED for multi-word records / when the slab path is switched off: use kb_shard_count ... instead.
- *   kb_shard_slab_extract  K1 + level 0 + peer stores on this rank's files; *cursors_dev = device array of n_digits u64 (this rank's
- *                          fill level of its slab of every digit, in the owner's buffer) for the all-gather.
- *   kb_shard_slab_search   gathered_cursors_dev = device array [n_ranks][n_digits] (all-gather result, rank-major).  Remaining
- *                          partition levels + bucket hash on this rank's receive buffer.  *status: 0 = result in *out, 1 = the plan
- *                          was too coarse for this input (option "shard_bb_extra" + 2 on EVERY rank, plan again), 2 = a slab
- *                          overflowed (repetitive input: use the exact exchange, kb_shard_count ...).  The host layer all-reduces
- *                          the status so that all ranks take the same decision (krisp_b200/sharded.py:slab_search).
+ *   kb_shard_slab_extract  K1 + level 0 on this rank's files: the slabs of its own digits go straight into its receive buffer, the
+ *                          others into a local staging buffer.  *cursors_dev = device array of n_digits u64 (this rank's fill level
+ *                          of its slab of every digit, in the coordinates of the owner's buffer) for the all-gather.
+ *   kb_shard_slab_send     enqueue, on `cuda_stream`, the bulk peer copies (copy engines over NVLink) of digit group `group` of
+ *                          `n_groups`: for every other owner the staged slabs of the group's digits as ONE contiguous copy (of which
+ *                          this call moves byte range `part` of `n_parts`: several streams keep several copy engines busy).  The
+ *                          host layer runs the groups in order on a copy stream and puts a tiny collective behind each group, after
+ *                          which every rank's copies of that group have landed.
+ *   kb_shard_slab_level    gathered_cursors_dev = device array [n_ranks][n_digits] (all-gather result, rank-major).  Partition
+ *                          level 1 + the bucket hash on the slabs of digit group `group` in this rank's receive buffer — group g
+ *                          is processed while group g + 1 is still in flight.  (Three-level plans and small inputs: one group.)
+ *   kb_shard_slab_finish   deferred buckets, group sizes, rows, download.  *status: 0 = result in *out, 1 = the plan was too coarse
+ *                          for this input (option "shard_bb_extra" + 2 on EVERY rank, plan again), 2 = a slab overflowed (repetitive
+ *                          input: use the exact exchange, kb_shard_count ...), 3 = the survivor table was too small and has been
+ *                          grown (search again).  The host layer all-reduces the status so that all ranks take the same decision
+ *                          (krisp_b200/sharded.py:slab_search).
  */
 int kb_shard_slab_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bases, uint64_t max_rank_bases, int* n_digits,
-                       uint64_t* recv_capacity_records);
+                       uint64_t* recv_capacity_records, int* max_groups);
 int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev);
-int kb_shard_slab_search(kb_ctx* ctx, const void* gathered_cursors_dev, int* status, kb_result** out);
+int kb_shard_slab_send(kb_ctx* ctx, int group, int n_groups, int part, int n_parts, void* cuda_stream);
+int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group, int n_groups);
+int kb_shard_slab_finish(kb_ctx* ctx, int* status, kb_result** out);
 
 /* Result accessors: borrowed pointers.  The survivor table (flank, masks, group sizes) and the rows live in the context's pinned
  * result arena — valid until kb_result_free OR the next search on the same context, whichever comes first (copy what must outlive

@@ -178,6 +178,7 @@ enum { SM_NOUT = 0, SM_NRES = 1, SM_STATS = 2 /*4*/, SM_NTAINT = 6, SM_ERR = 7, 
 
 #define KB_REPLAN 1                      // internal: the search gave up on its plan (never leaves the library)
 #define KB_SLABOVF 2                     // internal: a slab overflowed; repeat on the exact path
+#define KB_RESGROW 3                     // internal (pipelined multi-GPU search): the survivor table was too small and has been grown
 
 static int fail(kb_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -946,6 +947,8 @@ struct HashStage {            // what run_group needs to run the bucket-hash ker
     uint64_t n_kept = 0;                         // lazy records: elements the exact pass reads
     const unsigned long long* bend = nullptr;   // slab layout: fill level (absolute end) of every bucket
     uint64_t bcap = 0;                           // slab layout: bucket b starts at b * bcap
+    int phase = 0;                               // 0 = everything; 1 = only the main kernel, on buckets [bucket0, bucket0 + n_buckets);
+    uint32_t bucket0 = 0;                        // 2 = only what follows it (deferred buckets, group sizes) over all n_buckets
 };
 
 static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
@@ -964,9 +967,10 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
         TRY(ensure(ctx, ctx->deferred, (size_t)hs.n_buckets * 4 + 64));
         const int pwn = lo.n_files <= 64 ? 2 : (lo.n_files <= 128 ? 4 : 8);
         const bool spacer = lo.D == 1 && lo.FB == 54 && x.bb <= 22;
-        if (warp_kernel) {
+        if (warp_kernel && hs.phase != 2) {
             KbHWarpArgs xw{};
             xw.h = x;
+            xw.h.bucket0 = hs.bucket0;
             xw.deferred = (uint32_t*)ctx->deferred.p;
             xw.n_deferred = (unsigned long long*)ctx->small.p + SM_NTAINT;   // zeroed with the result counters
             const bool packed = lo.D == 1 && lo.FB <= 54;
@@ -997,7 +1001,8 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
             else { if (spacer) KB_LAUNCH_WARP(true, true, 8); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 8); else KB_LAUNCH_WARP(false, false, 8); }
 #undef KB_LAUNCH_WARP
             CU(cudaGetLastError());
-        } else {
+            if (hs.phase == 1) { ctx->launches++; return KB_OK; }
+        } else if (!warp_kernel) {
         KbHStreamArgs xs{};
         xs.h = x; xs.n_ptr = (const unsigned long long*)ctx->small.p + SM_NOUT;
         xs.deferred = (uint32_t*)ctx->deferred.p;
@@ -1172,7 +1177,23 @@ static int render_rows(kb_ctx* ctx, kb_result* res, uint64_t n_res, char* host_d
 }
 
 // K3 over sorted[0..n) + result download
-static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result** out, const HashStage* hs = nullptr) {
+static void fill_group_args(kb_ctx* ctx, KbGroupArgs& a, const uint64_t* sorted, uint64_t n) {
+    const KbLayout& lo = ctx->lo;
+    a.ent = sorted; a.n = n; a.recs = (const uint64_t*)ctx->recs.p; a.lo = lo;
+    for (int f = 0; f < lo.n_files; f++) {
+        a.full[f >> 5] |= 1u << (f & 31);
+        if (ctx->is_ingroup[f]) a.ingroup[f >> 5] |= 1u << (f & 31);
+    }
+    a.n_res = (unsigned long long*)ctx->small.p + SM_NRES;
+    a.cap = ctx->result_cap;
+    a.res_flank = (uint64_t*)ctx->res_flank.p; a.res_in = (uint32_t*)ctx->res_in.p; a.res_out = (uint32_t*)ctx->res_out.p;
+    a.res_size = (uint32_t*)ctx->res_size.p; a.res_run = (uint64_t*)ctx->res_run.p;
+    a.stats = (unsigned long long*)ctx->small.p + SM_STATS;
+}
+
+// tail_only (pipelined multi-GPU search): the main kernel already ran (per group of buckets) on zeroed counters; only the deferred
+// buckets, the group sizes and the download are left, and a survivor table that turned out too small cannot be repaired here.
+static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result** out, const HashStage* hs = nullptr, bool tail_only = false) {
     // (hs != null: n is an upper bound; the exact count arrives with the first read-back)
     const KbLayout& lo = ctx->lo;
     kb_result* res = new (std::nothrow) kb_result();
@@ -1188,17 +1209,8 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
         bool allow_fast = true;
         for (int attempt = 0; attempt < 4; attempt++) {
             KbGroupArgs a{};
-            a.ent = sorted; a.n = n; a.recs = (const uint64_t*)ctx->recs.p; a.lo = lo;
-            for (int f = 0; f < lo.n_files; f++) {
-                a.full[f >> 5] |= 1u << (f & 31);
-                if (ctx->is_ingroup[f]) a.ingroup[f >> 5] |= 1u << (f & 31);
-            }
-            a.n_res = (unsigned long long*)ctx->small.p + SM_NRES;
-            a.cap = ctx->result_cap;
-            a.res_flank = (uint64_t*)ctx->res_flank.p; a.res_in = (uint32_t*)ctx->res_in.p; a.res_out = (uint32_t*)ctx->res_out.p;
-            a.res_size = (uint32_t*)ctx->res_size.p; a.res_run = (uint64_t*)ctx->res_run.p;
-            a.stats = (unsigned long long*)ctx->small.p + SM_STATS;
-            cudaError_t e = cudaMemsetAsync((uint64_t*)ctx->small.p + SM_NRES, 0, 7 * 8, ctx->stream);
+            fill_group_args(ctx, a, sorted, n);
+            cudaError_t e = tail_only ? cudaSuccess : cudaMemsetAsync((uint64_t*)ctx->small.p + SM_NRES, 0, 7 * 8, ctx->stream);
             if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, cudaGetErrorString(e)); }
             prof_begin(ctx, hs ? "K3 bucket hash" : "K3 group");
             int rc = hs ? launch_hash(ctx, a, *hs) : launch_group(ctx, a, allow_fast);
@@ -1225,6 +1237,7 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
             if (n_res <= ctx->result_cap) break;
             rc = ensure_results(ctx, n_res + n_res / 8 + 16);       // table too small: grow and re-run the pass
             if (rc) { delete res; return rc; }
+            if (tail_only) { delete res; return KB_RESGROW; }
         }
         if (n_res > ctx->result_cap) { delete res; return fail(ctx, KB_EINTERNAL, "survivor table overflow"); }
     }
@@ -1475,7 +1488,7 @@ static int prepare_extract(kb_ctx* ctx) {
 // writes the slabs of level l into `out`.  rec_bound = records the pass can meet at most (sizes the grid in tile-map mode).
 static int launch_slab_level(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl, int l, const uint64_t* in, uint64_t* out,
                              const unsigned long long* pend, const unsigned long long* pbegin, uint32_t n_parents, const uint32_t* prow,
-                             uint64_t rec_bound) {
+                             uint64_t rec_bound, uint32_t psel_n = 0, uint32_t psel_j0 = 0, uint32_t psel_dps = 0) {
     uint8_t* P = (uint8_t*)ctx->plan.p;
     const size_t smem = kb_part_smem();
     CU(cudaFuncSetAttribute(kb_part_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1488,6 +1501,7 @@ static int launch_slab_level(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl
     a.tile_parent = (const uint32_t*)(P + sp.off_tilemap);
     a.prow = prow;
     a.n_parents = n_parents;
+    a.psel_n = psel_n; a.psel_j0 = psel_j0; a.psel_dps = psel_dps;
     a.shift = (uint32_t)shift; a.bits = (uint32_t)sp.bits[l];
     a.cursor = (unsigned long long*)(P + sp.off_cur[l]);
     a.ccap = sp.cap[l];
@@ -2052,7 +2066,7 @@ __global__ void __launch_bounds__(256) kb_shard_pend_kernel(const unsigned long 
 }
 
 int kb_shard_slab_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bases, uint64_t max_rank_bases, int* n_digits,
-                       uint64_t* recv_capacity_records) {
+                       uint64_t* recv_capacity_records, int* max_groups) {
     if (!ctx || n_shards < 1 || n_shards > 256 || shard_index < 0 || shard_index >= n_shards || !recv_capacity_records) return KB_EINVAL;
     if (!ctx->configured) return fail(ctx, KB_EINVAL, "kb_configure has not been called");
     const KbLayout& lo = ctx->lo;
@@ -2109,6 +2123,8 @@ int kb_shard_slab_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t tota
     ctx->shard_slab = true;
     if (n_digits) *n_digits = (int)nd0;
     *recv_capacity_records = (uint64_t)n_shards * dps * sp.cap[0] + 4096;
+    // digit groups of the pipelined exchange: two-level plans with tile-aligned slabs (kb_shard_slab_level)
+    if (max_groups) *max_groups = (sp.levels == 2 && sp.cap[0] % KB_PT_TILE == 0) ? (int)std::max<uint32_t>(1, nd0 / (uint32_t)n_shards) : 1;
     return KB_OK;
 }
 
@@ -2124,27 +2140,36 @@ int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev) {
     TRY(prepare_small(ctx));
     TRY(ensure(ctx, ctx->plan, sp.bytes + 64));
     uint8_t* P = (uint8_t*)ctx->plan.p;
-    // children levels on this GPU: level l writes buf[l & 1] (level 1 reads the receive buffer)
-    size_t need[2] = {0, 0};
+    // this GPU's buffers: entA = staging of the slabs bound for the other owners (slab d at d * cap0, copied out by kb_shard_slab_send),
+    // children levels: level l writes buf[l & 1] = entB for level 1 (which reads the receive buffer), entA again for level 2
+    TRY(ensure_results(ctx, std::max<uint64_t>(ctx->result_cap, (uint64_t)ctx->opt_result_cap)));
+    TRY(ensure(ctx, ctx->deferred, (size_t)sp.nc[sp.levels - 1] * 4 + 64));       // (the per-group launches must not reallocate it)
+    size_t need[2] = {(size_t)nd0 * sp.cap[0] + 4096, 0};
     for (int l = 1; l < sp.levels; l++) need[l & 1] = std::max(need[l & 1], (size_t)sp.nc[l] * sp.cap[l] + 4096);
-    if (need[0]) TRY(ensure(ctx, ctx->entA, need[0] * 8));
+    TRY(ensure(ctx, ctx->entA, need[0] * 8));
     if (need[1]) TRY(ensure(ctx, ctx->entB, need[1] * 8));
     for (int l = 1; l < sp.levels; l++) {
         kb_slab_init_kernel<<<(unsigned)std::min<uint32_t>((sp.nc[l] + 255) / 256, 1024), 256, 0, ctx->stream>>>((unsigned long long*)(P + sp.off_cur[l]), sp.nc[l], sp.cap[l]);
         CU(cudaGetLastError());
         ctx->launches++;
     }
-    // level-0 tables: digit d lives in the receive buffer of its owner o, slab (this rank, d - first(o))
+    // level-0 tables.  Own digits: straight into this rank's slabs of its receive buffer (slab (me, j)); the other owners' digits:
+    // into the local staging buffer, from where whole digit groups travel as bulk peer copies (kb_shard_slab_send).  The cursor of
+    // digit d counts in the coordinates of the OWNER's receive buffer either way, so the all-gathered cursors are the fill levels
+    // the owner needs.
     std::vector<uint64_t>& t0 = ctx->scatter_host;
     t0.assign((size_t)3 * KB_XP_MAXR, 0);
     for (int o = 0; o < N; o++) {
         const uint32_t d0 = shard_first_digit((uint32_t)o, (uint32_t)N, nd0), d1 = shard_first_digit((uint32_t)o + 1, (uint32_t)N, nd0);
         const uint64_t dps_o = d1 - d0;
         for (uint32_t d = d0; d < d1; d++) {
-            const uint64_t first = ((uint64_t)me * dps_o + (d - d0)) * sp.cap[0];
+            const uint64_t first = ((uint64_t)me * dps_o + (d - d0)) * sp.cap[0];                        // slab (me, d - d0) of owner o
             t0[d] = first + sp.cap[0];                                                                   // slab end
-            t0[KB_XP_MAXR + d] = (uint64_t)(reinterpret_cast<uintptr_t>(ctx->peer_ptr[o]) >> 3);       // destination buffer
             t0[2 * KB_XP_MAXR + d] = first;                                                              // cursor start
+            // element address that cursor value 0 stands for: the receive buffer itself, or the staging buffer shifted so that
+            // the slab lands at d * cap0
+            if (o == me) t0[KB_XP_MAXR + d] = (uint64_t)(reinterpret_cast<uintptr_t>(ctx->recvbuf.p) >> 3);
+            else t0[KB_XP_MAXR + d] = (uint64_t)(reinterpret_cast<uintptr_t>(ctx->entA.p) >> 3) + (uint64_t)d * sp.cap[0] - first;
         }
     }
     if ((uint64_t)N * (shard_first_digit((uint32_t)me + 1, (uint32_t)N, nd0) - shard_first_digit((uint32_t)me, (uint32_t)N, nd0)) * sp.cap[0] + 2048 > ctx->recvbuf.cap / 8)
@@ -2156,7 +2181,7 @@ int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev) {
     TRY(shard_extract_range(ctx, &pos_lo, &pos_hi, &tile0, &n_tiles));
     TRY(prepare_extract(ctx));
     const auto batches = extract_batches(ctx, tile0, n_tiles);
-    prof_begin(ctx, "K1 extract + partition 0 + exchange (peer stores)");
+    prof_begin(ctx, "K1 extract + partition 0");
     TRY(run_extract_part(ctx, tile0, n_tiles, pos_lo, pos_hi, (uint32_t)sp.bits[0], (unsigned long long*)(P + sp.off_cur[0]),
                          (const unsigned long long*)(P + sp.off_tab0), (const unsigned long long*)(P + sp.off_tab0) + KB_XP_MAXR, batches,
                          [](int, int, uint32_t) -> int { return KB_OK; }));
@@ -2165,9 +2190,34 @@ int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev) {
     return KB_OK;
 }
 
-int kb_shard_slab_search(kb_ctx* ctx, const void* gathered_cursors_dev, int* status, kb_result** out) {
-    if (!ctx || !gathered_cursors_dev || !status || !out) return KB_EINVAL;
-    *out = nullptr; *status = 0;
+int kb_shard_slab_send(kb_ctx* ctx, int group, int n_groups, int part, int n_parts, void* cuda_stream) {
+    if (!ctx || n_groups < 1 || group < 0 || group >= n_groups || n_parts < 1 || part < 0 || part >= n_parts) return KB_EINVAL;
+    if (!ctx->configured || !ctx->shard_slab) return fail(ctx, KB_EINVAL, "kb_shard_slab_plan has not been called");
+    if ((int)ctx->peer_ptr.size() != ctx->shard_n) return fail(ctx, KB_EINVAL, "kb_shard_ipc_import has not been called");
+    const SlabPlan& sp = ctx->shard_sp;
+    const uint32_t nd0 = sp.nc[0];
+    const uint32_t N = (uint32_t)ctx->shard_n, me = (uint32_t)ctx->shard_index;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(ctx->device));
+    // peer k of this call = rank (me + k) % N: at any time every receiver has one sender
+    for (uint32_t k = 1; k < N; k++) {
+        const uint32_t o = (me + k) % N;
+        const uint32_t d0 = shard_first_digit(o, N, nd0), dps_o = shard_first_digit(o + 1, N, nd0) - d0;
+        const uint32_t j0 = (uint32_t)(((uint64_t)group * dps_o) / (uint32_t)n_groups), j1 = (uint32_t)(((uint64_t)(group + 1) * dps_o) / (uint32_t)n_groups);
+        if (j1 <= j0) continue;
+        const uint64_t* src = (const uint64_t*)ctx->entA.p + (uint64_t)(d0 + j0) * sp.cap[0];
+        uint64_t* dst = (uint64_t*)ctx->peer_ptr[o] + ((uint64_t)me * dps_o + j0) * sp.cap[0];
+        // whole slabs (the fill levels travel separately); this call moves byte range `part` of `n_parts` of every copy, so that
+        // several streams = several copy engines share one group
+        const uint64_t total = (uint64_t)(j1 - j0) * sp.cap[0];
+        const uint64_t e0 = (total * (uint64_t)part / (uint64_t)n_parts) & ~1ULL, e1 = part + 1 == n_parts ? total : ((total * (uint64_t)(part + 1) / (uint64_t)n_parts) & ~1ULL);
+        if (e1 > e0) CU(cudaMemcpyAsync(dst + e0, src + e0, (size_t)(e1 - e0) * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    return KB_OK;
+}
+
+int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group, int n_groups) {
+    if (!ctx || !gathered_cursors_dev || n_groups < 1 || group < 0 || group >= n_groups) return KB_EINVAL;
     if (!ctx->configured || !ctx->shard_slab) return fail(ctx, KB_EINVAL, "kb_shard_slab_plan has not been called");
     const SlabPlan& sp = ctx->shard_sp;
     PartPlan pl = ctx->shard_plan;
@@ -2175,33 +2225,81 @@ int kb_shard_slab_search(kb_ctx* ctx, const void* gathered_cursors_dev, int* sta
     const uint32_t N = (uint32_t)ctx->shard_n, me = (uint32_t)ctx->shard_index;
     const uint32_t d_lo = shard_first_digit(me, N, nd0), dps = shard_first_digit(me + 1, N, nd0) - d_lo;
     const uint32_t np = N * dps;
+    if (n_groups > 1 && (sp.levels != 2 || sp.cap[0] % KB_PT_TILE != 0))
+        return fail(ctx, KB_EINVAL, "digit groups need a two-level plan with tile-aligned slabs (use one group)");
     CU(cudaSetDevice(ctx->device));
     uint8_t* P = (uint8_t*)ctx->plan.p;
     unsigned long long* pend = (unsigned long long*)(P + sp.off_snap);
     uint32_t* prow = (uint32_t*)(pend + np);
-    kb_shard_pend_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)gathered_cursors_dev, N, nd0, d_lo, dps, pend, prow);
-    CU(cudaGetLastError());
-    ctx->launches++;
+    if (group == 0) {
+        kb_shard_pend_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)gathered_cursors_dev, N, nd0, d_lo, dps, pend, prow);
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_NRES, 0, 7 * 8, ctx->stream));
+        ctx->launches++;
+    }
+    const uint32_t j0 = (uint32_t)(((uint64_t)group * dps) / (uint32_t)n_groups), j1 = (uint32_t)(((uint64_t)(group + 1) * dps) / (uint32_t)n_groups);
+    if (j1 <= j0) return KB_OK;
     const uint64_t n_est = 2 * ctx->shard_total_bases + 64;
     uint64_t* bufs[2] = {(uint64_t*)ctx->entA.p, (uint64_t*)ctx->entB.p};
-    prof_begin(ctx, "K2 partition 1");
-    TRY(launch_slab_level(ctx, sp, pl, 1, (const uint64_t*)ctx->recvbuf.p, bufs[1], pend, nullptr, np, prow, std::min<uint64_t>(n_est, (uint64_t)np * sp.cap[0])));
+    static const char* n1[8] = {"K2 partition 1 (group 0)", "K2 partition 1 (group 1)", "K2 partition 1 (group 2)", "K2 partition 1 (group 3)",
+                                "K2 partition 1 (group 4)", "K2 partition 1 (group 5)", "K2 partition 1 (group 6)", "K2 partition 1 (group 7+)"};
+    static const char* n3[8] = {"K3 bucket hash (group 0)", "K3 bucket hash (group 1)", "K3 bucket hash (group 2)", "K3 bucket hash (group 3)",
+                                "K3 bucket hash (group 4)", "K3 bucket hash (group 5)", "K3 bucket hash (group 6)", "K3 bucket hash (group 7+)"};
+    prof_begin(ctx, n_groups == 1 ? "K2 partition 1" : n1[std::min(group, 7)]);
+    if (n_groups == 1) {
+        TRY(launch_slab_level(ctx, sp, pl, 1, (const uint64_t*)ctx->recvbuf.p, bufs[1], pend, nullptr, np, prow, std::min<uint64_t>(n_est, (uint64_t)np * sp.cap[0])));
+    } else {
+        TRY(launch_slab_level(ctx, sp, pl, 1, (const uint64_t*)ctx->recvbuf.p, bufs[1], pend, nullptr, N * (j1 - j0), prow, 0, j1 - j0, j0, dps));
+    }
     prof_end(ctx);
-    ctx->alg_rec_bytes += 16;
-    // (launch_slab_level sized the tile tables by parents = np; deeper levels use the local child counts)
-    TRY(run_slab_levels(ctx, sp, pl, 2, bufs, sp.levels > 2 ? std::min<uint64_t>(n_est, (uint64_t)sp.nc[1] * sp.cap[1]) : n_est));
+    if (group == 0) ctx->alg_rec_bytes += 16;
+    if (sp.levels > 2) {
+        TRY(run_slab_levels(ctx, sp, pl, 2, bufs, std::min<uint64_t>(n_est, (uint64_t)sp.nc[1] * sp.cap[1])));
+    }
+    // bucket hash on the children of this group's digits: buckets [j0 << bits, j1 << bits)
+    const int last = sp.levels - 1;
+    uint32_t cb = 0;
+    for (int l = 1; l <= last; l++) cb += (uint32_t)sp.bits[l];
+    HashStage hs{};
+    hs.pl = &pl;
+    hs.n_buckets = n_groups == 1 ? sp.nc[last] : (j1 - j0) << cb;
+    hs.bucket0 = n_groups == 1 ? 0u : j0 << cb;
+    hs.bend = (const unsigned long long*)(P + sp.off_cur[last]);
+    hs.bcap = sp.cap[last];
+    hs.phase = 1;
+    KbGroupArgs a{};
+    fill_group_args(ctx, a, bufs[last & 1], n_est);
+    prof_begin(ctx, n_groups == 1 ? "K3 bucket hash" : n3[std::min(group, 7)]);
+    TRY(launch_hash(ctx, a, hs));
+    prof_end(ctx);
+    return KB_OK;
+}
+
+int kb_shard_slab_finish(kb_ctx* ctx, int* status, kb_result** out) {
+    if (!ctx || !status || !out) return KB_EINVAL;
+    *out = nullptr; *status = 0;
+    if (!ctx->configured || !ctx->shard_slab) return fail(ctx, KB_EINVAL, "kb_shard_slab_plan has not been called");
+    const SlabPlan& sp = ctx->shard_sp;
+    PartPlan pl = ctx->shard_plan;
+    CU(cudaSetDevice(ctx->device));
+    uint8_t* P = (uint8_t*)ctx->plan.p;
+    const uint64_t n_est = 2 * ctx->shard_total_bases + 64;
+    uint64_t* bufs[2] = {(uint64_t*)ctx->entA.p, (uint64_t*)ctx->entB.p};
+    const int last = sp.levels - 1;
     ctx->passes = sp.levels;
     HashStage hs{};
     hs.pl = &pl;
-    hs.n_buckets = sp.nc[sp.levels - 1];
-    hs.bend = (const unsigned long long*)(P + sp.off_cur[sp.levels - 1]);
-    hs.bcap = sp.cap[sp.levels - 1];
+    hs.n_buckets = sp.nc[last];
+    hs.bend = (const unsigned long long*)(P + sp.off_cur[last]);
+    hs.bcap = sp.cap[last];
+    hs.phase = 2;
     ctx->replan_ok = ctx->opt_bucket_bits < 0 && pl.bb < std::min(ctx->lo.FB, 24);
-    int rc = run_group(ctx, bufs[(sp.levels - 1) & 1], n_est, out, &hs);
+    int rc = run_group(ctx, bufs[last & 1], n_est, out, &hs, true);
     ctx->replan_ok = false;
     prof_collect(ctx);
     if (rc == KB_REPLAN) { *status = 1; return KB_OK; }
     if (rc == KB_SLABOVF) { *status = 2; return KB_OK; }
+    if (rc == KB_RESGROW) { *status = 3; return KB_OK; }
     return rc;
 }
 

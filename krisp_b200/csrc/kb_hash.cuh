@@ -40,6 +40,7 @@ struct KbHashArgs {
     const unsigned long long* brun;      // != null (generic kernel): bucket b = elements [brun[2b], brun[2b] + brun[2b+1]) (kb_prefilter.cuh)
     const unsigned long long* bend;      // != null: bucket b ends at bend[b] instead of bstart[b + 1]
     uint64_t bcap;                       // != 0 (slab layout, kb_extract_part.cuh): bucket b = [b * bcap, min(bend[b], (b + 1) * bcap)), bstart unused
+    uint32_t bucket0;                    // kb_hash_warp_kernel: this launch covers buckets [bucket0, bucket0 + n_buckets)
 };
 
 // element range of bucket b in every layout

@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(KB_HW_THREADS, 3) kb_hash_warp_kernel(const Kb
     bool over = false;                   // the current bucket is given up (warp-uniform)
     uint32_t par = 0;                    // SHARED: parity of the current bucket (selects its control words)
 
-    auto bucket_range = [&](uint32_t b, uint64_t& s, uint64_t& e) {
+    auto bucket_range = [&](uint32_t bl, uint64_t& s, uint64_t& e) {
+        const uint32_t b = x.bucket0 + bl;
         if (x.bcap) { s = (uint64_t)b * x.bcap; e = min((uint64_t)x.bend[b], s + x.bcap); }
         else { s = x.bstart[b]; e = x.bend ? x.bend[b] : x.bstart[b + 1]; }
         if (e < s) e = s;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(KB_HW_THREADS, 3) kb_hash_warp_kernel(const Kb
             for (int j = 0; j < PWN; j++) kb_sts32(pres_a + (slot * PWN + j) * 4, 0u);
             if (!packed) kb_sts64(msk_a + slot * 8, 0ULL);
         }
-        if (defer && (SHARED ? tid == 0 : lane == 0)) { const unsigned long long d = atomicAdd(xs.n_deferred, 1ULL); xs.deferred[d] = b; }
+        if (defer && (SHARED ? tid == 0 : lane == 0)) { const unsigned long long d = atomicAdd(xs.n_deferred, 1ULL); xs.deferred[d] = x.bucket0 + b; }
         if (defer && (SHARED ? warp == 0 : true)) n_defer++;
         if (SHARED) {
             if (tid == 0) { kb_sts32(ctl_a + 4 * (par ^ 1u), 0u); kb_sts32(ctl_a + 4 * (2 + (par ^ 1u)), 0u); kb_sts32(ctl_a + 4 * (4 + (par ^ 1u)), 0u); }

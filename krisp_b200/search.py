@@ -387,12 +387,13 @@ class Searcher:
 
     # slab exchange (K1 fused with partition level 0, peer stores into the owners' slabs; see include/krisp_b200.h)
     def shard_slab_plan(self, n_shards, shard_index, total_bases, max_rank_bases):
-        """-> (level-0 fan-out, receive-buffer capacity in records); raises UnsupportedError where the slab exchange does not apply."""
-        nd, cap = ctypes.c_int(), ctypes.c_uint64()
+        """-> (level-0 fan-out, receive-buffer capacity in records, most digit groups the exchange may be cut into); raises
+        UnsupportedError where the slab exchange does not apply."""
+        nd, cap, mg = ctypes.c_int(), ctypes.c_uint64(), ctypes.c_int()
         self._check(self._L.kb_shard_slab_plan(self._ctx, int(n_shards), int(shard_index), int(total_bases), int(max_rank_bases),
-                                               ctypes.byref(nd), ctypes.byref(cap)))
+                                               ctypes.byref(nd), ctypes.byref(cap), ctypes.byref(mg)))
         self._shard = (int(n_shards), int(shard_index), int(nd.value))
-        return int(nd.value), int(cap.value)
+        return int(nd.value), int(cap.value), int(mg.value)
 
     def shard_slab_extract(self):
         """K1 + level 0 + peer stores; -> device pointer of this rank's n_digits slab cursors (u64)."""
@@ -401,11 +402,18 @@ class Searcher:
         self._keep = []
         return int(ptr.value)
 
-    def shard_slab_search(self, gathered_ptr, have_outgroup=True):
-        """-> (SearchResult or None, status): status 1 = plan too coarse, 2 = slab overflow (see the header)."""
+    def shard_slab_send(self, group, n_groups, stream, part=0, n_parts=1):
+        """Bulk peer copies of one digit group (byte range `part` of `n_parts` of each) on the raw cudaStream_t `stream`."""
+        self._check(self._L.kb_shard_slab_send(self._ctx, int(group), int(n_groups), int(part), int(n_parts), ctypes.c_void_p(int(stream))))
+
+    def shard_slab_level(self, gathered_ptr, group, n_groups):
+        """Partition level 1 + bucket hash on one digit group of the receive buffer."""
+        self._check(self._L.kb_shard_slab_level(self._ctx, ctypes.c_void_p(int(gathered_ptr)), int(group), int(n_groups)))
+
+    def shard_slab_finish(self, have_outgroup=True):
+        """-> (SearchResult or None, status): 1 = plan too coarse, 2 = slab overflow, 3 = survivor table grown (see the header)."""
         res, status = ctypes.c_void_p(), ctypes.c_int()
-        self._set_have_outgroup(have_outgroup)
-        self._check(self._L.kb_shard_slab_search(self._ctx, ctypes.c_void_p(int(gathered_ptr)), ctypes.byref(status), ctypes.byref(res)))
+        self._check(self._L.kb_shard_slab_finish(self._ctx, ctypes.byref(status), ctypes.byref(res)))
         if status.value != 0 or not res.value:
             return None, int(status.value)
         return self._collect(res, have_outgroup), 0

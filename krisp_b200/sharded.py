@@ -182,6 +182,13 @@ def _ensure_ipc(searcher, device, group, need):
     searcher.shard_ipc_import([blob[64 * r:64 * (r + 1)] for r in range(world)])
 
 
+def _slab_groups(max_groups):
+    """Digit groups of the pipelined exchange: up to 8 where the library allows it (two-level plan, tile-aligned slabs: every rank
+    derives the same answer from the same plan), else one.  KRISP_SLAB_GROUPS overrides."""
+    env = os.environ.get("KRISP_SLAB_GROUPS")
+    return max(1, min(int(env) if env else 8, int(max_groups)))
+
+
 def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=None):
     """The exchange fused into K1 (one-word records): every rank's K1 + partition level 0 (csrc/kb_extract_part.cuh) store each
     level-0 digit's run straight into a fixed-capacity slab of the owner's receive buffer over NVLink peer memory.  There is no count
@@ -206,10 +213,10 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
     for _ in range(4):
         searcher.set_option("shard_bb_extra", extra)
         try:
-            nd, cap = searcher.shard_slab_plan(world, rank, total_bases, max_rank_bases)
+            nd, cap, max_groups = searcher.shard_slab_plan(world, rank, total_bases, max_rank_bases)
             ok = 1
         except UnsupportedError:
-            nd, cap, ok = 0, 0, 0
+            nd, cap, max_groups, ok = 0, 0, 1, 0
         caps = torch.tensor([cap if ok else -1], dtype=torch.int64, device=device)
         allc = torch.empty(world, dtype=torch.int64, device=device)
         dist.all_gather_into_tensor(allc, caps, group=group)
@@ -217,30 +224,63 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
         if min(need) < 0:
             return None                                               # (some rank cannot: nobody does)
         _ensure_ipc(searcher, device, group, need)
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
-        cur_ptr = searcher.shard_slab_extract()                       # K1 + level 0 + peer stores (asynchronous)
-        prof = list(searcher.last_profile())
-        ev[1].record()
+        n_groups = _slab_groups(max_groups)
+        main = torch.cuda.current_stream(device)
+        n_side = max(1, int(os.environ.get("KRISP_COPY_STREAMS", "3")))
+        sides = searcher.__dict__.setdefault("_copy_streams", [])
+        while len(sides) < n_side:
+            sides.append(torch.cuda.Stream(device=device))
+        side = sides[0]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        searcher._set_have_outgroup(have_outgroup)
+        ev[0].record(main)
+        cur_ptr = searcher.shard_slab_extract()                       # K1 + level 0 (asynchronous, main stream)
+        ev[1].record(main)
         cur = _wrap(cur_ptr, nd, device)
         gathered = torch.empty(world * nd, dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(gathered, cur, group=group)       # fill levels, on the device; every rank's stores have landed
-        ev[2].record()
-        res, status = searcher.shard_slab_search(gathered.data_ptr(), have_outgroup=have_outgroup)
+        dist.all_gather_into_tensor(gathered, cur, group=group)       # fill levels, on the device
+        # the exchange: digit groups as bulk peer copies on the side stream, a tiny collective behind each group = "every rank's
+        # copies of this group have landed"; the main stream processes group g while group g + 1 travels
+        for sd in sides[:n_side]:
+            sd.wait_event(ev[1])
+        landed = []
+        flag = searcher.__dict__.setdefault("_flag", torch.zeros(1, dtype=torch.int32, device=device))
+        for g in range(n_groups):
+            others = []
+            for k in range(1, n_side):                                # every copy of the group in n_side byte ranges, one per stream
+                searcher.shard_slab_send(g, n_groups, sides[k].cuda_stream, k, n_side)
+                ek = torch.cuda.Event()
+                ek.record(sides[k])
+                others.append(ek)
+            with torch.cuda.stream(side):
+                searcher.shard_slab_send(g, n_groups, side.cuda_stream, 0, n_side)
+                for ek in others:
+                    side.wait_event(ek)
+                dist.all_reduce(flag, group=group)
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(side)
+                landed.append(e)
+        for g in range(n_groups):
+            main.wait_event(landed[g])
+            searcher.shard_slab_level(gathered.data_ptr(), g, n_groups)
+        ev[2].record(main)
+        res, status = searcher.shard_slab_finish(have_outgroup=have_outgroup)
         st = torch.tensor([status], dtype=torch.int64, device=device)
         dist.all_reduce(st, op=dist.ReduceOp.MAX, group=group)        # same decision everywhere; also: nobody starts the next
-        status = int(st.item())                                       # search's stores while a peer still reads its buffer
+        status = int(st.item())                                       # search's copies while a peer still reads its buffer
         if status == 0:
-            ev[2].synchronize()
-            res.profile = [("K1 + partition 0 + exchange (launch to last store)", ev[0].elapsed_time(ev[1])),
-                           ("K4 cursor all-gather (barrier)", ev[1].elapsed_time(ev[2]))] + [p for p in res.profile]
-            res.profile = prof + res.profile
             lo_d, hi_d = first_digit(rank, world, nd), first_digit(rank + 1, world, nd)
-            res.exchange = {"slab": True, "digits": nd, "records_extracted": int(res.n_records), "own_digits": [lo_d, hi_d],
-                            "sent": int(res.n_records) - int(res.n_records) * (hi_d - lo_d) // max(nd, 1)}   # (uniform digits: the share that stays)
+            sent = int(res.n_records) - int(res.n_records) * (hi_d - lo_d) // max(nd, 1)       # (uniform digits: what does not stay)
+            t_x = ev[1].elapsed_time(landed[-1])
+            res.profile = list(res.profile) + [("K4 exchange (bulk peer copies, first send to last landed)", t_x)]
+            res.exchange = {"slab": True, "digits": nd, "groups": n_groups, "records_extracted": int(res.n_records), "own_digits": [lo_d, hi_d],
+                            "sent": sent, "sent_bytes": 8 * sent, "copied_bytes": 8 * (cap - 4096) * (world - 1) // max(world, 1),
+                            "exchange_ms": t_x}
             return res
         if status == 2:
             return None                                               # a slab overflowed somewhere: exact exchange for everybody
+        if status == 3:
+            continue                                                  # a survivor table was grown: once more, same plan
         extra += 2                                                    # plan too coarse somewhere: two more bucket bits for everybody
         searcher.__dict__["_shard_bb_extra"] = extra
     return None
