@@ -3,18 +3,26 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--genome-len BP]
 
-A "step" is one complete search (K1 extract -> K2 radix sort -> K3 group/filter -> survivor table on
-the host) over one synthetic panel.  N=1 workload = BASELINE.json configs[1]: 20 ingroup + 20 outgroup
-5 Mbp genomes, --conserved-left 25 --diagnostic 1 --conserved-right 2.  For N>1 (torchrun, one rank per
-GPU) the genomes are N times longer (weak scaling: 0.2 Gbp per GPU), every rank ingests 40/N... files
-round-robin, and records are exchanged once by flank-hash shard (NCCL all-to-all).
+A "step" is one complete search: K1 fused with partition level 0 (bases -> packed records in level-0 slabs) -> partition level 1
+-> bucket hash aggregation (intersection over all files + diagnostic filter) -> survivor table and CSV rows on the host.
+N=1 workload = BASELINE.json configs[1]: 20 ingroup + 20 outgroup 5 Mbp genomes, --conserved-left 25 --diagnostic 1
+--conserved-right 2.  For N>1 (torchrun, one rank per GPU) the genomes are N times longer (weak scaling: 0.2 Gbp per GPU), every
+rank ingests its files (round-robin), and the level-0 slabs travel once to the GPU that owns their flank-key range as bulk peer
+copies over NVLink, digit group by digit group, while the owner already works on the previous group (krisp_b200/sharded.py).
 
-`value`  : panel bases / device time of K steps, sequences already resident in HBM.
-`e2e`    : same through the C ABI with pinned HOST buffers: H2D of every base and D2H of the survivor
-           table inside the timed region, rows decoded on the host.
-`--impl reference` : the CPU restatement of the reference's algorithm (oracle/krisp_oracle.c, all host
-           threads) on a bounded sample of the same workload (the reference itself is pure Python at
-           ~4e-5 Gbp/s).
+`value`   : panel bases / device time of K steps, sequences already resident in HBM.
+`e2e`     : same through the C ABI with pinned HOST buffers: H2D of every base, D2H of the survivor table and of the rows (which
+            arrive as text, rendered and ordered on the device) inside the timed region.
+`roofline`: the kernel family with the largest share of the step; `kernel_families` lists all of them; `whole_step` = as-built
+            algorithmic bytes of the whole search / device time.
+`parity`  : (N>1) before timing, a sharded search of a panel small enough for the CPU oracle (25/1/2 and 32/60/32) is compared with
+            the oracle's rows; the bench aborts if they differ.
+`nvlink`  : (N>1) bytes every GPU sends / time from the first send to the last group landed, against 900 GB/s.
+`also`    : (N=1) short runs of the other BASELINE shapes that fit one GPU: C3 primer mode (32/60/32) and the top of the C5 sweep.
+`--impl reference` : the CPU restatement of the reference's algorithm (oracle/krisp_oracle.c, OpenMP, every host core — set
+            explicitly, torchrun exports OMP_NUM_THREADS=1) on a bounded sample of the same workload.  The unmodified Python
+            reference cannot travel to the GPU box; its timing in the build container is quoted as `python_reference`
+            (tools/time_reference.py -> profiles/r04_python_reference.json).
 """
 import argparse
 import json
@@ -103,22 +111,8 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_panel(genome_len, rank=0, world=1):
-    """This rank's genomes of the 20+20 panel: (global file id, is_ingroup, packed uint8 array)."""
-    from krisp_b200.panel import make_genome
-    import numpy as np
-    out = []
-    for i in range(N_IN + N_OUT):
-        if i % world != rank:
-            continue
-        is_in = i < N_IN
-        g = make_genome(i, is_in, is_in and (i % 2 == 1), f"ingroup{i}" if is_in else f"outgroup{i - N_IN}", genome_len, **PANEL_KW)
-        out.append((i, is_in, np.frombuffer(g.joined(), dtype=np.uint8)))
-    return out
-
-
 def cpu_baseline(sample_len, steps=1, warmup=0):
-    """The oracle port on a 20+20 x sample_len panel, all host threads."""
+    """The oracle port on a 20+20 x sample_len panel, all host threads (set explicitly: torchrun exports OMP_NUM_THREADS=1)."""
     from krisp_b200.panel import make_panel
     from oracle import oracle
     gs = make_panel(N_IN, N_OUT, sample_len)
@@ -126,15 +120,29 @@ def cpu_baseline(sample_len, steps=1, warmup=0):
     labels = [g.name for g in gs]
     ing = {g.name for g in gs if g.is_ingroup}
     bases = sum(g.n_bases for g in gs)
+    cores = os.cpu_count() or 1
     for _ in range(warmup):
-        oracle.search_records(recs, labels, ing, True, L_, D_, R_)
+        oracle.search_records(recs, labels, ing, True, L_, D_, R_, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(steps):
-        rows, _ = oracle.search_records(recs, labels, ing, True, L_, D_, R_)
+        rows, _ = oracle.search_records(recs, labels, ing, True, L_, D_, R_, nthreads=cores)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": bases / dt / 1e9, "unit": UNIT, "cores": oracle.threads(), "kind": "port",
-            "sample": f"{N_IN}+{N_OUT} genomes x {sample_len} bp ({bases / 1e6:.1f} Mbp), {L_}/{D_}/{R_}, oracle/krisp_oracle.c (OpenMP)",
+    return {"value": bases / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{N_IN}+{N_OUT} genomes x {sample_len} bp ({bases / 1e6:.1f} Mbp), {L_}/{D_}/{R_}, oracle/krisp_oracle.c (OpenMP, {cores} threads)",
             "seconds_per_step": dt, "rows": len(rows)}
+
+
+def python_reference_record():
+    """The UNMODIFIED Python reference cannot travel to the GPU box; its timing on the scaled panel of BASELINE.md
+    section 3 (20+20 x 100 kbp), taken in the build container by tools/time_reference.py, is committed under profiles/."""
+    p = os.path.join(ROOT, "profiles", "r04_python_reference.json")
+    try:
+        with open(p) as fh:
+            d = json.loads(fh.read().strip().splitlines()[-1])
+        return {k: d[k] for k in ("value", "unit", "cores", "kind", "sample", "seconds", "rows", "rows_equal_c_oracle") if k in d} | \
+               {"where": "build container (8 cores), not this box; see tools/time_reference.py"}
+    except Exception:
+        return None
 
 
 def run_reference(args):
@@ -147,12 +155,58 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"synthetic bacterial panel {N_IN}+{N_OUT} genomes, {L_}/{D_}/{R_}; bounded sample: {cb['sample']}"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "python_reference": python_reference_record(),
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
+_FAMILIES = {
+    "K1": ("kb_extract_part_kernel (K1 fused with partition level 0: bases -> records in level-0 slabs)", lambda k: k.startswith("K1 extract"),
+           lambda bases, n: bases + 8.0 * n),
+    "K2": ("kb_part_kernel (K2: one radix-partition level, read + write of every record)", lambda k: k.startswith("K2 partition") or k.startswith("K2 pass"),
+           lambda bases, n: 16.0 * n),
+    "K3": ("kb_hash_warp_kernel (K3: bucket hash aggregation, one read of every record)", lambda k: k.startswith("K3 bucket hash") or k == "K3 group",
+           lambda bases, n: 8.0 * n),
+    "K3a": ("kb_prefilter_kernel (K3a: flank-hash presence filter, one read of every element)", lambda k: k == "K3a hash prefilter", lambda bases, n: 8.0 * n),
+}
+
+
+def roofline_of(prof, local_bases, n_rec, direct, peak, peak_src):
+    """The kernel family with the largest share of the step: algorithmic bytes of the family per step / its device time per step."""
+    roof, best, fams = None, -1.0, {}
+    for key, (kname, match, nbytes) in _FAMILIES.items():
+        if key == "K3" and not direct:
+            continue                                      # (multi-word records: the exact pass only sees what the hash filter keeps)
+        per = {k: sum(v) / len(v) for k, v in prof.items() if match(k)}
+        if not per:
+            continue
+        total = sum(per.values())
+        b = nbytes(local_bases, n_rec) * (len({k.split(" (group")[0] for k in per}) if key == "K2" else 1)   # (K2: every level moves all records)
+        achieved = b / (total * 1e-3) / 1e9
+        fams[key] = {"ms_per_step": total, "achieved_gbs": achieved, "frac": achieved / peak, "launches_per_step": len(per)}
+        if total > best:
+            best = total
+            roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "traffic_note": "dram bytes per launch from ncu are in profiles/r04_summary.md (same build); not re-measured inside this run",
+                    "peak_source": peak_src, "algorithmic_bytes_per_step": b, "family_ms_per_step": total, "launches_per_step": len(per)}
+    return roof, fams
+
+
+def fold_stages(prof):
+    """Mean ms per stage; the per-group stages of the pipelined multi-GPU search are also summed per kernel."""
+    out, fold = {}, {}
+    for k, v in prof.items():
+        m = sum(v) / len(v)
+        out[k] = m
+        if " (group " in k:
+            fold[k.split(" (group ")[0] + " (all groups)"] = fold.get(k.split(" (group ")[0] + " (all groups)", 0.0) + m
+    out.update(fold)
+    return out
+
+
 def run_ours(args):
+    import hashlib
     import numpy as np
     import torch
     from krisp_b200.search import Searcher
@@ -169,176 +223,229 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-
-    genome_len = args.genome_len * world           # weak scaling: 0.2 Gbp of input per GPU
-    mine = build_panel(genome_len, rank, world)
-    total_bases = (N_IN + N_OUT) * genome_len       # bases of the whole panel (separators excluded: 4 records/genome)
-    is_in = [1] * N_IN + [0] * N_OUT
-
+    peak, peak_src = measured_peak()
     stream = torch.cuda.current_stream()
     s = Searcher(device=local_rank, stream=stream.cuda_stream)
-    s.configure(L_, D_, R_, is_in)
-    s.set_option("profile", 1)
-    for k, v in args.option or []:
-        s.set_option(k, int(v))
-
-    # pinned host copies (e2e arm) and device-resident copies (value arm)
-    pinned = []
-    for gid, _, arr in mine:
-        t = torch.empty(arr.size, dtype=torch.uint8, pin_memory=True)
-        t.numpy()[:] = arr
-        pinned.append((gid, t))
-    resident = [(gid, t.to(dev)) for gid, t in pinned]
-    h2d_bytes = sum(t.numel() for _, t in pinned)
-    s.reserve(h2d_bytes + len(pinned))
-
-    def load_resident():
-        s.clear_sequences()
-        for gid, t in resident:
-            s.add_sequence(gid, (t.data_ptr(), t.numel()))
-
-    def load_host():
-        s.clear_sequences()
-        for gid, t in pinned:
-            s.add_sequence(gid, t.numpy())
-
-    def search():
-        if world == 1:
-            return s.search(have_outgroup=True)
-        return sharded.sharded_search(s, dev, have_outgroup=True, total_bases=total_bases)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    results = {}
+    class Workload:
+        """One panel on this rank: pinned host copies (e2e arm) and device-resident copies (value arm)."""
 
-    host_ms = {}
+        def __init__(self, n_in, n_out, genome_len, ldr, panel_kw=None):
+            from krisp_b200.panel import make_genome
+            self.n_in, self.n_out, self.genome_len, self.ldr = n_in, n_out, genome_len, ldr
+            self.total_bases = (n_in + n_out) * genome_len
+            self.is_in = [1] * n_in + [0] * n_out
+            self.pinned = []
+            for i in range(n_in + n_out):
+                if i % world != rank:
+                    continue
+                g = make_genome(i, i < n_in, i < n_in and (i % 2 == 1), f"ingroup{i}" if i < n_in else f"outgroup{i - n_in}", genome_len, **(panel_kw or {}))
+                arr = np.frombuffer(g.joined(), dtype=np.uint8)
+                t = torch.empty(arr.size, dtype=torch.uint8, pin_memory=True)
+                t.numpy()[:] = arr
+                self.pinned.append((i, t))
+            self.resident = [(gid, t.to(dev)) for gid, t in self.pinned]
+            self.h2d_bytes = sum(t.numel() for _, t in self.pinned)
 
-    def timed(load, steps, collect_rows, sampler=None):
-        launches, prof_acc, d2h = 0, {}, 0
-        host_ms.clear()
-        barrier()
-        if sampler:
-            sampler.mark_begin()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            t_a = time.perf_counter()
-            if load is not None:
-                load()
-            t_b = time.perf_counter()
-            res = search()
-            t_c = time.perf_counter()
-            if collect_rows:
-                results["rows"] = res.csv_rows_text()          # the CSV body krisp_fasta prints (rendered + ordered on the device)
-            t_d = time.perf_counter()
-            for nm, dt in (("load", t_b - t_a), ("search", t_c - t_b), ("rows", t_d - t_c)):
-                host_ms[nm] = host_ms.get(nm, 0.0) + dt * 1e3 / steps
-            launches += s.last_counters()["kernel_launches"]
-            for name, ms in res.profile:
-                prof_acc.setdefault(name, []).append(ms)
-            d2h = res.n_groups * (8 * res.flank_words.shape[1] + 2 * 4 * res.in_words.shape[1] + 4 + 16 + res.row_bytes) + 64
-            results["last"] = res
-        e1.record(stream)
-        barrier()
-        if sampler:
-            sampler.mark_end()
-        ms = e0.elapsed_time(e1) / steps
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches, prof_acc, d2h
+        def configure(self, ldr=None):
+            if ldr:
+                self.ldr = ldr
+            s.configure(*self.ldr, self.is_in)
+            s.set_option("profile", 1)
+            for k, v in args.option or []:
+                s.set_option(k, int(v))
+            s.reserve(self.h2d_bytes + len(self.pinned))
 
-    # ---- value arm: sequences resident in HBM ----------------------------------------------------
-    load_resident()
-    s.synchronize()
+        def load_resident(self):
+            s.clear_sequences()
+            for gid, t in self.resident:
+                s.add_sequence(gid, (t.data_ptr(), t.numel()))
+
+        def load_host(self):
+            s.clear_sequences()
+            for gid, t in self.pinned:
+                s.add_sequence(gid, t.numpy())
+
+        def search(self):
+            if world == 1:
+                return s.search(have_outgroup=True)
+            return sharded.sharded_search(s, dev, have_outgroup=True, total_bases=self.total_bases)
+
+        def timed(self, load, steps, collect_rows, sampler=None):
+            out = {"launches": 0, "prof": {}, "host_ms": {}, "d2h": 0}
+            barrier()
+            if sampler:
+                sampler.mark_begin()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                t_a = time.perf_counter()
+                if load is not None:
+                    load()
+                t_b = time.perf_counter()
+                res = self.search()
+                t_c = time.perf_counter()
+                if collect_rows:
+                    out["rows"] = res.csv_rows_text()        # the CSV body krisp_fasta prints (rendered + ordered on the device)
+                t_d = time.perf_counter()
+                for nm, dt in (("load", t_b - t_a), ("search", t_c - t_b), ("rows", t_d - t_c)):
+                    out["host_ms"][nm] = out["host_ms"].get(nm, 0.0) + dt * 1e3 / steps
+                out["launches"] += s.last_counters()["kernel_launches"]
+                for name, ms in res.profile:
+                    out["prof"].setdefault(name, []).append(ms)
+                out["d2h"] = res.n_groups * (8 * res.flank_words.shape[1] + 2 * 4 * res.in_words.shape[1] + 4 + 16 + res.row_bytes) + 72
+                out["last"] = res
+            e1.record(stream)
+            barrier()
+            if sampler:
+                sampler.mark_end()
+            ms = e0.elapsed_time(e1) / steps
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            out["ms"] = ms
+            return out
+
+        def measure(self, steps, warmup, sampler=None):
+            """value arm (resident) + e2e arm (host buffers) -> dict for the JSON line."""
+            self.load_resident()
+            s.synchronize()
+            self.timed(None, warmup, False)
+            dv = self.timed(None, steps, False, sampler)
+            counters = s.last_counters()
+            self.timed(self.load_host, 1, True)
+            de = self.timed(self.load_host, steps, True)
+            rows = de["rows"]
+            assert sorted(rows.splitlines()) == de["last"].rows(), "device-rendered rows differ from the host decoder's"   # (outside the timed region)
+            n_rows = rows.count("\n")
+            if world > 1:
+                t = torch.tensor([n_rows], device=dev)
+                dist.all_reduce(t)
+                n_rows = int(t.item())
+            last = dv["last"]
+            direct = 2 * sum(self.ldr) + 8 <= 64
+            roof, fams = roofline_of(dv["prof"], self.h2d_bytes, last.n_records, direct, peak, peak_src)
+            rows_sha = hashlib.sha256("\n".join(sorted(rows.splitlines())).encode()).hexdigest() if world == 1 else None
+            return {"ms": dv["ms"], "value": self.total_bases / (dv["ms"] * 1e-3) / 1e9, "launches": dv["launches"], "counters": counters,
+                    "stage_ms": fold_stages(dv["prof"]), "roofline": roof, "families": fams, "last": last, "rows": n_rows, "rows_sha256": rows_sha,
+                    "e2e": {"value": self.total_bases / (de["ms"] * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": de["ms"],
+                            "h2d_bytes_per_step": self.h2d_bytes * world, "d2h_bytes_per_step": de["d2h"],
+                            "host_ms": de["host_ms"], "stage_ms": fold_stages(de["prof"])},
+                    "exchange": getattr(last, "exchange", None)}
+
+    # ---- N > 1: parity of the sharded search against the CPU oracle, before anything is timed ------------------------------------
+    parity = None
+    if world > 1:
+        from krisp_b200.panel import make_panel
+        parity = {"n": world, "cases": [], "ok": True}
+        for ldr in ((25, 1, 2), (32, 60, 32)):
+            gs = make_panel(5, 4, 200_000)
+            s.configure(*ldr, [1 if g.is_ingroup else 0 for g in gs])
+            s.clear_sequences()
+            for i, g in enumerate(gs):
+                if i % world == rank:
+                    s.add_sequence(i, np.frombuffer(g.joined(), dtype=np.uint8))
+            res = sharded.sharded_search(s, dev, have_outgroup=True)
+            rows = sharded.gather_rows(res.rows())
+            sha = hashlib.sha256("\n".join(rows).encode()).hexdigest()
+            case = {"panel": "5+4 x 200 kbp", "ldr": list(ldr), "rows": len(rows), "rows_sha256": sha, "exchange": "slab" if getattr(res, "exchange", {}).get("slab") else "exact"}
+            if rank == 0:
+                from oracle import oracle
+                want, _ = oracle.search_records([[r.tobytes() for r in g.records] for g in gs], [g.name for g in gs],
+                                                {g.name for g in gs if g.is_ingroup}, True, *ldr, nthreads=os.cpu_count() or 1)
+                case["oracle_sha256"] = hashlib.sha256("\n".join(want).encode()).hexdigest()
+                case["ok"] = case["oracle_sha256"] == sha and len(want) > 0
+                parity["ok"] = parity["ok"] and case["ok"]
+            parity["cases"].append(case)
+        ok = torch.tensor([1 if parity["ok"] else 0], device=dev)
+        dist.broadcast(ok, 0)
+        if not int(ok.item()):
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "sharded search differs from the CPU oracle", "parity": parity}))
+            dist.destroy_process_group()
+            raise SystemExit(1)
+
+    # ---- headline workload ------------------------------------------------------------------------------------------------------
+    genome_len = args.genome_len * world           # weak scaling: 0.2 Gbp of input per GPU
+    w = Workload(N_IN, N_OUT, genome_len, (L_, D_, R_), PANEL_KW)
+    w.configure()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    timed(None, args.warmup, False)
-    ms_dev, launches, prof, _ = timed(None, args.steps, False, clocks if rank == 0 else None)
+    m = w.measure(args.steps, args.warmup, clocks if rank == 0 else None)
     clk = clocks.stop() if rank == 0 else None
-    counters = s.last_counters()
-    last = results["last"]
-
-    # ---- e2e arm: pinned host buffers through the C ABI, rows decoded on the host -----------------
-    timed(load_host, 1, True)
-    ms_e2e, _, prof_e2e, d2h_bytes = timed(load_host, args.steps, True)
-    e2e_host_ms = dict(host_ms)
-    e2e_stage_ms = {k: sum(v) / len(v) for k, v in prof_e2e.items()}
-    rows = results["rows"]
-    n_rows_total = rows.count("\n")
-    assert sorted(rows.splitlines()) == results["last"].rows(), "device-rendered rows differ from the host decoder's"   # (outside the timed region)
-    if world > 1:
-        t = torch.tensor([n_rows_total], device=dev)
-        dist.all_reduce(t)
-        n_rows_total = int(t.item())
-
-    # ---- roofline of the dominant kernel: the kernel family with the largest share of the step --------------
-    peak, peak_src = measured_peak()
+    last, counters = m["last"], m["counters"]
     n_rec = last.n_records
-    local_bases = h2d_bytes
-    direct = 2 * (L_ + D_ + R_) + 8 <= 64        # (multi-word records: the exact K3 pass only sees what the hash filter keeps)
-    fam = {"K1": ("kb_extract_kernel (K1: bases -> packed records)", lambda k: k.startswith("K1 extract"), local_bases + 8.0 * n_rec),
-           "K2": ("kb_part_kernel (K2: one radix-partition level, read + write of every record)",
-                  lambda k: k.startswith("K2 partition") or k.startswith("K2 pass"), 16.0 * n_rec),
-           "K3": ("kb_hash_stream_kernel (K3: bucket hash aggregation, one read of every record)",
-                  lambda k: k in ("K3 bucket hash", "K3 group") and direct, 8.0 * n_rec),
-           "K3a": ("kb_prefilter_kernel (K3a: flank-hash presence filter, one read of every element)",
-                   lambda k: k == "K3a hash prefilter", 8.0 * n_rec)}
-    roof, best = None, -1.0
-    for key, (kname, match, bytes_per_launch) in fam.items():
-        per = [sum(v) / len(v) for k, v in prof.items() if match(k)]
-        if not per:
-            continue
-        total = sum(per)
-        if total > best:
-            best = total
-            avg = total / len(per)
-            achieved = bytes_per_launch / (avg * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "avg_launch_ms": avg, "launches_per_step": len(per), "family_ms_per_step": total}
-    if roof:
-        ncu_traffic = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-        if os.path.exists(ncu_traffic):
-            with open(ncu_traffic) as fh:
-                tj = json.load(fh)
-            if tj.get("records") == n_rec and tj.get("kernel", "") in roof["kernel"]:
-                roof["traffic"] = tj.get("dram_bytes_per_launch")
-    stage_ms = {k: sum(v) / len(v) for k, v in prof.items()}
     whole = {"algorithmic_bytes_per_step": counters["algorithmic_bytes"],
-             "achieved_gbs": counters["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9,
-             "frac_of_peak": counters["algorithmic_bytes"] / (ms_dev * 1e-3) / 1e9 / peak}
+             "achieved_gbs": counters["algorithmic_bytes"] / (m["ms"] * 1e-3) / 1e9,
+             "frac_of_peak": counters["algorithmic_bytes"] / (m["ms"] * 1e-3) / 1e9 / peak,
+             "note": "as-built bytes: K1 fused with partition level 0 (bases read + records written once), one more partition level (read + write), "
+                     "one read by the bucket hash = 1 + 4*8*(1 + P) B/bp with P = 1 standalone pass (SURVEY 8d); round 1 moved 97 B/bp (P = 2)",
+             "frac_of_peak_at_round1_bytes": (w.h2d_bytes + 48.0 * n_rec) / (m["ms"] * 1e-3) / 1e9 / peak}
+
+    # ---- also: the other BASELINE configurations that fit one GPU (N = 1 only; short runs) ------------------------------------------
+    also = []
+    if world == 1 and not args.no_also and not args.ldr and not args.genomes:
+        def sub(name, wl, steps=3, warmup=1):
+            mm = wl.measure(steps, warmup)
+            r = mm["roofline"] or {}
+            return {"config": name, "value": mm["value"], "unit": UNIT, "ms_per_step": mm["ms"], "steps": steps, "warmup": warmup,
+                    "e2e": {"value": mm["e2e"]["value"], "ms_per_step": mm["e2e"]["ms_per_step"]}, "rows": mm["rows"], "rows_sha256": mm["rows_sha256"],
+                    "records": int(mm["last"].n_records), "dominant_kernel": r.get("kernel"), "frac": r.get("frac"),
+                    "stage_ms": {k: round(v, 4) for k, v in mm["stage_ms"].items()}}
+        w.configure((32, 60, 32))
+        also.append(sub("C3 primer mode: the same 20+20 x 5 Mbp panel, --conserved-left 32 --diagnostic 60 --conserved-right 32 (124-mers, multi-word records)", w))
+        w.configure((L_, D_, R_))
+        del w
+        torch.cuda.empty_cache()
+        w5 = Workload(100, 100, args.genome_len, (L_, D_, R_), PANEL_KW)
+        w5.configure()
+        also.append(sub("C5 genome-count sweep, top end: 100+100 x 5 Mbp (1 Gbp), 25/1/2", w5))
+        del w5
 
     if rank != 0:
         if world > 1:
+            sharded.shutdown(s)
             dist.destroy_process_group()
         return
     cb = cpu_baseline(args.cpu_sample_len) if (world == 1 and not args.no_cpu_baseline) else None
     line = {
-        "metric": METRIC, "value": total_bases / (ms_dev * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+        "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 (2-bit packed bases)", "data": "synthetic",
         "config": {"workload": f"synthetic bacterial panel: {N_IN} ingroup + {N_OUT} outgroup genomes x {genome_len} bp "
                                f"with planted group SNPs, --conserved-left {L_} --diagnostic {D_} --conserved-right {R_} ({L_ + D_ + R_}-mer, "
                                f"{'one 64-bit record' if 2 * (L_ + D_ + R_) + 8 <= 64 else 'multi-word records'})",
-                   "total_bases": total_bases, "records": int(n_rec) if world == 1 else None,
-                   "radix_passes": counters["radix_passes"], "rows": n_rows_total, "k3_stats": dict(last.stats),
+                   "total_bases": N_IN * genome_len + N_OUT * genome_len, "records": int(n_rec) if world == 1 else None,
+                   "radix_passes": counters["radix_passes"], "rows": m["rows"], "rows_sha256": m["rows_sha256"], "k3_stats": dict(last.stats),
                    "l2": "inputs larger than L2 (>= 0.2 GB of bases, 3.2 GB of records per GPU; 126 MB L2)",
                    "parallelism": f"flank-hash sharded x{world}" if world > 1 else "single GPU"},
-        "e2e": {"value": total_bases / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes,
-                "host_ms": e2e_host_ms, "stage_ms": e2e_stage_ms},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "stage_ms": stage_ms,
+        "e2e": m["e2e"], "gpu_launches": m["launches"], "clocks": clk, "roofline": m["roofline"], "kernel_families": m["families"],
+        "whole_step": whole, "stage_ms": m["stage_ms"],
     }
+    if world > 1:
+        line["parity"] = parity
+        ex = m["exchange"] or {}
+        if ex.get("slab") and ex.get("exchange_ms"):
+            sent = float(ex["sent_bytes"])
+            line["nvlink"] = {"bytes_sent_per_gpu": sent, "bytes_copied_per_gpu": float(ex.get("copied_bytes", sent)), "ms": ex["exchange_ms"],
+                              "achieved_gbs": sent / (ex["exchange_ms"] * 1e-3) / 1e9, "peak": 900.0, "frac_of_900": sent / (ex["exchange_ms"] * 1e-3) / 1e9 / 900.0,
+                              "groups": ex.get("groups"), "how": "bulk peer copies (copy engines) of whole level-0 slabs, digit group by digit group, "
+                              "from the first send to the last group landed (rank 0); level 1 + bucket hash of group g run under the copies of group g + 1"}
+    if also:
+        line["also"] = also
     if cb:
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["python_reference"] = python_reference_record()
     print(json.dumps(line))
     if world > 1:
+        sharded.shutdown(s)
         dist.destroy_process_group()
 
 
@@ -351,6 +458,7 @@ def main():
     ap.add_argument("--genome-len", type=int, default=5_000_000, help="bases per genome per GPU (default: BASELINE config 2)")
     ap.add_argument("--cpu-sample-len", type=int, default=1_000_000, help="genome length of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the short C3 / C5 sub-records of the N = 1 line")
     ap.add_argument("--genomes", nargs=2, type=int, metavar=("N_IN", "N_OUT"), help="ingroup / outgroup genome counts (default 20 20; "
                     "50 50 = the shape of BASELINE config 4, 5..100 each = the genome-count sweep of config 5)")
     ap.add_argument("--ldr", nargs=3, type=int, metavar=("L", "D", "R"), help="--conserved-left / --diagnostic / --conserved-right "
