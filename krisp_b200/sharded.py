@@ -202,35 +202,47 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
     from ._lib import UnsupportedError
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     mine = int(getattr(searcher, "bases_added", 0))
-    t = torch.tensor([mine, -mine], dtype=torch.int64, device=device)
-    if total_bases is None:
-        s = torch.tensor([mine], dtype=torch.int64, device=device)
-        dist.all_reduce(s, group=group)
-        total_bases = int(s.item())
-    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    max_rank_bases = int(t[0].item())
     extra = int(searcher.__dict__.get("_shard_bb_extra", 0))
+    # The plan (three small collectives + host reads) is reused while nothing it depends on changed.  Only when the caller passes
+    # total_bases — on every rank alike — is "nothing changed" a collective fact; otherwise every search plans again.
+    key = (world, rank, total_bases, mine, tuple(getattr(searcher, "lo", ()) or ()), getattr(searcher, "n_files", None), extra)
+    cached = searcher.__dict__.get("_slab_plan") if total_bases is not None else None
     for _ in range(4):
-        searcher.set_option("shard_bb_extra", extra)
-        try:
-            nd, cap, max_groups = searcher.shard_slab_plan(world, rank, total_bases, max_rank_bases)
-            ok = 1
-        except UnsupportedError:
-            nd, cap, max_groups, ok = 0, 0, 1, 0
-        caps = torch.tensor([cap if ok else -1], dtype=torch.int64, device=device)
-        allc = torch.empty(world, dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(allc, caps, group=group)
-        need = [int(c) for c in allc.tolist()]
-        if min(need) < 0:
-            return None                                               # (some rank cannot: nobody does)
-        _ensure_ipc(searcher, device, group, need)
+        if cached is not None and cached[0] == key:
+            nd, cap, max_groups = cached[1]
+        else:
+            t = torch.tensor([mine], dtype=torch.int64, device=device)
+            if total_bases is None:
+                s = torch.tensor([mine], dtype=torch.int64, device=device)
+                dist.all_reduce(s, group=group)
+                total = int(s.item())
+            else:
+                total = int(total_bases)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            max_rank_bases = int(t[0].item())
+            searcher.set_option("shard_bb_extra", extra)
+            try:
+                nd, cap, max_groups = searcher.shard_slab_plan(world, rank, total, max_rank_bases)
+                ok = 1
+            except UnsupportedError:
+                nd, cap, max_groups, ok = 0, 0, 1, 0
+            caps = torch.tensor([cap if ok else -1], dtype=torch.int64, device=device)
+            allc = torch.empty(world, dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(allc, caps, group=group)
+            need = [int(c) for c in allc.tolist()]
+            if min(need) < 0:
+                return None                                           # (some rank cannot: nobody does)
+            _ensure_ipc(searcher, device, group, need)
+            searcher.__dict__["_slab_plan"] = (key, (nd, cap, max_groups))
+        cached = None
         n_groups = _slab_groups(max_groups)
         main = torch.cuda.current_stream(device)
-        n_side = max(1, int(os.environ.get("KRISP_COPY_STREAMS", "3")))
+        # streams: `side` carries nothing but the bulk copies, back to back; `vote` carries the tiny collectives ("every rank's copies
+        # of group g have landed"), so that a collective waiting for a free SM never holds up the next group's copies
         sides = searcher.__dict__.setdefault("_copy_streams", [])
-        while len(sides) < n_side:
+        while len(sides) < 2:
             sides.append(torch.cuda.Stream(device=device))
-        side = sides[0]
+        side, vote = sides[0], sides[1]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         searcher._set_have_outgroup(have_outgroup)
         ev[0].record(main)
@@ -239,26 +251,18 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
         cur = _wrap(cur_ptr, nd, device)
         gathered = torch.empty(world * nd, dtype=torch.int64, device=device)
         dist.all_gather_into_tensor(gathered, cur, group=group)       # fill levels, on the device
-        # the exchange: digit groups as bulk peer copies on the side stream, a tiny collective behind each group = "every rank's
-        # copies of this group have landed"; the main stream processes group g while group g + 1 travels
-        for sd in sides[:n_side]:
-            sd.wait_event(ev[1])
+        side.wait_event(ev[1])
         landed = []
         flag = searcher.__dict__.setdefault("_flag", torch.zeros(1, dtype=torch.int32, device=device))
         for g in range(n_groups):
-            others = []
-            for k in range(1, n_side):                                # every copy of the group in n_side byte ranges, one per stream
-                searcher.shard_slab_send(g, n_groups, sides[k].cuda_stream, k, n_side)
-                ek = torch.cuda.Event()
-                ek.record(sides[k])
-                others.append(ek)
-            with torch.cuda.stream(side):
-                searcher.shard_slab_send(g, n_groups, side.cuda_stream, 0, n_side)
-                for ek in others:
-                    side.wait_event(ek)
+            searcher.shard_slab_send(g, n_groups, side.cuda_stream)
+            sent = torch.cuda.Event()
+            sent.record(side)
+            vote.wait_event(sent)
+            with torch.cuda.stream(vote):
                 dist.all_reduce(flag, group=group)
                 e = torch.cuda.Event(enable_timing=True)
-                e.record(side)
+                e.record(vote)
                 landed.append(e)
         for g in range(n_groups):
             main.wait_event(landed[g])
@@ -280,9 +284,11 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
         if status == 2:
             return None                                               # a slab overflowed somewhere: exact exchange for everybody
         if status == 3:
+            cached = searcher.__dict__.get("_slab_plan")
             continue                                                  # a survivor table was grown: once more, same plan
         extra += 2                                                    # plan too coarse somewhere: two more bucket bits for everybody
         searcher.__dict__["_shard_bb_extra"] = extra
+        key = key[:-1] + (extra,)
     return None
 
 
@@ -290,6 +296,7 @@ def shutdown(searcher, group=None):
     """Collective teardown: every rank unmaps its peers' receive buffers, then a barrier, then the contexts may be destroyed
     (exported memory must not be freed while a peer still maps it or still stores into it)."""
     import torch.distributed as dist
+    searcher.__dict__.pop("_slab_plan", None)
     if hasattr(searcher, "synchronize"):
         searcher.synchronize()
     if hasattr(searcher, "shard_ipc_close"):
