@@ -197,7 +197,8 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_count
  *                          of its slab of every digit, in the coordinates of the owner's buffer) for the all-gather.
  *   kb_shard_slab_send     enqueue, on `cuda_stream`, the bulk peer copies (copy engines over NVLink) of digit group `group` of
  *                          `n_groups`: for every other owner the staged slabs of the group's digits as ONE contiguous copy (of which
- *                          this call moves byte range `part` of `n_parts`: several streams keep several copy engines busy).  The
+ *                          this call moves byte range `part` of `n_parts`; n_parts < 0: the whole copies of the peers k with
+ *                          (k - 1) % |n_parts| == part — several streams keep several copy engines busy).  The
  *                          host layer runs the groups in order on a copy stream and puts a tiny collective behind each group, after
  *                          which every rank's copies of that group have landed.
  *   kb_shard_slab_level    gathered_cursors_dev = device array [n_ranks][n_digits] (all-gather result, rank-major).  Partition
@@ -213,6 +214,10 @@ int kb_shard_slab_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t tota
                        uint64_t* recv_capacity_records, int* max_groups);
 int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev);
 int kb_shard_slab_send(kb_ctx* ctx, int group, int n_groups, int part, int n_parts, void* cuda_stream);
+/* For a host layer that moves the digit groups itself (e.g. one NCCL all-to-all per group instead of kb_shard_slab_send), valid after
+ * kb_shard_slab_extract: the staging buffer (slab of digit d at d * slab_records elements), this rank's receive buffer (slab
+ * (source rank s, own digit j) at (s * own_digits + j) * slab_records) and the slab capacity in 8-byte records. */
+int kb_shard_slab_buffers(kb_ctx* ctx, void** staging, void** receive, uint64_t* slab_records);
 int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group, int n_groups);
 int kb_shard_slab_finish(kb_ctx* ctx, int* status, kb_result** out);
 

@@ -2191,6 +2191,8 @@ int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev) {
 }
 
 int kb_shard_slab_send(kb_ctx* ctx, int group, int n_groups, int part, int n_parts, void* cuda_stream) {
+    const bool by_peer = n_parts < 0;                         // n_parts < 0: this call serves the peers k with (k - 1) % |n_parts| == part, whole copies
+    if (by_peer) n_parts = -n_parts;
     if (!ctx || n_groups < 1 || group < 0 || group >= n_groups || n_parts < 1 || part < 0 || part >= n_parts) return KB_EINVAL;
     if (!ctx->configured || !ctx->shard_slab) return fail(ctx, KB_EINVAL, "kb_shard_slab_plan has not been called");
     if ((int)ctx->peer_ptr.size() != ctx->shard_n) return fail(ctx, KB_EINVAL, "kb_shard_ipc_import has not been called");
@@ -2201,6 +2203,7 @@ int kb_shard_slab_send(kb_ctx* ctx, int group, int n_groups, int part, int n_par
     CU(cudaSetDevice(ctx->device));
     // peer k of this call = rank (me + k) % N: at any time every receiver has one sender
     for (uint32_t k = 1; k < N; k++) {
+        if (by_peer && (int)((k - 1) % (uint32_t)n_parts) != part) continue;
         const uint32_t o = (me + k) % N;
         const uint32_t d0 = shard_first_digit(o, N, nd0), dps_o = shard_first_digit(o + 1, N, nd0) - d0;
         const uint32_t j0 = (uint32_t)(((uint64_t)group * dps_o) / (uint32_t)n_groups), j1 = (uint32_t)(((uint64_t)(group + 1) * dps_o) / (uint32_t)n_groups);
@@ -2210,9 +2213,17 @@ int kb_shard_slab_send(kb_ctx* ctx, int group, int n_groups, int part, int n_par
         // whole slabs (the fill levels travel separately); this call moves byte range `part` of `n_parts` of every copy, so that
         // several streams = several copy engines share one group
         const uint64_t total = (uint64_t)(j1 - j0) * sp.cap[0];
-        const uint64_t e0 = (total * (uint64_t)part / (uint64_t)n_parts) & ~1ULL, e1 = part + 1 == n_parts ? total : ((total * (uint64_t)(part + 1) / (uint64_t)n_parts) & ~1ULL);
+        const uint64_t e0 = by_peer ? 0 : ((total * (uint64_t)part / (uint64_t)n_parts) & ~1ULL);
+        const uint64_t e1 = (by_peer || part + 1 == n_parts) ? total : ((total * (uint64_t)(part + 1) / (uint64_t)n_parts) & ~1ULL);
         if (e1 > e0) CU(cudaMemcpyAsync(dst + e0, src + e0, (size_t)(e1 - e0) * 8, cudaMemcpyDeviceToDevice, st));
     }
+    return KB_OK;
+}
+
+int kb_shard_slab_buffers(kb_ctx* ctx, void** staging, void** receive, uint64_t* slab_records) {
+    if (!ctx || !staging || !receive || !slab_records) return KB_EINVAL;
+    if (!ctx->configured || !ctx->shard_slab) return fail(ctx, KB_EINVAL, "kb_shard_slab_plan has not been called");
+    *staging = ctx->entA.p; *receive = ctx->recvbuf.p; *slab_records = ctx->shard_sp.cap[0];
     return KB_OK;
 }
 

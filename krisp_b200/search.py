@@ -406,6 +406,12 @@ class Searcher:
         """Bulk peer copies of one digit group (byte range `part` of `n_parts` of each) on the raw cudaStream_t `stream`."""
         self._check(self._L.kb_shard_slab_send(self._ctx, int(group), int(n_groups), int(part), int(n_parts), ctypes.c_void_p(int(stream))))
 
+    def shard_slab_buffers(self):
+        """(staging device pointer, receive-buffer device pointer, slab capacity in records) after shard_slab_extract."""
+        a, b, c = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(self._L.kb_shard_slab_buffers(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return int(a.value or 0), int(b.value or 0), int(c.value)
+
     def shard_slab_level(self, gathered_ptr, group, n_groups):
         """Partition level 1 + bucket hash on one digit group of the receive buffer."""
         self._check(self._L.kb_shard_slab_level(self._ctx, ctypes.c_void_p(int(gathered_ptr)), int(group), int(n_groups)))

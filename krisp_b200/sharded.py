@@ -239,10 +239,12 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
         main = torch.cuda.current_stream(device)
         # streams: `side` carries nothing but the bulk copies, back to back; `vote` carries the tiny collectives ("every rank's copies
         # of group g have landed"), so that a collective waiting for a free SM never holds up the next group's copies
+        n_copy = max(1, min(world - 1, int(os.environ.get("KRISP_COPY_STREAMS", "1"))))   # copy streams, each serving some of the peers
         sides = searcher.__dict__.setdefault("_copy_streams", [])
-        while len(sides) < 2:
+        while len(sides) < 1 + n_copy:
             sides.append(torch.cuda.Stream(device=device))
-        side, vote = sides[0], sides[1]
+        vote, side = sides[0], sides[1]
+        copies = sides[1:1 + n_copy]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         searcher._set_have_outgroup(have_outgroup)
         ev[0].record(main)
@@ -251,19 +253,51 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
         cur = _wrap(cur_ptr, nd, device)
         gathered = torch.empty(world * nd, dtype=torch.int64, device=device)
         dist.all_gather_into_tensor(gathered, cur, group=group)       # fill levels, on the device
-        side.wait_event(ev[1])
+        for cs in copies:
+            cs.wait_event(ev[1])
         landed = []
         flag = searcher.__dict__.setdefault("_flag", torch.zeros(1, dtype=torch.int32, device=device))
-        for g in range(n_groups):
-            searcher.shard_slab_send(g, n_groups, side.cuda_stream)
-            sent = torch.cuda.Event()
-            sent.record(side)
-            vote.wait_event(sent)
-            with torch.cuda.stream(vote):
-                dist.all_reduce(flag, group=group)
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(vote)
-                landed.append(e)
+        mode = os.environ.get("KRISP_SLAB_EXCHANGE", "a2a" if world > 2 else "copy")
+        if mode == "a2a":
+            # one NCCL all-to-all per digit group between the library's buffers (send/recv over NVLink on NCCL's channels): its
+            # completion on this rank IS "my slabs of the group have arrived", no separate vote
+            stg, rcv, cap0 = searcher.shard_slab_buffers()
+            ck = (stg, rcv, cap0, n_groups, world, rank, nd)
+            lists = searcher.__dict__.get("_a2a_lists")
+            if lists is None or lists[0] != ck:                       # (tensor views of the library's buffers: built once per plan)
+                firsts = [first_digit(o, world, nd) for o in range(world + 1)]
+                dps_me = firsts[rank + 1] - firsts[rank]
+                empty = torch.empty(0, dtype=torch.int64, device=device)
+                per_group = []
+                for g in range(n_groups):
+                    ins, outs = [], []
+                    j0m, j1m = g * dps_me // n_groups, (g + 1) * dps_me // n_groups
+                    for o in range(world):
+                        dps_o = firsts[o + 1] - firsts[o]
+                        j0, j1 = g * dps_o // n_groups, (g + 1) * dps_o // n_groups
+                        ins.append(empty if o == rank or j1 <= j0 else _wrap(stg + 8 * (firsts[o] + j0) * cap0, (j1 - j0) * cap0, device))
+                        outs.append(empty if o == rank or j1m <= j0m else _wrap(rcv + 8 * (o * dps_me + j0m) * cap0, (j1m - j0m) * cap0, device))
+                    per_group.append((outs, ins))
+                lists = (ck, per_group)
+                searcher.__dict__["_a2a_lists"] = lists
+            with torch.cuda.stream(side):
+                for outs, ins in lists[1]:
+                    dist.all_to_all(outs, ins, group=group)
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record(side)
+                    landed.append(e)
+        else:
+            for g in range(n_groups):
+                for i, cs in enumerate(copies):
+                    searcher.shard_slab_send(g, n_groups, cs.cuda_stream, i, -n_copy)
+                    sent = torch.cuda.Event()
+                    sent.record(cs)
+                    vote.wait_event(sent)
+                with torch.cuda.stream(vote):
+                    dist.all_reduce(flag, group=group)
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record(vote)
+                    landed.append(e)
         for g in range(n_groups):
             main.wait_event(landed[g])
             searcher.shard_slab_level(gathered.data_ptr(), g, n_groups)
@@ -279,7 +313,7 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
             res.profile = list(res.profile) + [("K4 exchange (bulk peer copies, first send to last landed)", t_x)]
             res.exchange = {"slab": True, "digits": nd, "groups": n_groups, "records_extracted": int(res.n_records), "own_digits": [lo_d, hi_d],
                             "sent": sent, "sent_bytes": 8 * sent, "copied_bytes": 8 * (cap - 4096) * (world - 1) // max(world, 1),
-                            "exchange_ms": t_x}
+                            "exchange_ms": t_x, "mode": mode}
             return res
         if status == 2:
             return None                                               # a slab overflowed somewhere: exact exchange for everybody

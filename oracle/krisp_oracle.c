@@ -60,6 +60,17 @@ typedef struct {
     int stride;
 } layout_t;
 
+/* Memory-lean runs of the checker on big panels: only k-mers whose (left,right) key hashes into part g_part of g_nparts are kept.
+ * Every rule of the search is local to one key (S5-S8), so the union of the rows over all parts is the full answer. */
+static int g_part = 0, g_nparts = 1;
+void ko_set_key_partition(int part, int nparts) { g_nparts = nparts > 1 ? nparts : 1; g_part = (part >= 0 && part < g_nparts) ? part : 0; }
+static uint32_t key_hash(const uint8_t* a, int na, const uint8_t* b, int nb) {
+    uint32_t h = 2166136261u;
+    for (int i = 0; i < na; i++) { h ^= a[i]; h *= 16777619u; }
+    for (int i = 0; i < nb; i++) { h ^= b[i]; h *= 16777619u; }
+    return h ^ (h >> 15);
+}
+
 static int cmp_stride;
 #pragma omp threadprivate(cmp_stride)
 static int cmp_rec(const void* a, const void* b) { return memcmp(a, b, (size_t)cmp_stride); }
@@ -112,6 +123,7 @@ static int extract_file(const uint8_t* bases, const uint64_t* rec_off, const int
             if (n_n > 0) continue;                  /* _disallow("Nn") after the complement; N<->N so both strands drop */
             for (int strand = 0; strand < 2; strand++) {
                 const uint8_t* q = strand ? x : w;
+                if (g_nparts > 1 && (int)(key_hash(q, L, q + L + D, R) % (uint32_t)g_nparts) != g_part) continue;
                 uint8_t* o = buf + n * S;
                 memcpy(o, q, (size_t)L);                        /* left  */
                 memcpy(o + L, q + L + D, (size_t)R);            /* right */
@@ -123,6 +135,7 @@ static int extract_file(const uint8_t* bases, const uint64_t* rec_off, const int
     }
     free(w);
     if (rc_err != KO_OK) { free(buf); return rc_err; }
+    if (g_nparts > 1) { uint8_t* sh = (uint8_t*)realloc(buf, n * S + 1); if (sh) buf = sh; }
     cmp_stride = S;
     qsort(buf, n, (size_t)S, cmp_rec);              /* stage B */
     out->rec = buf; out->n = n; *count = n;

@@ -55,6 +55,12 @@ def threads():
     return lib().ko_threads()
 
 
+def set_key_partition(part=0, nparts=1):
+    """Keep only the k-mers whose (left,right) key hashes into `part` of `nparts` (memory-lean runs on big panels: the union of the
+    rows over all parts is the full answer, every rule being local to one key).  (0, 1) switches it off."""
+    lib().ko_set_key_partition(int(part), int(nparts))
+
+
 def _pack(records_by_file):
     """records_by_file: list (per file) of list of str/bytes records -> (bases, rec_off, rec_file)."""
     chunks, offs, files = [], [0], []
