@@ -76,6 +76,9 @@ int kb_configure(kb_ctx* ctx, int L, int D, int R, int soft_mode, int n_files, c
  *                   a slab overflow (very repetitive input) repeats the search on the exact, histogram-based path.  "slab_cap" forces
  *                   the slab capacity (tests).  "hash_warp" 1 (default) = bucket hash with per-warp streaming (kb_hash_warp.cuh),
  *                   "hash_shared" 1 / 0 / -1 = one table per CTA / per warp / by table size
+ *   "sym"           1 = slab path with a strand-symmetric level 0 (0 = records; -1, the default = only on >= 4 GPUs, where it halves the exchange): both records of a window share the level-0 digit, so level 0
+ *                   (and the multi-GPU exchange) moves one 8-byte window item per window; records are formed by level 1
+ *                   (csrc/kb_extract_sym.cuh).  Needs >= 2 partition levels and a core of enough bases, else the record path is used
  *   "batch_level0"  1 (default) = with host buffers in flight K1 (+ partition levels 0 and 1) run per batch of arrived files
  *   "shard_bb_extra" bucket bits added to the sharded slab plan (kb_shard_slab_search status 1)
  */
@@ -216,8 +219,10 @@ int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev);
 int kb_shard_slab_send(kb_ctx* ctx, int group, int n_groups, int part, int n_parts, void* cuda_stream);
 /* For a host layer that moves the digit groups itself (e.g. one NCCL all-to-all per group instead of kb_shard_slab_send), valid after
  * kb_shard_slab_extract: the staging buffer (slab of digit d at d * slab_records elements), this rank's receive buffer (slab
- * (source rank s, own digit j) at (s * own_digits + j) * slab_records) and the slab capacity in 8-byte records. */
-int kb_shard_slab_buffers(kb_ctx* ctx, void** staging, void** receive, uint64_t* slab_records);
+ * (source rank s, own digit j) at (s * own_digits + j) * slab_records) and the slab capacity in 8-byte elements.  *window_items = 1:
+ * the elements are window items, one per k-mer window (strand-symmetric level 0, csrc/kb_extract_sym.cuh: half the bytes travel);
+ * 0: records, two per window. */
+int kb_shard_slab_buffers(kb_ctx* ctx, void** staging, void** receive, uint64_t* slab_records, int* window_items);
 int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group, int n_groups);
 int kb_shard_slab_finish(kb_ctx* ctx, int* status, kb_result** out);
 

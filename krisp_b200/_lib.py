@@ -89,7 +89,7 @@ def load():
     L.kb_shard_slab_plan.argtypes = [vp, i, i, u64, u64, ctypes.POINTER(i), ctypes.POINTER(u64), ctypes.POINTER(i)]
     L.kb_shard_slab_extract.argtypes = [vp, pvp]
     L.kb_shard_slab_send.argtypes = [vp, i, i, i, i, vp]
-    L.kb_shard_slab_buffers.argtypes = [vp, pvp, pvp, ctypes.POINTER(u64)]
+    L.kb_shard_slab_buffers.argtypes = [vp, pvp, pvp, ctypes.POINTER(u64), ctypes.POINTER(i)]
     L.kb_shard_slab_level.argtypes = [vp, vp, i, i]
     L.kb_shard_slab_finish.argtypes = [vp, ctypes.POINTER(i), pvp]
     L.kb_shard_extract.argtypes = [vp, pvp, ctypes.POINTER(u64), ctypes.POINTER(u64)]

@@ -20,6 +20,7 @@
 #include "kb_hash_stream.cuh"
 #include "kb_hash_warp.cuh"
 #include "kb_extract_part.cuh"
+#include "kb_extract_sym.cuh"
 #include "kb_ingest.cuh"
 #include "kb_prefilter.cuh"
 #include "kb_rows.cuh"
@@ -66,6 +67,8 @@ struct SlabPlan {
     uint64_t cap[3] = {0, 0, 0};
     size_t off_cur[3] = {0, 0, 0}, off_counts = 0, off_start = 0, off_part = 0, off_tab0 = 0, off_tile0[3] = {0, 0, 0}, off_tilemap = 0, off_snap = 0, bytes = 0;
     uint64_t max_tiles = 0;
+    bool sym = false;                    // level 0 moves one window item per window, ranked by the strand-symmetric core digit (kb_extract_sym.cuh)
+    uint64_t core_mask = 0;
 };
 
 // Level 0 of the partition per batch of input files (host buffers still in flight): see kb_batch_*_kernel in kb_part.cuh.
@@ -118,6 +121,9 @@ struct kb_ctx {
     long long opt_hash_warp = 1;         // 1 = bucket hash kernel with per-warp streaming (kb_hash_warp.cuh) instead of the CTA-wide stream kernel
     long long opt_hash_shared = -1;      // kb_hash_warp.cuh: 1 = one table per CTA, 0 = one per warp, -1 = by table size (>= 1024 slots: per CTA)
     long long opt_slab_cap = 0;          // != 0: force the capacity of every slab (tests: overflow -> exact path)
+    long long opt_sym = -1;              // slab path: 1 = strand-symmetric level 0 on window items where the layout allows it (kb_extract_sym.cuh),
+                                         // 0 = records, -1 = items only where the exchange is the bottleneck (>= 4 GPUs: half the NVLink bytes;
+                                         // on one GPU forming the records in level 1 costs more than level 0 saves)
     bool slab_off = false;               // a slab overflowed on these sequences: searches use the exact path until they change
     bool lazy_now = false;               // the running search uses it
     int bb_extra = 0;                    // bucket bits added to the size-based plan: learnt when a search deferred too many buckets
@@ -303,6 +309,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "lazy_records") ctx->opt_lazy_records = value ? 1 : 0;
     else if (n == "slab") { ctx->opt_slab = value ? 1 : 0; ctx->slab_off = false; }
     else if (n == "hash_warp") ctx->opt_hash_warp = value ? 1 : 0;
+    else if (n == "sym") ctx->opt_sym = value < 0 ? -1 : (value ? 1 : 0);
     else if (n == "hash_shared") ctx->opt_hash_shared = value < 0 ? -1 : (value ? 1 : 0);
     else if (n == "shard_bb_extra") { if (value < 0 || value > 12) return fail(ctx, KB_EINVAL, "shard_bb_extra must be in 0..12"); ctx->opt_shard_bb_extra = value; }
     else if (n == "slab_cap") { if (value < 0) return fail(ctx, KB_EINVAL, "slab_cap must be >= 0"); ctx->opt_slab_cap = value; ctx->slab_off = false; }
@@ -947,6 +954,8 @@ struct HashStage {            // what run_group needs to run the bucket-hash ker
     uint64_t n_kept = 0;                         // lazy records: elements the exact pass reads
     const unsigned long long* bend = nullptr;   // slab layout: fill level (absolute end) of every bucket
     uint64_t bcap = 0;                           // slab layout: bucket b starts at b * bcap
+    int bb_hash = -1;                            // >= 0: key bits the buckets already separate, as the hash kernels see them (symmetric level 0:
+                                                 // only the levels after it eat top bits of the mixed key); -1 = the plan's bucket bits
     int phase = 0;                               // 0 = everything; 1 = only the main kernel, on buckets [bucket0, bucket0 + n_buckets);
     uint32_t bucket0 = 0;                        // 2 = only what follows it (deferred buckets, group sizes) over all n_buckets
 };
@@ -955,7 +964,8 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
     const KbLayout& lo = g.lo;
     KbHashArgs x{};
     x.g = g;
-    x.bstart = hs.bstart; x.n_buckets = hs.n_buckets; x.slots_log2 = hs.slots_log2 ? hs.slots_log2 : hs.pl->slots_log2; x.bb = (uint32_t)hs.pl->bb;
+    x.bstart = hs.bstart; x.n_buckets = hs.n_buckets; x.slots_log2 = hs.slots_log2 ? hs.slots_log2 : hs.pl->slots_log2;
+    x.bb = (uint32_t)(hs.bb_hash >= 0 ? hs.bb_hash : hs.pl->bb);
     x.ingroup64 = (uint64_t)g.ingroup[0] | ((uint64_t)g.ingroup[1] << 32);
     x.full64 = (uint64_t)g.full[0] | ((uint64_t)g.full[1] << 32);
     x.err = (unsigned long long*)ctx->small.p + SM_ERR;
@@ -1404,15 +1414,26 @@ static uint64_t slab_capacity(const kb_ctx* ctx, uint64_t n_est, uint64_t nc, bo
     return (cap + 1) & ~1ULL;                                   // even: every slab starts 16-byte aligned
 }
 
+// strand-symmetric level 0 (window items): the core must carry enough bits for the level-0 digit, and level 1 must exist to expand
+static bool sym_ok(const kb_ctx* ctx, const PartPlan& pl, uint64_t* core_mask, int n_shards = 1) {
+    const KbLayout& lo = ctx->lo;
+    int core = 0;
+    const uint64_t m = kb_core_mask(lo.L, lo.D, lo.R, &core);
+    if (core_mask) *core_mask = m;
+    const bool want = ctx->opt_sym < 0 ? n_shards >= 4 : ctx->opt_sym != 0;
+    return want && lo.direct && lo.mix && pl.levels >= 2 && 2 * core >= pl.bits[0] + 10;
+}
+
 static SlabPlan make_slab_plan(const kb_ctx* ctx, const PartPlan& pl, uint64_t n_est) {
     SlabPlan sp;
     sp.levels = pl.levels;
+    sp.sym = sym_ok(ctx, pl, &sp.core_mask);
     uint32_t maxnc = 0;
     size_t off = 0;
     for (int l = 0; l < pl.levels; l++) {
         sp.bits[l] = pl.bits[l];
         sp.nc[l] = pl.nc[l];
-        sp.cap[l] = slab_capacity(ctx, n_est, pl.nc[l], l + 1 < pl.levels);
+        sp.cap[l] = slab_capacity(ctx, (l == 0 && sp.sym) ? n_est / 2 : n_est, pl.nc[l], l + 1 < pl.levels);   // (symmetric level 0: one item per window)
         maxnc = std::max(maxnc, sp.nc[l]);
         sp.off_cur[l] = off; off += (size_t)sp.nc[l] * 8;
     }
@@ -1438,7 +1459,7 @@ static bool slab_ok(const kb_ctx* ctx, const PartPlan& pl) {
 template <class F>
 static int run_extract_part(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint32_t bits,
                             unsigned long long* cursor, const unsigned long long* limit, const unsigned long long* out_elems,
-                            const std::vector<std::pair<uint32_t, cudaEvent_t>>& batches, F after_batch) {
+                            const std::vector<std::pair<uint32_t, cudaEvent_t>>& batches, F after_batch, bool sym = false, uint64_t core_mask = 0) {
     const KbLayout& lo = ctx->lo;
     KbXPartArgs a{};
     a.bases = (const uint8_t*)ctx->bases.p; a.n_bases = ctx->n_bases;
@@ -1452,8 +1473,9 @@ static int run_extract_part(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles, uint6
     a.n_out = (unsigned long long*)ctx->small.p + SM_NOUT;
     a.ovf = (unsigned long long*)ctx->small.p + SM_OVF;
     const bool spacer = lo.L == 25 && lo.D == 1 && lo.R == 2 && lo.mix;
-    const size_t smem = kb_xpart_smem();
-    if (spacer) CU(cudaFuncSetAttribute(kb_extract_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = sym ? kb_xsym_smem() : kb_xpart_smem();
+    if (sym) CU(cudaFuncSetAttribute(kb_extract_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (spacer) CU(cudaFuncSetAttribute(kb_extract_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else CU(cudaFuncSetAttribute(kb_extract_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t t0 = tile0;
     int bi = 0;
@@ -1462,7 +1484,11 @@ static int run_extract_part(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles, uint6
         const uint32_t nt = bt.first > t0 ? bt.first - t0 : 0;
         if (nt) {
             a.tile0 = t0; a.n_tiles = nt;
-            if (spacer) kb_extract_part_kernel<true><<<nt, KB_XP_THREADS, smem, ctx->stream>>>(a);
+            if (sym) {
+                KbXSymArgs as{};
+                as.x = a; as.core_mask = core_mask;
+                kb_extract_items_kernel<<<(nt + KB_XS_TPC - 1) / KB_XS_TPC, KB_XP_THREADS, smem, ctx->stream>>>(as);
+            } else if (spacer) kb_extract_part_kernel<true><<<nt, KB_XP_THREADS, smem, ctx->stream>>>(a);
             else kb_extract_part_kernel<false><<<nt, KB_XP_THREADS, smem, ctx->stream>>>(a);
             CU(cudaGetLastError());
             ctx->launches++;
@@ -1472,7 +1498,7 @@ static int run_extract_part(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles, uint6
         bi++;
     }
     ctx->alg_bytes += std::min<uint64_t>(pos_hi, ctx->n_bases) - pos_lo;
-    ctx->alg_rec_bytes += 8;
+    ctx->alg_rec_bytes += sym ? 4 : 8;                                        // (one 8-byte item per window = per two records)
     return KB_OK;
 }
 
@@ -1491,9 +1517,14 @@ static int launch_slab_level(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl
                              uint64_t rec_bound, uint32_t psel_n = 0, uint32_t psel_j0 = 0, uint32_t psel_dps = 0) {
     uint8_t* P = (uint8_t*)ctx->plan.p;
     const size_t smem = kb_part_smem();
-    CU(cudaFuncSetAttribute(kb_part_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool expand = sp.sym && l == 1;                      // the parents hold window items: form the records here
+    const KbLayout& lo = ctx->lo;
+    const bool spacer = lo.L == 25 && lo.D == 1 && lo.R == 2 && lo.mix;
+    if (expand && spacer) CU(cudaFuncSetAttribute(kb_part_expand_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (expand) CU(cudaFuncSetAttribute(kb_part_expand_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CU(cudaFuncSetAttribute(kb_part_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int shift = 64;
-    for (int i = 0; i <= l; i++) shift -= sp.bits[i];
+    for (int i = sp.sym ? 1 : 0; i <= l; i++) shift -= sp.bits[i];   // (symmetric level 0 eats no bits of the mixed key)
     KbPartArgs a{};
     a.in = in; a.out = out;
     a.pend = pend; a.pbegin = pbegin; a.pcap = sp.cap[l - 1];
@@ -1522,7 +1553,9 @@ static int launch_slab_level(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl
         ctx->launches += 2;
         grid = rec_bound / KB_PT_TILE + n_parents + 1;
     }
-    kb_part_kernel<2, false, true><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
+    if (expand && spacer) kb_part_expand_kernel<true><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a, lo);
+    else if (expand) kb_part_expand_kernel<false><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a, lo);
+    else kb_part_kernel<2, false, true><<<(unsigned)grid, KB_PT_THREADS, smem, ctx->stream>>>(a);
     CU(cudaGetLastError());
     ctx->launches++;
     return KB_OK;
@@ -1537,7 +1570,7 @@ static int run_slab_levels(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl, 
         TRY(launch_slab_level(ctx, sp, pl, l, bufs[(l - 1) & 1], bufs[l & 1], (const unsigned long long*)(P + sp.off_cur[l - 1]), nullptr,
                               sp.nc[l - 1], nullptr, n_est));
         prof_end(ctx);
-        ctx->alg_rec_bytes += 16;
+        ctx->alg_rec_bytes += (sp.sym && l == 1) ? 12 : 16;
     }
     return KB_OK;
 }
@@ -1581,9 +1614,9 @@ static int search_slab(kb_ctx* ctx, const PartPlan& pl, kb_result** out) {
                              CU(cudaMemcpyAsync(s1, cur0, (size_t)sp.nc[0] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
                              if (!nt) return KB_OK;
                              return launch_slab_level(ctx, sp, pl, 1, bufs[0], bufs[1], s1, s0, sp.nc[0], nullptr, 2ull * nt * KB_K1_TB);
-                         }));
+                         }, sp.sym, sp.core_mask));
     prof_end(ctx);
-    if (per_batch) ctx->alg_rec_bytes += 16;
+    if (per_batch) ctx->alg_rec_bytes += sp.sym ? 12 : 16;
     TRY(run_slab_levels(ctx, sp, pl, per_batch ? 2 : 1, bufs, n_est));
     ctx->passes = sp.levels;
     HashStage hs{};
@@ -1591,6 +1624,7 @@ static int search_slab(kb_ctx* ctx, const PartPlan& pl, kb_result** out) {
     hs.n_buckets = sp.nc[sp.levels - 1];
     hs.bend = (const unsigned long long*)(P + sp.off_cur[sp.levels - 1]);
     hs.bcap = sp.cap[sp.levels - 1];
+    if (sp.sym) hs.bb_hash = pl.bb - sp.bits[0];
     int rc = run_group(ctx, bufs[(sp.levels - 1) & 1], n_est, out, &hs);
     prof_collect(ctx);
     return rc;
@@ -2095,12 +2129,13 @@ int kb_shard_slab_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t tota
     const uint32_t dps = shard_first_digit((uint32_t)shard_index + 1, (uint32_t)n_shards, nd0) - d_lo;
     SlabPlan sp;
     sp.levels = pl.levels;
+    sp.sym = sym_ok(ctx, pl, &sp.core_mask, n_shards);
     size_t off = 0;
     uint32_t maxnc = std::max<uint32_t>(nd0, (uint32_t)n_shards * dps);
     uint32_t loc = dps;
     for (int l = 0; l < pl.levels; l++) {
         sp.bits[l] = pl.bits[l];
-        if (l == 0) { sp.nc[0] = nd0; sp.cap[0] = slab_capacity(ctx, 2 * max_rank_bases + 64, nd0, true); }
+        if (l == 0) { sp.nc[0] = nd0; sp.cap[0] = slab_capacity(ctx, (sp.sym ? 1 : 2) * max_rank_bases + 64, nd0, true); }   // (items / records of the largest rank)
         else { loc <<= pl.bits[l]; sp.nc[l] = loc; sp.cap[l] = slab_capacity(ctx, n_est, pl.nc[l], l + 1 < pl.levels); }
         pl.ncl[l] = l == 0 ? dps : loc;
         maxnc = std::max(maxnc, sp.nc[l]);
@@ -2184,7 +2219,7 @@ int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev) {
     prof_begin(ctx, "K1 extract + partition 0");
     TRY(run_extract_part(ctx, tile0, n_tiles, pos_lo, pos_hi, (uint32_t)sp.bits[0], (unsigned long long*)(P + sp.off_cur[0]),
                          (const unsigned long long*)(P + sp.off_tab0), (const unsigned long long*)(P + sp.off_tab0) + KB_XP_MAXR, batches,
-                         [](int, int, uint32_t) -> int { return KB_OK; }));
+                         [](int, int, uint32_t) -> int { return KB_OK; }, sp.sym, sp.core_mask));
     prof_end(ctx);
     *cursors_dev = P + sp.off_cur[0];
     return KB_OK;
@@ -2220,10 +2255,11 @@ int kb_shard_slab_send(kb_ctx* ctx, int group, int n_groups, int part, int n_par
     return KB_OK;
 }
 
-int kb_shard_slab_buffers(kb_ctx* ctx, void** staging, void** receive, uint64_t* slab_records) {
+int kb_shard_slab_buffers(kb_ctx* ctx, void** staging, void** receive, uint64_t* slab_records, int* window_items) {
     if (!ctx || !staging || !receive || !slab_records) return KB_EINVAL;
     if (!ctx->configured || !ctx->shard_slab) return fail(ctx, KB_EINVAL, "kb_shard_slab_plan has not been called");
     *staging = ctx->entA.p; *receive = ctx->recvbuf.p; *slab_records = ctx->shard_sp.cap[0];
+    if (window_items) *window_items = ctx->shard_sp.sym ? 1 : 0;
     return KB_OK;
 }
 
@@ -2263,7 +2299,7 @@ int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group
         TRY(launch_slab_level(ctx, sp, pl, 1, (const uint64_t*)ctx->recvbuf.p, bufs[1], pend, nullptr, N * (j1 - j0), prow, 0, j1 - j0, j0, dps));
     }
     prof_end(ctx);
-    if (group == 0) ctx->alg_rec_bytes += 16;
+    if (group == 0) ctx->alg_rec_bytes += sp.sym ? 12 : 16;
     if (sp.levels > 2) {
         TRY(run_slab_levels(ctx, sp, pl, 2, bufs, std::min<uint64_t>(n_est, (uint64_t)sp.nc[1] * sp.cap[1])));
     }
@@ -2277,6 +2313,7 @@ int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group
     hs.bucket0 = n_groups == 1 ? 0u : j0 << cb;
     hs.bend = (const unsigned long long*)(P + sp.off_cur[last]);
     hs.bcap = sp.cap[last];
+    if (sp.sym) hs.bb_hash = pl.bb - sp.bits[0];
     hs.phase = 1;
     KbGroupArgs a{};
     fill_group_args(ctx, a, bufs[last & 1], n_est);
@@ -2303,6 +2340,7 @@ int kb_shard_slab_finish(kb_ctx* ctx, int* status, kb_result** out) {
     hs.n_buckets = sp.nc[last];
     hs.bend = (const unsigned long long*)(P + sp.off_cur[last]);
     hs.bcap = sp.cap[last];
+    if (sp.sym) hs.bb_hash = pl.bb - sp.bits[0];
     hs.phase = 2;
     ctx->replan_ok = ctx->opt_bucket_bits < 0 && pl.bb < std::min(ctx->lo.FB, 24);
     int rc = run_group(ctx, bufs[last & 1], n_est, out, &hs, true);

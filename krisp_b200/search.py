@@ -407,10 +407,11 @@ class Searcher:
         self._check(self._L.kb_shard_slab_send(self._ctx, int(group), int(n_groups), int(part), int(n_parts), ctypes.c_void_p(int(stream))))
 
     def shard_slab_buffers(self):
-        """(staging device pointer, receive-buffer device pointer, slab capacity in records) after shard_slab_extract."""
-        a, b, c = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64()
-        self._check(self._L.kb_shard_slab_buffers(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
-        return int(a.value or 0), int(b.value or 0), int(c.value)
+        """(staging device pointer, receive-buffer device pointer, slab capacity in 8-byte elements, elements are window items)
+        after shard_slab_extract."""
+        a, b, c, w = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_int()
+        self._check(self._L.kb_shard_slab_buffers(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(w)))
+        return int(a.value or 0), int(b.value or 0), int(c.value), bool(w.value)
 
     def shard_slab_level(self, gathered_ptr, group, n_groups):
         """Partition level 1 + bucket hash on one digit group of the receive buffer."""

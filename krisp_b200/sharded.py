@@ -261,7 +261,7 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
         if mode == "a2a":
             # one NCCL all-to-all per digit group between the library's buffers (send/recv over NVLink on NCCL's channels): its
             # completion on this rank IS "my slabs of the group have arrived", no separate vote
-            stg, rcv, cap0 = searcher.shard_slab_buffers()
+            stg, rcv, cap0, _ = searcher.shard_slab_buffers()
             ck = (stg, rcv, cap0, n_groups, world, rank, nd)
             lists = searcher.__dict__.get("_a2a_lists")
             if lists is None or lists[0] != ck:                       # (tensor views of the library's buffers: built once per plan)
@@ -308,12 +308,14 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
         status = int(st.item())                                       # search's copies while a peer still reads its buffer
         if status == 0:
             lo_d, hi_d = first_digit(rank, world, nd), first_digit(rank + 1, world, nd)
-            sent = int(res.n_records) - int(res.n_records) * (hi_d - lo_d) // max(nd, 1)       # (uniform digits: what does not stay)
+            items = searcher.shard_slab_buffers()[3]                  # one 8-byte item per window instead of two records
+            elems = int(res.n_records) // (2 if items else 1)
+            sent = elems - elems * (hi_d - lo_d) // max(nd, 1)        # (uniform digits: what does not stay)
             t_x = ev[1].elapsed_time(landed[-1])
             res.profile = list(res.profile) + [("K4 exchange (bulk peer copies, first send to last landed)", t_x)]
             res.exchange = {"slab": True, "digits": nd, "groups": n_groups, "records_extracted": int(res.n_records), "own_digits": [lo_d, hi_d],
                             "sent": sent, "sent_bytes": 8 * sent, "copied_bytes": 8 * (cap - 4096) * (world - 1) // max(world, 1),
-                            "exchange_ms": t_x, "mode": mode}
+                            "exchange_ms": t_x, "mode": mode, "window_items": items}
             return res
         if status == 2:
             return None                                               # a slab overflowed somewhere: exact exchange for everybody

@@ -47,7 +47,7 @@ def main():
     from krisp_b200.panel import make_panel
     for (L, D, R), opts in [((25, 1, 2), {}), ((25, 1, 2), {"bucket_bits": 16, "shard_bits0": 4}), ((25, 1, 2), {"bucket_bits": 16, "shard_bits0": 4, "fused_hist": 0}),
                             ((25, 1, 2), {"bucket_bits": 12}), ((25, 1, 2), {"bucket_bits": 20, "shard_bits0": 5}), ((25, 1, 2), {"bucket_bits": 14, "hash_shared": 0, "hash_slots_log2": 6}),
-                            ((25, 1, 2), {"slab_cap": 2}), ((25, 1, 2), {"slab": 0}), ((12, 3, 12), {"bucket_bits": 10}),
+                            ((25, 1, 2), {"slab_cap": 2}), ((25, 1, 2), {"slab": 0}), ((25, 1, 2), {"sym": 1}), ((25, 1, 2), {"sym": 1, "bucket_bits": 16}), ((12, 3, 12), {"sym": 1, "bucket_bits": 10}), ((12, 3, 12), {"bucket_bits": 10}),
                             ((32, 60, 32), {}), ((32, 60, 32), {"bucket_bits": 16, "shard_bits0": 4})]:
         gs = make_panel(5, 4, 200_000)
         is_in = [1 if g.is_ingroup else 0 for g in gs]
@@ -66,7 +66,7 @@ def main():
             res = sharded.sharded_search(s, dev, have_outgroup=True)
             rows = sharded.gather_rows(res.rows())
         finally:
-            for k, v in (("bucket_bits", -1), ("shard_bits0", 0), ("fused_hist", 1), ("slab_cap", 0), ("slab", 1), ("hash_shared", -1), ("hash_slots_log2", 0)):
+            for k, v in (("bucket_bits", -1), ("shard_bits0", 0), ("fused_hist", 1), ("slab_cap", 0), ("slab", 1), ("sym", -1), ("hash_shared", -1), ("hash_slots_log2", 0)):
                 s.set_option(k, v)
         ok = rows == want and len(want) > 0
         if rank == 0:

@@ -30,7 +30,8 @@ def searcher():
     s.close()
 
 
-@pytest.mark.parametrize("opts", [{}, {"slab": 0}, {"bucket_bits": 18, "hash_slots_log2": 8, "hash_shared": 0}], ids=["default", "exact_path", "warp_tables"])
+@pytest.mark.parametrize("opts", [{}, {"sym": 1}, {"slab": 0}, {"bucket_bits": 18, "hash_slots_log2": 8, "hash_shared": 0}],
+                         ids=["default", "window_items", "exact_path", "warp_tables"])
 @pytest.mark.parametrize("which", sorted(_F))
 def test_full_size_rows_equal_the_oracle(which, opts, panel, searcher):
     f = _F[which]
@@ -39,7 +40,7 @@ def test_full_size_rows_equal_the_oracle(which, opts, panel, searcher):
     try:
         res = _search_panel(searcher, panel, f["L"], f["D"], f["R"], options=opts)
     finally:
-        for k, v in (("slab", 1), ("bucket_bits", -1), ("hash_slots_log2", 0), ("hash_shared", -1)):
+        for k, v in (("slab", 1), ("sym", -1), ("bucket_bits", -1), ("hash_slots_log2", 0), ("hash_shared", -1)):
             searcher.set_option(k, v)
     rows = res.rows()
     assert res.n_records == f["records"]

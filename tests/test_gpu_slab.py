@@ -11,7 +11,7 @@ from tests.test_gpu_parity import _oracle_panel, _search_panel
 pytestmark = pytest.mark.gpu
 _G = load_golden()
 
-_RESET = {"slab": 1, "hash_warp": 1, "hash_shared": -1, "bucket_bits": -1, "hash_slots_log2": 0, "slab_cap": 0, "want_records": 0, "profile": 0}
+_RESET = {"slab": 1, "sym": -1, "hash_warp": 1, "hash_shared": -1, "bucket_bits": -1, "hash_slots_log2": 0, "slab_cap": 0, "want_records": 0, "profile": 0}
 
 
 @pytest.fixture(scope="module")
@@ -36,7 +36,8 @@ def _slab(res):
     return any(nm.startswith("K1 extract + partition 0") for nm in _stages(res))
 
 
-@pytest.mark.parametrize("mode", [(1, 1, 0), (1, 1, 1), (0, 1, 0), (0, 1, 1), (0, 0, 0)], ids=["slab+warp", "slab+cta", "exact+warp", "exact+cta", "exact+stream"])
+@pytest.mark.parametrize("mode", [(1, 1, 0, 1), (1, 1, 1, 1), (1, 1, 1, 0), (0, 1, 0, 1), (0, 1, 1, 1), (0, 0, 0, 1)],
+                         ids=["slab+warp", "slab+cta", "slab_records+cta", "exact+warp", "exact+cta", "exact+stream"])
 @pytest.mark.parametrize("shape", [(6, 6, 300_000, 25, 1, 2, False), (6, 6, 300_000, 25, 1, 2, True), (3, 3, 400_000, 12, 3, 12, False),
                                    (20, 20, 100_000, 25, 1, 2, False), (40, 40, 40_000, 10, 4, 10, False), (50, 50, 40_000, 25, 1, 2, False),
                                    (70, 70, 20_000, 10, 4, 10, False), (2, 1, 40_000, 20, 0, 7, False), (3, 2, 300_000, 9, 8, 9, False)],
@@ -48,7 +49,7 @@ def test_slab_and_exact_paths_match_oracle(shape, mode, searcher):
     kw = dict(n_runs=1, run_len=30, noise=2e-4 if n_in + n_out <= 80 else 1e-4, dup_len=300, soft_block=100) if n_in + n_out > 64 else {}
     gs = make_panel(n_in, n_out, glen, **kw)
     try:
-        res = _search_panel(searcher, gs, L, D, R, omit, options={"slab": mode[0], "hash_warp": mode[1], "hash_shared": mode[2], "profile": 1}, want_records=True)
+        res = _search_panel(searcher, gs, L, D, R, omit, options={"slab": mode[0], "hash_warp": mode[1], "hash_shared": mode[2], "sym": mode[3], "profile": 1}, want_records=True)
     finally:
         _reset(searcher)
     want = _oracle_panel(gs, L, D, R, omit)
@@ -65,7 +66,7 @@ def test_slab_and_exact_paths_match_oracle(shape, mode, searcher):
         assert int(res.group_size[g]) == mine.size >= n_in + n_out
 
 
-@pytest.mark.parametrize("shared", [0, 1], ids=["warp", "cta"])
+@pytest.mark.parametrize("shared", [0, 1, 2], ids=["warp", "cta", "cta_records"])
 @pytest.mark.parametrize("bucket_bits,slots", [(1, 0), (3, 5), (9, 0), (10, 6), (13, 4), (17, 0), (18, 7), (20, 0), (2, 11), (4, 12)])
 @pytest.mark.parametrize("name", ["c1_spacer_25_1_2", "p_spacer_3x3", "p_5_2_3", "p_6_1_2", "c1_single_file", "p_spacer_4x5"])
 def test_slab_path_on_golden_cases_for_any_depth(name, bucket_bits, slots, shared, searcher):
@@ -76,7 +77,8 @@ def test_slab_path_on_golden_cases_for_any_depth(name, bucket_bits, slots, share
     L, D, R = deduce_ldr(case["flags"])
     try:
         res = search_files(ins, outs, L, D, R, omit_soft=case["omit_soft"], searcher=searcher,
-                           options={"bucket_bits": bucket_bits, "hash_slots_log2": slots, "hash_shared": shared, "profile": 1})
+                           options={"bucket_bits": bucket_bits, "hash_slots_log2": slots, "hash_shared": min(shared, 1), "sym": 0 if shared == 2 else 1,
+                                    "profile": 1})
     finally:
         _reset(searcher)
     rows = res.rows()
