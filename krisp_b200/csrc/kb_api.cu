@@ -1630,6 +1630,15 @@ static int search_slab(kb_ctx* ctx, const PartPlan& pl, kb_result** out) {
     return rc;
 }
 
+// every added file id must exist in the current configuration: an id >= n_files would set a presence bit outside the "all files"
+// mask and silently empty the result
+static int check_file_ids(kb_ctx* ctx) {
+    for (uint32_t g : ctx->file_gid)
+        if ((int)g >= ctx->lo.n_files)
+            return fail(ctx, KB_EINVAL, "a sequence was added with file id " + std::to_string(g) + " but kb_configure was told of " + std::to_string(ctx->lo.n_files) + " files");
+    return KB_OK;
+}
+
 static void begin_search(kb_ctx* ctx) {
     ctx->lazy_now = false;
     ctx->launches = 0; ctx->alg_bytes = 0; ctx->alg_rec_bytes = 0; ctx->passes = 0;
@@ -1663,6 +1672,7 @@ int kb_search(kb_ctx* ctx, kb_result** out) {
 }  // extern "C"
 
 static int search_once(kb_ctx* ctx, kb_result** out) {
+    TRY(check_file_ids(ctx));
     begin_search(ctx);
     TRY(prepare_small(ctx));
     const KbLayout& lo = ctx->lo;
@@ -1832,6 +1842,7 @@ int kb_shard_extract(kb_ctx* ctx, void** records, uint64_t* shard_counts, uint64
     const KbLayout& lo = ctx->lo;
     const PartPlan& pl = ctx->shard_plan;
     CU(cudaSetDevice(ctx->device));
+    TRY(check_file_ids(ctx));
     begin_search(ctx);
     TRY(prepare_small(ctx));
     // the plan buffer also has to hold this rank's tile map: its own records may outnumber the per-shard estimate
@@ -1920,6 +1931,7 @@ int kb_shard_count(kb_ctx* ctx, uint64_t* digit_counts) {
     const KbLayout& lo = ctx->lo;
     const PartPlan& pl = ctx->shard_plan;
     CU(cudaSetDevice(ctx->device));
+    TRY(check_file_ids(ctx));
     begin_search(ctx);
     TRY(prepare_small(ctx));
     const size_t tilemap_extra = (size_t)((2 * ctx->n_bases + 64) / KB_PT_TILE + 2) * 4;
@@ -2171,6 +2183,7 @@ int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev) {
     const uint32_t nd0 = sp.nc[0];
     const int N = ctx->shard_n, me = ctx->shard_index;
     CU(cudaSetDevice(ctx->device));
+    TRY(check_file_ids(ctx));
     begin_search(ctx);
     TRY(prepare_small(ctx));
     TRY(ensure(ctx, ctx->plan, sp.bytes + 64));

@@ -150,3 +150,15 @@ def test_host_buffers_in_batches_take_the_slab_path(searcher):
             assert res.rows() == want
     finally:
         _reset(searcher)
+
+
+def test_file_id_outside_the_configuration_is_an_error(searcher):
+    """An id >= n_files would set a presence bit outside the "all files" mask and silently empty the result."""
+    from krisp_b200._lib import KrispB200Error
+    searcher.configure(5, 1, 2, [1, 0])
+    searcher.clear_sequences()
+    searcher.add_sequence(0, np.frombuffer(b"ACGTACGTACGTAA", dtype=np.uint8))
+    searcher.add_sequence(3, np.frombuffer(b"ACGTACGTACGTAA", dtype=np.uint8))
+    with pytest.raises(KrispB200Error):
+        searcher.search()
+    searcher.clear_sequences()
