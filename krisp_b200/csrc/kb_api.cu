@@ -140,6 +140,17 @@ struct kb_ctx {
     std::vector<uint32_t> file_gid;
     DevBuf d_file_starts, d_file_gid;
 
+    // FASTA files whose raw bytes are on their way (copy stream) and whose de-lining kernels have not been enqueued yet
+    struct PendingFasta { size_t raw_off; uint64_t nb; int fasta; uint64_t slot_off; cudaEvent_t ev; size_t file_idx; };
+    std::vector<PendingFasta> pending_fasta;    // one per kb_add_fasta since the last clear, in file order
+    size_t fasta_done = 0;                       // how many of them have been de-lined
+    std::vector<int> fasta_of_file;              // local file index -> index into pending_fasta (-1: added as parsed sequence)
+    size_t raw_used = 0;                         // bytes of rawbuf in use
+#define KB_FA_STREAMS 8
+    cudaStream_t fa_stream[KB_FA_STREAMS] = {};  // the de-lining chains of different files overlap (each is a handful of tiny dependent launches)
+    DevBuf fa_work_s[KB_FA_STREAMS];
+    std::vector<cudaEvent_t> fa_done_ev;         // event pool: "file i is de-lined"
+
     // workspaces
     DevBuf rowkeyA, rowkeyB, rowtext;    // row rendering: survivor indices being sorted, the text
     DevBuf brun;                         // lazy records: per bucket (start, length) of the kept elements
@@ -278,6 +289,11 @@ void kb_destroy(kb_ctx* ctx) {
     for (size_t r = 0; r < ctx->peer_ptr.size(); r++) if (ctx->peer_ptr[r] && (int)r != ctx->shard_index) cudaIpcCloseMemHandle(ctx->peer_ptr[r]);
     if (ctx->recvbuf.p) cudaFree(ctx->recvbuf.p);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (int i = 0; i < KB_FA_STREAMS; i++) {
+        if (ctx->fa_stream[i]) { cudaStreamSynchronize(ctx->fa_stream[i]); cudaStreamDestroy(ctx->fa_stream[i]); }
+        if (ctx->fa_work_s[i].p) cudaFree(ctx->fa_work_s[i].p);
+    }
+    for (cudaEvent_t ev : ctx->fa_done_ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->copy_events) cudaEventDestroy(ev);
     if (ctx->main_event) cudaEventDestroy(ctx->main_event);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -371,6 +387,7 @@ int kb_clear_sequences(kb_ctx* ctx) {
     ctx->own_first = 0; ctx->own_count = -1;
     ctx->sep_filled = false;
     ctx->slab_off = false;
+    ctx->pending_fasta.clear(); ctx->fasta_done = 0; ctx->fasta_of_file.clear(); ctx->raw_used = 0;
     if (ctx->fa_flags.p) { cudaSetDevice(ctx->device); cudaMemsetAsync(ctx->fa_flags.p, 0, 8, ctx->stream); }
     return KB_OK;
 }
@@ -428,9 +445,12 @@ int kb_add_sequence(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_b
     ctx->file_starts.push_back(ctx->n_bases);
     ctx->file_gid.push_back((uint32_t)file_id);
     ctx->file_event.push_back(ev);
+    ctx->fasta_of_file.push_back(-1);
     ctx->n_bases += n_bytes + 1;
     return KB_OK;
 }
+
+static int deline_pending(kb_ctx* ctx, size_t upto);
 
 int kb_add_fasta(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_bytes) {
     if (!ctx) return KB_EINVAL;
@@ -443,48 +463,40 @@ int kb_add_fasta(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_byte
     const int fasta = (n_bytes && memchr(bytes, '>', nl ? (size_t)(nl - bytes) : (size_t)n_bytes)) ? 1 : 0;
     const uint8_t* body = bytes + first;
     const uint64_t nb = n_bytes - first;
+    // Asynchronous like kb_add_sequence: the raw bytes travel on the copy stream into their own region of the raw buffer (one event
+    // per file); the de-lining kernels are enqueued later, per batch of arrived files, right before K1 needs the bytes
+    // (deline_pending), so that nothing here waits for the device.  `bytes` must stay valid until the next synchronising call.
     if (ctx->bases.cap < padded_len(ctx->n_bases + nb + 1)) {
         CU(cudaStreamSynchronize(ctx->copy_stream));
+        TRY(deline_pending(ctx, ctx->pending_fasta.size()));                  // (their slots move with the buffer: write them first)
         TRY(ensure(ctx, ctx->bases, padded_len(ctx->n_bases + nb + 1), true));
     }
-    uint8_t* slot = (uint8_t*)ctx->bases.p + ctx->n_bases;
-    CU(cudaMemsetAsync(slot, '\n', nb + 1, ctx->stream));               // separators wherever the packed bytes do not reach
-    if (nb) {
-        const uint32_t tiles = (uint32_t)((nb + KB_FA_TILE - 1) / KB_FA_TILE);
-        TRY(ensure(ctx, ctx->rawbuf, nb + 64));
-        const uint32_t nblk = (tiles + KB_PLAN_BLOCK - 1) / KB_PLAN_BLOCK;
-        const size_t words = (size_t)tiles * 3 + 2 + 2 * (size_t)nblk + (tiles + 7) / 8 + 8;
-        TRY(ensure(ctx, ctx->fa_work, words * 8));
-        if (!ctx->fa_flags.p) { TRY(ensure(ctx, ctx->fa_flags, 8)); CU(cudaMemsetAsync(ctx->fa_flags.p, 0, 8, ctx->stream)); }
-        CU(cudaMemcpyAsync(ctx->rawbuf.p, body, nb, cudaMemcpyHostToDevice, ctx->stream));
-        KbFastaArgs a{};
-        a.in = (const uint8_t*)ctx->rawbuf.p; a.n = nb; a.fasta = fasta;
-        unsigned long long* q = (unsigned long long*)ctx->fa_work.p;
-        a.last_nl = q; q += tiles;
-        a.counts = q; q += tiles;
-        unsigned long long* start = q; q += tiles + 1;
-        unsigned long long* part = q; q += 2 * (size_t)nblk + 1;
-        a.hdr0 = (uint8_t*)q;
-        a.start = start;
-        a.out = slot;
-        a.flags = (unsigned int*)ctx->fa_flags.p;
-        kb_fa_lastnl_kernel<<<tiles, KB_FA_THREADS, 0, ctx->stream>>>(a);
-        CU(cudaGetLastError());
-        kb_fa_scan_kernel<<<1, 1024, 0, ctx->stream>>>(a, tiles);
-        CU(cudaGetLastError());
-        kb_fa_pack_kernel<false><<<tiles, KB_FA_THREADS, 0, ctx->stream>>>(a);
-        CU(cudaGetLastError());
-        KbPlanArgs pa{};
-        pa.counts = a.counts; pa.nc = tiles; pa.start = start; pa.cursor = nullptr; pa.tile0 = nullptr; pa.part = part;
-        PartPlan none;
-        TRY(launch_plan(ctx, pa, none));
-        kb_fa_pack_kernel<true><<<tiles, KB_FA_THREADS, 0, ctx->stream>>>(a);
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(ctx->stream));                           // `bytes` is borrowed only for the call; rawbuf is reused by the next file
+    const size_t raw_off = (ctx->raw_used + 15) & ~(size_t)15;
+    if (ctx->rawbuf.cap < raw_off + nb + 64) {
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        TRY(deline_pending(ctx, ctx->pending_fasta.size()));                  // (they read the old raw buffer)
+        TRY(ensure(ctx, ctx->rawbuf, std::max<size_t>(raw_off + nb + 64, (size_t)ctx->reserve_hint + 64 * (ctx->file_starts.size() + 2)), true));
     }
+    const size_t idx = ctx->file_starts.size();
+    if (ctx->pending_fasta.empty()) {
+        // the copy stream starts after whatever the main stream still does with the raw buffer (the previous search's de-lining)
+        CU(cudaEventRecord(ctx->main_event, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->main_event, 0));
+    }
+    while (ctx->copy_events.size() <= idx) {
+        cudaEvent_t ne;
+        CU(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming));
+        ctx->copy_events.push_back(ne);
+    }
+    cudaEvent_t ev = ctx->copy_events[idx];
+    if (nb) CU(cudaMemcpyAsync((uint8_t*)ctx->rawbuf.p + raw_off, body, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaEventRecord(ev, ctx->copy_stream));
+    ctx->pending_fasta.push_back({raw_off, nb, fasta, ctx->n_bases, ev, idx});
+    ctx->raw_used = raw_off + nb;
+    ctx->fasta_of_file.push_back((int)ctx->pending_fasta.size() - 1);
     ctx->file_starts.push_back(ctx->n_bases);
     ctx->file_gid.push_back((uint32_t)file_id);
-    ctx->file_event.push_back(nullptr);
+    ctx->file_event.push_back(ev);
     ctx->n_bases += nb + 1;
     return KB_OK;
 }
@@ -492,8 +504,9 @@ int kb_add_fasta(kb_ctx* ctx, int file_id, const uint8_t* bytes, uint64_t n_byte
 int kb_fasta_flags(kb_ctx* ctx, unsigned int* flags) {
     if (!ctx || !flags) return KB_EINVAL;
     *flags = 0;
-    if (!ctx->fa_flags.p) return KB_OK;
     CU(cudaSetDevice(ctx->device));
+    TRY(deline_pending(ctx, ctx->pending_fasta.size()));
+    if (!ctx->fa_flags.p) return KB_OK;
     CU(cudaMemcpyAsync(ctx->h_pinned + 16, ctx->fa_flags.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     *flags = (unsigned int)ctx->h_pinned[16];
@@ -508,6 +521,7 @@ int kb_get_sequence(kb_ctx* ctx, int local_index, uint8_t* out, uint64_t cap, ui
     *n_bytes = hi - lo;
     if (!out || cap < hi - lo) return KB_OK;                              // size query
     CU(cudaSetDevice(ctx->device));
+    TRY(deline_pending(ctx, ctx->pending_fasta.size()));
     CU(cudaStreamSynchronize(ctx->copy_stream));
     CU(cudaMemcpyAsync(out, (const uint8_t*)ctx->bases.p + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -517,6 +531,7 @@ int kb_get_sequence(kb_ctx* ctx, int local_index, uint8_t* out, uint64_t cap, ui
 int kb_synchronize(kb_ctx* ctx) {
     if (!ctx) return KB_EINVAL;
     CU(cudaSetDevice(ctx->device));
+    TRY(deline_pending(ctx, ctx->pending_fasta.size()));
     CU(cudaStreamSynchronize(ctx->copy_stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return KB_OK;
@@ -543,10 +558,82 @@ static int prepare_small(kb_ctx* ctx) {
     return KB_OK;
 }
 
-// Tile batches of K1: when the sequences are still arriving from the host (copy stream), K1 runs on the tiles whose bytes
-// (+ halo) are resident while the later files are in flight; otherwise one launch covers everything.  (end tile, event to wait for)
-static std::vector<std::pair<uint32_t, cudaEvent_t>> extract_batches(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles) {
-    std::vector<std::pair<uint32_t, cudaEvent_t>> batches;
+// De-lining kernels (kb_ingest.cuh) of the FASTA files added with kb_add_fasta, up to (not including) pending index `upto`, on the
+// main stream, each behind the event of its host-to-device copy.  Called per batch of arrived files right before K1 runs on them.
+static int deline_pending(kb_ctx* ctx, size_t upto) {
+    upto = std::min(upto, ctx->pending_fasta.size());
+    if (ctx->fasta_done >= upto) return KB_OK;
+    if (!ctx->fa_flags.p) { TRY(ensure(ctx, ctx->fa_flags, 8)); CU(cudaMemsetAsync(ctx->fa_flags.p, 0, 8, ctx->stream)); }
+    // the de-lining streams start after what the main stream had queued when the first file of this round came up (flag word,
+    // earlier users of the buffers) — not after the K1 batches queued since: those touch other files
+    const bool first_round = ctx->fasta_done == 0;
+    if (first_round) CU(cudaEventRecord(ctx->main_event, ctx->stream));
+    for (; ctx->fasta_done < upto; ctx->fasta_done++) {
+        const size_t i = ctx->fasta_done;
+        const kb_ctx::PendingFasta& f = ctx->pending_fasta[i];
+        static const int n_fa = []() { const char* e = getenv("KRISP_FA_STREAMS"); const int v = e ? atoi(e) : 8; return std::max(1, std::min(v, KB_FA_STREAMS)); }();
+        const int k = (int)(i % (size_t)n_fa);
+        if (!ctx->fa_stream[k]) CU(cudaStreamCreateWithFlags(&ctx->fa_stream[k], cudaStreamNonBlocking));
+        cudaStream_t st = ctx->fa_stream[k];
+        while (ctx->fa_done_ev.size() <= i) {
+            cudaEvent_t ne;
+            CU(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming));
+            ctx->fa_done_ev.push_back(ne);
+        }
+        uint8_t* slot = (uint8_t*)ctx->bases.p + f.slot_off;
+        if (first_round) CU(cudaStreamWaitEvent(st, ctx->main_event, 0));
+        CU(cudaStreamWaitEvent(st, f.ev, 0));
+        CU(cudaMemsetAsync(slot, '\n', f.nb + 1, st));                       // separators wherever the packed bytes do not reach
+        if (f.nb) {
+            const uint32_t tiles = (uint32_t)((f.nb + KB_FA_TILE - 1) / KB_FA_TILE);
+            const size_t words = (size_t)tiles * 4 + 2 + (tiles + 7) / 8 + 8;         // last_nl | counts x 2 | start (+1) | hdr0 bytes
+            DevBuf& wk = ctx->fa_work_s[k];
+            if (wk.cap < words * 8) {                                          // (rare: grows to the largest file; the stream's earlier chain is done first)
+                CU(cudaStreamSynchronize(st));
+                if (wk.p) CU(cudaFree(wk.p));
+                wk.p = nullptr; wk.cap = 0;
+                CU(cudaMalloc(&wk.p, words * 8 + words));
+                wk.cap = words * 8 + words;
+            }
+            KbFastaArgs a{};
+            a.in = (const uint8_t*)ctx->rawbuf.p + f.raw_off; a.n = f.nb; a.fasta = f.fasta;
+            unsigned long long* q = (unsigned long long*)wk.p;
+            a.last_nl = q; q += tiles;
+            a.counts = q; q += 2 * (size_t)tiles;
+            unsigned long long* start = q; q += tiles + 1;
+            a.hdr0 = (uint8_t*)q;
+            a.start = start;
+            a.out = slot;
+            a.flags = (unsigned int*)ctx->fa_flags.p;
+            kb_fa_count_kernel<<<tiles, KB_FA_THREADS, 0, st>>>(a, tiles);
+            CU(cudaGetLastError());
+            kb_fa_offsets_kernel<<<1, 1024, 0, st>>>(a, tiles, start);
+            CU(cudaGetLastError());
+            kb_fa_pack_kernel<true><<<tiles, KB_FA_THREADS, 0, st>>>(a);
+            CU(cudaGetLastError());
+            ctx->launches += 3;
+        }
+        CU(cudaEventRecord(ctx->fa_done_ev[i], st));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->fa_done_ev[i], 0));           // whatever the main stream does next sees the file
+    }
+    return KB_OK;
+}
+
+struct KBatch {
+    uint32_t first;          // end tile
+    cudaEvent_t second;      // event to wait for (null: none)
+    size_t last_file;        // local files [.., last_file] are complete once the event fired
+};
+
+// de-lining of every FASTA file up to local file `last_file` (kb_add_fasta defers it to here)
+static int deline_upto_file(kb_ctx* ctx, size_t last_file) {
+    size_t upto = ctx->fasta_done;
+    while (upto < ctx->pending_fasta.size() && ctx->pending_fasta[upto].file_idx <= last_file) upto++;
+    return deline_pending(ctx, upto);
+}
+
+static std::vector<KBatch> extract_batches(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles) {
+    std::vector<KBatch> batches;
     const size_t nf = ctx->file_starts.size();
     const uint32_t t_end = tile0 + n_tiles;
     const uint64_t step = std::max<uint64_t>(ctx->n_bases / 10, 8ull << 20);
@@ -557,14 +644,14 @@ static std::vector<std::pair<uint32_t, cudaEvent_t>> extract_batches(kb_ctx* ctx
         if (f + 1 < nf && resident < next) continue;
         next = resident + step;
         uint32_t t1 = f + 1 < nf ? (uint32_t)std::min<uint64_t>(t_end, resident > KB_K1_PAD ? (resident - KB_K1_MAXHALO - 64) / KB_K1_TB : 0) : t_end;
-        if (f + 1 == nf) { batches.push_back({t_end, ctx->file_event[f]}); break; }
-        if (t1 > tile0 && (batches.empty() || t1 > batches.back().first)) batches.push_back({t1, ctx->file_event[f]});
+        if (f + 1 == nf) { batches.push_back({t_end, ctx->file_event[f], f}); break; }
+        if (t1 > tile0 && (batches.empty() || t1 > batches.back().first)) batches.push_back({t1, ctx->file_event[f], f});
     }
     if (batches.empty() || batches.back().first < t_end) {
         // device-resident sequences (or none pending): everything at once, after every pending copy
         cudaEvent_t last = nullptr;
         for (size_t f = 0; f < nf; f++) if (ctx->file_event[f]) last = ctx->file_event[f];
-        batches.push_back({t_end, last});
+        batches.push_back({t_end, last, nf ? nf - 1 : 0});
     }
     return batches;
 }
@@ -600,12 +687,13 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
     const bool wide_hist = hist && hist_bits > 9;            // 4-group CTAs with the packed shared-memory histogram (<= 16 bits)
     const size_t smem = wide_hist ? kb_extract_smem(lo.k, 4, (int)hist_bits) : kb_extract_smem(lo.k);
     prof_begin(ctx, "K1 extract");
-    std::vector<std::pair<uint32_t, cudaEvent_t>> batches = extract_batches(ctx, tile0, n_tiles);
+    std::vector<KBatch> batches = extract_batches(ctx, tile0, n_tiles);
     uint32_t t0 = tile0;
     const bool batched_l0 = bl && bl->enabled && wide_hist && batches.size() > 1 && batches.size() <= KB_MAX_BATCHES;
     if (batched_l0) CU(cudaFuncSetAttribute(kb_part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb_part_smem()));
     for (auto& bt : batches) {
         if (bt.second) CU(cudaStreamWaitEvent(ctx->stream, bt.second, 0));
+        TRY(deline_upto_file(ctx, bt.last_file));
         const uint32_t nt = bt.first > t0 ? bt.first - t0 : 0;
         if (!nt) continue;
         a.tile0 = t0; a.n_tiles = nt;
@@ -1459,7 +1547,7 @@ static bool slab_ok(const kb_ctx* ctx, const PartPlan& pl) {
 template <class F>
 static int run_extract_part(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles, uint64_t pos_lo, uint64_t pos_hi, uint32_t bits,
                             unsigned long long* cursor, const unsigned long long* limit, const unsigned long long* out_elems,
-                            const std::vector<std::pair<uint32_t, cudaEvent_t>>& batches, F after_batch, bool sym = false, uint64_t core_mask = 0) {
+                            const std::vector<KBatch>& batches, F after_batch, bool sym = false, uint64_t core_mask = 0) {
     const KbLayout& lo = ctx->lo;
     KbXPartArgs a{};
     a.bases = (const uint8_t*)ctx->bases.p; a.n_bases = ctx->n_bases;
@@ -1481,6 +1569,7 @@ static int run_extract_part(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles, uint6
     int bi = 0;
     for (auto& bt : batches) {
         if (bt.second) CU(cudaStreamWaitEvent(ctx->stream, bt.second, 0));
+        TRY(deline_upto_file(ctx, bt.last_file));
         const uint32_t nt = bt.first > t0 ? bt.first - t0 : 0;
         if (nt) {
             a.tile0 = t0; a.n_tiles = nt;
@@ -1804,6 +1893,7 @@ int kb_shard_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t total_bas
 int kb_sequence_buffer(kb_ctx* ctx, void** device_bytes, uint64_t* n_bytes) {
     if (!ctx || !device_bytes || !n_bytes) return KB_EINVAL;
     CU(cudaSetDevice(ctx->device));
+    TRY(deline_pending(ctx, ctx->pending_fasta.size()));
     CU(cudaStreamSynchronize(ctx->copy_stream));
     CU(cudaStreamSynchronize(ctx->stream));
     *device_bytes = ctx->bases.p;

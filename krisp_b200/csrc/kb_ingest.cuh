@@ -11,9 +11,12 @@
 // Anything the fast path does not reproduce exactly (other whitespace that str.strip() would remove, 'U'/'u' — RNA) only
 // raises a flag; the host layer then re-ingests that input with its line-by-line restatement.
 //
-// Tiles of 4096 bytes.  A byte is inside a header iff the line that contains it starts with '>': (1) last '\n' of every tile,
-// (2) exclusive prefix-max over tiles -> line start before each tile -> header state at the tile start, (3) per-tile kept
-// counts, (4) exclusive scan (kb_plan_* kernels), (5) compaction through shared memory, coalesced byte stores.
+// Tiles of 4096 bytes.  A byte is inside a header iff the line that contains it starts with '>'.  Three launches per file:
+// (1) kb_fa_count_kernel: last '\n' of every tile + its kept-byte count under BOTH hypotheses for the header state at the tile start;
+// (2) kb_fa_offsets_kernel (one CTA): exclusive prefix-max over tiles -> line start before each tile -> header state at the tile
+//     start -> the right count -> exclusive scan = output offset of every tile;
+// (3) kb_fa_pack_kernel<true>: compaction through shared memory, coalesced byte stores.
+// (kb_fa_lastnl_kernel / kb_fa_scan_kernel / kb_fa_pack_kernel<false> + the kb_plan_* scan are the same steps as seven launches.)
 #pragma once
 #include "kb_common.cuh"
 
@@ -123,6 +126,89 @@ __device__ __forceinline__ KbFaWalk kb_fa_walk(const KbFastaArgs& a, const uint8
     return w;
 }
 
+// (1') last newline of the tile AND its kept-byte counts for both header states flowing into it: counts[t] (not in a header),
+//      counts[n_tiles + t] (inside a header line)
+__global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_count_kernel(const KbFastaArgs a, uint32_t n_tiles) {
+    __shared__ unsigned long long ws[KB_FA_THREADS / 32];
+    __shared__ uint32_t wstate[KB_FA_THREADS / 32], wsum0[KB_FA_THREADS / 32], wsum1[KB_FA_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t tile_base = (uint64_t)blockIdx.x * KB_FA_TILE;
+    uint8_t b[KB_FA_PER]; uint32_t nv;
+    kb_fa_load(a, tile_base, tid, b, nv);
+    unsigned long long last = 0;                       // position + 1, 0 = none
+#pragma unroll
+    for (int i = 0; i < KB_FA_PER; i++) if (i < (int)nv && b[i] == '\n') last = tile_base + (uint64_t)tid * KB_FA_PER + i + 1;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, d));
+    if (lane == 0) ws[warp] = last;
+    const uint64_t p0 = tile_base + (uint64_t)tid * KB_FA_PER;
+    const uint8_t prev = (p0 == 0 || p0 > a.n) ? (uint8_t)'\n' : a.in[p0 - 1];
+    const uint8_t next = (p0 + nv < a.n) ? a.in[p0 + nv] : (uint8_t)'\n';
+    const KbFaWalk probe = kb_fa_walk(a, b, nv, prev, next, 0);
+    uint32_t x = probe.has_ls ? (2u | probe.end_state) : 0u;             // bit 1: defines the state, bit 0: the state
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (uint32_t)d && !(x & 2u)) x = o; }
+    if (lane == 31) wstate[warp] = x;
+    __syncthreads();
+    uint32_t in = 0;                                                     // bit 1 set: a line start earlier in this tile fixes the state
+    for (uint32_t w = 0; w < warp; w++) if (wstate[w] & 2u) in = wstate[w];
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+    if (lane > 0 && (up & 2u)) in = up;
+    uint32_t c0, c1;
+    if (in & 2u) { c0 = c1 = __popc(kb_fa_walk(a, b, nv, prev, next, in & 1u).keep); }
+    else { c0 = __popc(probe.keep); c1 = __popc(kb_fa_walk(a, b, nv, prev, next, 1u).keep); }
+    c0 = __reduce_add_sync(0xFFFFFFFFu, c0); c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
+    if (lane == 0) { wsum0[warp] = c0; wsum1[warp] = c1; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long m = 0; uint32_t t0 = 0, t1 = 0;
+        for (int w = 0; w < KB_FA_THREADS / 32; w++) { m = max(m, ws[w]); t0 += wsum0[w]; t1 += wsum1[w]; }
+        a.last_nl[blockIdx.x] = m;
+        a.counts[blockIdx.x] = t0;
+        a.counts[n_tiles + blockIdx.x] = t1;
+    }
+}
+
+// (2') ONE CTA: line start before every tile, header state at its start, the matching count, exclusive scan -> start[0 .. n_tiles]
+__global__ void __launch_bounds__(1024) kb_fa_offsets_kernel(const KbFastaArgs a, uint32_t n_tiles, unsigned long long* start) {
+    __shared__ unsigned long long ws[32], wc[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (n_tiles + 1023u) / 1024u;
+    const uint32_t c0 = min(n_tiles, tid * per), c1 = min(n_tiles, c0 + per);
+    unsigned long long m = 0;
+    for (uint32_t c = c0; c < c1; c++) m = max(m, a.last_nl[c]);
+    unsigned long long x = m;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (uint32_t)d) x = max(x, o); }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    unsigned long long before = 0;
+    for (uint32_t w = 0; w < warp; w++) before = max(before, ws[w]);
+    const unsigned long long ex = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+    if (lane > 0) before = max(before, ex);
+    unsigned long long run = before, sum = 0;          // line start before tile c0; kept bytes of this thread's tiles
+    for (uint32_t c = c0; c < c1; c++) {
+        const unsigned long long mine = a.last_nl[c];
+        const uint8_t h = (a.fasta && run < a.n && a.in[run] == '>') ? 1 : 0;
+        a.last_nl[c] = run;
+        a.hdr0[c] = h;
+        sum += a.counts[(h ? n_tiles : 0u) + c];
+        run = max(run, mine);
+    }
+    unsigned long long y = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, y, d); if (lane >= (uint32_t)d) y += o; }
+    if (lane == 31) wc[warp] = y;
+    __syncthreads();
+    unsigned long long off = y - sum;
+    for (uint32_t w = 0; w < warp; w++) off += wc[w];
+    for (uint32_t c = c0; c < c1; c++) {
+        start[c] = off;
+        off += a.counts[(a.hdr0[c] ? n_tiles : 0u) + c];
+    }
+    if (tid == 1023) start[n_tiles] = off;
+}
+
 // (3) kept bytes per tile / (5) compaction.  WRITE = false: counts only.
 template <bool WRITE>
 __global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_pack_kernel(const KbFastaArgs a) {
@@ -161,6 +247,7 @@ __global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_pack_kernel(const KbFasta
         if (w.flags) atomicOr(a.flags, w.flags);
         return;
     }
+    if (w.flags) atomicOr(a.flags, w.flags);
     uint32_t o = add + inc - cnt;
 #pragma unroll
     for (int i = 0; i < KB_FA_PER; i++) if ((w.keep >> i) & 1u) stage[o++] = ((w.sep >> i) & 1u) ? (uint8_t)'\n' : b[i];

@@ -241,10 +241,13 @@ class Searcher:
         self._check(self._L.kb_add_sequence(self._ctx, int(file_id), ctypes.c_void_p(arr.ctypes.data), int(arr.size), 0))
 
     def add_fasta(self, file_id, raw):
-        """`raw`: the decompressed file content (bytes): headers and line breaks are removed on the device (kb_add_fasta)."""
-        arr = np.frombuffer(raw, dtype=np.uint8)
+        """`raw`: the decompressed file content (bytes or a uint8 array, ideally pinned): headers and line breaks are removed on the
+        device (kb_add_fasta).  Asynchronous: the copy runs on the library's copy stream, the de-lining kernels are enqueued by the
+        search, per batch of arrived files, right before K1 needs them."""
+        arr = raw if isinstance(raw, np.ndarray) else np.frombuffer(raw, dtype=np.uint8)
         self.bases_added += int(arr.size)
         self.added_ids.append(int(file_id))
+        self._keep.append(arr)                       # the copy is asynchronous: the bytes must outlive it (pinned memory = no staging)
         self._check(self._L.kb_add_fasta(self._ctx, int(file_id), ctypes.c_void_p(arr.ctypes.data if arr.size else 0), int(arr.size)))
 
     def fasta_flags(self):
@@ -511,6 +514,9 @@ def search_files(ingroup_files, outgroup_files, L, D, R, omit_soft=False, want_r
         s.reserve(sum(len(r) + 1 for r in raws))
         for i, raw in enumerate(raws):
             s.add_fasta(i, raw)
+        res = s.search(have_outgroup=have_out)
+        # de-lining happened on the device, under the search; inputs it does not reproduce byte for byte (RNA, stray whitespace) have
+        # raised a flag by now and are re-ingested with the host restatement of the reference parser — rare, so checked afterwards
         if s.fasta_flags():
             s.clear_sequences()
             packed = []
@@ -523,8 +529,8 @@ def search_files(ingroup_files, outgroup_files, L, D, R, omit_soft=False, want_r
             s.reserve(sum(a.size + 1 for a in packed))
             for i, arr in enumerate(packed):
                 s.add_sequence(i, arr)
+            res = s.search(have_outgroup=have_out)
         del raws
-        res = s.search(have_outgroup=have_out)
         res.labels = labels
         res.is_ingroup = is_in
         return res

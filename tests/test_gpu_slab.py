@@ -162,3 +162,36 @@ def test_file_id_outside_the_configuration_is_an_error(searcher):
     with pytest.raises(KrispB200Error):
         searcher.search()
     searcher.clear_sequences()
+
+
+def test_raw_fasta_files_in_batches(searcher):
+    """kb_add_fasta is asynchronous: raw file bytes travel on the copy stream, the de-lining kernels and K1 + the partition levels run
+    per batch of arrived files.  Rows == oracle, twice in a row (buffers reused), flags clean."""
+    import torch
+    from krisp_b200.panel import make_panel
+    gs = make_panel(10, 10, 1_000_000)
+    want = _oracle_panel(gs, 25, 1, 2)
+    pinned = []
+    for g in gs:
+        raw = np.frombuffer(g.fasta_text(), dtype=np.uint8)
+        t = torch.empty(raw.size, dtype=torch.uint8, pin_memory=True)
+        t.numpy()[:] = raw
+        pinned.append(t)
+    try:
+        searcher.configure(25, 1, 2, [1 if g.is_ingroup else 0 for g in gs])
+        searcher.set_option("profile", 1)
+        for _ in range(2):
+            searcher.clear_sequences()
+            searcher.reserve(sum(t.numel() + 1 for t in pinned))
+            for i, t in enumerate(pinned):
+                searcher.add_fasta(i, t.numpy())
+            res = searcher.search(have_outgroup=True)
+            assert res.rows() == want
+            assert searcher.fasta_flags() == 0
+        # pageable bytes objects work too (the CLI path)
+        searcher.clear_sequences()
+        for i, g in enumerate(gs):
+            searcher.add_fasta(i, g.fasta_text())
+        assert searcher.search(have_outgroup=True).rows() == want
+    finally:
+        _reset(searcher)
