@@ -309,7 +309,8 @@ def run_ours(args):
                 out["launches"] += s.last_counters()["kernel_launches"]
                 for name, ms in res.profile:
                     out["prof"].setdefault(name, []).append(ms)
-                out["d2h"] = res.n_groups * (8 * res.flank_words.shape[1] + 2 * 4 * res.in_words.shape[1] + 4 + 16 + res.row_bytes) + 72
+                # one copy of the result image: flank words | ingroup sets | outgroup sets | rows text (+ 72 B of counters)
+                out["d2h"] = res.n_groups * (8 * res.flank_words.shape[1] + 2 * 4 * res.in_words.shape[1] + res.row_bytes) + 72
                 out["last"] = res
             e1.record(stream)
             barrier()
@@ -411,6 +412,38 @@ def run_ours(args):
                      "one read by the bucket hash = 1 + 4*8*(1 + P) B/bp with P = 1 standalone pass (SURVEY 8d); round 1 moved 97 B/bp (P = 2)",
              "frac_of_peak_at_round1_bytes": (w.h2d_bytes + 48.0 * n_rec) / (m["ms"] * 1e-3) / 1e9 / peak}
 
+    if args.diag and world > 1:
+        variants = [("default", {}, {}), ("groups=1", {"KRISP_SLAB_GROUPS": "1"}, {}), ("groups=2", {"KRISP_SLAB_GROUPS": "2"}, {}),
+                    ("groups=4", {"KRISP_SLAB_GROUPS": "4"}, {}), ("copy_streams=2", {"KRISP_COPY_STREAMS": "2"}, {}),
+                    ("copy_streams=4", {"KRISP_COPY_STREAMS": "4"}, {}), ("records (sym=0)", {}, {"sym": 0}),
+                    ("records, copy_streams=4", {"KRISP_COPY_STREAMS": "4"}, {"sym": 0}), ("a2a", {"KRISP_SLAB_EXCHANGE": "a2a"}, {})]
+        os.environ["KRISP_TIMELINE"] = "1"
+        for name, env, opts in variants:
+            for k, v in env.items():
+                os.environ[k] = v
+            for k, v in opts.items():
+                s.set_option(k, v)
+            s.__dict__.pop("_slab_plan", None)
+            try:
+                w.load_resident()
+                s.synchronize()
+                w.timed(None, 2, False)
+                dv = w.timed(None, 5, False)
+                ex = getattr(dv["last"], "exchange", None) or {}
+                rec = {"diag": name, "n_gpus": world, "ms": dv["ms"], "stage_ms": {k: round(v, 3) for k, v in fold_stages(dv["prof"]).items()},
+                       "exchange_ms": ex.get("exchange_ms"), "groups": ex.get("groups"), "window_items": ex.get("window_items"),
+                       "timeline": {k: ([round(x, 3) for x in v] if isinstance(v, list) else round(v, 3)) for k, v in (ex.get("timeline") or {}).items()}}
+            except Exception as exc:                                   # (a variant that does not apply must not end the run)
+                rec = {"diag": name, "error": repr(exc)}
+            if rank == 0:
+                print(json.dumps(rec), file=sys.stderr, flush=True)
+            for k in env:
+                os.environ.pop(k, None)
+            for k in opts:
+                s.set_option(k, -1 if k == "sym" else 0)
+            s.__dict__.pop("_slab_plan", None)
+        os.environ.pop("KRISP_TIMELINE", None)
+
     # ---- also: the other BASELINE configurations that fit one GPU (N = 1 only; short runs) ------------------------------------------
     also = []
     if world == 1 and not args.no_also and not args.ldr and not args.genomes:
@@ -487,6 +520,8 @@ def main():
                     "(default 25 1 2 = BASELINE config 2; 32 60 32 = config 3, primer mode)")
     ap.add_argument("--noise", type=float, help="private substitution rate per genome (default 1e-3); higher = more divergent genomes, "
                     "fewer shared k-mers (robustness probe, not the BASELINE workload)")
+    ap.add_argument("--diag", action="store_true", help="N > 1: after the headline measurement, time the resident search under exchange variants "
+                    "(digit groups, copy streams, records instead of window items, NCCL all-to-all) and print one JSON line each on stderr")
     ap.add_argument("--option", nargs=2, action="append", metavar=("NAME", "VALUE"), help="kb_set_option passthrough")
     args = ap.parse_args()
     global L_, D_, R_, N_IN, N_OUT

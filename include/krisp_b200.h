@@ -79,6 +79,9 @@ int kb_configure(kb_ctx* ctx, int L, int D, int R, int soft_mode, int n_files, c
  *   "sym"           1 = slab path with a strand-symmetric level 0 (0 = records; -1, the default = only on >= 4 GPUs, where it halves the exchange): both records of a window share the level-0 digit, so level 0
  *                   (and the multi-GPU exchange) moves one 8-byte window item per window; records are formed by level 1
  *                   (csrc/kb_extract_sym.cuh).  Needs >= 2 partition levels and a core of enough bases, else the record path is used
+ *   "group_sizes"   1 = fill kb_result_view.group_size (one more read of every survivor's bucket; implied by want_records).
+ *                   "rank_rows" 1 (default) = up to 8192 survivors are ordered by counting ranks (one launch) instead of the chunked radix sort.
+ *                   "hash_warps" 8 / 10 = warps per CTA of the shared-table bucket hash (0, the default: 8)
  *   "batch_level0"  1 (default) = with host buffers in flight K1 (+ partition levels 0 and 1) run per batch of arrived files
  *   "shard_bb_extra" bucket bits added to the sharded slab plan (kb_shard_slab_search status 1)
  */
@@ -241,7 +244,8 @@ typedef struct {
     const uint64_t* flank;      /* [n_groups][flank_words]                                        */
     const uint32_t* in_mask;    /* [n_groups][mask_words]  bit0 A, bit1 C, bit2 G, bit3 T         */
     const uint32_t* out_mask;   /* [n_groups][mask_words]                                         */
-    const uint32_t* group_size; /* [n_groups] records in the group                                */
+    const uint32_t* group_size; /* [n_groups] records in the group; NULL unless option "group_sizes"
+                                   or "want_records" is set (the rows do not need them)           */
     const uint64_t* run_offset; /* [n_groups + 1] range of the group's run in `records`           */
     const uint64_t* records;    /* [n_run_records][record_words]; a run may hold records of other
                                    flank keys too (prefix sort): filter by the flank bits          */

@@ -119,6 +119,9 @@ struct kb_ctx {
     long long opt_lazy_records = 1;      // multi-word records: 1 = filter by flank hash, build records only for what is left (kb_prefilter.cuh)
     long long opt_slab = 1;              // one-word records: 1 = K1 fused with partition level 0 into fixed-capacity slabs (kb_extract_part.cuh)
     long long opt_hash_warp = 1;         // 1 = bucket hash kernel with per-warp streaming (kb_hash_warp.cuh) instead of the CTA-wide stream kernel
+    long long opt_group_sizes = 0;       // survivors' group sizes on the bucket-hash path: 1 = always, 0 = only with want_records (the record gather needs them)
+    long long opt_rank_rows = 1;         // rows of <= KB_RANK_MAX survivors ordered by counting ranks (one launch) instead of the chunked LSD sort
+    long long opt_hash_warps = 0;        // kb_hash_warp.cuh, shared table: warps per CTA (8 or 10); 0 = 8
     long long opt_hash_shared = -1;      // kb_hash_warp.cuh: 1 = one table per CTA, 0 = one per warp, -1 = by table size (>= 1024 slots: per CTA)
     long long opt_slab_cap = 0;          // != 0: force the capacity of every slab (tests: overflow -> exact path)
     long long opt_sym = -1;              // slab path: 1 = strand-symmetric level 0 on window items where the layout allows it (kb_extract_sym.cuh),
@@ -327,6 +330,12 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "hash_warp") ctx->opt_hash_warp = value ? 1 : 0;
     else if (n == "sym") ctx->opt_sym = value < 0 ? -1 : (value ? 1 : 0);
     else if (n == "hash_shared") ctx->opt_hash_shared = value < 0 ? -1 : (value ? 1 : 0);
+    else if (n == "group_sizes") ctx->opt_group_sizes = value ? 1 : 0;
+    else if (n == "rank_rows") ctx->opt_rank_rows = value ? 1 : 0;
+    else if (n == "hash_warps") {
+        if (value != 0 && value != KB_HW_WARPS && value != KB_HW_WARPS_WIDE) return fail(ctx, KB_EINVAL, "hash_warps: 0 (automatic), 8 or 10");
+        ctx->opt_hash_warps = value;
+    }
     else if (n == "shard_bb_extra") { if (value < 0 || value > 12) return fail(ctx, KB_EINVAL, "shard_bb_extra must be in 0..12"); ctx->opt_shard_bb_extra = value; }
     else if (n == "slab_cap") { if (value < 0) return fail(ctx, KB_EINVAL, "slab_cap must be >= 0"); ctx->opt_slab_cap = value; ctx->slab_off = false; }
     else if (n == "render_rows") ctx->opt_render_rows = value ? 1 : 0;
@@ -1048,6 +1057,9 @@ struct HashStage {            // what run_group needs to run the bucket-hash ker
     uint32_t bucket0 = 0;                        // 2 = only what follows it (deferred buckets, group sizes) over all n_buckets
 };
 
+// group sizes of the survivors (kb_result_view.group_size): the rows do not need them, the alignment renderer does
+static bool group_sizes_on(const kb_ctx* ctx) { return ctx->opt_want_records != 0 || ctx->opt_group_sizes != 0; }
+
 static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
     const KbLayout& lo = g.lo;
     KbHashArgs x{};
@@ -1074,29 +1086,36 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
             const bool packed = lo.D == 1 && lo.FB <= 54;
             bool shared = ctx->opt_hash_shared < 0 ? xw.h.slots_log2 >= 10 : ctx->opt_hash_shared != 0;
             if (!shared && xw.h.slots_log2 > 10) shared = true;                  // (a warp scans at most 32 x 32 slots)
-            auto smem_of = [&](uint32_t l2) {
-                return (size_t)(shared ? kb_hash_cta_tbytes(l2, pwn, packed) : 0) + (size_t)KB_HW_WARPS * kb_hash_warp_wbytes(l2, pwn, packed, shared) + 16;
+            // warps per CTA: 8; the shared-table arrangement can run 10 (option hash_warps; 3 CTAs = 30 warps per SM)
+            auto smem_nw = [&](uint32_t l2, uint32_t nw) {
+                return (size_t)(shared ? kb_hash_cta_tbytes(l2, pwn, packed) : 0) + (size_t)nw * kb_hash_warp_wbytes(l2, pwn, packed, shared) + 16;
             };
-            while (xw.h.slots_log2 > 4 && (smem_of(xw.h.slots_log2) > 224 * 1024 || xw.h.slots_log2 > 13)) xw.h.slots_log2--;
+            auto fit_per_sm = [&](size_t smem) { return (size_t)(228 * 1024) / (smem + 1024); };
+            while (xw.h.slots_log2 > 4 && (smem_nw(xw.h.slots_log2, KB_HW_WARPS) > 224 * 1024 || xw.h.slots_log2 > 13)) xw.h.slots_log2--;
+            uint32_t nw = KB_HW_WARPS;
+            if (shared && ctx->opt_hash_warps == KB_HW_WARPS_WIDE) nw = KB_HW_WARPS_WIDE;   // measured on C2: 30 warps per SM 2.23 ms, 24 warps 2.11 ms
+                                                                                             // (the kernel is bound by the shared-memory pipe, not by latency)
             xw.wbytes = kb_hash_warp_wbytes(xw.h.slots_log2, pwn, packed, shared);
             xw.tbytes = shared ? kb_hash_cta_tbytes(xw.h.slots_log2, pwn, packed) : 0;
-            const size_t smem = smem_of(xw.h.slots_log2);
-            const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(shared ? 4 : 3, (224 * 1024) / (smem + 1024)));
+            const size_t smem = smem_nw(xw.h.slots_log2, nw);
+            const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(shared ? 4 : 3, fit_per_sm(smem)));
             const uint32_t units = shared ? hs.n_buckets : (hs.n_buckets + KB_HW_WARPS - 1) / KB_HW_WARPS;
             const unsigned wgrid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->n_sm * per_sm, units));
+#define KB_LAUNCH_WARP_(D1_, SP_, PW_, SH_, NW_)                                                                               \
+            do {                                                                                                               \
+                CU(cudaFuncSetAttribute(kb_hash_warp_kernel<D1_, SP_, PW_, SH_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                kb_hash_warp_kernel<D1_, SP_, PW_, SH_, NW_><<<wgrid, 32 * NW_, smem, ctx->stream>>>(xw);                        \
+            } while (0)
 #define KB_LAUNCH_WARP(D1_, SP_, PW_)                                                                                          \
             do {                                                                                                               \
-                if (shared) {                                                                                                  \
-                    CU(cudaFuncSetAttribute(kb_hash_warp_kernel<D1_, SP_, PW_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                    kb_hash_warp_kernel<D1_, SP_, PW_, true><<<wgrid, KB_HW_THREADS, smem, ctx->stream>>>(xw);                   \
-                } else {                                                                                                       \
-                    CU(cudaFuncSetAttribute(kb_hash_warp_kernel<D1_, SP_, PW_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                    kb_hash_warp_kernel<D1_, SP_, PW_, false><<<wgrid, KB_HW_THREADS, smem, ctx->stream>>>(xw);                  \
-                }                                                                                                              \
+                if (shared && nw == KB_HW_WARPS_WIDE) KB_LAUNCH_WARP_(D1_, SP_, PW_, true, KB_HW_WARPS_WIDE);                  \
+                else if (shared) KB_LAUNCH_WARP_(D1_, SP_, PW_, true, KB_HW_WARPS);                                            \
+                else KB_LAUNCH_WARP_(D1_, SP_, PW_, false, KB_HW_WARPS);                                                       \
             } while (0)
             if (pwn == 2) { if (spacer) KB_LAUNCH_WARP(true, true, 2); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 2); else KB_LAUNCH_WARP(false, false, 2); }
             else if (pwn == 4) { if (spacer) KB_LAUNCH_WARP(true, true, 4); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 4); else KB_LAUNCH_WARP(false, false, 4); }
             else { if (spacer) KB_LAUNCH_WARP(true, true, 8); else if (lo.D == 1) KB_LAUNCH_WARP(true, false, 8); else KB_LAUNCH_WARP(false, false, 8); }
+#undef KB_LAUNCH_WARP_
 #undef KB_LAUNCH_WARP
             CU(cudaGetLastError());
             if (hs.phase == 1) { ctx->launches++; return KB_OK; }
@@ -1144,11 +1163,14 @@ static int launch_hash(kb_ctx* ctx, const KbGroupArgs& g, const HashStage& hs) {
             kb_hash_kernel<1><<<(unsigned)ctx->n_sm * 2, KB_KH_THREADS, fsmem, ctx->stream>>>(fb);
         }
         CU(cudaGetLastError());
-        KbHSizeArgs sz{};
-        sz.ent = g.ent; sz.n_res = g.n_res; sz.cap = g.cap; sz.res_flank = g.res_flank; sz.res_run = g.res_run; sz.res_size = g.res_size; sz.lo = lo;
-        kb_hsize_kernel<<<(unsigned)ctx->n_sm * 4, 256, 0, ctx->stream>>>(sz);
-        CU(cudaGetLastError());
-        ctx->launches += 3;
+        ctx->launches += 2;
+        if (group_sizes_on(ctx)) {                            // one more read of every survivor's bucket: only where the sizes are used
+            KbHSizeArgs sz{};
+            sz.ent = g.ent; sz.n_res = g.n_res; sz.cap = g.cap; sz.res_flank = g.res_flank; sz.res_run = g.res_run; sz.res_size = g.res_size; sz.lo = lo;
+            kb_hsize_kernel<<<(unsigned)ctx->n_sm * 4, 256, 0, ctx->stream>>>(sz);
+            CU(cudaGetLastError());
+            ctx->launches++;
+        }
         return KB_OK;
     }
     if (hs.pl->fast) {
@@ -1229,49 +1251,68 @@ static int launch_group(kb_ctx* ctx, const KbGroupArgs& a, bool allow_fast) {
     return KB_OK;
 }
 
-// CSV rows of the n_res survivors in the result table: order by flank words (chunked LSD sort of the indices), render, download
-static int render_rows(kb_ctx* ctx, kb_result* res, uint64_t n_res, char* host_dst) {
+// CSV rows of the n_res survivors in the result table: order by flank words (few survivors: ranks by counting, one launch; else the
+// chunked LSD sort of the indices), rendered into dev_dst (the rows section of the staging image that run_group downloads)
+static int render_rows(kb_ctx* ctx, kb_result* res, uint64_t n_res, char* dev_dst, char* host_dst) {
     const KbLayout& lo = ctx->lo;
     if (!n_res || (lo.R == 0 && lo.D > 0)) return KB_OK;
     if (n_res >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 survivors");
-    const long long prof = ctx->opt_profile;
-    const int passes = ctx->passes;
-    const uint64_t alg = ctx->alg_bytes;
-    ctx->opt_profile = 0;                                    // (the sort below is bookkeeping on kilobytes, not a stage of the search)
     TRY(ensure(ctx, ctx->rowkeyA, (size_t)(n_res + 2048) * 8));
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_res + 255) / 256, (uint64_t)ctx->n_sm * 8));
-    kb_iota_kernel<<<grid, 256, 0, ctx->stream>>>((uint64_t*)ctx->rowkeyA.p, n_res);
-    CU(cudaGetLastError());
-    DevBuf* in = &ctx->rowkeyA; DevBuf* other = &ctx->rowkeyB;
-    uint64_t* sorted = (uint64_t*)in->p;
-    const uint32_t chunks = ((uint32_t)lo.FB + 31) / 32;
-    for (int c = (int)chunks - 1; c >= 0; c--) {
-        KbChunkKeyArgs ck{};
-        ck.ent = (uint64_t*)in->p; ck.n = n_res; ck.recs = (const uint64_t*)ctx->res_flank.p; ck.W = (uint32_t)lo.FW;
-        ck.bit_pos = 32u * (uint32_t)c; ck.nbits = std::min<uint32_t>(32, (uint32_t)lo.FB - ck.bit_pos);
-        kb_chunk_key_kernel<<<grid, 256, 0, ctx->stream>>>(ck);
+    uint64_t* sorted = (uint64_t*)ctx->rowkeyA.p;
+    if (n_res <= KB_RANK_MAX && ctx->opt_rank_rows) {
+        KbRankArgs rk{};
+        rk.flank = (const uint64_t*)ctx->res_flank.p; rk.n = (uint32_t)n_res; rk.order = sorted;
+        const unsigned rgrid = (unsigned)((n_res + KB_RANK_THREADS - 1) / KB_RANK_THREADS);
+        switch (lo.FW) {
+            case 1: kb_rank_kernel<1><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 2: kb_rank_kernel<2><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 3: kb_rank_kernel<3><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 4: kb_rank_kernel<4><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 5: kb_rank_kernel<5><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 6: kb_rank_kernel<6><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 7: kb_rank_kernel<7><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 8: kb_rank_kernel<8><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            default: return fail(ctx, KB_EINTERNAL, "flank wider than 8 words");
+        }
         CU(cudaGetLastError());
-        CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_HIST, 0, 9 * 256 * 8, ctx->stream));
-        CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_TICKET, 0, 8 * 8, ctx->stream));
-        TRY(run_sort(ctx, *in, *other, n_res, 4, &sorted));
-        if (sorted != (uint64_t*)in->p) std::swap(in, other);
+        ctx->launches++;
+    } else {
+        const long long prof = ctx->opt_profile;
+        const int passes = ctx->passes;
+        const uint64_t alg = ctx->alg_bytes;
+        ctx->opt_profile = 0;                                    // (the sort below is bookkeeping on kilobytes, not a stage of the search)
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_res + 255) / 256, (uint64_t)ctx->n_sm * 8));
+        kb_iota_kernel<<<grid, 256, 0, ctx->stream>>>((uint64_t*)ctx->rowkeyA.p, n_res);
+        CU(cudaGetLastError());
+        DevBuf* in = &ctx->rowkeyA; DevBuf* other = &ctx->rowkeyB;
+        const uint32_t chunks = ((uint32_t)lo.FB + 31) / 32;
+        for (int c = (int)chunks - 1; c >= 0; c--) {
+            KbChunkKeyArgs ck{};
+            ck.ent = (uint64_t*)in->p; ck.n = n_res; ck.recs = (const uint64_t*)ctx->res_flank.p; ck.W = (uint32_t)lo.FW;
+            ck.bit_pos = 32u * (uint32_t)c; ck.nbits = std::min<uint32_t>(32, (uint32_t)lo.FB - ck.bit_pos);
+            kb_chunk_key_kernel<<<grid, 256, 0, ctx->stream>>>(ck);
+            CU(cudaGetLastError());
+            CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_HIST, 0, 9 * 256 * 8, ctx->stream));
+            CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_TICKET, 0, 8 * 8, ctx->stream));
+            TRY(run_sort(ctx, *in, *other, n_res, 4, &sorted));
+            if (sorted != (uint64_t*)in->p) std::swap(in, other);
+            ctx->launches++;
+        }
+        ctx->opt_profile = prof; ctx->passes = passes; ctx->alg_bytes = alg;
         ctx->launches++;
     }
-    ctx->opt_profile = prof; ctx->passes = passes; ctx->alg_bytes = alg;
     const size_t bytes = (size_t)n_res * (size_t)res->row_bytes;
-    TRY(ensure(ctx, ctx->rowtext, bytes));
     KbRowsArgs ra{};
     ra.order = sorted; ra.n = n_res; ra.flank = (const uint64_t*)ctx->res_flank.p;
     ra.in_mask = (const uint32_t*)ctx->res_in.p; ra.out_mask = (const uint32_t*)ctx->res_out.p;
     ra.L = lo.L; ra.D = lo.D; ra.R = lo.R; ra.FW = lo.FW; ra.MW = std::max(lo.MW, 1);
     ra.all_occurrences = ctx->opt_have_outgroup ? 0 : 1;
-    ra.out = (char*)ctx->rowtext.p;
+    ra.out = dev_dst;
     kb_rows_kernel<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((bytes + 255) / 256, (uint64_t)ctx->n_sm * 16)), 256, 0, ctx->stream>>>(ra);
     CU(cudaGetLastError());
-    ctx->launches += 2;
-    CU(cudaMemcpyAsync(host_dst, ctx->rowtext.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->launches++;
     res->rows = host_dst; res->rows_len = bytes;
-    return KB_OK;                                            // (the caller synchronises with the other result copies)
+    return KB_OK;                                            // (the caller downloads the image)
 }
 
 // K3 over sorted[0..n) + result download
@@ -1346,6 +1387,7 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
     const size_t mw = (size_t)std::max(lo.MW, 1);
     const bool rows_on = ctx->opt_render_rows && !(lo.R == 0 && lo.D > 0);
     const bool need_runs = ctx->opt_want_records && !hs;
+    const bool sizes_on = !hs || !hs->pl->stream || group_sizes_on(ctx);   // (only the streaming bucket hash needs an extra pass, kb_hsize_kernel, for them)
     auto up = [](size_t x) { return (x + 63) & ~(size_t)63; };
     const size_t o_flank = 0, o_in = o_flank + up(n_res * lo.FW * 8), o_out = o_in + up(n_res * mw * 4), o_size = o_out + up(n_res * mw * 4),
                  o_runs = o_size + up(n_res * 4), o_rows = o_runs + up(need_runs ? n_res * 16 : 0),
@@ -1358,16 +1400,31 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
         ctx->h_arena_cap = want;
     }
     uint8_t* A = ctx->h_arena;
-    if (lo.MW == 0) memset(A + o_in, 0, (o_size - o_in));
     const uint32_t* h_size = (const uint32_t*)(A + o_size);
     const uint64_t* runs = (const uint64_t*)(A + o_runs);
-    if (rows_on) { int rc = render_rows(ctx, res, n_res, (char*)(A + o_rows)); if (rc) { delete res; return rc; } }
     if (n_res) {
-        cudaError_t e = cudaMemcpyAsync(A + o_flank, ctx->res_flank.p, n_res * lo.FW * 8, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess && lo.MW) e = cudaMemcpyAsync(A + o_in, ctx->res_in.p, n_res * lo.MW * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess && lo.MW) e = cudaMemcpyAsync(A + o_out, ctx->res_out.p, n_res * lo.MW * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(A + o_size, ctx->res_size.p, n_res * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess && need_runs) e = cudaMemcpyAsync(A + o_runs, ctx->res_run.p, n_res * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        // the device builds an image of the arena (table columns + rows text), which then travels as ONE copy
+        int rc = ensure(ctx, ctx->rowtext, total_bytes);
+        uint8_t* img = (uint8_t*)ctx->rowtext.p;
+        if (!rc && rows_on) rc = render_rows(ctx, res, n_res, (char*)(img + o_rows), (char*)(A + o_rows));
+        if (rc) { delete res; return rc; }
+        KbPackArgs pk{};
+        pk.image = img;
+        int ns = 0;
+        auto seg = [&](const void* src, size_t off, size_t bytes) { if (bytes) { pk.src[ns] = (const uint32_t*)src; pk.dst_off[ns] = off; pk.words[ns] = bytes / 4; ns++; } };
+        seg(ctx->res_flank.p, o_flank, n_res * lo.FW * 8);
+        if (lo.MW) { seg(ctx->res_in.p, o_in, n_res * lo.MW * 4); seg(ctx->res_out.p, o_out, n_res * lo.MW * 4); }
+        if (sizes_on) seg(ctx->res_size.p, o_size, n_res * 4);
+        if (need_runs) seg(ctx->res_run.p, o_runs, n_res * 16);
+        cudaError_t e = cudaSuccess;
+        if (!lo.MW) e = cudaMemsetAsync(img + o_in, 0, o_size - o_in, ctx->stream);
+        if (e == cudaSuccess) {
+            const uint64_t most = n_res * std::max<uint64_t>(2 * (uint64_t)lo.FW, 4);
+            kb_pack_kernel<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((most + 255) / 256, (uint64_t)ctx->n_sm * 4)), 256, 0, ctx->stream>>>(pk);
+            e = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(A, img, total_bytes - 64, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { delete res; return fail(ctx, KB_ECUDA, std::string("result download: ") + cudaGetErrorString(e)); }
     }
@@ -1414,7 +1471,7 @@ static int run_group(kb_ctx* ctx, const uint64_t* sorted, uint64_t n, kb_result*
     res->v.flank = (const uint64_t*)(A + o_flank);
     res->v.in_mask = (const uint32_t*)(A + o_in);
     res->v.out_mask = (const uint32_t*)(A + o_out);
-    res->v.group_size = h_size;
+    res->v.group_size = sizes_on ? h_size : nullptr;
     res->v.run_offset = res->run_offset.data();
     res->v.records = res->records.data();
     *out = res;

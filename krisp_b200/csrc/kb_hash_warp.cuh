@@ -20,6 +20,7 @@
 // Buckets whose distinct keys overflow the table or that hold more than KB_HW_MAX_INLINE survivors are deferred to
 // kb_hash_fast_kernel / kb_hash_kernel exactly like in the stream kernel; group sizes come from kb_hsize_kernel.
 #pragma once
+#include <type_traits>
 #include "kb_hash_stream.cuh"
 
 #define KB_HW_PER 4                           // records per lane and chunk
@@ -27,7 +28,8 @@
 #define KB_HW_STAGES 3
 #define KB_HW_QCAP (32 + KB_HW_CH)            // the queue is drained to < 32 entries after every chunk
 #define KB_HW_MAX_INLINE 8
-#define KB_HW_WARPS 8                         // warps per CTA
+#define KB_HW_WARPS 8                         // warps per CTA (per-warp tables; the shared-table arrangement also runs with KB_HW_WARPS_WIDE)
+#define KB_HW_WARPS_WIDE 10                   // shared table: 10 warps x 3 CTAs = 30 warps per SM still fit the shared memory (2048-slot table)
 #define KB_HW_THREADS (32 * KB_HW_WARPS)
 
 struct KbHWarpArgs {
@@ -49,10 +51,12 @@ static inline uint32_t kb_hash_warp_wbytes(uint32_t slots_log2, int pwn, bool pa
 }
 static inline uint32_t kb_hash_cta_tbytes(uint32_t slots_log2, int pwn, bool packed) { return kb_hash_table_bytes(slots_log2, pwn, packed) + 64u; }
 
-__device__ __forceinline__ void kb_hw_bar() { asm volatile("bar.sync 1, %0;" :: "n"(KB_HW_THREADS) : "memory"); }
+template <int NT>
+__device__ __forceinline__ void kb_hw_bar() { asm volatile("bar.sync 1, %0;" :: "n"(NT) : "memory"); }
 
-template <bool D1, bool SPACER, int PWN, bool SHARED>
-__global__ void __launch_bounds__(KB_HW_THREADS, 3) kb_hash_warp_kernel(const KbHWarpArgs xs) {
+template <bool D1, bool SPACER, int PWN, bool SHARED, int NW = KB_HW_WARPS>
+__global__ void __launch_bounds__(32 * NW, 3) kb_hash_warp_kernel(const KbHWarpArgs xs) {
+    constexpr uint32_t NTHREADS = 32u * NW;
     extern __shared__ __align__(16) unsigned char kb_smem_raw[];
     const KbHashArgs& x = xs.h;
     const KbGroupArgs& a = x.g;
@@ -60,10 +64,10 @@ __global__ void __launch_bounds__(KB_HW_THREADS, 3) kb_hash_warp_kernel(const Kb
     const uint32_t S = 1u << x.slots_log2, smask = S - 1u;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // bucket / chunk ownership
-    const uint32_t b_first = SHARED ? blockIdx.x : blockIdx.x * KB_HW_WARPS + warp;
-    const uint32_t b_step = SHARED ? gridDim.x : gridDim.x * KB_HW_WARPS;
+    const uint32_t b_first = SHARED ? blockIdx.x : blockIdx.x * NW + warp;
+    const uint32_t b_step = SHARED ? gridDim.x : gridDim.x * NW;
     const uint32_t c_first = SHARED ? warp : 0u;
-    constexpr uint32_t c_step = SHARED ? KB_HW_WARPS : 1u;
+    constexpr uint32_t c_step = SHARED ? (uint32_t)NW : 1u;
     const bool packed = SPACER || (D1 && lo.FB <= 54);       // both 4-bit base sets inside the key word (bits 56-63)
 
     uint32_t smem_a = kb_smem_u32(kb_smem_raw);
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(KB_HW_THREADS, 3) kb_hash_warp_kernel(const Kb
 
     // table slots this thread scans / clears
     const uint32_t t_first = SHARED ? tid : lane;
-    constexpr uint32_t t_step = SHARED ? KB_HW_THREADS : 32u;
+    constexpr uint32_t t_step = SHARED ? NTHREADS : 32u;
     for (uint32_t i = t_first; i < S; i += t_step) {
         kb_sts64(keys_a + i * 8, KB_KH_EMPTY);
 #pragma unroll
@@ -232,28 +236,33 @@ __global__ void __launch_bounds__(KB_HW_THREADS, 3) kb_hash_warp_kernel(const Kb
             const uint32_t cnt = (uint32_t)min((uint64_t)KB_HW_CH, n_al - (uint64_t)ck * KB_HW_CH);
             const uint32_t first = ck == 0 ? skip : 0u;
             if (!over) {
-                uint64_t e[KB_HW_PER], k[KB_HW_PER];
-                uint32_t sl[KB_HW_PER], m[KB_HW_PER];
-                bool hit[KB_HW_PER];
+                // FULL: a whole chunk of 128 records (all but the first / last chunk of a bucket) — no per-record bounds tests
+                auto chunk = [&](auto full_c) {
+                    constexpr bool FULL = decltype(full_c)::value;
+                    uint64_t e[KB_HW_PER], k[KB_HW_PER];
+                    uint32_t sl[KB_HW_PER], m[KB_HW_PER];
+                    bool hit[KB_HW_PER], miss[KB_HW_PER];
 #pragma unroll
-                for (int j = 0; j < KB_HW_PER; j++) e[j] = kb_lds64(stage_a + (j * 32 + lane) * 8);
+                    for (int j = 0; j < KB_HW_PER; j++) e[j] = kb_lds64(stage_a + (j * 32 + lane) * 8);
 #pragma unroll
-                for (int j = 0; j < KB_HW_PER; j++) { sl[j] = slot_of(e[j]); k[j] = kb_lds64(keys_a + sl[j] * 8); }
+                    for (int j = 0; j < KB_HW_PER; j++) { sl[j] = slot_of(e[j]); k[j] = kb_lds64(keys_a + sl[j] * 8); }
 #pragma unroll
-                for (int j = 0; j < KB_HW_PER; j++) {
-                    const uint32_t idx = (uint32_t)(j * 32) + lane;
-                    const bool act = idx >= first && idx < cnt;
-                    hit[j] = act && (packed ? (k[j] & KB_HS_KEYMASK) : k[j]) == (e[j] >> kshift);
-                    m[j] = __ballot_sync(0xFFFFFFFFu, act && !hit[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < KB_HW_PER; j++) {
-                    if (m[j]) {
-                        if ((m[j] >> lane) & 1u) kb_sts64(q_a + (qn + __popc(m[j] & lt_mask)) * 8, e[j]);
-                        qn += __popc(m[j]);
+                    for (int j = 0; j < KB_HW_PER; j++) {
+                        const uint32_t idx = (uint32_t)(j * 32) + lane;
+                        const bool act = FULL || (idx >= first && idx < cnt);
+                        hit[j] = act && (packed ? (k[j] & KB_HS_KEYMASK) : k[j]) == (e[j] >> kshift);
+                        miss[j] = act && !hit[j];
+                        m[j] = __ballot_sync(0xFFFFFFFFu, miss[j]);
                     }
-                    if (hit[j]) accumulate(sl[j], e[j], (uint32_t)(k[j] >> 32));
-                }
+#pragma unroll
+                    for (int j = 0; j < KB_HW_PER; j++) {
+                        if (miss[j]) kb_sts64(q_a + (qn + __popc(m[j] & lt_mask)) * 8, e[j]);      // (no branch around the whole step: most chunks have a miss in every row)
+                        qn += __popc(m[j]);
+                        if (hit[j]) accumulate(sl[j], e[j], (uint32_t)(k[j] >> 32));
+                    }
+                };
+                if (first == 0u && cnt == (uint32_t)KB_HW_CH) chunk(std::true_type{});
+                else chunk(std::false_type{});
                 __syncwarp();
                 while (qn >= 32 && !over) drain();
             }
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(KB_HW_THREADS, 3) kb_hash_warp_kernel(const Kb
         __syncwarp();
         while (qn && !over) drain();
         __syncwarp();
-        if (SHARED) { kb_hw_bar(); over = kb_lds32(ctl_a + 4 * par) != 0; }      // (uniform over the CTA from here on)
+        if (SHARED) { kb_hw_bar<NTHREADS>(); over = kb_lds32(ctl_a + 4 * par) != 0; }      // (uniform over the CTA from here on)
         n_rounds++;
         uint32_t flags = 0, n_surv = 0, n_closed = 0, n_present = 0;
         if (!over) {
@@ -290,10 +299,10 @@ __global__ void __launch_bounds__(KB_HW_THREADS, 3) kb_hash_warp_kernel(const Kb
             n_surv = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(flags));
             if (SHARED) {
                 if (lane == 0 && n_surv) kb_atoms_add(ctl_a + 4 * (4 + par), n_surv);
-                kb_hw_bar();
+                kb_hw_bar<NTHREADS>();
                 n_surv = kb_lds32(ctl_a + 4 * (4 + par));
             }
-        } else if (SHARED) kb_hw_bar();
+        } else if (SHARED) kb_hw_bar<NTHREADS>();
         const bool defer = over || n_surv > KB_HW_MAX_INLINE;
         if (!defer) { n_closed_t += n_closed; n_present_t += n_present; }
         for (uint32_t q = 0, slot = t_first; slot < S; q++, slot += t_step) {
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(KB_HW_THREADS, 3) kb_hash_warp_kernel(const Kb
         if (defer && (SHARED ? warp == 0 : true)) n_defer++;
         if (SHARED) {
             if (tid == 0) { kb_sts32(ctl_a + 4 * (par ^ 1u), 0u); kb_sts32(ctl_a + 4 * (2 + (par ^ 1u)), 0u); kb_sts32(ctl_a + 4 * (4 + (par ^ 1u)), 0u); }
-            kb_hw_bar();                                                         // table and the next bucket's control words are clean
+            kb_hw_bar<NTHREADS>();                                                         // table and the next bucket's control words are clean
             par ^= 1u;
             if (warp != 0) n_rounds--;                                           // (one count per CTA)
         } else __syncwarp();

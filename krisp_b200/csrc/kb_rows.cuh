@@ -48,3 +48,63 @@ __global__ void __launch_bounds__(256) kb_rows_kernel(const KbRowsArgs a) {
 __global__ void __launch_bounds__(256) kb_iota_kernel(uint64_t* ent, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) ent[i] = i;
 }
+
+// Few survivors (the usual case: thousands of rows out of 1e8 records): their order by flank words comes from counting, one launch
+// instead of the chunked LSD sort's twenty — rank(i) = #{j : flank[j] < flank[i]} (+ ties by index; flank keys of one search are
+// distinct anyway).  Every thread owns one survivor and walks all of them through shared memory (all lanes read the same element:
+// broadcast).  n <= KB_RANK_MAX keeps the n^2 walk in the microseconds.
+#define KB_RANK_MAX 8192
+#define KB_RANK_THREADS 128
+
+struct KbRankArgs {
+    const uint64_t* flank;       // [n][FW]
+    uint32_t n;
+    uint64_t* order;             // [n] order[rank] = survivor index
+};
+
+template <int FW>
+__global__ void __launch_bounds__(KB_RANK_THREADS) kb_rank_kernel(const KbRankArgs a) {
+    __shared__ uint64_t tile[FW][KB_RANK_THREADS];
+    const uint32_t tid = threadIdx.x, i = blockIdx.x * KB_RANK_THREADS + tid;
+    uint64_t mine[FW];
+#pragma unroll
+    for (int w = 0; w < FW; w++) mine[w] = i < a.n ? a.flank[(uint64_t)i * FW + w] : 0ULL;
+    uint32_t rank = 0;
+    for (uint32_t base = 0; base < a.n; base += KB_RANK_THREADS) {
+        __syncthreads();
+        const uint32_t j = base + tid;
+#pragma unroll
+        for (int w = 0; w < FW; w++) tile[w][tid] = j < a.n ? a.flank[(uint64_t)j * FW + w] : 0ULL;
+        __syncthreads();
+        const uint32_t cnt = min((uint32_t)KB_RANK_THREADS, a.n - base);
+#pragma unroll 4
+        for (uint32_t jj = 0; jj < cnt; jj++) {
+            bool less = false, eq = true;
+#pragma unroll
+            for (int w = 0; w < FW; w++) {
+                const uint64_t t = tile[w][jj];
+                if (eq && t != mine[w]) { less = t < mine[w]; eq = false; }
+            }
+            rank += (less || (eq && base + jj < i)) ? 1u : 0u;
+        }
+    }
+    if (i < a.n) a.order[rank] = i;
+}
+
+// The survivor table's columns (flank words, base sets, sizes, runs) copied into ONE staging image laid out like the host's result
+// arena, next to the rows text: the whole result then leaves the device as a single copy.
+#define KB_PACK_SEGS 5
+struct KbPackArgs {
+    const uint32_t* src[KB_PACK_SEGS];
+    uint64_t dst_off[KB_PACK_SEGS];      // byte offset in the image (multiple of 4)
+    uint64_t words[KB_PACK_SEGS];        // 32-bit words to copy (0: segment unused)
+    uint8_t* image;
+};
+
+__global__ void __launch_bounds__(256) kb_pack_kernel(const KbPackArgs a) {
+#pragma unroll
+    for (int s = 0; s < KB_PACK_SEGS; s++) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(a.image + a.dst_off[s]);
+        for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < a.words[s]; t += (uint64_t)gridDim.x * 256) dst[t] = a.src[s][t];
+    }
+}

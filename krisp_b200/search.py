@@ -305,7 +305,7 @@ class Searcher:
             out.flank_words = flank
             out.in_words = arr(view.in_mask, n * MW, np.uint32).reshape(n, MW)
             out.out_words = arr(view.out_mask, n * MW, np.uint32).reshape(n, MW)
-            out.group_size = arr(view.group_size, n, np.uint32)
+            out.group_size = arr(view.group_size, n, np.uint32) if view.group_size else None   # (option group_sizes / want_records)
             out.run_offset = arr(view.run_offset, n + 1, np.uint64)
             nrr = int(view.n_run_records)
             out.records = arr(view.records, nrr * W, np.uint64).reshape(nrr, W)

@@ -300,9 +300,18 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
                     e = torch.cuda.Event(enable_timing=True)
                     e.record(vote)
                     landed.append(e)
+        timeline = os.environ.get("KRISP_TIMELINE") == "1"
+        marks = []
         for g in range(n_groups):
             main.wait_event(landed[g])
+            if timeline:
+                a = torch.cuda.Event(enable_timing=True)
+                a.record(main)
             searcher.shard_slab_level(gathered.data_ptr(), g, n_groups)
+            if timeline:
+                b = torch.cuda.Event(enable_timing=True)
+                b.record(main)
+                marks.append((a, b))
         ev[2].record(main)
         res, status = searcher.shard_slab_finish(have_outgroup=have_outgroup)
         st = torch.tensor([status], dtype=torch.int64, device=device)
@@ -318,6 +327,10 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
             res.exchange = {"slab": True, "digits": nd, "groups": n_groups, "records_extracted": int(res.n_records), "own_digits": [lo_d, hi_d],
                             "sent": sent, "sent_bytes": 8 * sent, "copied_bytes": 8 * (cap - 4096) * (world - 1) // max(world, 1),
                             "exchange_ms": t_x, "mode": mode, "window_items": items}
+            if timeline:                                              # ms since the search began (this rank's clock)
+                res.exchange["timeline"] = {"k1_end": ev[0].elapsed_time(ev[1]), "landed": [ev[0].elapsed_time(e) for e in landed],
+                                            "level_begin": [ev[0].elapsed_time(a) for a, _ in marks],
+                                            "level_end": [ev[0].elapsed_time(b) for _, b in marks], "levels_done": ev[0].elapsed_time(ev[2])}
             return res
         if status == 2:
             return None                                               # a slab overflowed somewhere: exact exchange for everybody

@@ -371,7 +371,10 @@ def test_full_size_panel_properties(searcher):
     radix sort + segmented pass) return the same rows; every row is a planted group SNP whose column separates the groups."""
     from krisp_b200.panel import make_panel
     gs = make_panel(20, 20, 5_000_000)
-    res = _search_panel(searcher, gs, 25, 1, 2)
+    try:
+        res = _search_panel(searcher, gs, 25, 1, 2, options={"group_sizes": 1})
+    finally:
+        searcher.set_option("group_sizes", 0)
     assert res.n_records == _valid_windows(gs, 28)
     rows = res.rows()
     try:

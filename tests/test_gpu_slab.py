@@ -11,7 +11,8 @@ from tests.test_gpu_parity import _oracle_panel, _search_panel
 pytestmark = pytest.mark.gpu
 _G = load_golden()
 
-_RESET = {"slab": 1, "sym": -1, "hash_warp": 1, "hash_shared": -1, "bucket_bits": -1, "hash_slots_log2": 0, "slab_cap": 0, "want_records": 0, "profile": 0}
+_RESET = {"slab": 1, "sym": -1, "hash_warp": 1, "hash_shared": -1, "bucket_bits": -1, "hash_slots_log2": 0, "slab_cap": 0, "want_records": 0, "profile": 0,
+          "hash_warps": 0, "rank_rows": 1, "group_sizes": 0}
 
 
 @pytest.fixture(scope="module")
@@ -104,6 +105,33 @@ def test_slab_overflow_falls_back_to_the_exact_path(searcher):
         assert res3.rows() == want and _slab(res3)
     finally:
         _reset(searcher)
+
+
+@pytest.mark.parametrize("warps", [8, 10])
+@pytest.mark.parametrize("rank_rows", [0, 1], ids=["radix_rows", "rank_rows"])
+@pytest.mark.parametrize("shape", [(6, 6, 300_000, 25, 1, 2), (3, 3, 400_000, 12, 3, 12), (50, 50, 40_000, 25, 1, 2), (3, 2, 200_000, 40, 6, 50)],
+                         ids=["spacer", "12_3_12", "100_files", "multiword"])
+def test_result_tail_variants_agree(shape, rank_rows, warps, searcher):
+    """The shared-table bucket hash with 8 or 10 warps per CTA, rows ordered by counting ranks or by the chunked radix sort, group
+    sizes asked for or not: same rows in the same (ascending) order as the host decoder, sizes only where asked for."""
+    from krisp_b200.panel import make_panel
+    n_in, n_out, glen, L, D, R = shape
+    kw = dict(n_runs=1, run_len=30, noise=1e-4, dup_len=300, soft_block=100) if n_in + n_out > 64 else {}
+    gs = make_panel(n_in, n_out, glen, **kw)
+    want = _oracle_panel(gs, L, D, R)
+    try:
+        res = _search_panel(searcher, gs, L, D, R, options={"hash_warps": warps, "hash_shared": 1, "rank_rows": rank_rows, "group_sizes": rank_rows})
+    finally:
+        _reset(searcher)
+    assert len(want) > 0 and res.rows() == want
+    text = res.csv_rows_text().splitlines()
+    assert sorted(text) == want
+    from krisp_b200.render import csv_rows
+    assert text == csv_rows(res)                                  # device order == ascending (left, right)
+    if rank_rows or 2 * (L + D + R) + 8 > 64:                     # (multi-word records: the generic hash kernel counts as it goes)
+        assert res.group_size is not None and int(res.group_size.min()) >= n_in + n_out
+    else:
+        assert res.group_size is None
 
 
 def test_repeats_overflow_one_slab_and_still_give_the_oracle_rows(searcher):
