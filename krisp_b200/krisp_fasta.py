@@ -4,7 +4,8 @@ Mirrors ``krisp.krisp_fasta.krisp_fasta:main`` (krisp_fasta/krisp_fasta.py:126-2
 surface :128-176, (L, D, R, amplicon) deduction :178-213, stage sequence :236-291.  The three
 file-to-file stages (sortedKmers*, mergeFiles, filterAlignments) are one device search; the host
 renders the survivors.  ``--cores`` and ``--workdir`` are accepted and ignored (no worker processes,
-no temporary k-mer files).  ``--primer3`` needs primer3-py exactly as the reference does.
+no temporary k-mer files).  ``--primer3`` runs the reference's Primer3 post-filter on the survivors (host, ``render.run_primer3``);
+it needs primer3-py, as the reference does.
 """
 import argparse
 import sys
@@ -119,10 +120,11 @@ def main(argv=None):
         try:
             import primer3  # noqa: F401
         except ImportError:
-            print("ERROR: --primer3 needs the primer3-py package (as in the reference)", file=sys.stderr)
+            print("ERROR: --primer3 needs the primer3-py package (the reference imports it unconditionally, Amplicon.py:3)", file=sys.stderr)
             sys.exit(1)
-        print("ERROR: --primer3 post-filtering is not wired to the GPU path yet", file=sys.stderr)
-        sys.exit(1)
+    # Primer3 settings travel as a dict (the reference parks them in a class attribute, krisp_fasta.py:218-221)
+    p3_args = {k: v for k, v in vars(args).items()
+               if k in ("tm", "gc", "primer_size", "amp_size", "max_sec_tm", "gc_clamp", "max_end_gc")}
     L, R = args.conserved_left, args.conserved_right
     D = args.amplicon - L - R           # the middle kstream's split [L, -R] really leaves (krisp_fasta.py:37)
     start_t = time.time()
@@ -141,7 +143,7 @@ def main(argv=None):
         print("Rendering output ... ", file=sys.stderr)
     ingroup = [simplename(f) for f in args.files] if len(args.outgroup) else None     # krisp_fasta.py:281-283
     found = render_output(res, getattr(res, "labels", None), ingroup=ingroup, out_csv=args.out_csv,
-                          out_align=args.out_align, dot=args.dot_alignment)
+                          out_align=args.out_align, dot=args.dot_alignment, find_primers=bool(args.primer3), p3_args=p3_args)
     if args.verbose:
         print(f"=> Found {found:,} regions in {time.time() - start_t:.2f} s", file=sys.stderr)
     return 0

@@ -16,6 +16,89 @@ from .search import _IUPAC, _decode_bases
 
 CSV_HEADER = "left_seq,diag_seq,right_seq"
 
+# ---- Primer3 post-filter (host, off the timed path; north_star: "Primer3 filtering ... stay on the host") ---------------------------
+# The reference runs primer3-py on every surviving region and keeps the ones with at least one primer pair
+# (ConservedEndAmplicons.find_primers, Amplicon.py:560-564; run_primer3 :103-151; CSV columns outputAlignments.py:10-31;
+# alignment annotations Amplicon.py:640-660, _render_primer3_stats :566-595).  Same call, same settings, same columns here.
+P3_COLS = ("PRIMER_PAIR_0_PRODUCT_SIZE", "PRIMER_PAIR_0_PENALTY", "PRIMER_LEFT_0_SEQUENCE", "PRIMER_RIGHT_0_SEQUENCE",
+           "PRIMER_LEFT_0_PENALTY", "PRIMER_RIGHT_0_PENALTY", "PRIMER_LEFT_0_TM", "PRIMER_RIGHT_0_TM",
+           "PRIMER_LEFT_0_GC_PERCENT", "PRIMER_RIGHT_0_GC_PERCENT", "PRIMER_LEFT_0_SELF_ANY_TH", "PRIMER_RIGHT_0_SELF_ANY_TH",
+           "PRIMER_LEFT_0_SELF_END_TH", "PRIMER_RIGHT_0_SELF_END_TH", "PRIMER_LEFT_0_HAIRPIN_TH", "PRIMER_RIGHT_0_HAIRPIN_TH",
+           "PRIMER_LEFT_0_END_STABILITY", "PRIMER_RIGHT_0_END_STABILITY", "PRIMER_PAIR_0_COMPL_ANY_TH", "PRIMER_PAIR_0_COMPL_END_TH")
+P3_KEYS = tuple(n.replace("PRIMER_", "").replace("_0", "").lower() for n in P3_COLS)
+
+
+class Primer3Unavailable(ImportError):
+    """--primer3 was asked for but primer3-py is not importable (the reference cannot even start without it: Amplicon.py:3)."""
+
+
+def run_primer3(template, target_start, target_len, tm=(53, 68), gc=(40, 70), amp_size=(80, 300), primer_size=(25, 35),
+                max_sec_tm=40, gc_clamp=1, max_end_gc=4):
+    """One primer3 design call on `template` = left + consensus + right with the diagnostic region as target — the settings of
+    run_primer3 (Amplicon.py:103-151).  Returns primer3's result dict."""
+    try:
+        import primer3
+    except ImportError as exc:
+        raise Primer3Unavailable("--primer3 needs the primer3-py package (pip install primer3-py)") from exc
+    from statistics import mean                 # (statistics.mean keeps [25, 35] -> 30 an int, as primer3 wants PRIMER_OPT_SIZE)
+    settings = {
+        "PRIMER_TASK": "generic", "PRIMER_PICK_LEFT_PRIMER": 1, "PRIMER_PICK_RIGHT_PRIMER": 1, "PRIMER_LIBERAL_BASE": 1,
+        "PRIMER_OPT_SIZE": mean(primer_size), "PRIMER_MIN_SIZE": primer_size[0], "PRIMER_MAX_SIZE": primer_size[1],
+        "PRIMER_OPT_TM": mean(tm), "PRIMER_MIN_TM": tm[0], "PRIMER_MAX_TM": tm[1], "PRIMER_MIN_GC": gc[0], "PRIMER_MAX_GC": gc[1],
+        "PRIMER_MAX_POLY_X": 4, "PRIMER_MAX_NS_ACCEPTED": 0, "PRIMER_THERMODYNAMIC_OLIGO_ALIGNMENT": 1,
+        "PRIMER_MAX_SELF_ANY_TH": max_sec_tm, "PRIMER_MAX_SELF_END_TH": max_sec_tm, "PRIMER_PAIR_MAX_COMPL_ANY_TH": max_sec_tm,
+        "PRIMER_PAIR_MAX_COMPL_END_TH": max_sec_tm, "PRIMER_MAX_HAIRPIN_TH": max_sec_tm, "PRIMER_PRODUCT_SIZE_RANGE": [amp_size],
+        "PRIMER_GC_CLAMP": gc_clamp, "PRIMER_MAX_END_GC": max_end_gc,
+    }
+    return primer3.bindings.design_primers({"SEQUENCE_TEMPLATE": template, "SEQUENCE_TARGET": [target_start, target_len]}, settings)
+
+
+def _plain_table(header, rows):
+    """Borderless left-aligned table: prettytable's ``get_string(border=False)`` with ``align = 'l'`` (one blank of padding on either
+    side of every cell, no rules).  prettytable itself is used when it is importable."""
+    try:
+        from prettytable import PrettyTable
+        t = PrettyTable(list(header))
+        for r in rows:
+            t.add_row(list(r))
+        t.align = "l"
+        return t.get_string(border=False)
+    except ImportError:
+        cells = [[str(x) for x in header]] + [[str(x) for x in r] for r in rows]
+        width = [max(len(r[c]) for r in cells) for c in range(len(header))]
+        return "\n".join("".join(" " + r[c].ljust(width[c]) + " " for c in range(len(header))) for r in cells)
+
+
+def primer3_stats_text(p3):
+    """The two statistics tables under an alignment (_render_primer3_stats, Amplicon.py:566-595)."""
+    left = {k[14:]: v for k, v in p3.items() if "PRIMER_LEFT_0_" in k}
+    right = {k[15:]: v for k, v in p3.items() if "PRIMER_RIGHT_0_" in k}
+    pair = {k[14:]: v for k, v in p3.items() if "PRIMER_PAIR_0_" in k}
+    names = lambda ks: [x.title().replace("_", " ") for x in ks]
+    values = lambda vs: [str(round(x, 5)) if isinstance(x, float) else x for x in vs]
+    primers = _plain_table(["Direction"] + names(left.keys()), [["Forward"] + values(left.values()), ["Reverse"] + values(right.values())])
+    pairs = _plain_table(names(pair.keys()), [values(pair.values())])
+    return "\nPrimer statistics:\n" + primers + "\n\nPair statistics:\n" + pairs
+
+
+def annotate_alignment(block, p3, dot=False):
+    """Add the primer positions and the statistics to one rendered alignment block (Amplicon.py:640-660): in bracket mode the
+    annotation is merged into the bracket line, in dot mode it is a line of its own."""
+    result = block[:-1].split("\n") if block.endswith("\n") else block.split("\n")
+    fwd, rev = p3["PRIMER_LEFT_0_SEQUENCE"], p3["PRIMER_RIGHT_0_SEQUENCE"]
+    f0 = p3["PRIMER_LEFT_0"][0]
+    r0 = p3["PRIMER_RIGHT_0"][0] - p3["PRIMER_RIGHT_0"][1]
+    text = (" " * f0 + "\u2514" + "Forward".center(len(fwd) - 2, "\u2500") + "\u2518" + " " * (r0 - f0 - len(fwd) + 1)
+            + "\u2514" + "Reverse".center(len(rev) - 2, "\u2500") + "\u2518")
+    if dot:
+        result.append(text)
+    else:
+        last = result[-1].ljust(len(text))
+        result[-1] = "".join(a if b == " " else b for b, a in zip(last, text))
+    result.append(primer3_stats_text(p3))
+    result[-1] += "\n"
+    return "\n".join(result)
+
 
 def _group_order(res):
     keys = [(res.left[i].tobytes(), res.right[i].tobytes()) for i in range(res.n_groups)]
@@ -140,23 +223,40 @@ def write_interchange(res, labels, filename):
     return len(lines)
 
 
-def render_output(res, labels, ingroup=None, out_csv=None, out_align=None, dot=False):
-    """Write the CSV (stdout when out_csv is None) and, if asked, the alignment file.  Returns the number of regions."""
+def render_output(res, labels, ingroup=None, out_csv=None, out_align=None, dot=False, find_primers=False, p3_args=None):
+    """Write the CSV (stdout when out_csv is None) and, if asked, the alignment file.  Returns the number of regions written
+    (render_output, outputAlignments.py:101-162).  find_primers: every region goes through Primer3 first, regions without a primer
+    pair are dropped, the CSV gains the primer columns and the alignments the primer annotation (render_output_part :67-98)."""
     text = res.csv_rows_text()                   # rendered and ordered on the device (ascending (left, right))
-    n_rows = text.count("\n")
+    lines = text.splitlines()
+    p3s = None
+    if find_primers:
+        p3s = []
+        for ln in lines:
+            left, cons, right = ln.split(",")
+            p3 = run_primer3(left + cons + right, target_start=len(left), target_len=len(cons), **(p3_args or {}))
+            p3s.append(p3 if p3["PRIMER_PAIR_NUM_RETURNED"] != 0 else None)
+        lines = [ln + "," + ",".join(str(p3[n]) for n in P3_COLS) for ln, p3 in zip(lines, p3s) if p3 is not None]
+        text = "".join(ln + "\n" for ln in lines)
+    n_rows = len(lines)
     stream = sys.stdout if out_csv is None else open(out_csv, "w")
     try:
-        stream.write(CSV_HEADER + "\n" + text)
+        stream.write(CSV_HEADER + ("," + ",".join(P3_KEYS) if find_primers else "") + "\n" + text)
     finally:
         if out_csv is not None:
             stream.close()
     if out_align is not None:
-        order = _group_order(res)
+        order = _group_order(res)               # the same ascending (left, right) order as the rows
         if os.path.isfile(out_align):
             os.remove(out_align)
         ing = frozenset(ingroup) if ingroup is not None else None
         with open(out_align, "a") as fh:
-            for g in order:
+            for i, g in enumerate(order):
+                if p3s is not None and (i >= len(p3s) or p3s[i] is None):
+                    continue
                 amps = group_amplicons(res, g, labels)
-                print(render_alignment(res.left[g].tobytes().decode(), res.right[g].tobytes().decode(), amps, ing, dot), file=fh)
+                block = render_alignment(res.left[g].tobytes().decode(), res.right[g].tobytes().decode(), amps, ing, dot)
+                if p3s is not None:
+                    block = annotate_alignment(block, p3s[i], dot)
+                print(block, file=fh)
     return n_rows

@@ -264,3 +264,56 @@ def test_decode_table_handles_one_word_and_multi_word_records():
         arr = np.array(recs, dtype=np.uint64).reshape(len(recs), W)
         got = decode_table(arr if W > 1 else arr[:, 0], L, D, R)
         assert got == want and len(got) == n, (L, D, R)
+
+
+def test_primer3_post_filter_wiring(tmp_path, monkeypatch):
+    """--primer3 (render.render_output find_primers=True): every region's template left + consensus + right goes to
+    primer3.bindings.design_primers with the diagnostic region as target and the reference's settings (Amplicon.py:103-151), regions
+    without a primer pair are dropped, the CSV gains the 20 primer columns (outputAlignments.py:10-31) and the alignment the primer
+    annotation and statistics (Amplicon.py:640-660).  primer3-py is not in this image: a stand-in module records the calls."""
+    import sys
+    import types
+    calls = []
+
+    def design_primers(seq_args, global_args):
+        calls.append((seq_args, global_args))
+        if seq_args["SEQUENCE_TEMPLATE"].startswith("GT"):
+            return {"PRIMER_PAIR_NUM_RETURNED": 0}
+        out = {"PRIMER_PAIR_NUM_RETURNED": 1, "PRIMER_LEFT_0": (0, 4), "PRIMER_RIGHT_0": (11, 4)}
+        for i, n in enumerate(render.P3_COLS):
+            out[n] = "ACGA" if n == "PRIMER_LEFT_0_SEQUENCE" else ("TTCA" if n == "PRIMER_RIGHT_0_SEQUENCE" else 1.5 + i)
+        return out
+
+    fake = types.ModuleType("primer3")
+    fake.bindings = types.SimpleNamespace(design_primers=design_primers)
+    monkeypatch.setitem(sys.modules, "primer3", fake)
+
+    res = SearchResult(L=4, D=3, R=5, have_outgroup=True)
+    res.left = np.frombuffer(b"ACGAGTTT", dtype=np.uint8).reshape(2, 4)
+    res.right = np.frombuffer(b"GTGAATCCCC", dtype=np.uint8).reshape(2, 5)
+    res.in_mask = np.array([[1, 3, 8], [8, 4, 2]], dtype=np.uint8)
+    res.out_mask = np.array([[2, 4, 1], [1, 1, 1]], dtype=np.uint8)
+    res.rows_blob = None                                   # rows from the host decoder
+    csv = tmp_path / "out.csv"
+    n = render.render_output(res, ["a", "b"], ingroup=["a"], out_csv=str(csv), find_primers=True,
+                             p3_args={"tm": [53, 68], "gc": [40, 70], "amp_size": [70, 150], "primer_size": [25, 35], "max_sec_tm": 40, "gc_clamp": 1, "max_end_gc": 4})
+    assert n == 1
+    lines = csv.read_text().splitlines()
+    assert lines[0] == "left_seq,diag_seq,right_seq," + ",".join(render.P3_KEYS)
+    assert lines[0].split(",")[3:6] == ["pair_product_size", "pair_penalty", "left_sequence"] and len(lines[0].split(",")) == 23
+    assert len(lines) == 2 and lines[1].startswith("ACGA,AMT,GTGAA,1.5,2.5,ACGA,TTCA,")
+    assert [c[0]["SEQUENCE_TEMPLATE"] for c in calls] == ["ACGAAMTGTGAA", "GTTTTGCTCCCC"]
+    assert all(c[0]["SEQUENCE_TARGET"] == [4, 3] for c in calls)
+    g = calls[0][1]
+    assert g["PRIMER_PRODUCT_SIZE_RANGE"] == [[70, 150]] and g["PRIMER_OPT_SIZE"] == 30 and g["PRIMER_OPT_TM"] == 60.5
+    assert g["PRIMER_MIN_GC"] == 40 and g["PRIMER_MAX_HAIRPIN_TH"] == 40 and g["PRIMER_TASK"] == "generic" and len(g) == 23
+    # annotation: merged into the bracket line, statistics underneath
+    block = render.render_alignment("ACGA", "GTGAA", {"AAT": ["a"], "CCA": ["b"]}, frozenset(["a"]), False)
+    p3 = design_primers({"SEQUENCE_TEMPLATE": "ACGAAMTGTGAA"}, {})
+    text = render.annotate_alignment(block, p3, False).split("\n")
+    assert text[0].startswith("ACGAAATGTGAA : a") and text[1].startswith("ACGACCAGTGAA : b")
+    assert text[2] == "└Fo{###}┘    └Reverse┘"      # annotation from the primer positions, the bracket's own characters win
+    assert text[3] == "" and text[4] == "Primer statistics:" and "Direction" in text[5] and text[6].lstrip().startswith("Forward")
+    assert "Pair statistics:" in text
+    dot = render.annotate_alignment(render.render_alignment("ACGA", "GTGAA", {"AAT": ["a"], "CCA": ["b"]}, frozenset(["a"]), True), p3, True).split("\n")
+    assert dot[1].startswith("....CCA..... : b") and dot[2] == "└Forward┘    └Reverse┘"
