@@ -205,6 +205,41 @@ def fold_stages(prof):
     return out
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and thereby the pinned host buffers it is about to allocate: first touch) to the NUMA node its GPU hangs
+    off, so that the host -> device copies of concurrent ranks do not cross the socket interconnect.  Returns a record for the JSON
+    line; never fatal."""
+    rec = {"node": None, "cpus": None}
+    try:
+        import torch
+        pci = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        bus = None
+        if pci is not None:
+            dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+            dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+            bus = f"{dom:04x}:{pci:02x}:{dev:02x}.0"
+        if bus is None:
+            return rec
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        rec["pci"] = bus
+        rec["node"] = node
+        if node < 0:
+            return rec
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            rec["cpus"] = len(allowed)
+    except Exception as exc:                                           # (containers without /sys access: leave the default placement)
+        rec["error"] = repr(exc)[:120]
+    return rec
+
+
 def run_ours(args):
     import hashlib
     import numpy as np
@@ -219,6 +254,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — krisp_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("KRISP_NUMA_BIND", "1") == "1" else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -413,10 +449,9 @@ def run_ours(args):
              "frac_of_peak_at_round1_bytes": (w.h2d_bytes + 48.0 * n_rec) / (m["ms"] * 1e-3) / 1e9 / peak}
 
     if args.diag and world > 1:
-        variants = [("default", {}, {}), ("groups=1", {"KRISP_SLAB_GROUPS": "1"}, {}), ("groups=2", {"KRISP_SLAB_GROUPS": "2"}, {}),
-                    ("groups=4", {"KRISP_SLAB_GROUPS": "4"}, {}), ("copy_streams=2", {"KRISP_COPY_STREAMS": "2"}, {}),
-                    ("copy_streams=4", {"KRISP_COPY_STREAMS": "4"}, {}), ("records (sym=0)", {}, {"sym": 0}),
-                    ("records, copy_streams=4", {"KRISP_COPY_STREAMS": "4"}, {"sym": 0}), ("a2a", {"KRISP_SLAB_EXCHANGE": "a2a"}, {})]
+        variants = [("default", {}, {}), ("own_first=0", {"KRISP_OWN_FIRST": "0"}, {}), ("groups=4", {"KRISP_SLAB_GROUPS": "4"}, {}),
+                    ("groups=16", {"KRISP_SLAB_GROUPS": "16"}, {}), ("groups=2", {"KRISP_SLAB_GROUPS": "2"}, {}),
+                    ("records (sym=0)", {}, {"sym": 0}), ("a2a", {"KRISP_SLAB_EXCHANGE": "a2a"}, {})]
         os.environ["KRISP_TIMELINE"] = "1"
         for name, env, opts in variants:
             for k, v in env.items():
@@ -486,6 +521,11 @@ def run_ours(args):
     }
     if world > 1:
         line["parity"] = parity
+        # the e2e arm at N > 1 is bound by the host: N ranks read their pinned buffers at once (copy phase = the K1 stage of the e2e arm)
+        k1 = next((v for k, v in m["e2e"]["stage_ms"].items() if k.startswith("K1 extract")), None)
+        line["e2e"]["h2d"] = {"bytes_per_gpu": m["e2e"]["h2d_bytes_per_step"] // world, "copy_phase_ms": k1,
+                              "gbs_per_gpu": (m["e2e"]["h2d_bytes_per_step"] / world / (k1 * 1e-3) / 1e9) if k1 else None,
+                              "numa_binding_rank0": numa}
         ex = m["exchange"] or {}
         if ex.get("slab") and ex.get("exchange_ms"):
             sent = float(ex["sent_bytes"])

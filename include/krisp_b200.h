@@ -207,6 +207,9 @@ int kb_shard_search(kb_ctx* ctx, uint64_t n_records, const uint64_t* piece_count
  *                          (k - 1) % |n_parts| == part — several streams keep several copy engines busy).  The
  *                          host layer runs the groups in order on a copy stream and puts a tiny collective behind each group, after
  *                          which every rank's copies of that group have landed.
+ *   kb_shard_slab_own      optional, before the first kb_shard_slab_level of a pipelined search (n_groups > 1): partition level 1 on the
+ *                          slabs this rank filled itself — they are complete when K1 ends, so this runs while the first digit group
+ *                          is still on the wire; kb_shard_slab_level then covers the other source ranks only.
  *   kb_shard_slab_level    gathered_cursors_dev = device array [n_ranks][n_digits] (all-gather result, rank-major).  Partition
  *                          level 1 + the bucket hash on the slabs of digit group `group` in this rank's receive buffer — group g
  *                          is processed while group g + 1 is still in flight.  (Three-level plans and small inputs: one group.)
@@ -226,6 +229,7 @@ int kb_shard_slab_send(kb_ctx* ctx, int group, int n_groups, int part, int n_par
  * the elements are window items, one per k-mer window (strand-symmetric level 0, csrc/kb_extract_sym.cuh: half the bytes travel);
  * 0: records, two per window. */
 int kb_shard_slab_buffers(kb_ctx* ctx, void** staging, void** receive, uint64_t* slab_records, int* window_items);
+int kb_shard_slab_own(kb_ctx* ctx, const void* gathered_cursors_dev);
 int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group, int n_groups);
 int kb_shard_slab_finish(kb_ctx* ctx, int* status, kb_result** out);
 
@@ -273,8 +277,11 @@ int kb_last_counters(const kb_ctx* ctx, uint64_t* kernel_launches, uint64_t* alg
  * kstream path: one file's k-mers as a packed table sorted like the reference's `*.{k}mers` file
  * (LC_ALL=C order on left, right, then middle).  Replaces kstream.write + sortInPlace
  * (kstream/kstream.py:250-325, :83-119); the count equals kstream.write's return value.
- * `local_index` = order of the kb_add_sequence call.  Records are one 64-bit word each
- * (only k-mers with 2k + 8 <= 64 bits are supported on this path).
+ * `local_index` = order of the kb_add_sequence call.  Records are one 64-bit word each for 2k + 8 <= 64, else W words
+ * (kb_table_get: record_words).  Option "strands" selects the stream the table holds: 0 (default) = every window and its reverse
+ * complement (--complements, kstream.py:644-677), 1 = the windows only (kstream's default), 2 = the alphabetically first of the
+ * two (--canonicals, :679-694); 1 and 2 need one-word records (k <= 28).  A layout (L, D, R) = (k, 0, 0) gives the unsplit table
+ * (whole k-mers in LC_ALL=C order).
  */
 int kb_extract_sorted(kb_ctx* ctx, int local_index, kb_table** out);
 int kb_table_get(const kb_table* t, const uint64_t** records, uint64_t* n_records, int* record_words);

@@ -18,7 +18,7 @@ EXPORTS = ["kb_version", "kb_create", "kb_destroy", "kb_last_error", "kb_set_str
            "kb_set_option", "kb_clear_sequences", "kb_reserve", "kb_add_sequence", "kb_add_fasta", "kb_fasta_flags",
            "kb_get_sequence", "kb_synchronize",
            "kb_search", "kb_shard_plan", "kb_shard_child_counts", "kb_shard_set_child_counts", "kb_sequence_buffer", "kb_shard_own_files", "kb_shard_ipc_export", "kb_shard_ipc_import", "kb_shard_ipc_close", "kb_shard_count",
-           "kb_shard_scatter", "kb_shard_slab_plan", "kb_shard_slab_extract", "kb_shard_slab_send", "kb_shard_slab_buffers", "kb_shard_slab_level", "kb_shard_slab_finish", "kb_shard_extract", "kb_shard_recv_buffer", "kb_shard_search", "kb_result_get", "kb_result_rows",
+           "kb_shard_scatter", "kb_shard_slab_plan", "kb_shard_slab_extract", "kb_shard_slab_send", "kb_shard_slab_buffers", "kb_shard_slab_own", "kb_shard_slab_level", "kb_shard_slab_finish", "kb_shard_extract", "kb_shard_recv_buffer", "kb_shard_search", "kb_result_get", "kb_result_rows",
            "kb_result_free", "kb_last_profile", "kb_last_counters", "kb_extract_sorted", "kb_table_get",
            "kb_table_free"]
 
@@ -90,6 +90,7 @@ def load():
     L.kb_shard_slab_extract.argtypes = [vp, pvp]
     L.kb_shard_slab_send.argtypes = [vp, i, i, i, i, vp]
     L.kb_shard_slab_buffers.argtypes = [vp, pvp, pvp, ctypes.POINTER(u64), ctypes.POINTER(i)]
+    L.kb_shard_slab_own.argtypes = [vp, vp]
     L.kb_shard_slab_level.argtypes = [vp, vp, i, i]
     L.kb_shard_slab_finish.argtypes = [vp, ctypes.POINTER(i), pvp]
     L.kb_shard_extract.argtypes = [vp, pvp, ctypes.POINTER(u64), ctypes.POINTER(u64)]

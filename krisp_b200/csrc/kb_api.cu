@@ -116,6 +116,7 @@ struct kb_ctx {
     long long opt_batch_level0 = 1;      // 1 = partition level 0 per batch of arriving files (hidden under the host -> device copy)
     long long opt_render_rows = 1;       // CSV rows of the survivors rendered + ordered on the device (kb_result_rows)
     long long opt_have_outgroup = 1;     // consensus letters: ingroup only (an outgroup was given) / every occurrence
+    long long opt_strands = 0;           // kb_extract_sorted only: 0 = windows + reverse complements, 1 = windows only, 2 = canonical k-mers
     long long opt_lazy_records = 1;      // multi-word records: 1 = filter by flank hash, build records only for what is left (kb_prefilter.cuh)
     long long opt_slab = 1;              // one-word records: 1 = K1 fused with partition level 0 into fixed-capacity slabs (kb_extract_part.cuh)
     long long opt_hash_warp = 1;         // 1 = bucket hash kernel with per-warp streaming (kb_hash_warp.cuh) instead of the CTA-wide stream kernel
@@ -129,6 +130,7 @@ struct kb_ctx {
                                          // on one GPU forming the records in level 1 costs more than level 0 saves)
     bool slab_off = false;               // a slab overflowed on these sequences: searches use the exact path until they change
     bool lazy_now = false;               // the running search uses it
+    int strands_now = 0;                 // strand mode of the running K1 (kb_extract_sorted; searches always use both strands)
     int bb_extra = 0;                    // bucket bits added to the size-based plan: learnt when a search deferred too many buckets
                                          // (divergent genomes: far more distinct keys per record than the plan assumes); kept per layout
     bool replan_ok = false;              // the running search may give up on a too coarse plan (kb_search retries with bb_extra + 2)
@@ -147,6 +149,7 @@ struct kb_ctx {
     struct PendingFasta { size_t raw_off; uint64_t nb; int fasta; uint64_t slot_off; cudaEvent_t ev; size_t file_idx; };
     std::vector<PendingFasta> pending_fasta;    // one per kb_add_fasta since the last clear, in file order
     size_t fasta_done = 0;                       // how many of them have been de-lined
+    size_t fa_round = 0;                         // de-lining launches so far (they take the side streams in turn)
     std::vector<int> fasta_of_file;              // local file index -> index into pending_fasta (-1: added as parsed sequence)
     size_t raw_used = 0;                         // bytes of rawbuf in use
 #define KB_FA_STREAMS 8
@@ -186,6 +189,7 @@ struct kb_ctx {
     int own_first = 0, own_count = -1;   // replicated sequences: K1 of the shard calls covers only these local files (-1: all)
     int shard_direct = 0;                // the last exchange went through kb_shard_scatter (input of kb_shard_search = recvbuf)
     bool shard_slab = false;             // kb_shard_slab_plan succeeded: shard_sp / shard_plan describe the slab exchange
+    bool shard_own_done = false;         // kb_shard_slab_own ran level 1 on this rank's own slabs: the group passes skip that source
     long long opt_shard_bb_extra = 0;    // bucket bits added to the sharded slab plan (set on every rank alike after a re-plan vote)
     uint64_t shard_total_bases = 0;
     uint64_t shard_n_records = 0;
@@ -326,6 +330,7 @@ int kb_set_option(kb_ctx* ctx, const char* name, long long value) {
     else if (n == "pair_hist") ctx->opt_pair_hist = value ? 1 : 0;
     else if (n == "batch_level0") ctx->opt_batch_level0 = value ? 1 : 0;
     else if (n == "lazy_records") ctx->opt_lazy_records = value ? 1 : 0;
+    else if (n == "strands") { if (value < 0 || value > 2) return fail(ctx, KB_EINVAL, "strands: 0 (both), 1 (forward) or 2 (canonical)"); ctx->opt_strands = value; }
     else if (n == "slab") { ctx->opt_slab = value ? 1 : 0; ctx->slab_off = false; }
     else if (n == "hash_warp") ctx->opt_hash_warp = value ? 1 : 0;
     else if (n == "sym") ctx->opt_sym = value < 0 ? -1 : (value ? 1 : 0);
@@ -577,53 +582,73 @@ static int deline_pending(kb_ctx* ctx, size_t upto) {
     // earlier users of the buffers) — not after the K1 batches queued since: those touch other files
     const bool first_round = ctx->fasta_done == 0;
     if (first_round) CU(cudaEventRecord(ctx->main_event, ctx->stream));
-    for (; ctx->fasta_done < upto; ctx->fasta_done++) {
-        const size_t i = ctx->fasta_done;
-        const kb_ctx::PendingFasta& f = ctx->pending_fasta[i];
-        static const int n_fa = []() { const char* e = getenv("KRISP_FA_STREAMS"); const int v = e ? atoi(e) : 8; return std::max(1, std::min(v, KB_FA_STREAMS)); }();
-        const int k = (int)(i % (size_t)n_fa);
+    static const int n_fa = []() { const char* e = getenv("KRISP_FA_STREAMS"); const int v = e ? atoi(e) : 2; return std::max(1, std::min(v, KB_FA_STREAMS)); }();
+    // the files [fasta_done, upto) have arrived together (one batch): they share the three launches, KB_FA_MAXF files at a time
+    while (ctx->fasta_done < upto) {
+        const size_t i0 = ctx->fasta_done, i1 = std::min(upto, i0 + (size_t)KB_FA_MAXF);
+        const int k = (int)(ctx->fa_round++ % (size_t)n_fa);
         if (!ctx->fa_stream[k]) CU(cudaStreamCreateWithFlags(&ctx->fa_stream[k], cudaStreamNonBlocking));
         cudaStream_t st = ctx->fa_stream[k];
-        while (ctx->fa_done_ev.size() <= i) {
+        while (ctx->fa_done_ev.size() <= i0) {
             cudaEvent_t ne;
             CU(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming));
             ctx->fa_done_ev.push_back(ne);
         }
-        uint8_t* slot = (uint8_t*)ctx->bases.p + f.slot_off;
         if (first_round) CU(cudaStreamWaitEvent(st, ctx->main_event, 0));
-        CU(cudaStreamWaitEvent(st, f.ev, 0));
-        CU(cudaMemsetAsync(slot, '\n', f.nb + 1, st));                       // separators wherever the packed bytes do not reach
-        if (f.nb) {
+        CU(cudaStreamWaitEvent(st, ctx->pending_fasta[i1 - 1].ev, 0));          // (the copies arrive in order: the last file's event covers the batch)
+        // separators wherever the packed bytes will not reach: the slots of the batch are contiguous
+        {
+            const kb_ctx::PendingFasta& fa = ctx->pending_fasta[i0];
+            const kb_ctx::PendingFasta& fb = ctx->pending_fasta[i1 - 1];
+            CU(cudaMemsetAsync((uint8_t*)ctx->bases.p + fa.slot_off, '\n', fb.slot_off + fb.nb + 1 - fa.slot_off, st));
+        }
+        KbFastaBatch b{};
+        size_t words = 0;
+        uint32_t tiles_total = 0;
+        for (size_t i = i0; i < i1; i++) {
+            const kb_ctx::PendingFasta& f = ctx->pending_fasta[i];
+            if (!f.nb) continue;
             const uint32_t tiles = (uint32_t)((f.nb + KB_FA_TILE - 1) / KB_FA_TILE);
-            const size_t words = (size_t)tiles * 4 + 2 + (tiles + 7) / 8 + 8;         // last_nl | counts x 2 | start (+1) | hdr0 bytes
-            DevBuf& wk = ctx->fa_work_s[k];
-            if (wk.cap < words * 8) {                                          // (rare: grows to the largest file; the stream's earlier chain is done first)
-                CU(cudaStreamSynchronize(st));
-                if (wk.p) CU(cudaFree(wk.p));
-                wk.p = nullptr; wk.cap = 0;
-                CU(cudaMalloc(&wk.p, words * 8 + words));
-                wk.cap = words * 8 + words;
-            }
-            KbFastaArgs a{};
+            words += (size_t)tiles * 4 + 2 + (tiles + 7) / 8 + 8;                // last_nl | counts x 2 | start (+1) | hdr0 bytes
+        }
+        DevBuf& wk = ctx->fa_work_s[k];
+        if (wk.cap < words * 8) {                                                 // (rare: grows to the largest batch; the stream's earlier chain is done first)
+            CU(cudaStreamSynchronize(st));
+            if (wk.p) CU(cudaFree(wk.p));
+            wk.p = nullptr; wk.cap = 0;
+            CU(cudaMalloc(&wk.p, words * 8 + words));
+            wk.cap = words * 8 + words;
+        }
+        unsigned long long* q = (unsigned long long*)wk.p;
+        for (size_t i = i0; i < i1; i++) {
+            const kb_ctx::PendingFasta& f = ctx->pending_fasta[i];
+            if (!f.nb) continue;
+            const uint32_t tiles = (uint32_t)((f.nb + KB_FA_TILE - 1) / KB_FA_TILE);
+            KbFastaArgs& a = b.f[b.n_files];
             a.in = (const uint8_t*)ctx->rawbuf.p + f.raw_off; a.n = f.nb; a.fasta = f.fasta;
-            unsigned long long* q = (unsigned long long*)wk.p;
             a.last_nl = q; q += tiles;
             a.counts = q; q += 2 * (size_t)tiles;
-            unsigned long long* start = q; q += tiles + 1;
-            a.hdr0 = (uint8_t*)q;
-            a.start = start;
-            a.out = slot;
+            b.start_w[b.n_files] = q; a.start = q; q += tiles + 1;
+            a.hdr0 = (uint8_t*)q; q += (tiles + 7) / 8 + 1;
+            a.out = (uint8_t*)ctx->bases.p + f.slot_off;
             a.flags = (unsigned int*)ctx->fa_flags.p;
-            kb_fa_count_kernel<<<tiles, KB_FA_THREADS, 0, st>>>(a, tiles);
+            b.tile0[b.n_files] = tiles_total;
+            tiles_total += tiles;
+            b.n_files++;
+            b.tile0[b.n_files] = tiles_total;
+        }
+        if (b.n_files) {
+            kb_fa_count_kernel<<<tiles_total, KB_FA_THREADS, 0, st>>>(b);
             CU(cudaGetLastError());
-            kb_fa_offsets_kernel<<<1, 1024, 0, st>>>(a, tiles, start);
+            kb_fa_offsets_kernel<<<(unsigned)b.n_files, 1024, 0, st>>>(b);
             CU(cudaGetLastError());
-            kb_fa_pack_kernel<true><<<tiles, KB_FA_THREADS, 0, st>>>(a);
+            kb_fa_pack_kernel<<<tiles_total, KB_FA_THREADS, 0, st>>>(b);
             CU(cudaGetLastError());
             ctx->launches += 3;
         }
-        CU(cudaEventRecord(ctx->fa_done_ev[i], st));
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->fa_done_ev[i], 0));           // whatever the main stream does next sees the file
+        CU(cudaEventRecord(ctx->fa_done_ev[i0], st));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->fa_done_ev[i0], 0));             // whatever the main stream does next sees these files
+        ctx->fasta_done = i1;
     }
     return KB_OK;
 }
@@ -641,6 +666,10 @@ static int deline_upto_file(kb_ctx* ctx, size_t last_file) {
     return deline_pending(ctx, upto);
 }
 
+// Batches of arriving files (host buffers on the copy stream): about ten, each ending at a file boundary.  Uniform on purpose — per
+// file the GPU's work (K1 + level 1 of the batch, ~80 us per 5 Mbp) is about what its copy takes (~92 us), so the last batch's work
+// after the end of the copy is what is exposed; uneven schedules (small first / last batches) were measured and lose: the big
+// batches in the middle make the GPU wait for data it could already have worked on (parsed sequences 6.36 -> 6.64 ms).
 static std::vector<KBatch> extract_batches(kb_ctx* ctx, uint32_t tile0, uint32_t n_tiles) {
     std::vector<KBatch> batches;
     const size_t nf = ctx->file_starts.size();
@@ -689,6 +718,7 @@ static int run_extract(kb_ctx* ctx, const KbLayout& lo, uint32_t tile0, uint32_t
     a.out_entries = (uint64_t*)ctx->entA.p;
     a.out_recs = (uint64_t*)ctx->recs.p;
     a.lazy = ctx->lazy_now ? 1 : 0;
+    a.strand_mode = ctx->strands_now;
     a.n_out = (unsigned long long*)ctx->small.p + SM_NOUT;
     a.tile0 = tile0; a.n_tiles = n_tiles;
     a.pos_lo = pos_lo; a.pos_hi = pos_hi;
@@ -1259,23 +1289,29 @@ static int render_rows(kb_ctx* ctx, kb_result* res, uint64_t n_res, char* dev_ds
     if (n_res >= (1ULL << 32)) return fail(ctx, KB_EUNSUPPORTED, "more than 2^32 survivors");
     TRY(ensure(ctx, ctx->rowkeyA, (size_t)(n_res + 2048) * 8));
     uint64_t* sorted = (uint64_t*)ctx->rowkeyA.p;
+    const uint32_t* rank = nullptr;
     if (n_res <= KB_RANK_MAX && ctx->opt_rank_rows) {
         KbRankArgs rk{};
-        rk.flank = (const uint64_t*)ctx->res_flank.p; rk.n = (uint32_t)n_res; rk.order = sorted;
+        rk.flank = (const uint64_t*)ctx->res_flank.p; rk.n = (uint32_t)n_res; rk.rank = (uint32_t*)ctx->rowkeyA.p;
         const unsigned rgrid = (unsigned)((n_res + KB_RANK_THREADS - 1) / KB_RANK_THREADS);
+        const unsigned rows_y = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(32, (n_res + 255) / 256));      // CTA rows: slices of >= 256 survivors
+        rk.slice = (uint32_t)((n_res + rows_y - 1) / rows_y);
+        CU(cudaMemsetAsync(rk.rank, 0, (size_t)n_res * 4, ctx->stream));
+        const dim3 g2(rgrid, rows_y);
         switch (lo.FW) {
-            case 1: kb_rank_kernel<1><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
-            case 2: kb_rank_kernel<2><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
-            case 3: kb_rank_kernel<3><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
-            case 4: kb_rank_kernel<4><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
-            case 5: kb_rank_kernel<5><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
-            case 6: kb_rank_kernel<6><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
-            case 7: kb_rank_kernel<7><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
-            case 8: kb_rank_kernel<8><<<rgrid, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 1: kb_rank_kernel<1><<<g2, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 2: kb_rank_kernel<2><<<g2, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 3: kb_rank_kernel<3><<<g2, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 4: kb_rank_kernel<4><<<g2, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 5: kb_rank_kernel<5><<<g2, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 6: kb_rank_kernel<6><<<g2, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 7: kb_rank_kernel<7><<<g2, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
+            case 8: kb_rank_kernel<8><<<g2, KB_RANK_THREADS, 0, ctx->stream>>>(rk); break;
             default: return fail(ctx, KB_EINTERNAL, "flank wider than 8 words");
         }
         CU(cudaGetLastError());
         ctx->launches++;
+        rank = rk.rank;
     } else {
         const long long prof = ctx->opt_profile;
         const int passes = ctx->passes;
@@ -1303,7 +1339,7 @@ static int render_rows(kb_ctx* ctx, kb_result* res, uint64_t n_res, char* dev_ds
     }
     const size_t bytes = (size_t)n_res * (size_t)res->row_bytes;
     KbRowsArgs ra{};
-    ra.order = sorted; ra.n = n_res; ra.flank = (const uint64_t*)ctx->res_flank.p;
+    ra.rank = rank; ra.order = sorted; ra.n = n_res; ra.flank = (const uint64_t*)ctx->res_flank.p;
     ra.in_mask = (const uint32_t*)ctx->res_in.p; ra.out_mask = (const uint32_t*)ctx->res_out.p;
     ra.L = lo.L; ra.D = lo.D; ra.R = lo.R; ra.FW = lo.FW; ra.MW = std::max(lo.MW, 1);
     ra.all_occurrences = ctx->opt_have_outgroup ? 0 : 1;
@@ -1660,7 +1696,7 @@ static int prepare_extract(kb_ctx* ctx) {
 // writes the slabs of level l into `out`.  rec_bound = records the pass can meet at most (sizes the grid in tile-map mode).
 static int launch_slab_level(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl, int l, const uint64_t* in, uint64_t* out,
                              const unsigned long long* pend, const unsigned long long* pbegin, uint32_t n_parents, const uint32_t* prow,
-                             uint64_t rec_bound, uint32_t psel_n = 0, uint32_t psel_j0 = 0, uint32_t psel_dps = 0) {
+                             uint64_t rec_bound, uint32_t psel_n = 0, uint32_t psel_j0 = 0, uint32_t psel_dps = 0, uint32_t psel_skip = 0xFFFFFFFFu) {
     uint8_t* P = (uint8_t*)ctx->plan.p;
     const size_t smem = kb_part_smem();
     const bool expand = sp.sym && l == 1;                      // the parents hold window items: form the records here
@@ -1678,7 +1714,7 @@ static int launch_slab_level(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl
     a.tile_parent = (const uint32_t*)(P + sp.off_tilemap);
     a.prow = prow;
     a.n_parents = n_parents;
-    a.psel_n = psel_n; a.psel_j0 = psel_j0; a.psel_dps = psel_dps;
+    a.psel_n = psel_n; a.psel_j0 = psel_j0; a.psel_dps = psel_dps; a.psel_skip = psel_skip;
     a.shift = (uint32_t)shift; a.bits = (uint32_t)sp.bits[l];
     a.cursor = (unsigned long long*)(P + sp.off_cur[l]);
     a.ccap = sp.cap[l];
@@ -2332,6 +2368,7 @@ int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev) {
     CU(cudaSetDevice(ctx->device));
     TRY(check_file_ids(ctx));
     begin_search(ctx);
+    ctx->shard_own_done = false;
     TRY(prepare_small(ctx));
     TRY(ensure(ctx, ctx->plan, sp.bytes + 64));
     uint8_t* P = (uint8_t*)ctx->plan.p;
@@ -2438,7 +2475,7 @@ int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group
     uint8_t* P = (uint8_t*)ctx->plan.p;
     unsigned long long* pend = (unsigned long long*)(P + sp.off_snap);
     uint32_t* prow = (uint32_t*)(pend + np);
-    if (group == 0) {
+    if (group == 0 && !ctx->shard_own_done) {
         kb_shard_pend_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)gathered_cursors_dev, N, nd0, d_lo, dps, pend, prow);
         CU(cudaGetLastError());
         CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_NRES, 0, 7 * 8, ctx->stream));
@@ -2456,7 +2493,9 @@ int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group
     if (n_groups == 1) {
         TRY(launch_slab_level(ctx, sp, pl, 1, (const uint64_t*)ctx->recvbuf.p, bufs[1], pend, nullptr, np, prow, std::min<uint64_t>(n_est, (uint64_t)np * sp.cap[0])));
     } else {
-        TRY(launch_slab_level(ctx, sp, pl, 1, (const uint64_t*)ctx->recvbuf.p, bufs[1], pend, nullptr, N * (j1 - j0), prow, 0, j1 - j0, j0, dps));
+        // (this rank's own slabs went through kb_shard_slab_own already: the group passes then cover the other sources only)
+        if (ctx->shard_own_done) { if (N > 1) TRY(launch_slab_level(ctx, sp, pl, 1, (const uint64_t*)ctx->recvbuf.p, bufs[1], pend, nullptr, (N - 1) * (j1 - j0), prow, 0, j1 - j0, j0, dps, me)); }
+        else TRY(launch_slab_level(ctx, sp, pl, 1, (const uint64_t*)ctx->recvbuf.p, bufs[1], pend, nullptr, N * (j1 - j0), prow, 0, j1 - j0, j0, dps));
     }
     prof_end(ctx);
     if (group == 0) ctx->alg_rec_bytes += sp.sym ? 12 : 16;
@@ -2480,6 +2519,33 @@ int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group
     prof_begin(ctx, n_groups == 1 ? "K3 bucket hash" : n3[std::min(group, 7)]);
     TRY(launch_hash(ctx, a, hs));
     prof_end(ctx);
+    return KB_OK;
+}
+
+int kb_shard_slab_own(kb_ctx* ctx, const void* gathered_cursors_dev) {
+    if (!ctx || !gathered_cursors_dev) return KB_EINVAL;
+    if (!ctx->configured || !ctx->shard_slab) return fail(ctx, KB_EINVAL, "kb_shard_slab_plan has not been called");
+    const SlabPlan& sp = ctx->shard_sp;
+    PartPlan pl = ctx->shard_plan;
+    if (sp.levels != 2 || sp.cap[0] % KB_PT_TILE != 0) return fail(ctx, KB_EINVAL, "needs a two-level plan with tile-aligned slabs (as digit groups do)");
+    const uint32_t nd0 = sp.nc[0];
+    const uint32_t N = (uint32_t)ctx->shard_n, me = (uint32_t)ctx->shard_index;
+    const uint32_t d_lo = shard_first_digit(me, N, nd0), dps = shard_first_digit(me + 1, N, nd0) - d_lo;
+    const uint32_t np = N * dps;
+    CU(cudaSetDevice(ctx->device));
+    uint8_t* P = (uint8_t*)ctx->plan.p;
+    unsigned long long* pend = (unsigned long long*)(P + sp.off_snap);
+    uint32_t* prow = (uint32_t*)(pend + np);
+    kb_shard_pend_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>((const unsigned long long*)gathered_cursors_dev, N, nd0, d_lo, dps, pend, prow);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync((uint64_t*)ctx->small.p + SM_NRES, 0, 7 * 8, ctx->stream));
+    ctx->launches++;
+    uint64_t* bufs[2] = {(uint64_t*)ctx->entA.p, (uint64_t*)ctx->entB.p};
+    prof_begin(ctx, "K2 partition 1 (own slabs)");
+    // parents = slab (me, j) for every digit j of this shard: q -> me * dps + q
+    if (dps) TRY(launch_slab_level(ctx, sp, pl, 1, (const uint64_t*)ctx->recvbuf.p, bufs[1], pend, nullptr, dps, prow, 0, dps, me * dps, dps));
+    prof_end(ctx);
+    ctx->shard_own_done = true;
     return KB_OK;
 }
 
@@ -2556,8 +2622,12 @@ int kb_extract_sorted(kb_ctx* ctx, int local_index, kb_table** out) {
     const uint64_t pos_hi = local_index + 1 < (int)ctx->file_starts.size() ? ctx->file_starts[local_index + 1] : ctx->n_bases;
     const uint32_t tile0 = (uint32_t)(pos_lo / KB_K1_TB);
     const uint32_t tile1 = (uint32_t)((pos_hi + KB_K1_TB - 1) / KB_K1_TB);
+    if (ctx->opt_strands && !lo.direct) return fail(ctx, KB_EUNSUPPORTED, "strands 1 / 2 (no complements, canonicals): one-word records only (k <= 28)");
     uint64_t n = 0;
-    TRY(run_extract(ctx, lo, tile0, tile1 - tile0, pos_lo, pos_hi, &n));
+    ctx->strands_now = (int)ctx->opt_strands;
+    const int rc_x = run_extract(ctx, lo, tile0, tile1 - tile0, pos_lo, pos_hi, &n);
+    ctx->strands_now = 0;
+    TRY(rc_x);
     uint64_t* sorted = nullptr;
     if (!lo.direct) {
         // multi-word records: K1 wrote them in extraction order; sort their indices by 32-bit chunks of the base bits, least
@@ -2600,6 +2670,14 @@ int kb_extract_sorted(kb_ctx* ctx, int local_index, kb_table** out) {
         return KB_OK;
     }
     TRY(run_sort(ctx, ctx->entA, ctx->entB, n, lo.P, &sorted));
+    if (ctx->opt_strands && n) {                 // every record was written twice: one of each sorted pair stays
+        uint64_t* other = sorted == (uint64_t*)ctx->entA.p ? (uint64_t*)ctx->entB.p : (uint64_t*)ctx->entA.p;
+        n /= 2;
+        kb_every_second_kernel<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->n_sm * 16)), 256, 0, ctx->stream>>>(sorted, other, n);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        sorted = other;
+    }
     kb_table* t = new (std::nothrow) kb_table();
     if (!t) return fail(ctx, KB_ENOMEM, "host allocation failed");
     t->records.resize(n);

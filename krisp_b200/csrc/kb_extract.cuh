@@ -46,6 +46,10 @@ struct KbExtractArgs {
     uint64_t pos_lo, pos_hi;     // only windows starting in [pos_lo, pos_hi) are emitted (one-file tables)
     unsigned long long* hist;    // != null: histogram of digit (element >> hist_shift) & (2^hist_bits - 1), hist_bits <= 9
     uint32_t hist_shift, hist_bits;   // (first partition level of kb_part.cuh, fused here to save a read of the elements)
+    int strand_mode;             // one-word records of the kstream table path: 0 = every window and its reverse complement (_complements,
+                                 // kstream.py:644-677), 1 = the window only (no --complements), 2 = the alphabetically first of the two
+                                 // (_canonicals :679-694).  Modes 1 / 2 still write TWO records per window — the same one twice —
+                                 // so that the tile bookkeeping stays put; the table path keeps every second record after the sort
 };
 
 // 4 ASCII bytes (little-endian in x) -> 8 bits of 2-bit codes (first base in the top bits) and 4 "bad" bits
@@ -212,8 +216,10 @@ __global__ void __launch_bounds__(KB_K1_THREADS * GROUPS) kb_extract_kernel(cons
             if constexpr (DIRECT) {
                 const uint32_t D2 = 2 * lo.D, R2 = 2 * lo.R, K2 = 2 * k;
                 const uint64_t mD = kb_lowmask(D2), mR = kb_lowmask(R2), mK = kb_lowmask(K2);
-                const uint64_t win = kb_get_bits(fwd, 2 * p, K2);
-                const uint64_t rcw = kb_rc64(win << (64 - K2)) & mK;
+                uint64_t win = kb_get_bits(fwd, 2 * p, K2);
+                uint64_t rcw = kb_rc64(win << (64 - K2)) & mK;
+                if (a.strand_mode == 1) rcw = win;
+                else if (a.strand_mode == 2) { win = min(win, rcw); rcw = win; }   // (2-bit codes A < C < G < T: numeric = alphabetical order)
                 uint64_t r[2];
 #pragma unroll
                 for (int st = 0; st < 2; st++) {

@@ -11,9 +11,10 @@
 // Anything the fast path does not reproduce exactly (other whitespace that str.strip() would remove, 'U'/'u' — RNA) only
 // raises a flag; the host layer then re-ingests that input with its line-by-line restatement.
 //
-// Tiles of 4096 bytes.  A byte is inside a header iff the line that contains it starts with '>'.  Three launches per file:
+// Tiles of 4096 bytes.  A byte is inside a header iff the line that contains it starts with '>'.  Three launches per batch of
+// arrived files (KbFastaBatch: up to KB_FA_MAXF files share a launch):
 // (1) kb_fa_count_kernel: last '\n' of every tile + its kept-byte count under BOTH hypotheses for the header state at the tile start;
-// (2) kb_fa_offsets_kernel (one CTA): exclusive prefix-max over tiles -> line start before each tile -> header state at the tile
+// (2) kb_fa_offsets_kernel (one CTA per file): exclusive prefix-max over tiles -> line start before each tile -> header state at the tile
 //     start -> the right count -> exclusive scan = output offset of every tile;
 // (3) kb_fa_pack_kernel<true>: compaction through shared memory, coalesced byte stores.
 #pragma once
@@ -174,11 +175,11 @@ __device__ __forceinline__ KbFaChunk kb_fa_chunk(const KbFastaArgs& a, uint64_t 
 
 // (1) last newline of the tile AND its kept-byte counts for both header states flowing into it: counts[t] (not in a header),
 //      counts[n_tiles + t] (inside a header line)
-__global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_count_kernel(const KbFastaArgs a, uint32_t n_tiles) {
+__device__ __forceinline__ void kb_fa_count_tile(const KbFastaArgs& a, uint32_t n_tiles, uint32_t tile) {
     __shared__ unsigned long long ws[KB_FA_THREADS / 32];
     __shared__ uint32_t wstate[KB_FA_THREADS / 32], wsum0[KB_FA_THREADS / 32], wsum1[KB_FA_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t tile_base = (uint64_t)blockIdx.x * KB_FA_TILE;
+    const uint64_t tile_base = (uint64_t)tile * KB_FA_TILE;
     const KbFaChunk ch = kb_fa_chunk(a, tile_base, tid);
     const KbFaBits m = kb_fa_bits(ch.w, ch.nv, ch.prev_nl, a.fasta);
     unsigned long long last = m.NL ? tile_base + (uint64_t)tid * KB_FA_PER + (32u - (uint32_t)__clz(m.NL)) : 0ULL;   // position + 1, 0 = none
@@ -206,14 +207,14 @@ __global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_count_kernel(const KbFast
     if (tid == 0) {
         unsigned long long mx = 0; uint32_t t0 = 0, t1 = 0;
         for (int w = 0; w < KB_FA_THREADS / 32; w++) { mx = max(mx, ws[w]); t0 += wsum0[w]; t1 += wsum1[w]; }
-        a.last_nl[blockIdx.x] = mx;
-        a.counts[blockIdx.x] = t0;
-        a.counts[n_tiles + blockIdx.x] = t1;
+        a.last_nl[tile] = mx;
+        a.counts[tile] = t0;
+        a.counts[n_tiles + tile] = t1;
     }
 }
 
 // (2) ONE CTA: line start before every tile, header state at its start, the matching count, exclusive scan -> start[0 .. n_tiles]
-__global__ void __launch_bounds__(1024) kb_fa_offsets_kernel(const KbFastaArgs a, uint32_t n_tiles, unsigned long long* start) {
+__device__ __forceinline__ void kb_fa_offsets_file(const KbFastaArgs& a, uint32_t n_tiles, unsigned long long* start) {
     __shared__ unsigned long long ws[32], wc[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t per = (n_tiles + 1023u) / 1024u;
@@ -254,11 +255,11 @@ __global__ void __launch_bounds__(1024) kb_fa_offsets_kernel(const KbFastaArgs a
 
 // (3) compaction.  (WRITE = false: kept bytes per tile only.)
 template <bool WRITE>
-__global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_pack_kernel(const KbFastaArgs a) {
+__device__ __forceinline__ void kb_fa_pack_tile(const KbFastaArgs& a, uint32_t tile) {
     __shared__ uint32_t wstate[KB_FA_THREADS / 32], wsum[KB_FA_THREADS / 32];
     __shared__ __align__(16) uint8_t stage[KB_FA_TILE + 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t tile_base = (uint64_t)blockIdx.x * KB_FA_TILE;
+    const uint64_t tile_base = (uint64_t)tile * KB_FA_TILE;
     const KbFaChunk ch = kb_fa_chunk(a, tile_base, tid);
     const KbFaBits m = kb_fa_bits(ch.w, ch.nv, ch.prev_nl, a.fasta);
     // header state at this thread's first byte: "last line start wins" scan over the threads of the tile
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_pack_kernel(const KbFasta
     for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (uint32_t)d && !(x & 2u)) x = o; }
     if (lane == 31) wstate[warp] = x;
     __syncthreads();
-    uint32_t in = 2u | a.hdr0[blockIdx.x];                               // state flowing into the tile
+    uint32_t in = 2u | a.hdr0[tile];                               // state flowing into the tile
     for (uint32_t w = 0; w < warp; w++) if (wstate[w] & 2u) in = wstate[w];
     const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, x, 1);
     if (lane > 0 && (up & 2u)) in = up;
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_pack_kernel(const KbFasta
     uint32_t add = 0, total = 0;
     for (uint32_t q = 0; q < KB_FA_THREADS / 32; q++) { if (q < warp) add += wsum[q]; total += wsum[q]; }
     if (!WRITE) {
-        if (tid == 0) a.counts[blockIdx.x] = total;
+        if (tid == 0) a.counts[tile] = total;
         if (w.flags) atomicOr(a.flags, w.flags);
         return;
     }
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_pack_kernel(const KbFasta
     __syncthreads();
     // out of the CTA: bytes up to the first 16-byte boundary of the destination, then aligned 16-byte stores assembled from the
     // (differently aligned) staged bytes, then the remainder
-    uint8_t* dst = a.out + a.start[blockIdx.x];
+    uint8_t* dst = a.out + a.start[tile];
     const uint32_t head = min(total, (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
     if (tid < head) dst[tid] = stage[tid];
     const uint32_t nvec = (total - head) / 16u;
@@ -308,4 +309,46 @@ __global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_pack_kernel(const KbFasta
         *reinterpret_cast<uint4*>(dst + so) = ov;
     }
     for (uint32_t i = head + 16u * nvec + tid; i < total; i += KB_FA_THREADS) dst[i] = stage[i];
+}
+
+// ---- launches: the files of one arrived batch share each of the three launches (<= KB_FA_MAXF files per launch) -----------------
+#define KB_FA_MAXF 8
+struct KbFastaBatch {
+    int n_files;
+    uint32_t tile0[KB_FA_MAXF + 1];              // first tile of every file in the grid of the tile kernels
+    unsigned long long* start_w[KB_FA_MAXF];     // = f[i].start, writable for the offsets kernel
+    KbFastaArgs f[KB_FA_MAXF];
+};
+
+// file and file-relative tile of grid tile `g` (field-by-field selects: no dynamic indexing into the parameter space)
+__device__ __forceinline__ KbFastaArgs kb_fa_locate(const KbFastaBatch& b, uint32_t g, uint32_t& tile, uint32_t& n_tiles) {
+    KbFastaArgs a = b.f[0];
+    uint32_t t0 = b.tile0[0], t1 = b.tile0[1];
+#pragma unroll
+    for (int i = 1; i < KB_FA_MAXF; i++)
+        if (i < b.n_files && g >= b.tile0[i]) { a = b.f[i]; t0 = b.tile0[i]; t1 = b.tile0[i + 1]; }
+    tile = g - t0; n_tiles = t1 - t0;
+    return a;
+}
+
+__global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_count_kernel(const KbFastaBatch b) {
+    uint32_t tile, n_tiles;
+    const KbFastaArgs a = kb_fa_locate(b, blockIdx.x, tile, n_tiles);
+    kb_fa_count_tile(a, n_tiles, tile);
+}
+
+__global__ void __launch_bounds__(1024) kb_fa_offsets_kernel(const KbFastaBatch b) {                 // one CTA per file
+    KbFastaArgs a = b.f[0];
+    unsigned long long* start = b.start_w[0];
+    uint32_t n_tiles = b.tile0[1] - b.tile0[0];
+#pragma unroll
+    for (int i = 1; i < KB_FA_MAXF; i++)
+        if ((int)blockIdx.x == i) { a = b.f[i]; start = b.start_w[i]; n_tiles = b.tile0[i + 1] - b.tile0[i]; }
+    kb_fa_offsets_file(a, n_tiles, start);
+}
+
+__global__ void __launch_bounds__(KB_FA_THREADS) kb_fa_pack_kernel(const KbFastaBatch b) {
+    uint32_t tile, n_tiles;
+    const KbFastaArgs a = kb_fa_locate(b, blockIdx.x, tile, n_tiles);
+    kb_fa_pack_tile<true>(a, tile);
 }

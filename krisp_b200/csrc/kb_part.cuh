@@ -49,8 +49,10 @@ struct KbPartArgs {
     const unsigned long long* pend;     // != null: parent p = elements [p * pcap, min(pend[p], (p + 1) * pcap)) of `in` (pstart unused)
     const unsigned long long* pbegin;   // != null (with pend): only the segment from pbegin[p] on — what a batch of input files appended to the slab
     uint64_t pcap;
-    uint32_t psel_n, psel_j0, psel_dps;  // psel_n != 0 (tile-by-division mode): the q-th parent of this launch is slab (q / psel_n) * psel_dps + psel_j0 + q % psel_n
-                                        // (multi-GPU: the slabs (source rank, digit j0 .. j0 + n) of one group of level-0 digits)
+    uint32_t psel_n, psel_j0, psel_dps;  // psel_n != 0 (tile-by-division mode): the q-th parent of this launch is slab src * psel_dps + psel_j0 + q % psel_n,
+    uint32_t psel_skip;                 // src = q / psel_n, + 1 from psel_skip on (psel_skip = 0xFFFFFFFF: no source is left out)
+                                        // (multi-GPU: the slabs (source rank, digit j0 .. j0 + n) of one group of level-0 digits; this rank's own
+                                        //  slabs, resident since K1, go through a launch of their own before the first group has arrived)
     uint64_t ccap;                      // != 0: child c owns [c * ccap, (c + 1) * ccap) of `out` (its cursor starts at c * ccap); a run that
     unsigned long long* ovf;            // does not fit is dropped and *ovf is raised (the host repeats the search on the exact path)
 };
@@ -72,7 +74,12 @@ __device__ __forceinline__ bool kb_part_tile(const KbPartArgs& a, uint32_t tile,
         const uint32_t tpp = (uint32_t)(a.pcap / KB_PT_TILE);
         const uint32_t q = tile / tpp;
         if (q >= a.n_parents) return false;
-        const uint32_t parent = a.psel_n ? (q / a.psel_n) * a.psel_dps + a.psel_j0 + q % a.psel_n : q;
+        uint32_t parent = q;
+        if (a.psel_n) {
+            uint32_t src = q / a.psel_n;
+            if (src >= a.psel_skip) src++;
+            parent = src * a.psel_dps + a.psel_j0 + q % a.psel_n;
+        }
         uint64_t ps, pe;
         kb_part_parent(a, parent, ps, pe);
         s = ps + (uint64_t)(tile - q * tpp) * KB_PT_TILE;

@@ -11,6 +11,7 @@
 #include "kb_common.cuh"
 
 struct KbRowsArgs {
+    const uint32_t* rank;        // != null: [n] row of survivor g (kb_rank_kernel); else `order` is used
     const uint64_t* order;       // [n] sorted elements, low 32 bits = survivor index
     uint64_t n;
     const uint64_t* flank;       // [n][FW]
@@ -27,7 +28,8 @@ __global__ void __launch_bounds__(256) kb_rows_kernel(const KbRowsArgs a) {
     for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (uint64_t)gridDim.x * 256) {
         const uint64_t r = t / width;
         const uint32_t p = (uint32_t)(t % width);
-        const uint64_t g = a.order[r] & 0xFFFFFFFFULL;
+        const uint64_t g = a.rank ? r : (a.order[r] & 0xFFFFFFFFULL);           // ranks: walk the survivors, write row rank[g]
+        const uint64_t dst = a.rank ? (uint64_t)a.rank[r] * width + p : t;
         char ch;
         if (p == (uint32_t)a.L || p == (uint32_t)(a.L + 1 + a.D)) ch = ',';
         else if (p == width - 1) ch = '\n';
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(256) kb_rows_kernel(const KbRowsArgs a) {
             const uint64_t w = a.flank[g * a.FW + (b >> 5)];
             ch = "ACGT"[(w >> (62 - 2 * (b & 31))) & 3ULL];
         }
-        a.out[t] = ch;
+        a.out[dst] = ch;
     }
 }
 
@@ -51,15 +53,16 @@ __global__ void __launch_bounds__(256) kb_iota_kernel(uint64_t* ent, uint64_t n)
 
 // Few survivors (the usual case: thousands of rows out of 1e8 records): their order by flank words comes from counting, one launch
 // instead of the chunked LSD sort's twenty — rank(i) = #{j : flank[j] < flank[i]} (+ ties by index; flank keys of one search are
-// distinct anyway).  Every thread owns one survivor and walks all of them through shared memory (all lanes read the same element:
-// broadcast).  n <= KB_RANK_MAX keeps the n^2 walk in the microseconds.
+// distinct anyway).  Every thread owns one survivor and walks a slice of all of them through shared memory (all lanes read the same
+// element: broadcast; the slices of the CTA rows add up with one atomic each).  n <= KB_RANK_MAX keeps the n^2 walk in the microseconds.
 #define KB_RANK_MAX 8192
 #define KB_RANK_THREADS 128
 
 struct KbRankArgs {
     const uint64_t* flank;       // [n][FW]
     uint32_t n;
-    uint64_t* order;             // [n] order[rank] = survivor index
+    uint32_t slice;              // survivors j every CTA row (blockIdx.y) compares against: [y * slice, (y + 1) * slice)
+    uint32_t* rank;              // [n] zeroed; every CTA row adds its share
 };
 
 template <int FW>
@@ -70,14 +73,15 @@ __global__ void __launch_bounds__(KB_RANK_THREADS) kb_rank_kernel(const KbRankAr
 #pragma unroll
     for (int w = 0; w < FW; w++) mine[w] = i < a.n ? a.flank[(uint64_t)i * FW + w] : 0ULL;
     uint32_t rank = 0;
-    for (uint32_t base = 0; base < a.n; base += KB_RANK_THREADS) {
+    const uint32_t j0 = blockIdx.y * a.slice, j1 = min(a.n, j0 + a.slice);
+    for (uint32_t base = j0; base < j1; base += KB_RANK_THREADS) {
         __syncthreads();
         const uint32_t j = base + tid;
 #pragma unroll
-        for (int w = 0; w < FW; w++) tile[w][tid] = j < a.n ? a.flank[(uint64_t)j * FW + w] : 0ULL;
+        for (int w = 0; w < FW; w++) tile[w][tid] = j < j1 ? a.flank[(uint64_t)j * FW + w] : 0ULL;
         __syncthreads();
-        const uint32_t cnt = min((uint32_t)KB_RANK_THREADS, a.n - base);
-#pragma unroll 4
+        const uint32_t cnt = min((uint32_t)KB_RANK_THREADS, j1 - base);
+#pragma unroll 8
         for (uint32_t jj = 0; jj < cnt; jj++) {
             bool less = false, eq = true;
 #pragma unroll
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(KB_RANK_THREADS) kb_rank_kernel(const KbRankAr
             rank += (less || (eq && base + jj < i)) ? 1u : 0u;
         }
     }
-    if (i < a.n) a.order[rank] = i;
+    if (i < a.n && rank) atomicAdd(a.rank + i, rank);
 }
 
 // The survivor table's columns (flank words, base sets, sizes, runs) copied into ONE staging image laid out like the host's result

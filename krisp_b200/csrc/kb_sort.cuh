@@ -303,3 +303,9 @@ __global__ void __launch_bounds__(256) kb_table_gather_kernel(const KbTableGathe
         a.out[t] = a.recs[(a.ent[i] & 0xFFFFFFFFULL) * a.W + j];
     }
 }
+
+// kstream tables without --complements / with --canonicals: K1 wrote every record twice (KbExtractArgs.strand_mode), the sort left
+// the copies next to each other: keep one of each pair.
+__global__ void __launch_bounds__(256) kb_every_second_kernel(const uint64_t* in, uint64_t* out, uint64_t n_out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n_out; i += (uint64_t)gridDim.x * 256) out[i] = in[2 * i];
+}

@@ -1,13 +1,22 @@
 """``kstream`` on the B200 path: one file's sorted k-mer table.
 
-Mirrors the reference's ``kstream`` class / CLI (kstream/kstream.py:122-248, :835-952) for the
-configuration ``krisp_fasta`` drives it with (``extractSortedKmers``, krisp_fasta/krisp_fasta.py:16-43):
-``kmers=k, complements=True, disallow="Nn", mapsoft | omitsoft, split=[L,-R], sort=True, sortcols=[0,2]``.
-That configuration is one K1 launch + one radix sort on the device (``kb_extract_sorted``; for k > 28 an
-LSD sort of the record indices over 32-bit chunks of the multi-word records); the lines come back in the
-reference's ``LC_ALL=C sort -t, -k1,1 -k3,3`` order.  Other option combinations
-(``--canonicals``, ``--allow``, ``--expand-iupac``, several k, unsorted streaming) are the reference's
-generic text pipeline and are not on the hot path: they raise ``UnsupportedError`` here (no CPU fallback).
+Mirrors the reference's ``kstream`` class / CLI (kstream/kstream.py:122-248, :835-952) for the sorted tables the device
+produces — one K1 launch + one radix sort (``kb_extract_sorted``; for k > 28 an LSD sort of the record indices over 32-bit
+chunks of the multi-word records):
+
+* the configuration ``krisp_fasta`` drives it with (``extractSortedKmers``, krisp_fasta/krisp_fasta.py:16-43):
+  ``kmers=k, complements=True, disallow="Nn", mapsoft | omitsoft, split=[L,-R], sort=True, sortcols=[0,2]`` — lines in the
+  reference's ``LC_ALL=C sort -t, -k1,1 -k3,3`` order;
+* the strand choices: ``complements`` (windows + reverse complements, :644-677), neither (kstream's default: the windows only),
+  ``canonicals`` (the alphabetically first of the two, :679-694) — the last two for k <= 28;
+* no ``split`` (whole k-mers, plain ``LC_ALL=C sort``);
+* ``allow`` = A, C, G, T (any case): exactly what the 2-bit records can hold, so no k-mer is lost or kept differently from the
+  reference; ``disallow`` = letters outside ACGT (e.g. "Nn"; other IUPAC letters then break k-mers here while the reference
+  keeps them: divergence E1).
+
+What stays the reference's generic text pipeline and raises ``UnsupportedError`` here (no CPU fallback): unsorted streaming
+(the device emits records in tile order), several k at once, ``expandiupac``, neither ``mapsoft`` nor ``omitsoft`` (lower-case
+letters kept as such), ``allow`` sets with other letters, other ``split`` / ``sortcols`` shapes.
 """
 import argparse
 import sys
@@ -58,27 +67,40 @@ class kstream:
         self.omitsoft = bool(omitsoft)
         self.device = device
         why = None
+        up = lambda chars: {c for c in chars if not c.islower()}                       # (k-mers are upper case by the time allow / disallow see them)
         if self.kmers is None or len(self.kmers) != 1:
             why = "exactly one k-mer length"
-        elif not complements or canonicals:
-            why = "complements=True"
-        elif allow is not None or expandiupac:
-            why = "no allow / expandiupac"
-        elif disallow is None or set(disallow) != set("Nn"):
-            why = 'disallow="Nn"'
+        elif expandiupac:
+            why = "no expandiupac"
+        elif allow is not None and up(allow) != set("ACGT"):
+            why = 'allow="ACGT"'
+        elif allow is None and (disallow is None or up(disallow) & set("ACGT") or "N" not in up(disallow)):
+            why = 'disallow="Nn" (letters outside ACGT) or allow="ACGT"'
+        elif allow is not None and disallow is not None and up(disallow) & set("ACGT"):
+            why = "disallow without A, C, G, T"
         elif not (omitsoft or mapsoft):
             why = "mapsoft or omitsoft"
-        elif self.split is None or len(self.split) != 2 or self.split[0] < 0 or self.split[1] > 0:
-            why = "split=[L,-R]"
-        elif not sort or (sortcols is not None and list(sortcols) != [0, 2]):
-            why = "sort=True, sortcols=[0,2]"
+        elif self.split is not None and (len(self.split) != 2 or self.split[0] < 0 or self.split[1] > 0):
+            why = "split=[L,-R] or no split"
+        elif not sort:
+            why = "sort=True"
+        elif self.split is not None and (sortcols is None or list(sortcols) != [0, 2]):
+            why = "sortcols=[0,2] with split=[L,-R]"
+        elif self.split is None and sortcols is not None and list(sortcols) != [0]:
+            why = "no sortcols without split"
         if why:
-            raise UnsupportedError(KB_EUNSUPPORTED, f"krisp_b200.kstream implements the krisp_fasta configuration only ({why})")
+            raise UnsupportedError(KB_EUNSUPPORTED, f"krisp_b200.kstream builds sorted tables on the device only ({why})")
         k = self.kmers[0]
-        self.L, self.R = self.split[0], -self.split[1]
+        self.strands = 0 if complements else (2 if canonicals else 1)
+        if self.split is None:
+            self.L, self.R = k, 0                                                      # whole k-mers: the sort key is the k-mer
+        else:
+            self.L, self.R = self.split[0], -self.split[1]
         self.D = k - self.L - self.R
         if self.D < 0:
             raise ValueError("split lengths exceed the k-mer length")
+        if self.strands and 2 * k + 8 > 64:
+            raise UnsupportedError(KB_EUNSUPPORTED, "krisp_b200.kstream: tables without complements / with canonicals need k <= 28")
 
     def _table(self, sequences):
         if sequences is None:
@@ -101,6 +123,7 @@ class kstream:
         s = Searcher(self.device)
         try:
             s.configure(self.L, self.D, self.R, [1], omit_soft=self.omitsoft)
+            s.set_option("strands", self.strands)
             s.clear_sequences()
             s.add_sequence(0, packed)
             recs = s.extract_sorted(0)
@@ -108,9 +131,13 @@ class kstream:
             s.close()
         return recs, rna
 
+    def _lines(self, recs, rna):
+        lines = decode_table(recs, self.L, self.D, self.R, rna)
+        return [ln[:self.L] for ln in lines] if self.split is None else lines          # (no split: the bare k-mer)
+
     def __call__(self, sequences):
         recs, rna = self._table(sequences)
-        return iter(decode_table(recs, self.L, self.D, self.R, rna))
+        return iter(self._lines(recs, rna))
 
     def __iter__(self):
         return iter(self.__call__(self.sequences))
@@ -118,7 +145,7 @@ class kstream:
     def write(self, filename, sequences=None):
         """Write the sorted table to `filename`; returns the number of lines (kstream.py:250-325)."""
         recs, rna = self._table(self.sequences if sequences is None else sequences)
-        lines = decode_table(recs, self.L, self.D, self.R, rna)
+        lines = self._lines(recs, rna)
         with open(filename, "w") as fh:
             for ln in lines:
                 fh.write(ln)

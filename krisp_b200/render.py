@@ -260,3 +260,81 @@ def render_output(res, labels, ingroup=None, out_csv=None, out_align=None, dot=F
                     block = annotate_alignment(block, p3s[i], dot)
                 print(block, file=fh)
     return n_rows
+
+
+# ---- the renderer stage on an interchange FILE (host; survivors only) ---------------------------------------------------------------
+_IUPAC_OF = {frozenset("A"): "A", frozenset("C"): "C", frozenset("G"): "G", frozenset("T"): "T", frozenset("AC"): "M", frozenset("AG"): "R",
+             frozenset("AT"): "W", frozenset("CG"): "S", frozenset("CT"): "Y", frozenset("GT"): "K", frozenset("ACG"): "V", frozenset("ACT"): "H",
+             frozenset("AGT"): "D", frozenset("CGT"): "B", frozenset("ACGT"): "N"}
+
+
+def _collapse(seqs):
+    """collapse_to_iupac (Amplicon.py:42-66) for equally long strings over ACGT (+ N / * / ? -> N)."""
+    out = []
+    for col in zip(*seqs):
+        c = frozenset(col)
+        out.append("N" if c & frozenset("N*?") else _IUPAC_OF[c])
+    return "".join(out)
+
+
+def read_interchange(kmerfile):
+    """Groups of an interchange file (``left,mid,right,label(n);...`` lines, equal (left, right) adjacent: alignmentStream,
+    shared.py:442-475): [((left, right), [(mid, [label, ...]), ...]), ...] in file order."""
+    import re
+    groups = []
+    with open(kmerfile) as fh:
+        for ln in fh:
+            ln = ln.rstrip("\n")
+            if not ln:
+                continue
+            left, mid, right, labs = ln.split(",")
+            labels = []
+            for item in labs.split(";"):
+                m = re.fullmatch(r"(.+?)(?:\((\d+)\))?", item)
+                labels.extend([m.group(1)] * int(m.group(2) or 1))
+            if not groups or groups[-1][0] != (left, right):
+                groups.append(((left, right), []))
+            groups[-1][1].append((mid, labels))
+    return groups
+
+
+def render_output_file(kmerfile, out_align=None, out_csv=None, cores=1, print_block=10, ingroup=None, find_primers=False, dot=False, p3_args=None):
+    """``render_output(kmerfile, ...)`` of the reference (outputAlignments.py:101-162) on an interchange file — e.g. the one
+    ``write_interchange`` wrote, or the reference's own ``filtered.txt``: CSV rows (header first; stdout when out_csv is None), the
+    alignment file when asked for, Primer3 post-filter when asked for.  Returns the number of regions written.  `cores` and
+    `print_block` are accepted for compatibility (one process; the reference's row order with --cores 1).  `dot` stands for the
+    reference's class-wide ``ConservedEndAmplicons.ENABLE_DOT`` switch (krisp_fasta.py:215)."""
+    ing = frozenset(ingroup) if ingroup is not None else None
+    rows, blocks = [], []
+    for (left, right), amps in read_interchange(kmerfile):
+        pick = amps
+        if len(amps) > 1 and ing is not None:                          # render_csv, Amplicon.py:663-671: one amplicon -> its own sequence
+            pick = [(m, labs) for m, labs in amps if set(labs) <= ing]
+        cons = _collapse([m for m, _ in pick]) if pick and len(amps[0][0]) else ""
+        row = f"{left},{cons},{right}"
+        p3 = None
+        if find_primers:
+            p3 = run_primer3(left + cons + right, target_start=len(left), target_len=len(cons), **(p3_args or {}))
+            if p3["PRIMER_PAIR_NUM_RETURNED"] == 0:
+                continue
+            row += "," + ",".join(str(p3[n]) for n in P3_COLS)
+        rows.append(row)
+        if out_align is not None:
+            merged = {}
+            for m, labs in amps:
+                merged.setdefault(m, []).extend(labs)
+            block = render_alignment(left, right, merged, ing, dot)
+            blocks.append(annotate_alignment(block, p3, dot) if p3 is not None else block)
+    stream = sys.stdout if out_csv is None else open(out_csv, "w")
+    try:
+        stream.write(CSV_HEADER + ("," + ",".join(P3_KEYS) if find_primers else "") + "\n" + "".join(r + "\n" for r in rows))
+    finally:
+        if out_csv is not None:
+            stream.close()
+    if out_align is not None:
+        if os.path.isfile(out_align):
+            os.remove(out_align)
+        with open(out_align, "a") as fh:
+            for b in blocks:
+                print(b, file=fh)
+    return len(rows)

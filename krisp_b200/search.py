@@ -416,6 +416,10 @@ class Searcher:
         self._check(self._L.kb_shard_slab_buffers(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(w)))
         return int(a.value or 0), int(b.value or 0), int(c.value), bool(w.value)
 
+    def shard_slab_own(self, gathered_ptr):
+        """Partition level 1 on the slabs this rank filled itself (complete when K1 ends), ahead of the first digit group."""
+        self._check(self._L.kb_shard_slab_own(self._ctx, ctypes.c_void_p(int(gathered_ptr))))
+
     def shard_slab_level(self, gathered_ptr, group, n_groups):
         """Partition level 1 + bucket hash on one digit group of the receive buffer."""
         self._check(self._L.kb_shard_slab_level(self._ctx, ctypes.c_void_p(int(gathered_ptr)), int(group), int(n_groups)))

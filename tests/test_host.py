@@ -317,3 +317,29 @@ def test_primer3_post_filter_wiring(tmp_path, monkeypatch):
     assert "Pair statistics:" in text
     dot = render.annotate_alignment(render.render_alignment("ACGA", "GTGAA", {"AAT": ["a"], "CCA": ["b"]}, frozenset(["a"]), True), p3, True).split("\n")
     assert dot[1].startswith("....CCA..... : b") and dot[2] == "└Forward┘    └Reverse┘"
+
+
+def test_render_output_file_reproduces_reference_rows_and_alignments(tmp_path):
+    """The renderer stage on a FILE (render.render_output_file = render_output(kmerfile, ...), outputAlignments.py:101-162): fed the
+    reference's own filtered.txt / merged_file.txt (tests/golden/interchange.json) it writes the reference's CSV rows and, where
+    the golden case has it, the reference's --out_align text."""
+    import json
+    from krisp_b200.names import simplename
+    with open(os.path.join(GOLDEN_DIR, "interchange.json")) as fh:
+        inter = json.load(fh)
+    checked_align = 0
+    for name, text in inter.items():
+        case = next(c for c in _G["cases"] if c["name"] == name)
+        if "rows" not in case:
+            continue
+        src = tmp_path / f"{name}.txt"
+        src.write_text(text)
+        ingroup = [simplename(p) for p in case["ingroup"]] if case["outgroup"] else None
+        csv, align = tmp_path / f"{name}.csv", tmp_path / f"{name}.align"
+        n = render.render_output_file(str(src), out_align=str(align) if "out_align" in case else None, out_csv=str(csv), ingroup=ingroup, dot=case["dot"])
+        lines = csv.read_text().splitlines()
+        assert lines[0] == render.CSV_HEADER and sorted(lines[1:]) == case["rows"] and n == len(case["rows"]), name
+        if "out_align" in case:
+            assert align.read_text() == case["out_align"], name
+            checked_align += 1
+    assert checked_align >= 1
