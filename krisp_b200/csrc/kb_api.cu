@@ -1722,7 +1722,14 @@ static int launch_slab_level(kb_ctx* ctx, const SlabPlan& sp, const PartPlan& pl
     const bool by_division = !pbegin && sp.cap[l - 1] % KB_PT_TILE == 0;
     uint64_t grid = (uint64_t)n_parents * (sp.cap[l - 1] / KB_PT_TILE);
     if (by_division) { a.ptile0 = nullptr; a.tile_parent = nullptr; }
-    else {
+    else if (n_parents <= KB_PLAN_BLOCK) {
+        // few parents (the level-0 slabs of a batch of files): counts, tile prefix and tile map in one single-CTA launch
+        kb_slab_plan_fused_kernel<<<1, KB_PLAN_BLOCK, 0, ctx->stream>>>(pend, pbegin, n_parents, a.pcap, (unsigned long long*)(P + sp.off_start),
+                                                                        (uint32_t*)(P + sp.off_tile0[l - 1]), (uint32_t*)(P + sp.off_tilemap));
+        CU(cudaGetLastError());
+        ctx->launches++;
+        grid = rec_bound / KB_PT_TILE + n_parents + 1;
+    } else {
         unsigned long long* counts = (unsigned long long*)(P + sp.off_counts);
         kb_slab_counts_kernel<<<(unsigned)std::min<uint32_t>((n_parents + 255) / 256, 1024), 256, 0, ctx->stream>>>(pend, pbegin, n_parents, a.pcap, counts);
         CU(cudaGetLastError());

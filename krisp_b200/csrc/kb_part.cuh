@@ -383,5 +383,33 @@ __global__ void __launch_bounds__(256) kb_slab_counts_kernel(const unsigned long
     }
 }
 
+// kb_slab_counts_kernel + kb_plan_{reduce,scan,apply}_kernel + kb_tilemap_kernel in ONE launch for up to KB_PLAN_BLOCK parents (one
+// CTA): segment sizes of the parents -> exclusive prefix of their tile counts (tile0) -> tile -> parent map.  This is the planner
+// of level 1 per batch of arriving files, where five tiny launches per batch were a tenth of the batch's GPU time.
+__global__ void __launch_bounds__(KB_PLAN_BLOCK) kb_slab_plan_fused_kernel(const unsigned long long* cursor, const unsigned long long* begin, uint32_t nc, uint64_t cap,
+                                                                           unsigned long long* start, uint32_t* tile0, uint32_t* tile_parent) {
+    __shared__ unsigned long long ws[32], wt[32];
+    __shared__ uint32_t st0[KB_PLAN_BLOCK + 1];
+    const uint32_t i = threadIdx.x;
+    unsigned long long v = 0;
+    if (i < nc) {
+        unsigned long long s = (unsigned long long)i * cap;
+        const unsigned long long e = min(cursor[i], s + cap);
+        if (begin) s = max(s, begin[i]);
+        v = e > s ? e - s : 0ULL;
+    }
+    const unsigned long long t = (v + KB_PT_TILE - 1) / KB_PT_TILE;
+    unsigned long long x = v, y = t, tx, ty;
+    kb_block_scan2(x, y, ws, wt, tx, ty);
+    if (i < nc) { start[i] = x - v; tile0[i] = (uint32_t)(y - t); st0[i] = (uint32_t)(y - t); }
+    if (i + 1 == nc) { start[nc] = x; tile0[nc] = (uint32_t)y; st0[nc] = (uint32_t)y; }
+    __syncthreads();
+    const uint32_t lane = i & 31;
+    for (uint32_t p = i >> 5; p < nc; p += KB_PLAN_BLOCK / 32) {
+        const uint32_t t0 = st0[p], t1 = st0[p + 1];
+        for (uint32_t q = t0 + lane; q < t1; q += 32) tile_parent[q] = p;
+    }
+}
+
 static inline size_t kb_part_smem() { return (size_t)KB_PT_TILE * 8 + KB_PT_MAXR * 8 + KB_PT_MAXR * 4 + (KB_PT_MAXR / 32) * 4 + 16; }
 static_assert(KB_PT_THREADS >= KB_PT_MAXR, "one thread per digit");

@@ -296,9 +296,11 @@ class Searcher:
             n, FW, MW, W = int(view.n_groups), int(view.flank_words), int(view.mask_words), int(view.record_words)
 
             def arr(ptr, count, dtype):
+                # one memcpy out of the library's arena (np.ctypeslib.as_array costs ~40 us per call — five of them per search
+                # were most of the host time between two searches)
                 if count == 0:
                     return np.zeros(0, dtype=dtype)
-                return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+                return np.frombuffer(bytearray(ctypes.string_at(ptr, count * np.dtype(dtype).itemsize)), dtype=dtype)
 
             flank = arr(view.flank, n * FW, np.uint64).reshape(n, FW)
             out = SearchResult(L=L, D=D, R=R, n_records=int(view.n_records), have_outgroup=have_outgroup)
