@@ -11,8 +11,9 @@ rank ingests its files (round-robin), and the level-0 slabs travel once to the G
 copies over NVLink, digit group by digit group, while the owner already works on the previous group (krisp_b200/sharded.py).
 
 `value`   : panel bases / device time of K steps, sequences already resident in HBM.
-`e2e`     : same through the C ABI with pinned HOST buffers: H2D of every base, D2H of the survivor table and of the rows (which
-            arrive as text, rendered and ordered on the device) inside the timed region.
+`e2e`     : same through the C ABI from RAW FASTA FILE BYTES in pinned host memory (kb_add_fasta): H2D of every byte, de-lining on the
+            device, one D2H of the result image (survivor table + the rows, which arrive as text, rendered and ordered on the device)
+            inside the timed region; `e2e.parsed_sequences` = the same from already parsed sequences (kb_add_sequence).
 `roofline`: the kernel family with the largest share of the step; `kernel_families` lists all of them; `whole_step` = as-built
             algorithmic bytes of the whole search / device time.
 `parity`  : (N>1) before timing, a sharded search of a panel small enough for the CPU oracle (25/1/2 and 32/60/32) is compared with
@@ -449,9 +450,9 @@ def run_ours(args):
              "frac_of_peak_at_round1_bytes": (w.h2d_bytes + 48.0 * n_rec) / (m["ms"] * 1e-3) / 1e9 / peak}
 
     if args.diag and world > 1:
-        variants = [("default", {}, {}), ("own_first=0", {"KRISP_OWN_FIRST": "0"}, {}), ("groups=4", {"KRISP_SLAB_GROUPS": "4"}, {}),
-                    ("groups=16", {"KRISP_SLAB_GROUPS": "16"}, {}), ("groups=2", {"KRISP_SLAB_GROUPS": "2"}, {}),
-                    ("records (sym=0)", {}, {"sym": 0}), ("a2a", {"KRISP_SLAB_EXCHANGE": "a2a"}, {})]
+        variants = [("default", {}, {}), ("copy_streams=1", {"KRISP_COPY_STREAMS": "1"}, {}), ("copy_streams=2", {"KRISP_COPY_STREAMS": "2"}, {}),
+                    ("copy_streams=3", {"KRISP_COPY_STREAMS": "3"}, {}), ("groups=8", {"KRISP_SLAB_GROUPS": "8"}, {}),
+                    ("groups=8, copy_streams=2", {"KRISP_SLAB_GROUPS": "8", "KRISP_COPY_STREAMS": "2"}, {}), ("own_first=0", {"KRISP_OWN_FIRST": "0"}, {})]
         os.environ["KRISP_TIMELINE"] = "1"
         for name, env, opts in variants:
             for k, v in env.items():

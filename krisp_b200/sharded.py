@@ -1,20 +1,25 @@
 """Multi-GPU search: one process per GPU, records sharded by the top bits of the mixed flank key.
 
 Every rule of the search is local to one (left,right) key, so after ONE exchange step the GPUs are
-independent:
+independent.  Three exchanges, all between library-owned device buffers:
 
-  0. all ranks agree on the partition plan (``kb_shard_plan``: same shard count, same total size);
-  1. each rank ingests its own subset of the input files and runs K1 + partition level 0
-     (``kb_shard_extract``): records grouped by level-0 digit, hence by owner shard (contiguous digit ranges);
-  2. counts all-to-all, per-digit counts all-gather, then the records all-to-all
-     (``torch.distributed.all_to_all_single`` over NCCL / NVLink; ``gloo`` in the CPU tests) straight between
-     library-owned device buffers;
-  3. each rank runs the remaining partition levels and the bucket hash on its shard (``kb_shard_search``); the
-     (source rank, digit) pieces it received are the parents of level 1; survivor rows are gathered on rank 0
-     (set semantics: no ordering step).
+``slab_search`` (default; one-word records):
+  1. all ranks derive the same plan (``kb_shard_slab_plan``); each rank ingests its own files and runs K1 fused with partition
+     level 0 (``kb_shard_slab_extract``): every level-0 digit's records sit in a fixed-capacity slab laid out as in the owner's
+     receive buffer — no count exchange before the data;
+  2. the slab fill levels are all-gathered on the device; level 1 of the rank's OWN slabs starts at once (``kb_shard_slab_own``);
+  3. digit groups travel as bulk peer copies (copy engines over NVLink, CUDA IPC mappings) behind each other on a copy stream, a
+     tiny all-reduce per group on a vote stream says "landed everywhere";
+  4. level 1 + bucket hash per group on the owner (``kb_shard_slab_level``) while the next group is in flight;
+  5. ``kb_shard_slab_finish`` + an all-reduce of the status: re-plan (divergent genomes), slab overflow (-> exact exchange) and a grown
+     survivor table are decided by all ranks alike.
+``direct_search`` (multi-word records; slab overflow): K1 with the level-0 histogram, digit counts all-gathered, partition level 0 =
+  peer stores straight into the owners' buffers (``kb_shard_scatter``), then ``kb_shard_search``.
+``exchange_mode="nccl"``: local partition + ``all_to_all_single`` (also what the gloo CPU tests drive, with a test double).
 
-The reference has no counterpart (it is single-host multiprocessing, krisp_fasta.py:86-123); the file
-fan-out mirrors ``sortedKmersParallel``: files are independent extraction units.
+Survivor rows of different ranks are disjoint (set semantics: concatenate and sort, ``gather_rows``).  The reference has no
+counterpart (it is single-host multiprocessing, krisp_fasta.py:86-123); the file fan-out mirrors ``sortedKmersParallel``: files
+are independent extraction units.
 """
 import os
 import sys
@@ -241,7 +246,12 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
         main = torch.cuda.current_stream(device)
         # streams: `side` carries nothing but the bulk copies, back to back; `vote` carries the tiny collectives ("every rank's copies
         # of group g have landed"), so that a collective waiting for a free SM never holds up the next group's copies
-        n_copy = max(1, min(world - 1, int(os.environ.get("KRISP_COPY_STREAMS", "1"))))   # copy streams, each serving some of the peers
+        # copy streams (= copy engines working at once; KRISP_COPY_STREAMS).  Two GPUs: the one peer's copy is cut into byte ranges;
+        # more: every stream serves some of the peers.  The streams stay in step group by group (below), so that group g is complete
+        # before anybody spends bandwidth on group g + 1.  One stream is the default: on 2 GPUs 1 / 2 / 3 streams land a 400 MB group
+        # every 0.82 ms alike (~480 GB/s each way while level 1 and the bucket hash run) — the engines are not what limits it.
+        n_copy = int(os.environ.get("KRISP_COPY_STREAMS", "1"))
+        n_copy = max(1, min(n_copy, 4 if world == 2 else world - 1))
         sides = searcher.__dict__.setdefault("_copy_streams", [])
         while len(sides) < 1 + n_copy:
             sides.append(torch.cuda.Stream(device=device))
@@ -291,12 +301,19 @@ def slab_search(searcher, device, have_outgroup=True, group=None, total_bases=No
                     e.record(side)
                     landed.append(e)
         else:
+            prev = []
             for g in range(n_groups):
+                cur = []
                 for i, cs in enumerate(copies):
-                    searcher.shard_slab_send(g, n_groups, cs.cuda_stream, i, -n_copy)
+                    for j, e in enumerate(prev):
+                        if j != i:
+                            cs.wait_event(e)                           # the other streams' share of group g - 1 first
+                    searcher.shard_slab_send(g, n_groups, cs.cuda_stream, i, n_copy if world == 2 else -n_copy)
                     sent = torch.cuda.Event()
                     sent.record(cs)
                     vote.wait_event(sent)
+                    cur.append(sent)
+                prev = cur if n_copy > 1 else []
                 with torch.cuda.stream(vote):
                     dist.all_reduce(flag, group=group)
                     e = torch.cuda.Event(enable_timing=True)
