@@ -173,6 +173,28 @@ _FAMILIES = {
 }
 
 
+def ncu_traffic(kname, n_rec):
+    """DRAM bytes (read + written) of one launch of the kernel from the committed ncu capture (profiles/r05_kernel_traffic.json) — only
+    while the kernel's source files are still the ones that were profiled (sha256), and only for the headline workload it was taken on."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "r05_kernel_traffic.json")) as fh:
+            doc = json.load(fh)
+        if int(n_rec) != int(doc["records_per_launch"]):
+            return None, "the ncu capture in profiles/r05_kernel_traffic.json is of the headline workload (panel C2 on one GPU), not of this one"
+        rec = doc["kernels"]
+        k = next(v for name, v in rec.items() if name in kname)
+        h = hashlib.sha256()
+        for f in k["source_files"]:
+            with open(os.path.join(ROOT, "krisp_b200", "csrc", f), "rb") as fh:
+                h.update(fh.read())
+        if h.hexdigest() != k["source_sha256"]:
+            return None, "the kernel's sources changed since the ncu capture in profiles/r05_kernel_traffic.json: traffic not reported"
+        return k["dram_bytes"], f"ncu --set full, one launch on panel C2 (profiles/r05_kernel_traffic.json: {k['kernel']}, sources unchanged since)"
+    except Exception as exc:
+        return None, f"no ncu record ({exc!r})"[:160]
+
+
 def roofline_of(prof, local_bases, n_rec, direct, peak, peak_src):
     """The kernel family with the largest share of the step: algorithmic bytes of the family per step / its device time per step."""
     roof, best, fams = None, -1.0, {}
@@ -189,8 +211,9 @@ def roofline_of(prof, local_bases, n_rec, direct, peak, peak_src):
         if total > best:
             best = total
             roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "traffic_note": "dram bytes per launch from ncu are in profiles/r04_summary.md (same build); not re-measured inside this run",
                     "peak_source": peak_src, "algorithmic_bytes_per_step": b, "family_ms_per_step": total, "launches_per_step": len(per)}
+    if roof:
+        roof["traffic"], roof["traffic_note"] = ncu_traffic(roof["kernel"], n_rec)
     return roof, fams
 
 

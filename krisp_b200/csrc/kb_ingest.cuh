@@ -173,6 +173,15 @@ __device__ __forceinline__ KbFaChunk kb_fa_chunk(const KbFastaArgs& a, uint64_t 
     return c;
 }
 
+// Header state flowing into this lane from the lanes below it (inside one warp): the nearest lower lane with a line start decides.
+// Returns bit 1 = some lower lane decides, bit 0 = its state; *warp_code = what the whole warp hands on (same encoding).
+__device__ __forceinline__ uint32_t kb_fa_lane_state_in(bool defines, uint32_t state, uint32_t lane, uint32_t* warp_code) {
+    const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, defines), smask = __ballot_sync(0xFFFFFFFFu, defines && state);
+    *warp_code = dmask ? (2u | ((smask >> (31u - (uint32_t)__clz(dmask))) & 1u)) : 0u;
+    const uint32_t below = dmask & ((1u << lane) - 1u);
+    return below ? (2u | ((smask >> (31u - (uint32_t)__clz(below))) & 1u)) : 0u;
+}
+
 // (1) last newline of the tile AND its kept-byte counts for both header states flowing into it: counts[t] (not in a header),
 //      counts[n_tiles + t] (inside a header line)
 __device__ __forceinline__ void kb_fa_count_tile(const KbFastaArgs& a, uint32_t n_tiles, uint32_t tile) {
@@ -182,19 +191,14 @@ __device__ __forceinline__ void kb_fa_count_tile(const KbFastaArgs& a, uint32_t 
     const uint64_t tile_base = (uint64_t)tile * KB_FA_TILE;
     const KbFaChunk ch = kb_fa_chunk(a, tile_base, tid);
     const KbFaBits m = kb_fa_bits(ch.w, ch.nv, ch.prev_nl, a.fasta);
-    unsigned long long last = m.NL ? tile_base + (uint64_t)tid * KB_FA_PER + (32u - (uint32_t)__clz(m.NL)) : 0ULL;   // position + 1, 0 = none
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, d));
-    if (lane == 0) ws[warp] = last;
-    uint32_t x = m.LS ? (2u | kb_fa_end_state(m, 0)) : 0u;                // bit 1: defines the state, bit 0: the state
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (uint32_t)d && !(x & 2u)) x = o; }
-    if (lane == 31) wstate[warp] = x;
+    // last newline of the tile: tile-relative position + 1 (0 = none), one reduction per warp
+    const uint32_t last_rel = __reduce_max_sync(0xFFFFFFFFu, m.NL ? tid * KB_FA_PER + (32u - (uint32_t)__clz(m.NL)) : 0u);
+    if (lane == 0) ws[warp] = last_rel ? tile_base + last_rel : 0ULL;
+    uint32_t wcode;
+    uint32_t in = kb_fa_lane_state_in(m.LS != 0, m.LS ? kb_fa_end_state(m, 0) : 0u, lane, &wcode);   // bit 1 set: a line start earlier in this tile fixes the state
+    if (lane == 31) wstate[warp] = wcode;
     __syncthreads();
-    uint32_t in = 0;                                                     // bit 1 set: a line start earlier in this tile fixes the state
-    for (uint32_t w = 0; w < warp; w++) if (wstate[w] & 2u) in = wstate[w];
-    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, x, 1);
-    if (lane > 0 && (up & 2u)) in = up;
+    if (!(in & 2u)) for (uint32_t w = 0; w < warp; w++) if (wstate[w] & 2u) in = wstate[w];
     uint32_t c0, c1;
     if (in & 2u) { c0 = c1 = __popc(kb_fa_walk_bits(m, ch.w, ch.nv, ch.next_nl, a.fasta, in & 1u).keep); }
     else {
@@ -262,16 +266,16 @@ __device__ __forceinline__ void kb_fa_pack_tile(const KbFastaArgs& a, uint32_t t
     const uint64_t tile_base = (uint64_t)tile * KB_FA_TILE;
     const KbFaChunk ch = kb_fa_chunk(a, tile_base, tid);
     const KbFaBits m = kb_fa_bits(ch.w, ch.nv, ch.prev_nl, a.fasta);
-    // header state at this thread's first byte: "last line start wins" scan over the threads of the tile
-    uint32_t x = m.LS ? (2u | kb_fa_end_state(m, 0)) : 0u;                // bit 1: defines the state, bit 0: the state
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= (uint32_t)d && !(x & 2u)) x = o; }
-    if (lane == 31) wstate[warp] = x;
+    // header state at this thread's first byte: the nearest line start before it decides — in this warp, in an earlier warp of the
+    // tile, or what flows into the tile
+    uint32_t wcode;
+    uint32_t in = kb_fa_lane_state_in(m.LS != 0, m.LS ? kb_fa_end_state(m, 0) : 0u, lane, &wcode);
+    if (lane == 31) wstate[warp] = wcode;
     __syncthreads();
-    uint32_t in = 2u | a.hdr0[tile];                               // state flowing into the tile
-    for (uint32_t w = 0; w < warp; w++) if (wstate[w] & 2u) in = wstate[w];
-    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, x, 1);
-    if (lane > 0 && (up & 2u)) in = up;
+    if (!(in & 2u)) {
+        in = 2u | a.hdr0[tile];                                           // state flowing into the tile
+        for (uint32_t w = 0; w < warp; w++) if (wstate[w] & 2u) in = wstate[w];
+    }
     const KbFaWalk w = kb_fa_walk_bits(m, ch.w, ch.nv, ch.next_nl, a.fasta, in & 1u);
     const uint32_t cnt = __popc(w.keep);
     uint32_t inc = cnt;
