@@ -367,7 +367,10 @@ def run_ours(args):
                 for nm, dt in (("load", t_b - t_a), ("search", t_c - t_b), ("rows", t_d - t_c)):
                     out["host_ms"][nm] = out["host_ms"].get(nm, 0.0) + dt * 1e3 / steps
                 out["launches"] += s.last_counters()["kernel_launches"]
-                for name, ms in res.profile:
+                per_step = {}
+                for name, ms in res.profile:                          # (a stage name may occur twice in one search, e.g. the bucket hash
+                    per_step[name] = per_step.get(name, 0.0) + ms     #  and its deferred-bucket fallback: they add up, they do not average)
+                for name, ms in per_step.items():
                     out["prof"].setdefault(name, []).append(ms)
                 # one copy of the result image: flank words | ingroup sets | outgroup sets | rows text (+ 72 B of counters)
                 out["d2h"] = res.n_groups * (8 * res.flank_words.shape[1] + 2 * 4 * res.in_words.shape[1] + res.row_bytes) + 72

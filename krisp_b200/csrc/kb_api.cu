@@ -161,6 +161,7 @@ struct kb_ctx {
     DevBuf rowkeyA, rowkeyB, rowtext;    // row rendering: survivor indices being sorted, the text
     DevBuf brun;                         // lazy records: per bucket (start, length) of the kept elements
     DevBuf batchbuf, rawbuf, fa_work, fa_flags;   // FASTA de-lining: raw file bytes, tile tables, flag word
+    DevBuf entC;                         // sharded slab search with three levels: output of level 2 (entA is the staging buffer the copies still read)
     DevBuf entA, entB, recs, status, small, res_flank, res_in, res_out, res_size, res_run, gather_off, gather_out, taint, plan, deferred;
     uint64_t* h_pinned = nullptr;        // 64 x u64 scratch for small D2H reads
     uint8_t* h_arena = nullptr;          // pinned result arena: survivor table + rows of the LAST search (no pageable copies)
@@ -287,7 +288,7 @@ void kb_destroy(kb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->recs, &ctx->status,
+    DevBuf* bufs[] = {&ctx->bases, &ctx->d_file_starts, &ctx->d_file_gid, &ctx->entA, &ctx->entB, &ctx->entC, &ctx->recs, &ctx->status,
                       &ctx->small, &ctx->res_flank, &ctx->res_in, &ctx->res_out, &ctx->res_size, &ctx->res_run,
                       &ctx->gather_off, &ctx->gather_out, &ctx->taint, &ctx->plan, &ctx->deferred, &ctx->shard_tab, &ctx->batchbuf, &ctx->rawbuf, &ctx->fa_work, &ctx->fa_flags, &ctx->brun, &ctx->rowkeyA, &ctx->rowkeyB, &ctx->rowtext};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -2360,8 +2361,9 @@ int kb_shard_slab_plan(kb_ctx* ctx, int n_shards, int shard_index, uint64_t tota
     ctx->shard_slab = true;
     if (n_digits) *n_digits = (int)nd0;
     *recv_capacity_records = (uint64_t)n_shards * dps * sp.cap[0] + 4096;
-    // digit groups of the pipelined exchange: two-level plans with tile-aligned slabs (kb_shard_slab_level)
-    if (max_groups) *max_groups = (sp.levels == 2 && sp.cap[0] % KB_PT_TILE == 0) ? (int)std::max<uint32_t>(1, nd0 / (uint32_t)n_shards) : 1;
+    // digit groups of the pipelined exchange: tile-aligned parent slabs (kb_shard_slab_level); three-level plans put level 2 into a buffer of its own
+    if (max_groups) *max_groups = (sp.cap[0] % KB_PT_TILE == 0 && (sp.levels == 2 || (sp.levels == 3 && sp.cap[1] % KB_PT_TILE == 0)))
+                                      ? (int)std::max<uint32_t>(1, nd0 / (uint32_t)n_shards) : 1;
     return KB_OK;
 }
 
@@ -2380,13 +2382,14 @@ int kb_shard_slab_extract(kb_ctx* ctx, void** cursors_dev) {
     TRY(ensure(ctx, ctx->plan, sp.bytes + 64));
     uint8_t* P = (uint8_t*)ctx->plan.p;
     // this GPU's buffers: entA = staging of the slabs bound for the other owners (slab d at d * cap0, copied out by kb_shard_slab_send),
-    // children levels: level l writes buf[l & 1] = entB for level 1 (which reads the receive buffer), entA again for level 2
+    // children levels: level 1 (which reads the receive buffer) writes entB, level 2 entC — not entA: the copies of later digit groups still read it
     TRY(ensure_results(ctx, std::max<uint64_t>(ctx->result_cap, (uint64_t)ctx->opt_result_cap)));
     TRY(ensure(ctx, ctx->deferred, (size_t)sp.nc[sp.levels - 1] * 4 + 64));       // (the per-group launches must not reallocate it)
-    size_t need[2] = {(size_t)nd0 * sp.cap[0] + 4096, 0};
-    for (int l = 1; l < sp.levels; l++) need[l & 1] = std::max(need[l & 1], (size_t)sp.nc[l] * sp.cap[l] + 4096);
+    size_t need[3] = {(size_t)nd0 * sp.cap[0] + 4096, 0, 0};
+    for (int l = 1; l < sp.levels; l++) need[l] = (size_t)sp.nc[l] * sp.cap[l] + 4096;
     TRY(ensure(ctx, ctx->entA, need[0] * 8));
     if (need[1]) TRY(ensure(ctx, ctx->entB, need[1] * 8));
+    if (need[2]) TRY(ensure(ctx, ctx->entC, need[2] * 8));
     for (int l = 1; l < sp.levels; l++) {
         kb_slab_init_kernel<<<(unsigned)std::min<uint32_t>((sp.nc[l] + 255) / 256, 1024), 256, 0, ctx->stream>>>((unsigned long long*)(P + sp.off_cur[l]), sp.nc[l], sp.cap[l]);
         CU(cudaGetLastError());
@@ -2476,8 +2479,9 @@ int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group
     const uint32_t N = (uint32_t)ctx->shard_n, me = (uint32_t)ctx->shard_index;
     const uint32_t d_lo = shard_first_digit(me, N, nd0), dps = shard_first_digit(me + 1, N, nd0) - d_lo;
     const uint32_t np = N * dps;
-    if (n_groups > 1 && (sp.levels != 2 || sp.cap[0] % KB_PT_TILE != 0))
-        return fail(ctx, KB_EINVAL, "digit groups need a two-level plan with tile-aligned slabs (use one group)");
+    const bool three = sp.levels == 3;
+    if (n_groups > 1 && (sp.levels < 2 || sp.levels > 3 || sp.cap[0] % KB_PT_TILE != 0 || (three && sp.cap[1] % KB_PT_TILE != 0)))
+        return fail(ctx, KB_EINVAL, "digit groups need tile-aligned parent slabs (use one group)");
     CU(cudaSetDevice(ctx->device));
     uint8_t* P = (uint8_t*)ctx->plan.p;
     unsigned long long* pend = (unsigned long long*)(P + sp.off_snap);
@@ -2506,8 +2510,20 @@ int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group
     }
     prof_end(ctx);
     if (group == 0) ctx->alg_rec_bytes += sp.sym ? 12 : 16;
-    if (sp.levels > 2) {
-        TRY(run_slab_levels(ctx, sp, pl, 2, bufs, std::min<uint64_t>(n_est, (uint64_t)sp.nc[1] * sp.cap[1])));
+    if (three) {
+        // level 2 on the level-1 slabs of this group's digits ([j0 << bits1, j1 << bits1): complete once level 1 has seen every source)
+        static const char* n2[8] = {"K2 partition 2 (group 0)", "K2 partition 2 (group 1)", "K2 partition 2 (group 2)", "K2 partition 2 (group 3)",
+                                    "K2 partition 2 (group 4)", "K2 partition 2 (group 5)", "K2 partition 2 (group 6)", "K2 partition 2 (group 7+)"};
+        prof_begin(ctx, n_groups == 1 ? "K2 partition 2" : n2[std::min(group, 7)]);
+        const unsigned long long* pend1 = (const unsigned long long*)(P + sp.off_cur[1]);
+        if (n_groups == 1) {
+            TRY(launch_slab_level(ctx, sp, pl, 2, bufs[1], (uint64_t*)ctx->entC.p, pend1, nullptr, sp.nc[1], nullptr, std::min<uint64_t>(n_est, (uint64_t)sp.nc[1] * sp.cap[1])));
+        } else {
+            const uint32_t np2 = (j1 - j0) << sp.bits[1];
+            TRY(launch_slab_level(ctx, sp, pl, 2, bufs[1], (uint64_t*)ctx->entC.p, pend1, nullptr, np2, nullptr, 0, np2, j0 << sp.bits[1], 0));
+        }
+        prof_end(ctx);
+        if (group == 0) ctx->alg_rec_bytes += 16;
     }
     // bucket hash on the children of this group's digits: buckets [j0 << bits, j1 << bits)
     const int last = sp.levels - 1;
@@ -2522,7 +2538,7 @@ int kb_shard_slab_level(kb_ctx* ctx, const void* gathered_cursors_dev, int group
     if (sp.sym) hs.bb_hash = pl.bb - sp.bits[0];
     hs.phase = 1;
     KbGroupArgs a{};
-    fill_group_args(ctx, a, bufs[last & 1], n_est);
+    fill_group_args(ctx, a, three ? (uint64_t*)ctx->entC.p : bufs[1], n_est);
     prof_begin(ctx, n_groups == 1 ? "K3 bucket hash" : n3[std::min(group, 7)]);
     TRY(launch_hash(ctx, a, hs));
     prof_end(ctx);
@@ -2534,7 +2550,7 @@ int kb_shard_slab_own(kb_ctx* ctx, const void* gathered_cursors_dev) {
     if (!ctx->configured || !ctx->shard_slab) return fail(ctx, KB_EINVAL, "kb_shard_slab_plan has not been called");
     const SlabPlan& sp = ctx->shard_sp;
     PartPlan pl = ctx->shard_plan;
-    if (sp.levels != 2 || sp.cap[0] % KB_PT_TILE != 0) return fail(ctx, KB_EINVAL, "needs a two-level plan with tile-aligned slabs (as digit groups do)");
+    if (sp.levels < 2 || sp.levels > 3 || sp.cap[0] % KB_PT_TILE != 0) return fail(ctx, KB_EINVAL, "needs tile-aligned level-0 slabs (as digit groups do)");
     const uint32_t nd0 = sp.nc[0];
     const uint32_t N = (uint32_t)ctx->shard_n, me = (uint32_t)ctx->shard_index;
     const uint32_t d_lo = shard_first_digit(me, N, nd0), dps = shard_first_digit(me + 1, N, nd0) - d_lo;
@@ -2576,7 +2592,7 @@ int kb_shard_slab_finish(kb_ctx* ctx, int* status, kb_result** out) {
     if (sp.sym) hs.bb_hash = pl.bb - sp.bits[0];
     hs.phase = 2;
     ctx->replan_ok = ctx->opt_bucket_bits < 0 && pl.bb < std::min(ctx->lo.FB, 24);
-    int rc = run_group(ctx, bufs[last & 1], n_est, out, &hs, true);
+    int rc = run_group(ctx, sp.levels == 3 ? (uint64_t*)ctx->entC.p : bufs[last & 1], n_est, out, &hs, true);
     ctx->replan_ok = false;
     prof_collect(ctx);
     if (rc == KB_REPLAN) { *status = 1; return KB_OK; }

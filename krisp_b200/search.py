@@ -25,7 +25,8 @@ class SearchResult:
     """Survivor table of one search.
 
     Packed, as the library returns it: ``flank_words`` [n_groups, FW] (MSB-first flank bits), ``in_words`` / ``out_words``
-    [n_groups, MW] (column sets), ``group_size`` [n_groups], and with want_records ``run_offset`` [n_groups + 1] into
+    [n_groups, MW] (column sets), ``group_size`` [n_groups] (None unless option ``group_sizes`` or want_records asked for
+    it: the rows do not need it), and with want_records ``run_offset`` [n_groups + 1] into
     ``records`` [n, W].  Decoded lazily on first access: ``left`` [n_groups, L] / ``right`` [n_groups, R] ASCII,
     ``in_mask`` / ``out_mask`` [n_groups, D] 4-bit base sets over the ingroup-labelled / the other occurrences.
     """

@@ -72,6 +72,35 @@ def main():
         if rank == 0:
             print(("ok   " if ok else "FAIL ") + f"panel {L}/{D}/{R} {opts}", len(rows), flush=True)
         bad += 0 if ok else 1
+    # a three-level plan with digit groups: level 2 runs per group too, into a buffer of its own (the staging buffer is still being
+    # copied out of); the forced slab capacity is a multiple of the partition tile, which is what lets tiles map to parent slabs
+    gs = make_panel(5, 4, 50_000)
+    is_in = [1 if g.is_ingroup else 0 for g in gs]
+    s.configure(25, 1, 2, is_in)
+    s.clear_sequences()
+    for i, g in enumerate(gs):
+        s.add_sequence(i, np.frombuffer(g.joined(), dtype=np.uint8))
+    want = s.search(have_outgroup=True).rows()
+    for sym in (0, 1):
+        for k, v in (("bucket_bits", 12), ("shard_bits0", 2), ("slab_cap", 262144), ("sym", sym), ("profile", 1)):
+            s.set_option(k, v)
+        try:
+            s.clear_sequences()
+            for i, g in enumerate(gs):
+                if i % world == rank:
+                    s.add_sequence(i, np.frombuffer(g.joined(), dtype=np.uint8))
+            res = sharded.sharded_search(s, dev, have_outgroup=True)
+            rows = sharded.gather_rows(res.rows())
+        finally:
+            for k, v in (("bucket_bits", -1), ("shard_bits0", 0), ("slab_cap", 0), ("sym", -1), ("profile", 0)):
+                s.set_option(k, v)
+        stages = [nm for nm, _ in res.profile]
+        ex = getattr(res, "exchange", None) or {}
+        grouped3 = any(nm.startswith("K2 partition 2 (group") for nm in stages)
+        ok = rows == want and len(want) > 0 and (grouped3 or ex.get("groups", 1) == 1)
+        if rank == 0:
+            print(("ok   " if ok else "FAIL ") + f"three-level grouped plan, sym {sym}: groups {ex.get('groups')}, level 2 per group: {grouped3}", len(rows), flush=True)
+        bad += 0 if ok else 1
     # divergent genomes (3 % private substitutions): the sharded plan is too coarse at first; every rank must vote for the re-plan
     # and the rows must still be the single-GPU rows
     gs = make_panel(7, 5, 400_000, noise=3e-2, snp_every=200)

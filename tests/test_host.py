@@ -343,3 +343,34 @@ def test_render_output_file_reproduces_reference_rows_and_alignments(tmp_path):
             assert align.read_text() == case["out_align"], name
             checked_align += 1
     assert checked_align >= 1
+
+
+def test_kstream_constructor_accepts_device_tables_and_rejects_the_text_pipeline():
+    """krisp_b200.kstream maps the reference's constructor arguments (kstream.py:122-248) onto the sorted tables the device builds
+    and raises UnsupportedError — never a silent CPU fallback — for what stays the reference's generic text pipeline."""
+    from krisp_b200._lib import UnsupportedError
+    from krisp_b200.kstream import kstream
+    ok = [(dict(kmers=28, complements=True, disallow="Nn", mapsoft=True, split=[25, -2], sort=True, sortcols=[0, 2]), (25, 1, 2, 0)),
+          (dict(kmers=28, disallow="Nn", mapsoft=True, sort=True), (28, 0, 0, 1)),
+          (dict(kmers=28, canonicals=True, allow="ACGT", mapsoft=True, split=[25, -2], sort=True, sortcols=[0, 2]), (25, 1, 2, 2)),
+          (dict(kmers=15, canonicals=True, allow="ACGTacgt", omitsoft=True, sort=True), (15, 0, 0, 2)),
+          (dict(kmers=124, complements=True, disallow="Nn", omitsoft=True, split=[32, -32], sort=True, sortcols=[0, 2]), (32, 60, 32, 0))]
+    for kw, want in ok:
+        k = kstream(**kw)
+        assert (k.L, k.D, k.R, k.strands) == want
+    bad = [dict(kmers=28, disallow="Nn", mapsoft=True),                                   # unsorted streaming
+           dict(kmers=[5, 6], disallow="Nn", mapsoft=True, sort=True),                     # several k
+           dict(kmers=28, allow="ACGTN", mapsoft=True, sort=True),                         # letters the 2-bit records cannot hold
+           dict(kmers=28, disallow="NnA", mapsoft=True, sort=True),
+           dict(kmers=28, disallow="Nn", sort=True),                                       # lower case kept as such
+           dict(kmers=28, disallow="Nn", mapsoft=True, expandiupac=True, sort=True),
+           dict(kmers=40, canonicals=True, disallow="Nn", mapsoft=True, sort=True),        # strand modes beyond one-word records
+           dict(kmers=28, disallow="Nn", mapsoft=True, split=[25, -2], sort=True),         # split without its sort columns
+           dict(kmers=28, disallow="Nn", mapsoft=True, split=[5, 5, 5], sort=True, sortcols=[0, 2])]
+    for kw in bad:
+        with pytest.raises(UnsupportedError):
+            kstream(**kw)
+    with pytest.raises(ValueError):
+        kstream(kmers=28, complements=True, canonicals=True)
+    with pytest.raises(ValueError):
+        kstream(kmers=28, omitsoft=True, mapsoft=True)
