@@ -374,3 +374,21 @@ def test_kstream_constructor_accepts_device_tables_and_rejects_the_text_pipeline
         kstream(kmers=28, complements=True, canonicals=True)
     with pytest.raises(ValueError):
         kstream(kmers=28, omitsoft=True, mapsoft=True)
+
+
+def test_bit_parallel_fasta_walk_equals_byte_walk(tmp_path):
+    """The de-lining kernels' per-thread logic (csrc/kb_ingest.cuh: SWAR byte classes, prefix propagation of the header state, keep /
+    separator masks) against its byte-at-a-time form on 4 M random 16-byte chunks — host code compiled from the same header
+    (tools/fa_walk_check.cu), no GPU needed."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(GOLDEN_DIR.rstrip("/")).rsplit("/tests", 1)[0]
+    exe = str(tmp_path / "fa_walk_check")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run([nvcc, "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(root, "krisp_b200", "csrc"),
+                    "-o", exe, os.path.join(root, "tools", "fa_walk_check.cu")], check=True, capture_output=True, env=env)
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0 and "0 mismatches" in p.stdout, p.stdout[-2000:]
