@@ -10,6 +10,8 @@ No CPU fallback: everything that touches sequence data runs in libkrisp_b200.so.
 """
 import ctypes
 
+import weakref
+
 import numpy as np
 
 from . import _lib, ingest
@@ -36,13 +38,76 @@ class SearchResult:
                  in_words=None, out_words=None):
         self.L, self.D, self.R, self.n_records = L, D, R, n_records
         self._left, self._right, self._in_mask, self._out_mask = left, right, in_mask, out_mask
+        self._own, self._views = {}, {}     # packed arrays: owned copies / views of library memory not copied yet (see _collect)
+        self._n = None                      # number of groups, known without touching an array
+        self.flank_word_count = self.mask_word_count = None
         self.in_words, self.out_words = in_words, out_words
         self.group_size, self.flank_words, self.run_offset, self.records = group_size, flank_words, run_offset, records
         self.stats, self.profile, self.have_outgroup = stats or {}, profile or [], have_outgroup
-        self.rows_blob, self.row_bytes = None, 0      # CSV rows rendered on the device, ascending (left, right) (kb_result_rows)
+        self._rows_blob, self._rows_ref, self.row_bytes = None, None, 0   # CSV rows rendered on the device, ascending (left, right) (kb_result_rows)
+        self._borrow = None      # (free function, kb_result handle): the packed arrays are VIEWS of library memory until _detach()
+
+    def _packed(name):                      # noqa: N805 — property factory for the packed arrays
+        def get(self):
+            v = self._views.pop(name, None)
+            if v is not None:                # first use: one memcpy out of the library's memory; callers only ever see owned arrays
+                self._own[name] = np.array(v, copy=True)
+            return self._own.get(name)
+
+        def put(self, value):
+            self._views.pop(name, None)
+            self._own[name] = value
+        return property(get, put)
+
+    flank_words, in_words, out_words = _packed("flank_words"), _packed("in_words"), _packed("out_words")
+    group_size, run_offset, records = _packed("group_size"), _packed("run_offset"), _packed("records")
+    del _packed
+
+    def _detach(self):
+        """Copy what is still a view of the library's result arena / kb_result and release the handle.  The Searcher calls this on
+        a still-living result right before its next search overwrites the arena; arrays nobody looked at are never copied when the
+        result is dropped before that."""
+        if self._borrow is None:
+            return
+        for name in list(self._views):
+            self._own[name] = np.array(self._views.pop(name), copy=True)
+        if self._rows_blob is None and self._rows_ref is not None:
+            self._rows_blob = ctypes.string_at(*self._rows_ref)
+        self._rows_ref = None
+        free, handle = self._borrow
+        self._borrow = None
+        free(handle)
+
+    def __del__(self):
+        try:
+            if self._borrow is not None:
+                free, handle = self._borrow
+                self._borrow = None
+                free(handle)
+        except Exception:
+            pass
+
+    @property
+    def rows_blob(self):
+        if self._rows_blob is None and self._rows_ref is not None:
+            self._rows_blob = ctypes.string_at(*self._rows_ref)      # (one memcpy out of the pinned arena, on first use)
+        return self._rows_blob
+
+    @rows_blob.setter
+    def rows_blob(self, value):
+        self._rows_blob, self._rows_ref = value, None
+
+    def csv_rows_bytes(self):
+        """csv_rows_text() as bytes (what a caller writes to the CSV file; no decoding)."""
+        blob = self.rows_blob
+        if blob is not None and (blob or self.n_groups == 0 or (self.R == 0 and self.D > 0)):
+            return blob
+        return self.csv_rows_text().encode("ascii")
 
     @property
     def n_groups(self):
+        if self._n is not None:
+            return self._n
         if self.flank_words is not None:
             return int(self.flank_words.shape[0])
         return 0 if self._left is None else int(self._left.shape[0])
@@ -188,12 +253,14 @@ class Searcher:
             # a raw cudaStream_t handle; 0 is the default stream (torch's default), not "none"
             self._check(self._L.kb_set_stream(self._ctx, ctypes.c_void_p(int(stream))))
         self._keep = []          # host buffers that must outlive the async copies
+        self._last = None        # weak reference to the last SearchResult while its arrays are views of the result arena
         self.bases_added = 0     # bytes handed to add_sequence since the last clear_sequences
         self.added_ids = []      # global file ids in the order they were added
         self.lo = None
 
     def close(self):
         if self._ctx:
+            self._detach_last()                    # (kb_destroy frees the arena a living result may still look at)
             self._L.kb_destroy(self._ctx)
             self._ctx = None
 
@@ -289,42 +356,61 @@ class Searcher:
         self._keep = []
 
     # ---- search ------------------------------------------------------------------------------------
+    def _detach_last(self):
+        """The previous result (if somebody still holds it) copies its arrays out of the arena before the next search reuses it."""
+        last = self._last() if self._last is not None else None
+        if last is not None:
+            last._detach()
+        self._last = None
+
     def _collect(self, res_ptr, have_outgroup):
+        """kb_result -> SearchResult whose packed arrays are views of the library's memory (the pinned result arena; run offsets and
+        records inside the kb_result): nothing is copied unless the result outlives the next search (_detach_last)."""
         L, D, R = self.lo
         view = _lib.ResultView()
+        ok = False
         try:
             self._check(self._L.kb_result_get(res_ptr, ctypes.byref(view)))
             n, FW, MW, W = int(view.n_groups), int(view.flank_words), int(view.mask_words), int(view.record_words)
 
             def arr(ptr, count, dtype):
-                # one memcpy out of the library's arena (np.ctypeslib.as_array costs ~40 us per call — five of them per search
-                # were most of the host time between two searches)
-                if count == 0:
+                if count == 0 or not ptr:
                     return np.zeros(0, dtype=dtype)
-                return np.frombuffer(bytearray(ctypes.string_at(ptr, count * np.dtype(dtype).itemsize)), dtype=dtype)
+                nbytes = count * np.dtype(dtype).itemsize
+                return np.frombuffer((ctypes.c_ubyte * nbytes).from_address(ctypes.addressof(ptr.contents)), dtype=dtype)
 
-            flank = arr(view.flank, n * FW, np.uint64).reshape(n, FW)
             out = SearchResult(L=L, D=D, R=R, n_records=int(view.n_records), have_outgroup=have_outgroup)
-            out.flank_words = flank
-            out.in_words = arr(view.in_mask, n * MW, np.uint32).reshape(n, MW)
-            out.out_words = arr(view.out_mask, n * MW, np.uint32).reshape(n, MW)
-            out.group_size = arr(view.group_size, n, np.uint32) if view.group_size else None   # (option group_sizes / want_records)
-            out.run_offset = arr(view.run_offset, n + 1, np.uint64)
+            out._n, out.flank_word_count, out.mask_word_count = n, FW, MW
+            out._views = {"flank_words": arr(view.flank, n * FW, np.uint64).reshape(n, FW),
+                          "in_words": arr(view.in_mask, n * MW, np.uint32).reshape(n, MW),
+                          "out_words": arr(view.out_mask, n * MW, np.uint32).reshape(n, MW),
+                          "run_offset": arr(view.run_offset, n + 1, np.uint64)}
+            if view.group_size:                                        # (option group_sizes / want_records; else None)
+                out._views["group_size"] = arr(view.group_size, n, np.uint32)
             nrr = int(view.n_run_records)
-            out.records = arr(view.records, nrr * W, np.uint64).reshape(nrr, W)
+            out._views["records"] = arr(view.records, nrr * W, np.uint64).reshape(nrr, W)
             out.stats = dict(zip(("runs", "queued_runs", "groups_in_every_file", "mixed_runs"), [int(x) for x in view.stats]))
             text, nb, rb = ctypes.c_void_p(), ctypes.c_uint64(), ctypes.c_int()
             self._check(self._L.kb_result_rows(res_ptr, ctypes.byref(text), ctypes.byref(nb), ctypes.byref(rb)))
-            out.rows_blob = ctypes.string_at(text.value, int(nb.value)) if nb.value else b""
+            if nb.value:
+                out._rows_ref = (text.value, int(nb.value))
+            else:
+                out.rows_blob = b""
             out.row_bytes = int(rb.value)
+            free = self._L.kb_result_free
+            out._borrow = (free, ctypes.c_void_p(res_ptr.value))
+            self._last = weakref.ref(out)
+            ok = True
         finally:
-            self._L.kb_result_free(res_ptr)
+            if not ok:
+                self._L.kb_result_free(res_ptr)
         out.profile = self.last_profile()
         return out
 
     def search(self, have_outgroup=True):
         """Run K1 -> K2 -> K3 on the sequences added so far."""
         res = ctypes.c_void_p()
+        self._detach_last()
         self._set_have_outgroup(have_outgroup)
         self._check(self._L.kb_search(self._ctx, ctypes.byref(res)))
         self._keep = []
@@ -430,6 +516,7 @@ class Searcher:
     def shard_slab_finish(self, have_outgroup=True):
         """-> (SearchResult or None, status): 1 = plan too coarse, 2 = slab overflow, 3 = survivor table grown (see the header)."""
         res, status = ctypes.c_void_p(), ctypes.c_int()
+        self._detach_last()
         self._check(self._L.kb_shard_slab_finish(self._ctx, ctypes.byref(status), ctypes.byref(res)))
         if status.value != 0 or not res.value:
             return None, int(status.value)
@@ -448,6 +535,7 @@ class Searcher:
         """piece_counts: flat [source rank][digit of this shard] record counts, in arrival order."""
         arr = (ctypes.c_uint64 * max(1, len(piece_counts)))(*[int(c) for c in piece_counts])
         res = ctypes.c_void_p()
+        self._detach_last()
         self._set_have_outgroup(have_outgroup)
         self._check(self._L.kb_shard_search(self._ctx, int(n_records), arr, ctypes.byref(res)))
         return self._collect(res, have_outgroup)
