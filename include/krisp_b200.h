@@ -1,7 +1,8 @@
 /*
  * krisp_b200.h — C ABI of libkrisp_b200.so: the B200 (sm_100a) implementation of krisp_fasta's
- * diagnostic-region search hot path (k-mer extraction -> radix sort -> intersection over all
- * files -> diagnostic filter).
+ * diagnostic-region search hot path (k-mer extraction -> grouping by conserved flanks: radix
+ * partition + per-bucket hash, a full radix sort only for the kstream tables -> intersection over
+ * all files -> diagnostic filter).
  *
  * The reference (grunwaldlab/krisp 0.1.6) is pure Python and has no FFI for this path; the
  * boundary it crosses today is its Python stage functions and the text k-mer files between them.
@@ -14,8 +15,9 @@
  * One kb_ctx drives one GPU (one process per GPU; multi-GPU = one ctx per rank, see kb_shard_*).
  * A ctx is not thread-safe.  The library owns all device memory and the host result buffers
  * until the matching *_free / kb_destroy; input pointers are borrowed for the duration of the
- * call.  Output *content* is deterministic; output *order* is not (the host canonical-sorts rows,
- * as the reference's own row order depends on --cores).
+ * call.  Output *content* is deterministic.  The survivor TABLE comes in no particular order (the
+ * host canonical-sorts where it compares sets); the CSV rows of kb_result_rows are in ascending
+ * (left, right) order, the reference's order with --cores 1.
  */
 #ifndef KRISP_B200_H
 #define KRISP_B200_H
